@@ -1,0 +1,181 @@
+/*
+ * obmarkers.h -- C ABI of libobmarkers.so, the B200 (sm_100a) marker scanner.
+ *
+ * Drop-in boundary for the marker-scanning hot path of vmware-tanzu-labs/operator-builder
+ * (reference @ 2827f233; file:line citations are relative to the reference tree).
+ *
+ * The reference has no FFI at this seam; the seam is three exported Go methods consumed only by
+ * internal/markers/parser:
+ *     func NewLexer(r io.Reader) *Lexer          internal/markers/lexer/lexer.go:27
+ *     func (l *Lexer) Run()                      internal/markers/lexer/lexer.go:43
+ *     func (l *Lexer) NextLexeme() Lexeme        internal/markers/lexer/lexer.go:51
+ *     type Lexeme struct{Type; Value; Pos}       internal/markers/lexer/lexeme.go:32-36
+ * A cgo shim (operator-builder_b200/go/lexer_gpu.go) keeps that surface and feeds it
+ * from the entry points below: one obm_lex_batch() per `create api` replaces one lexer goroutine
+ * per YAML node (internal/markers/inspect/yaml.go:94), and obm_stream_* replays a document's
+ * tuples as the exact Lexeme sequence the Go lexer would have sent on its channel.
+ *
+ * All entry points use plain pointers and sizes.  The callee keeps no pointer after return (cgo
+ * rule).  Lexical errors/warnings are IN-BAND tuples (the reference sends them in-band as
+ * LexemeError / LexemeWarning, lexer/error.go:15-45); infrastructure failures (CUDA, capacity,
+ * arguments) are negative return codes plus obm_last_error().
+ *
+ * There is no CPU fallback: every lexing entry point fails with OBM_E_NO_DEVICE when no CUDA
+ * device is usable.  obm_stream_* / obm_parse_* are host-side consumers of tuples the GPU produced.
+ */
+#ifndef OBMARKERS_H
+#define OBMARKERS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OBM_ABI_VERSION 1
+
+/* ---------------------------------------------------------------------------------------------
+ * Tuple stream.  One 64-bit little-endian word per tuple:
+ *     bits  0..31  off   byte offset inside the document
+ *     bits 32..58  len   byte length (27 bits)
+ *     bits 59..63  kind
+ * Kinds 0..20 are the reference's LexemeType values (lexer/lexeme.go:8-30).  Kinds 21..29 are
+ * pseudo-tuples the host decoder folds away so that the decoded stream is byte-identical to the
+ * reference's (Type, Value, Pos) sequence, including its implementation artefacts:
+ *   PART    text that sits in the reference lexer's `buffer` without having been emitted; it is
+ *           prepended to the Value of the next real lexeme (emit.go:8-17 clears buffer only on emit)
+ *   FLUSH   the reference called flush() (discard.go:68-71; state.go:81,128)
+ *   DRIFT   the second backup() of state.go:79/126 shortened the column by one (position.go:44-45)
+ *   LINE    position basis: off = byte offset of column 1, len = line number (low 27 bits);
+ *           emitted before the first located tuple that is not on the previously announced line
+ *   LINEHI  high bits (>> 27) of the next LINE's line number (documents with > 134M lines)
+ *   WARN_ / ERR_  in-band warnings / fatal errors; the decoder formats the reference's exact text
+ * Kinds 0 (Error) and 19 (Warning) never appear raw; 14..17 are never emitted by the reference.
+ * ------------------------------------------------------------------------------------------- */
+typedef uint64_t obm_tuple;
+
+enum obm_kind {
+    OBM_K_ERROR = 0, OBM_K_COMMENT = 1, OBM_K_MARKER_START = 2, OBM_K_SCOPE = 3, OBM_K_SEPARATOR = 4,
+    OBM_K_ARG = 5, OBM_K_ARG_ASSIGNMENT = 6, OBM_K_ARG_DELIMITER = 7, OBM_K_STRING_LITERAL = 8,
+    OBM_K_FLOAT_LITERAL = 9, OBM_K_INTEGER_LITERAL = 10, OBM_K_SYNTHETIC_BOOL = 11, OBM_K_BOOL_LITERAL = 12,
+    OBM_K_QUOTE = 13, OBM_K_MARKER_END = 18, OBM_K_WARNING = 19, OBM_K_EOF = 20,
+    OBM_K_PART = 21, OBM_K_FLUSH = 22, OBM_K_DRIFT = 23, OBM_K_LINE = 24, OBM_K_LINEHI = 25,
+    OBM_K_WARN_NOSCOPE = 26,   /* "marker without scope found"  state.go:95,105 ; off = position */
+    OBM_K_WARN_INVALID = 27,   /* "invalid marker found"        state.go:114    ; off = position */
+    OBM_K_ERR_MALFORMED = 28,  /* "malformed argument: %s"      state.go:152,173,315 ; off = position */
+    OBM_K_ERR_UNMATCHED = 29,  /* "unmatched string delimiter"  state.go:193,199,209 ; off = position */
+    OBM_K_ERR_FLOAT = 30,      /* "invalid float literal"       state.go:259 ; off,len = the literal */
+    OBM_K_ERR_INT = 31         /* "invalid integer literal"     state.go:270 ; off,len = the literal */
+};
+
+#define OBM_LEN_BITS 27
+#define OBM_MAX_LEN ((1u << OBM_LEN_BITS) - 1u)
+#define OBM_TUPLE(kind, off, len) (((uint64_t)(kind) << 59) | ((uint64_t)(len) << 32) | (uint64_t)(uint32_t)(off))
+#define OBM_TUPLE_KIND(t) ((unsigned)((t) >> 59))
+#define OBM_TUPLE_LEN(t) ((uint32_t)(((t) >> 32) & OBM_MAX_LEN))
+#define OBM_TUPLE_OFF(t) ((uint32_t)((t) & 0xFFFFFFFFu))
+
+/* A document may be at most 2^32 - 2 bytes (offsets are 32-bit inside a document). */
+#define OBM_MAX_DOC_BYTES 0xFFFFFFFEull
+
+/* return codes */
+enum obm_status {
+    OBM_OK = 0,
+    OBM_E_NO_DEVICE = -1,   /* no CUDA device / driver: there is no CPU fallback */
+    OBM_E_CUDA = -2,        /* a CUDA call failed; see obm_last_error */
+    OBM_E_CAPACITY = -3,    /* `out_cap` too small; *out_count holds the required tuple count */
+    OBM_E_ARG = -4,         /* bad argument (null pointer, non-monotonic doc_off, oversize document) */
+    OBM_E_NOMEM = -5
+};
+
+typedef struct obm_handle obm_handle;
+
+/* Counters filled by a scan (all per call). */
+typedef struct obm_stats {
+    uint64_t n_tuples;        /* tuples written (incl. pseudo-tuples) */
+    uint64_t n_markers;       /* MarkerStart lexemes  */
+    uint64_t n_lexemes;       /* real lexemes a reference lexer would have sent (incl. EOF/warnings/errors) */
+    uint64_t n_docs_exact;    /* documents that took the exact (sequential) device path */
+    uint64_t n_docs_fatal;    /* documents that ended in a fatal lexical error */
+    uint64_t bytes;           /* input bytes scanned */
+    float    ms_kernels;      /* device time of the scan kernels (CUDA events), host-buffer calls also: */
+    float    ms_total;        /* H2D + kernels + D2H as seen by CUDA events on the handle's stream */
+} obm_stats;
+
+/* --- lifetime ------------------------------------------------------------------------------ */
+int obm_abi_version(void);
+/* Creates a scanner bound to CUDA device `device_ordinal` with its own stream. */
+int obm_create(int device_ordinal, obm_handle **out);
+void obm_destroy(obm_handle *h);
+/* Message of the last failure on this handle (or a static message when h is NULL). */
+const char *obm_last_error(const obm_handle *h);
+
+/* --- the hot path -------------------------------------------------------------------------- */
+/*
+ * Lex a packed batch of documents held in HOST memory (replaces, for every document d,
+ * lexer.NewLexer(bytes.NewBuffer(bytes[doc_off[d]:doc_off[d+1]])) + Run + drain, lexer.go:27-53).
+ *   bytes        packed documents, back to back
+ *   doc_off      ndocs+1 ascending byte offsets into `bytes`
+ *   out          receives tuples; document d's tuples are out[doc_tuple_off[d] .. doc_tuple_off[d+1])
+ *   out_cap      capacity of `out` in tuples.  If too small: returns OBM_E_CAPACITY with the needed
+ *                count in *out_count and doc_tuple_off filled; nothing is written to `out`.
+ *                Pass out = NULL, out_cap = 0 to size a buffer.
+ *   stats        optional
+ */
+int obm_lex_batch(obm_handle *h, const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs,
+                  obm_tuple *out, uint64_t out_cap, uint64_t *out_count, uint64_t *doc_tuple_off,
+                  obm_stats *stats);
+
+/*
+ * Same scan on DEVICE-resident buffers (benchmarking / pipelines that keep manifests in HBM).
+ * All pointers are device pointers on the handle's device; `stream` is a cudaStream_t (NULL = the
+ * handle's stream).  Asynchronous: returns after enqueueing.  d_doc_tuple_off[ndocs] holds the
+ * total tuple count; if it exceeds out_cap the kernels write nothing past out_cap and set
+ * d_status[0] = 1 (d_status is a device uint32[4]: {overflow, n_docs_exact, n_docs_fatal, reserved}).
+ * d_counts (device uint64[2], may be NULL) receives {n_markers, n_lexemes}.
+ */
+int obm_lex_batch_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
+                         uint64_t total_bytes, void *d_out, uint64_t out_cap, void *d_doc_tuple_off,
+                         void *d_status, void *d_counts, void *stream);
+
+/* Bytes of device scratch obm_lex_batch_device needs for `ndocs`/`total_bytes` (allocated lazily,
+ * grown on demand and kept by the handle). */
+uint64_t obm_scratch_bytes(uint32_t ndocs, uint64_t total_bytes);
+
+/* Deterministic synthetic corpus generated ON DEVICE (BASELINE.md config C2/C3/C4 generator; the
+ * same generator exists on the host in operator-builder_b200/corpus.py for parity tests).
+ * Writes ndocs documents of exactly doc_bytes bytes starting at global document index first_doc.
+ * flavour: 0 = standalone markers, 1 = collection markers. */
+int obm_generate_corpus_device(obm_handle *h, void *d_bytes, void *d_doc_off, uint32_t ndocs,
+                               uint32_t doc_bytes, uint64_t first_doc, int flavour, void *stream);
+
+/* --- host-side consumers of the tuple stream (no GPU needed; no lexing happens here) ------- */
+/*
+ * Replays one document's tuples as the reference's Lexeme sequence.  Mirrors
+ * NewLexer/Run/NextLexeme: after the last lexeme (EOF, or a fatal Error) obm_stream_next returns 0
+ * and yields the zero Lexeme {Type: 0, Value: ""} like a closed Go channel (lexer.go:47,51-53).
+ */
+typedef struct obm_stream obm_stream;
+typedef struct obm_lexeme {
+    int32_t type;          /* reference LexemeType 0..20 */
+    const uint8_t *value;  /* valid until the next call on this stream */
+    uint64_t value_len;
+    int64_t line, column;  /* Pos; {0,0} for synthetic lexemes (emit.go:24-33) */
+} obm_lexeme;
+obm_stream *obm_stream_new(const uint8_t *doc, uint64_t doc_len, const obm_tuple *tuples, uint64_t ntuples);
+int obm_stream_next(obm_stream *s, obm_lexeme *out); /* 1 = lexeme produced, 0 = stream closed */
+void obm_stream_free(obm_stream *s);
+/*
+ * Decodes a whole document into a flat buffer of records
+ *     [u8 type][u32 line][u32 col][u32 vlen][value bytes] ...
+ * (*out is malloc'd; release with obm_free).  Returns the number of lexemes or a negative status.
+ */
+int64_t obm_decode_doc(const uint8_t *doc, uint64_t doc_len, const obm_tuple *tuples, uint64_t ntuples,
+                       uint8_t **out, uint64_t *out_len);
+void obm_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBMARKERS_H */

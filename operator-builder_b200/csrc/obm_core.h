@@ -1,0 +1,497 @@
+/*
+ * obm_core.h -- the exact marker lexer as straight-line code over an in-memory document, emitting
+ * the canonical tuple stream defined in include/obmarkers.h.
+ *
+ * Compiled for the device by nvcc (used by every kernel in obm_kernels.cu) and, for logic tests
+ * only, for the host by g++ (tests/hostsim).  It is NOT a CPU fallback: libobmarkers.so exports no
+ * host lexing entry point.
+ *
+ * What it restates (reference: internal/markers/lexer @ 2827f233):
+ *   state machine            state.go:15-317   (lex, lexComment, lexMarkerStart, lexMarker, lexArgs,
+ *                                               lexArgValueInitial + literal lexers, lexMoreArgs)
+ *   next/backup/positions    position.go:18-65
+ *   peek windows             peek.go:20-96 over bufio.Reader (default 4096-byte buffer, lexer.go:38)
+ *   discard / flush          discard.go:17-71
+ *   emit / emitSynthetic     emit.go:7-32
+ * Because the document is resident in memory, bufio.Reader.Peek(n) is the closed form
+ * "min(n, 4096, remaining) bytes at the read offset" ("peek window").
+ *
+ * The reference's `buffer` string is represented implicitly: un-emitted text is doc[s, p) plus the
+ * PART tuples already sent; `start` is the offset s.  See obmarkers.h for the pseudo-tuples.
+ */
+#ifndef OBM_CORE_H
+#define OBM_CORE_H
+
+#include <stdint.h>
+#include "../../include/obmarkers.h"
+
+#if defined(__CUDACC__)
+#define OBM_HD __host__ __device__ __forceinline__
+#define OBM_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define OBM_HD inline
+#define OBM_HD_NOINLINE inline
+#endif
+
+namespace obm {
+
+/* Range tables + constants reachable from both host and device builds. */
+struct Tables {
+    const unsigned int (*letter)[2]; int n_letter;
+    const unsigned int (*number)[2]; int n_number;
+    const char *f64_overflow_digits; /* decimal digits of 2^1024 - 2^970 (309 of them) */
+};
+
+enum { RUNE_ERR = 0xFFFD, RUNE_EOF = -1 };
+enum { BUFIO_WINDOW = 4096 }; /* bufio.defaultBufSize, lexer.go:38 */
+
+/* utf8.DecodeRune over doc[at, lim) */
+OBM_HD int decode_rune(const uint8_t *d, uint32_t at, uint32_t lim, uint32_t &w) {
+    if (at >= lim) { w = 0; return RUNE_EOF; }
+    uint32_t c0 = d[at];
+    if (c0 < 0x80) { w = 1; return (int)c0; }
+    w = 1;
+    if (c0 < 0xC2 || c0 > 0xF4) return RUNE_ERR;
+    uint32_t avail = lim - at;
+    if (c0 < 0xE0) {
+        if (avail < 2 || (d[at + 1] & 0xC0) != 0x80) return RUNE_ERR;
+        w = 2; return (int)(((c0 & 0x1F) << 6) | (d[at + 1] & 0x3Fu));
+    }
+    if (c0 < 0xF0) {
+        uint32_t lo = 0x80, hi = 0xBF;
+        if (c0 == 0xE0) lo = 0xA0; else if (c0 == 0xED) hi = 0x9F;
+        if (avail < 3) return RUNE_ERR;
+        uint32_t c1 = d[at + 1], c2 = d[at + 2];
+        if (c1 < lo || c1 > hi || (c2 & 0xC0) != 0x80) return RUNE_ERR;
+        w = 3; return (int)(((c0 & 0x0F) << 12) | ((c1 & 0x3F) << 6) | (c2 & 0x3F));
+    }
+    {
+        uint32_t lo = 0x80, hi = 0xBF;
+        if (c0 == 0xF0) lo = 0x90; else if (c0 == 0xF4) hi = 0x8F;
+        if (avail < 4) return RUNE_ERR;
+        uint32_t c1 = d[at + 1], c2 = d[at + 2], c3 = d[at + 3];
+        if (c1 < lo || c1 > hi || (c2 & 0xC0) != 0x80 || (c3 & 0xC0) != 0x80) return RUNE_ERR;
+        w = 4; return (int)(((c0 & 0x07) << 18) | ((c1 & 0x3F) << 12) | ((c2 & 0x3F) << 6) | (c3 & 0x3F));
+    }
+}
+
+OBM_HD bool in_ranges(const unsigned int (*t)[2], int n, int r) {
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        if ((unsigned)r < t[mid][0]) hi = mid - 1;
+        else if ((unsigned)r > t[mid][1]) lo = mid + 1;
+        else return true;
+    }
+    return false;
+}
+/* unicode.IsSpace (White_Space) */
+OBM_HD bool is_space(int r) {
+    if (r < 0) return false;
+    if (r < 0x80) return r == ' ' || (r >= 0x09 && r <= 0x0D);
+    if (r <= 0xFF) return r == 0x85 || r == 0xA0;
+    return r == 0x1680 || (r >= 0x2000 && r <= 0x200A) || r == 0x2028 || r == 0x2029 || r == 0x202F || r == 0x205F || r == 0x3000;
+}
+OBM_HD bool is_letter(const Tables &T, int r) {
+    if (r < 0) return false;
+    if (r < 0x80) { unsigned c = (unsigned)r | 0x20u; return c >= 'a' && c <= 'z'; }
+    return in_ranges(T.letter, T.n_letter, r);
+}
+OBM_HD bool is_number(const Tables &T, int r) {
+    if (r < 0) return false;
+    if (r < 0x80) return r >= '0' && r <= '9';
+    return in_ranges(T.number, T.n_number, r);
+}
+
+/* Delimiter sets of consumeUntil (state.go:72-76, 119-123, 289-293) as 128-bit ASCII masks.
+ * name set:  : = SP " ' ` , + { } [ ] ( ) ; \n      naked-value set: the same without ';' */
+OBM_HD bool is_name_delim(uint32_t c) {
+    if (c >= 0x80) return false;
+    /* word0: \n(10)                               -> bit 10
+     * word1: SP(32) "(34) '(39) ((40) )(41) +(43) ,(44) :(58) ;(59) =(61)
+     * word2: [(91) ](93) `(96)
+     * word3: {(123) }(125) */
+    const uint32_t m0 = 1u << 10;
+    const uint32_t m1 = (1u << 0) | (1u << 2) | (1u << 7) | (1u << 8) | (1u << 9) | (1u << 11) | (1u << 12) | (1u << 26) | (1u << 27) | (1u << 29);
+    const uint32_t m2 = (1u << (91 - 64)) | (1u << (93 - 64));
+    const uint32_t m3 = (1u << 0) | (1u << (123 - 96)) | (1u << (125 - 96));
+    uint32_t m = (c < 32) ? m0 : (c < 64) ? m1 : (c < 96) ? m2 : m3;
+    return (m >> (c & 31)) & 1u;
+}
+OBM_HD bool is_naked_delim(uint32_t c) { return c != ';' && is_name_delim(c); }
+
+/* strconv.ParseFloat(s, 64) error class: 0 ok, 1 invalid syntax, 2 value out of range (state.go:258).
+ * Restated from Go 1.16 strconv/atof.go (special, readFloat) for decimal input; see oracle notes. */
+OBM_HD_NOINLINE int parse_float_err(const Tables &T, const uint8_t *s, uint32_t n) {
+    if (n == 0) return 1;
+    uint32_t i = 0;
+    {
+        uint32_t j = 0; uint32_t c0 = s[0];
+        if (c0 == '+' || c0 == '-') j = 1;
+        if (j < n && (j == 1 || (c0 | 0x20) == 'i')) {
+            const char inf[9] = {'i', 'n', 'f', 'i', 'n', 'i', 't', 'y', 0};
+            uint32_t k = 0;
+            while (j + k < n && k < 8 && (uint32_t)(s[j + k] | 0x20) == (uint32_t)inf[k]) k++;
+            if (k > 3 && k < 8) k = 3;
+            if (k == 3 || k == 8) return (j + k == n) ? 0 : 1;
+        } else if ((c0 | 0x20) == 'n') {
+            if (n >= 3 && (s[1] | 0x20) == 'a' && (s[2] | 0x20) == 'n') return n == 3 ? 0 : 1;
+        }
+    }
+    if (s[i] == '+' || s[i] == '-') i++;
+    if (i + 2 < n && s[i] == '0' && (s[i + 1] | 0x20) == 'x') return 1; /* hex floats: unreachable from the lexer's alphabet */
+    bool sawdot = false, sawdigits = false, nonzero = false;
+    long long nd = 0, dp = 0;
+    uint32_t dbeg = i;
+    for (; i < n; i++) {
+        uint32_t c = s[i];
+        if (c == '_') return 1; /* underscores need a base prefix */
+        if (c == '.') { if (sawdot) break; sawdot = true; dp = nd; continue; }
+        if (c >= '0' && c <= '9') {
+            sawdigits = true;
+            if (c == '0' && nd == 0) { dp--; continue; }
+            nd++; nonzero = true; continue;
+        }
+        break;
+    }
+    uint32_t dend = i;
+    if (!sawdigits) return 1;
+    if (!sawdot) dp = nd;
+    if (i < n && (s[i] | 0x20) == 'e') {
+        i++;
+        if (i >= n) return 1;
+        int esign = 1;
+        if (s[i] == '+') i++; else if (s[i] == '-') { i++; esign = -1; }
+        if (i >= n || s[i] < '0' || s[i] > '9') return 1;
+        long long e = 0;
+        for (; i < n && ((s[i] >= '0' && s[i] <= '9') || s[i] == '_'); i++) {
+            if (s[i] == '_') return 1;
+            if (e < 10000) e = e * 10 + (s[i] - '0');
+        }
+        dp += e * esign;
+    }
+    if (i != n) return 1;
+    if (!nonzero) return 0;
+    if (dp > 309) return 2;
+    if (dp < 309) return 0;
+    uint32_t k = 0; bool started = false;
+    for (uint32_t j = dbeg; j < dend; j++) {
+        uint32_t c = s[j];
+        if (c == '.') continue;
+        if (!started) { if (c == '0') continue; started = true; }
+        if (k < 309) {
+            uint32_t t = (uint32_t)T.f64_overflow_digits[k];
+            if (c > t) return 2;
+            if (c < t) return 0;
+            k++;
+        } else return 2;
+    }
+    for (; k < 309; k++) if (T.f64_overflow_digits[k] != '0') return 0;
+    return 2;
+}
+
+/* strconv.Atoi error class (state.go:269); int is 64-bit; overflow is reported when it happens. */
+OBM_HD_NOINLINE int atoi_err(const uint8_t *s, uint32_t n) {
+    uint32_t i = 0; bool neg = false;
+    if (n == 0) return 1;
+    if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; }
+    if (i >= n) return 1;
+    const uint64_t cutoff = 0xFFFFFFFFFFFFFFFFull / 10 + 1;
+    uint64_t v = 0;
+    for (; i < n; i++) {
+        if (s[i] < '0' || s[i] > '9') return 1;
+        if (v >= cutoff) return 2;
+        v *= 10;
+        uint64_t v1 = v + (uint64_t)(s[i] - '0');
+        if (v1 < v) return 2;
+        v = v1;
+    }
+    if (!neg && v >= (1ull << 63)) return 2;
+    if (neg && v > (1ull << 63)) return 2;
+    return 0;
+}
+
+/* ---- sinks ---------------------------------------------------------------------------------- */
+struct CountSink {
+    uint64_t n_tuples = 0; uint32_t n_markers = 0; uint32_t n_lexemes = 0;
+    OBM_HD void put(uint32_t kind, uint32_t off, uint32_t len) {
+        (void)off; (void)len;
+        n_tuples++;
+        n_markers += (kind == OBM_K_MARKER_START);
+        n_lexemes += (kind <= OBM_K_EOF) || (kind >= OBM_K_WARN_NOSCOPE);
+    }
+};
+struct WriteSink {
+    obm_tuple *out; uint64_t cap; /* tuples beyond cap are dropped (caller detects via count) */
+    uint64_t n_tuples = 0; uint32_t n_markers = 0; uint32_t n_lexemes = 0;
+    OBM_HD WriteSink(obm_tuple *o, uint64_t c) : out(o), cap(c) {}
+    OBM_HD void put(uint32_t kind, uint32_t off, uint32_t len) {
+        if (n_tuples < cap) out[n_tuples] = OBM_TUPLE(kind, off, len);
+        n_tuples++;
+        n_markers += (kind == OBM_K_MARKER_START);
+        n_lexemes += (kind <= OBM_K_EOF) || (kind >= OBM_K_WARN_NOSCOPE);
+    }
+};
+
+enum RunStatus { RUN_EOF = 0, RUN_LINE_END = 1, RUN_FATAL = 2 };
+enum TopState { TOP_LEX = 0, TOP_COMMENT = 1, TOP_FATAL = 2 };
+
+template <class Sink>
+struct Lexer {
+    const Tables &T;
+    const uint8_t *d; uint32_t n;
+    uint32_t p, s;                      /* read offset; `start` offset */
+    uint32_t line_p, base_p, drift_p;   /* l.pos   == {line_p, p - base_p + 1 - drift_p} */
+    uint32_t line_s, base_s;            /* l.start == {line_s, s - base_s + 1 - (drift of that line)} */
+    uint32_t line_e, base_e;            /* basis announced by the last LINE tuple */
+    uint32_t sv_line, sv_base, sv_drift;/* basis before the '\n' just read by next(), for backup() */
+    uint32_t last_w; int last_r;        /* l.width / rune of the last next() */
+    uint32_t last_type;                 /* l.lastEmittedLexeme.Type */
+    Sink &out;
+
+    /* `first_line`/`line_start`: where this lexer instance begins (doc start: 1, 0). */
+    OBM_HD Lexer(const Tables &t, const uint8_t *doc, uint32_t len, Sink &sink, uint32_t start_off = 0,
+                 uint32_t first_line = 1, bool announce_first = false)
+        : T(t), d(doc), n(len), p(start_off), s(start_off), line_p(first_line), base_p(start_off), drift_p(0),
+          line_s(first_line), base_s(start_off), line_e(announce_first ? 0u : 1u), base_e(0),
+          sv_line(first_line), sv_base(start_off), sv_drift(0), last_w(0), last_r(RUNE_EOF), last_type(0), out(sink) {}
+
+    /* ---- tuple plumbing ---- */
+    OBM_HD void ensure_line(uint32_t line, uint32_t base) {
+        if (line != line_e || base != base_e) {
+            if (line >> OBM_LEN_BITS) out.put(OBM_K_LINEHI, line >> OBM_LEN_BITS, 0);
+            out.put(OBM_K_LINE, base, line & OBM_MAX_LEN);
+            line_e = line; base_e = base;
+        }
+    }
+    OBM_HD void sync_start() { s = p; line_s = line_p; base_s = base_p; }
+    /* un-emitted text doc[s,p) becomes a PART (kept in the decoder's pending buffer) */
+    OBM_HD void part_tail() {
+        if (p > s) {
+            ensure_line(line_s, base_s);
+            uint32_t off = s, len = p - s;
+            while (len > OBM_MAX_LEN) { out.put(OBM_K_PART, off, OBM_MAX_LEN); off += OBM_MAX_LEN; len -= OBM_MAX_LEN; }
+            out.put(OBM_K_PART, off, len);
+            sync_start();
+        }
+    }
+    /* emit.go:7-19 */
+    OBM_HD void emit(uint32_t kind) {
+        ensure_line(line_s, base_s);
+        uint32_t off = s, len = p - s;
+        while (len > OBM_MAX_LEN) { out.put(OBM_K_PART, off, OBM_MAX_LEN); off += OBM_MAX_LEN; len -= OBM_MAX_LEN; }
+        out.put(kind, off, len);
+        last_type = kind;
+        sync_start();
+    }
+    /* emit.go:23-32 */
+    OBM_HD void emit_synthetic(uint32_t kind) { out.put(kind, p, 0); last_type = kind; }
+    /* discard.go:68-71 */
+    OBM_HD void flush() { out.put(OBM_K_FLUSH, p, 0); sync_start(); }
+    /* error.go:37-45 (continues in lexComment) / error.go:15-34 (terminates) */
+    OBM_HD void located_at_pos(uint32_t kind) { part_tail(); ensure_line(line_p, base_p); out.put(kind, p, 0); }
+    OBM_HD void numeric_error(uint32_t kind) { ensure_line(line_s, base_s); out.put(kind, s, p - s); }
+
+    /* ---- reader primitives ---- */
+    OBM_HD int peek(uint32_t &w) const { return decode_rune(d, p, n, w); }
+    OBM_HD int peek() const { uint32_t w; return decode_rune(d, p, n, w); }
+    OBM_HD uint32_t peek_byte() const { return p < n ? d[p] : 0x100u; } /* 0x100 = EOF sentinel */
+    /* position.go:18-39 */
+    OBM_HD int next() {
+        uint32_t w; int r = decode_rune(d, p, n, w);
+        last_w = w; last_r = r;
+        if (r == RUNE_EOF) return r;
+        p += w;
+        if (r == '\n') { sv_line = line_p; sv_base = base_p; sv_drift = drift_p; line_p++; base_p = p; drift_p = 0; }
+        return r;
+    }
+    /* position.go:43-57, first call after a next() */
+    OBM_HD void backup() {
+        if (last_w != 0) {
+            p -= last_w;
+            if (last_r == '\n') { line_p = sv_line; base_p = sv_base; drift_p = sv_drift; }
+        }
+    }
+    /* position.go:43-57, second call (state.go:79,126): UnreadRune fails, the column still moves */
+    OBM_HD void backup_again() {
+        if (last_w != 0) { drift_p += last_w; ensure_line(line_p, base_p); out.put(OBM_K_DRIFT, p, 0); }
+    }
+    /* discard.go:12-38 discard() == discardN(1) */
+    OBM_HD void discard1() {
+        uint32_t w; int r = decode_rune(d, p, n, w);
+        if (r == RUNE_EOF) { flush(); return; }
+        part_tail();
+        uint32_t adv = (r == RUNE_ERR && w == 1) ? 3u : w; /* utf8.RuneLen(U+FFFD) == 3, discard.go:27-28 */
+        if (adv > n - p) adv = n - p;
+        p += adv;
+        if (r == '\n') { line_p++; base_p = p; drift_p = 0; }
+        sync_start();
+    }
+    OBM_HD bool has_prefix2(uint32_t a, uint32_t b) const { return p + 1 < n && d[p] == a && d[p + 1] == b; }
+    /* consume.go:65-80 with an ASCII delimiter class; returns `consumed` */
+    template <bool NAKED>
+    OBM_HD bool consume_until() {
+        bool consumed = false;
+        for (;;) {
+            int r = next();
+            if (r == RUNE_EOF) { backup(); return consumed; }
+            if (r < 0x80 && (NAKED ? is_naked_delim((uint32_t)r) : is_name_delim((uint32_t)r))) { backup(); return consumed; }
+            consumed = true;
+        }
+    }
+    /* peek.go:65-89 for one ASCII token `tok[0..t)`: on success returns true and sets `width`
+     * (= l.width after the final peekN: whitespace BYTES + token bytes). */
+    OBM_HD bool peeked_whitespaced(const char *tok, uint32_t t, uint32_t &width) const {
+        uint32_t lim = (n - p > (uint32_t)BUFIO_WINDOW) ? p + (uint32_t)BUFIO_WINDOW : n;
+        uint32_t o = p;
+        for (;;) {
+            uint32_t w; int r = decode_rune(d, o, lim, w);
+            if (r == RUNE_EOF) return false; /* r[i] == eof (real end of input or end of the 4096-byte window) */
+            if (!is_space(r)) break;
+            o += w;
+        }
+        if (o + t > lim) return false;
+        for (uint32_t k = 0; k < t; k++) if (d[o + k] != (uint8_t)tok[k]) return false;
+        width = (o - p) + t;
+        return true;
+    }
+    OBM_HD bool peeked_whitespaced_comment(uint32_t &width) const {
+        return peeked_whitespaced("//", 2, width) || peeked_whitespaced("#", 1, width);
+    }
+    /* consume.go:37-47: consumes `width` RUNES (width is a byte count) */
+    OBM_HD bool consumed_whitespaced(const char *tok, uint32_t t) {
+        uint32_t width;
+        if (!peeked_whitespaced(tok, t, width)) return false;
+        for (uint32_t k = 0; k < width; k++) next();
+        return true;
+    }
+
+    /* ---- marker states; each returns the top-level state to continue in ---- */
+    /* state.go:60-68, entered with '+' just consumed */
+    OBM_HD int marker_start() {
+        if (is_letter(T, peek())) { emit(OBM_K_MARKER_START); return lex_marker(); }
+        return TOP_COMMENT;
+    }
+    /* state.go:71-116 */
+    OBM_HD int lex_marker() {
+        for (;;) {
+            if (!consume_until<false>()) { backup_again(); flush(); return TOP_COMMENT; }
+            uint32_t c = peek_byte();
+            if (c == ':') { emit(OBM_K_SCOPE); next(); emit(OBM_K_SEPARATOR); continue; }
+            if (c == ' ' || c == '\n' || c == 0x100u) {
+                if (last_type != OBM_K_SEPARATOR) { located_at_pos(OBM_K_WARN_NOSCOPE); return TOP_COMMENT; }
+                emit(OBM_K_ARG); emit_synthetic(OBM_K_SYNTHETIC_BOOL); emit_synthetic(OBM_K_MARKER_END);
+                return TOP_COMMENT;
+            }
+            if (c == '=') {
+                if (last_type != OBM_K_SEPARATOR) { located_at_pos(OBM_K_WARN_NOSCOPE); return TOP_COMMENT; }
+                emit(OBM_K_ARG); next(); emit(OBM_K_ARG_ASSIGNMENT);
+                return lex_arg_value();
+            }
+            located_at_pos(OBM_K_WARN_INVALID);
+            return TOP_COMMENT;
+        }
+    }
+    /* state.go:118-154 (lexArgs) and state.go:304-317 (lexMoreArgs), as one loop */
+    OBM_HD int lex_more_args() {
+        for (;;) {
+            uint32_t c = peek_byte();
+            if (c == ',') { next(); emit(OBM_K_ARG_DELIMITER); }
+            else if (c == ' ' || c == '\n' || c == 0x100u) { emit_synthetic(OBM_K_MARKER_END); return TOP_COMMENT; }
+            else { located_at_pos(OBM_K_ERR_MALFORMED); return TOP_FATAL; }
+            /* lexArgs */
+            if (!consume_until<false>()) { backup_again(); flush(); emit_synthetic(OBM_K_MARKER_END); return TOP_LEX; }
+            emit(OBM_K_ARG);
+            c = peek_byte();
+            if (c == '=') { next(); emit(OBM_K_ARG_ASSIGNMENT); int st = lex_arg_value_inner(); if (st != -1) return st; continue; }
+            if (c == ' ' || c == '\n' || c == 0x100u) { emit_synthetic(OBM_K_SYNTHETIC_BOOL); emit_synthetic(OBM_K_MARKER_END); return TOP_COMMENT; }
+            if (c == ',') { emit_synthetic(OBM_K_SYNTHETIC_BOOL); continue; }
+            located_at_pos(OBM_K_ERR_MALFORMED);
+            return TOP_FATAL;
+        }
+    }
+    OBM_HD int lex_arg_value() { int st = lex_arg_value_inner(); return st != -1 ? st : lex_more_args(); }
+    /* state.go:156-302; returns -1 to continue in lexMoreArgs, else a TopState (fatal) */
+    OBM_HD int lex_arg_value_inner() {
+        uint32_t c = peek_byte();
+        /* lexStringLiteral, state.go:176-221 */
+        if (c == '\'' || c == '"' || c == '`') {
+            next(); emit(OBM_K_QUOTE);
+            for (;;) {
+                uint32_t b = peek_byte();
+                if (b == 0x100u) { located_at_pos(OBM_K_ERR_UNMATCHED); return TOP_FATAL; }
+                if (b == '\n') {
+                    if (c != '`') { located_at_pos(OBM_K_ERR_UNMATCHED); return TOP_FATAL; }
+                    next();
+                    uint32_t width;
+                    if (peeked_whitespaced_comment(width)) {
+                        while (!(has_prefix2('/', '/') || peek_byte() == '#')) discard1(); /* discardUntil */
+                        discard1();
+                    }
+                } else if (b == c) {
+                    emit(OBM_K_STRING_LITERAL); next(); emit(OBM_K_QUOTE);
+                    return -1;
+                } else {
+                    next();
+                }
+            }
+        }
+        /* lexNumericLiteral, state.go:223-276 */
+        {
+            int r0 = peek();
+            if (r0 == '.' || r0 == '-' || is_number(T, r0)) {
+                bool isfloat = (r0 == '.');
+                for (;;) {
+                    next();
+                    uint32_t b = peek_byte();
+                    if (b == '.' || b == 'e' || b == 'E' || b == '-') { isfloat = true; continue; }
+                    if (!is_number(T, peek())) break;
+                }
+                int code = isfloat ? parse_float_err(T, d + s, p - s) : atoi_err(d + s, p - s);
+                if (code) { numeric_error(isfloat ? OBM_K_ERR_FLOAT : OBM_K_ERR_INT); return TOP_FATAL; }
+                emit(isfloat ? OBM_K_FLOAT_LITERAL : OBM_K_INTEGER_LITERAL);
+                return -1;
+            }
+        }
+        /* lexBooleanLiteral, state.go:278-286 */
+        if (consumed_whitespaced("true", 4) || consumed_whitespaced("false", 5)) { emit(OBM_K_BOOL_LITERAL); return -1; }
+        /* lexNakedStringLiteral, state.go:288-302 */
+        if (consume_until<true>()) { emit(OBM_K_STRING_LITERAL); return -1; }
+        located_at_pos(OBM_K_ERR_MALFORMED);
+        return TOP_FATAL;
+    }
+
+    /* ---- top level: state.go:15-57.  LINE_MODE stops after discarding the first top-level '\n'
+     *      at or beyond `line_end` (the fast path's per-line owner); otherwise runs to EOF and
+     *      emits the EOF tuple itself. ---- */
+    template <bool LINE_MODE>
+    OBM_HD int run(uint32_t line_end = 0) {
+        int st = TOP_LEX;
+        for (;;) {
+            if (st == TOP_LEX) {
+                uint32_t w; int r = peek(w);
+                if (r == RUNE_EOF) { if (!LINE_MODE) out.put(OBM_K_EOF, n, 0); return RUN_EOF; }
+                if (is_space(r)) {
+                    bool stop = LINE_MODE && r == '\n' && p >= line_end;
+                    discard1();
+                    if (stop) return RUN_LINE_END;
+                    continue;
+                }
+                if (has_prefix2('/', '/')) { next(); next(); emit(OBM_K_COMMENT); st = TOP_COMMENT; }
+                else if (r == '#') { next(); emit(OBM_K_COMMENT); st = TOP_COMMENT; }
+                else if (r == '+') { next(); st = marker_start(); }
+                else discard1();
+            } else if (st == TOP_COMMENT) {
+                uint32_t c = peek_byte();
+                if (c == '+') { next(); st = marker_start(); }
+                else if (c == '\n' || c == 0x100u) st = TOP_LEX;
+                else discard1();
+            } else {
+                return RUN_FATAL;
+            }
+        }
+    }
+};
+
+} /* namespace obm */
+#endif /* OBM_CORE_H */

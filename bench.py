@@ -1,0 +1,336 @@
+#!/usr/bin/env python3
+"""bench.py -- marker-scan throughput on B200 (BASELINE.json metric: YAML MB/s scanned + markers/s,
+% of the HBM-read roofline, next to the reference's CPU path).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+    python bench.py --impl reference ...                     (the reference's CPU path on the host cores)
+
+A "step" is one pass of the hot path over the whole synthetic batch:
+  workload  BASELINE.json configs[3] / the north-star target: 2,621,440 synthetic manifests x 4,096 B
+            = 10 GiB (generator: obm_corpus.h, splitmix64(0x0B200 ^ doc index), 8 markers per file),
+            resident in HBM, sharded by file over the N ranks ("strong" scaling: total work fixed).
+            Inputs are 10 GiB >> 126 MB L2, so no L2 flush is needed between timed iterations.
+  value     total input MB / device time of (scan + emit [+ the N>1 index all-gather]), max over ranks
+  e2e       the same metric through the C-ABI host entry point obm_lex_batch: pinned host buffers,
+            H2D of the manifests and D2H of tuples + offsets inside the timed region (bounded sample)
+  roofline  algorithmic bytes = 1 byte read per input byte / time of all scan kernels,
+            against the measured HBM copy peak in MEASURED_PEAKS.json
+  cpu_baseline  the oracle (C restatement of the reference's Go lexer; no Go toolchain here) on all
+            host cores over a bounded sample of the same corpus
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DOC_BYTES = 4096
+FULL_DOCS = 2_621_440  # 10 GiB
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(sample_docs, threads, steps, warmup, flavour):
+    """Times the oracle (C restatement of internal/markers/lexer) over a bounded sample on the host cores."""
+    import operator_builder_b200 as ob  # host generator only (no lexing)
+    import oracle
+    data, off = ob.generate_corpus_host(sample_docs, DOC_BYTES, 0, flavour)
+    for _ in range(warmup):
+        oracle.scan_batch(data[:min(len(data), 64 * DOC_BYTES)], off[:65], threads)
+    t0 = time.perf_counter()
+    markers = lexemes = 0
+    for _ in range(steps):
+        nl, nm, _h = oracle.scan_batch(data, off, threads)
+        markers, lexemes = nm, nl
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"mb_s": len(data) / dt / 1e6, "ms_per_step": dt * 1e3, "markers_per_s": markers / dt, "lexemes": lexemes,
+            "sample": f"{sample_docs} docs x {DOC_BYTES} B ({sample_docs * DOC_BYTES / 2**20:.0f} MiB) of the same generator, "
+                      f"{steps} pass(es), {threads} pthreads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--docs", type=int, default=int(os.environ.get("OBM_BENCH_DOCS", FULL_DOCS)), help="total documents (default 10 GiB worth)")
+    ap.add_argument("--flavour", type=int, default=0)
+    ap.add_argument("--e2e-docs", type=int, default=int(os.environ.get("OBM_BENCH_E2E_DOCS", 262144)), help="documents per rank in the e2e leg (1 GiB)")
+    ap.add_argument("--cpu-docs", type=int, default=int(os.environ.get("OBM_BENCH_CPU_DOCS", 65536)), help="documents in the CPU baseline sample (256 MiB)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--mode", type=int, default=0, help="0 auto (fast path), 1 exact path only")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+
+    config = {"workload": f"configs[3]: {args.docs} synthetic manifests x {DOC_BYTES} B = {args.docs * DOC_BYTES / 2**30:.2f} GiB, "
+                          f"8 markers/file, sharded by file over {world} rank(s), HBM-resident",
+              "docs": args.docs, "doc_bytes": DOC_BYTES, "flavour": args.flavour, "parallelism": f"file-shard x{world}",
+              "l2": "inputs (>= 1.25 GiB per rank) exceed the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        # The reference's own CPU implementation of the path; Go cannot be built here, so this is the
+        # oracle port of internal/markers/lexer on all host cores (kind "port").  Rank 0 only.
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, 3))
+        r = cpu_reference_run(args.cpu_docs, cores, steps, min(args.warmup, 1), args.flavour)
+        line = {"impl": "reference", "metric": "manifest_scan_throughput", "value": r["mb_s"], "unit": "MB/s", "n_gpus": world,
+                "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                "markers_per_s": r["markers_per_s"],
+                "cpu_baseline": {"value": r["mb_s"], "unit": "MB/s", "cores": cores, "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["mb_s"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import operator_builder_b200 as ob
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: operator-builder_b200 has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    d0, d1 = args.docs * rank // world, args.docs * (rank + 1) // world
+    ndocs = d1 - d0
+    nbytes = ndocs * DOC_BYTES
+    sc = ob.Scanner(local_rank)
+    sc.set_mode(args.mode)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    d_bytes = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_off = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
+    sc.generate_corpus_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, DOC_BYTES, d0, args.flavour, sp)
+    cap = nbytes // 16  # tuples (8 B each): 0.5 B of tuples per input byte; measured need is ~0.32
+    d_out = torch.empty(cap, dtype=torch.int64, device=dev)
+    d_toff = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
+    d_status = torch.zeros(4, dtype=torch.int32, device=dev)
+    d_counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    # N>1: the one exchange step -- every rank learns every document's tuple count (the global
+    # doc_tuple_off index), 4 B/document, one all-gather.  Full-tuple all-gather is timed separately.
+    counts_local = torch.empty(ndocs, dtype=torch.int32, device=dev) if world > 1 else None
+    counts_all = torch.empty(ndocs * world, dtype=torch.int32, device=dev) if world > 1 and args.docs % world == 0 else None
+
+    def step():
+        sc.lex_batch_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, nbytes, d_out.data_ptr(), cap, d_toff.data_ptr(),
+                            d_status.data_ptr(), d_counts.data_ptr(), sp)
+        if counts_all is not None:
+            torch.sub(d_toff[1:], d_toff[:-1], out=counts_local)
+            dist.all_gather_into_tensor(counts_all, counts_local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ob._native.lib().obm_launches_last_call(sc.handle) * args.steps
+
+    # scan-only time (no collective) for the roofline, same stream, same events
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    k0.record(stream)
+    for _ in range(args.steps):
+        sc.lex_batch_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, nbytes, d_out.data_ptr(), cap, d_toff.data_ptr(),
+                            d_status.data_ptr(), d_counts.data_ptr(), sp)
+    k1.record(stream)
+    barrier()
+    ms_scan = k0.elapsed_time(k1) / args.steps
+
+    n_tuples = int(d_toff[-1].item())
+    n_markers, n_lexemes = int(d_counts[0].item()), int(d_counts[1].item())
+    status = d_status.cpu().tolist()
+    if status[0]:
+        print(json.dumps({"error": "tuple buffer overflow in bench", "needed": n_tuples, "cap": cap}))
+        return 3
+
+    # full-tuple all-gather, timed separately (SURVEY.md section 7 hard part 1: it, not the scan, bounds N=8)
+    gather = None
+    if world > 1:
+        mx = torch.tensor([n_tuples], dtype=torch.int64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        pad = int(mx.item())
+        g_out = torch.empty(pad * world, dtype=torch.int64, device=dev)
+        src = d_out[:pad]
+        dist.all_gather_into_tensor(g_out, src)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(3):
+            dist.all_gather_into_tensor(g_out, src)
+        g1.record(stream)
+        barrier()
+        gms = g0.elapsed_time(g1) / 3
+        gather = {"ms": gms, "bytes_received_per_rank": pad * 8 * (world - 1), "gb_s_per_rank": pad * 8 * (world - 1) / gms / 1e6}
+        del g_out
+
+    # max over ranks
+    t = torch.tensor([ms, ms_scan], dtype=torch.float64, device=dev)
+    agg = torch.tensor([n_tuples, n_markers, n_lexemes, status[1], status[2]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    ms, ms_scan = float(t[0].item()), float(t[1].item())
+    tot_tuples, tot_markers, tot_lexemes, docs_exact, docs_fatal = [int(x) for x in agg.tolist()]
+    total_bytes = args.docs * DOC_BYTES
+
+    # ---- e2e: C-ABI host entry point, pinned host buffers, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        e_docs = min(args.e2e_docs, ndocs)
+        e_bytes = e_docs * DOC_BYTES
+        h_bytes = torch.empty(e_bytes, dtype=torch.uint8).pin_memory()
+        h_bytes.copy_(d_bytes[:e_bytes])
+        h_off = np.arange(e_docs + 1, dtype=np.uint64) * DOC_BYTES
+        e_cap = e_bytes // 16
+        h_out = torch.empty(e_cap, dtype=torch.int64).pin_memory()
+        hb, ho = h_bytes.numpy(), h_out.numpy().view(np.uint64)
+        del d_out
+        torch.cuda.empty_cache()
+        res = sc.lex_batch(hb, h_off, out=ho)  # warm-up (allocates the handle's device staging)
+        res = sc.lex_batch(hb, h_off, out=ho)
+        barrier()
+        t0 = time.perf_counter()
+        e_steps = max(3, min(args.steps, 10))
+        for _ in range(e_steps):
+            res = sc.lex_batch(hb, h_off, out=ho)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e_steps
+        et = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        dt = float(et.item())
+        d2h = int(res.stats["n_tuples"]) * 8 + (e_docs + 1) * 8
+        e2e = {"value": e_bytes * world / dt / 1e6, "unit": "MB/s", "h2d_bytes_per_step": e_bytes + (e_docs + 1) * 8,
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "api": "obm_lex_batch (C ABI, pinned host buffers)",
+               "sample": f"{e_docs} docs x {DOC_BYTES} B per rank", "markers_per_s": res.stats["n_markers"] * world / dt,
+               "ms_kernels_inside": res.stats["ms_kernels"]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    achieved = (total_bytes / world) / (ms_scan / 1e3) / 1e9  # per-GPU GB/s of algorithmic input bytes
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    cpu = None
+    if not args.no_cpu and world >= 1:
+        r = cpu_reference_run(args.cpu_docs, cores, 1, 1, args.flavour)
+        cpu = {"value": r["mb_s"], "unit": "MB/s", "cores": cores, "kind": "port", "sample": r["sample"],
+               "markers_per_s": r["markers_per_s"]}
+
+    line = {"metric": "manifest_scan_throughput", "value": total_bytes / (ms / 1e3) / 1e6, "unit": "MB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+            "markers_per_s": tot_markers / (ms / 1e3), "lexemes_per_s": tot_lexemes / (ms / 1e3),
+            "tuples": tot_tuples, "tuple_bytes_per_input_byte": tot_tuples * 8 / total_bytes,
+            "docs_exact_path": docs_exact, "docs_fatal": docs_fatal, "mode": args.mode,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "ms_scan_kernels": ms_scan,
+                         "algorithmic_bytes_per_launch": total_bytes // world,
+                         "note": "1 B read per input byte (SURVEY 8d); time = all kernels of one scan, per GPU"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "exchange": ({"index_allgather": "4 B/doc counts inside the timed step", "full_tuple_allgather": gather} if world > 1 else None)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

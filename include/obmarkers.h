@@ -150,6 +150,22 @@ uint64_t obm_scratch_bytes(uint32_t ndocs, uint64_t total_bytes);
 int obm_generate_corpus_device(obm_handle *h, void *d_bytes, void *d_doc_off, uint32_t ndocs,
                                uint32_t doc_bytes, uint64_t first_doc, int flavour, void *stream);
 
+/* Host copy of the same generator (test / bench utility; performs no lexing). */
+int obm_generate_corpus_host(uint8_t *bytes, uint64_t *doc_off, uint32_t ndocs, uint32_t doc_bytes,
+                             uint64_t first_doc, int flavour);
+
+/* Scanning strategy: 0 = auto (tile fast path, exact path for irregular documents; default),
+ * 1 = exact path for every document.  Both produce the identical tuple stream. Returns the old mode. */
+int obm_set_mode(obm_handle *h, int mode);
+
+/* Number of this library's kernels launched by the last scan call on this handle. */
+uint32_t obm_launches_last_call(const obm_handle *h);
+
+/* Page-locked host memory so that obm_lex_batch's copies run at DMA speed (the cgo shim keeps
+ * manifest bytes in C memory anyway). */
+void *obm_pinned_alloc(uint64_t bytes);
+void obm_pinned_free(void *p);
+
 /* --- host-side consumers of the tuple stream (no GPU needed; no lexing happens here) ------- */
 /*
  * Replays one document's tuples as the reference's Lexeme sequence.  Mirrors

@@ -1,0 +1,423 @@
+/*
+ * obm_lib.cu -- libobmarkers.so: CUDA kernels (sm_100a) + the C ABI of include/obmarkers.h.
+ *
+ * Replaces, for a whole batch of manifests at once, the per-document
+ *     lexer.NewLexer(r) ; go l.Run() ; for { l.NextLexeme() }      (internal/markers/lexer/lexer.go:27-53)
+ * that internal/markers/parser/parser.go:35,47 starts once per YAML node
+ * (internal/markers/inspect/yaml.go:94), driven per manifest by
+ * internal/workload/v1/kinds/workload.go:224-285.
+ *
+ * Kernels in this file
+ *   k_exact_count / k_exact_fill   exact path: one thread per document runs obm::Lexer (obm_core.h);
+ *                                  handles every input (non-ASCII, invalid UTF-8, multi-line
+ *                                  literals, fatal errors, documents of any size)
+ *   k_scan_*                       exclusive prefix sum of per-document tuple counts -> doc_tuple_off
+ *   k_generate_corpus              synthetic manifests generated in HBM (obm_corpus.h)
+ * The fast path (k_tile_scan, obm_fast.cuh) is layered on top of the same core; see DESIGN.md.
+ *
+ * There is no CPU fallback: without a CUDA device every lexing entry point returns OBM_E_NO_DEVICE.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "../../include/obmarkers.h"
+#include "go_unicode_tables.h"
+#include "obm_core.h"
+#include "obm_corpus.h"
+
+/* ------------------------------------------------------------------------------------------- */
+/* device constants                                                                             */
+/* ------------------------------------------------------------------------------------------- */
+__device__ const char D_F64_OVERFLOW_DIGITS[] = GO_F64_OVERFLOW_DIGITS;
+
+__device__ __forceinline__ obm::Tables device_tables() {
+    obm::Tables T;
+    T.letter = D_GO_LETTER_RANGES; T.n_letter = D_GO_LETTER_RANGES_N;
+    T.number = D_GO_NUMBER_RANGES; T.n_number = D_GO_NUMBER_RANGES_N;
+    T.f64_overflow_digits = D_F64_OVERFLOW_DIGITS;
+    return T;
+}
+
+/* status words (device uint32[4]) */
+enum { ST_OVERFLOW = 0, ST_DOCS_EXACT = 1, ST_DOCS_FATAL = 2, ST_RESERVED = 3 };
+
+#include "obm_fast.cuh"
+
+/* ------------------------------------------------------------------------------------------- */
+/* exact path: one thread per document                                                          */
+/* ------------------------------------------------------------------------------------------- */
+/* doc_list == nullptr: documents [0, ndocs); otherwise the ids in doc_list[0..ndocs). */
+__global__ void __launch_bounds__(128)
+k_exact_count(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, const uint32_t *__restrict__ doc_list,
+              uint32_t ndocs, uint32_t *__restrict__ counts, unsigned long long *__restrict__ totals /* {markers, lexemes} */,
+              uint32_t *__restrict__ status) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t markers = 0, lexemes = 0, fatal = 0;
+    if (i < ndocs) {
+        uint32_t d = doc_list ? doc_list[i] : i;
+        uint64_t o0 = doc_off[d], o1 = doc_off[d + 1];
+        obm::Tables T = device_tables();
+        obm::CountSink sink;
+        obm::Lexer<obm::CountSink> lx(T, bytes + o0, (uint32_t)(o1 - o0), sink);
+        int st = lx.run<false>();
+        counts[d] = (uint32_t)sink.n_tuples;
+        markers = sink.n_markers; lexemes = sink.n_lexemes; fatal = (st == obm::RUN_FATAL);
+    }
+    /* block-level reduction of the counters, one atomic per block */
+    __shared__ uint32_t sm[3];
+    if (threadIdx.x < 3) sm[threadIdx.x] = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+        markers += __shfl_down_sync(0xffffffffu, markers, o);
+        lexemes += __shfl_down_sync(0xffffffffu, lexemes, o);
+        fatal += __shfl_down_sync(0xffffffffu, fatal, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sm[0], markers); atomicAdd(&sm[1], lexemes); atomicAdd(&sm[2], fatal); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (totals) { atomicAdd(&totals[0], (unsigned long long)sm[0]); atomicAdd(&totals[1], (unsigned long long)sm[1]); }
+        if (status) {
+            if (sm[2]) atomicAdd(&status[ST_DOCS_FATAL], sm[2]);
+            uint32_t first = blockIdx.x * blockDim.x;
+            atomicAdd(&status[ST_DOCS_EXACT], min(blockDim.x, ndocs - first));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_exact_fill(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, const uint32_t *__restrict__ doc_list,
+             uint32_t ndocs, const uint64_t *__restrict__ tuple_off, obm_tuple *__restrict__ out, uint64_t out_cap) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ndocs) return;
+    uint32_t d = doc_list ? doc_list[i] : i;
+    uint64_t o0 = doc_off[d], o1 = doc_off[d + 1];
+    uint64_t t0 = tuple_off[d];
+    uint64_t room = t0 < out_cap ? out_cap - t0 : 0;
+    obm::Tables T = device_tables();
+    obm::WriteSink sink(out + t0, room);
+    obm::Lexer<obm::WriteSink> lx(T, bytes + o0, (uint32_t)(o1 - o0), sink);
+    lx.run<false>();
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* exclusive scan u32 counts -> u64 offsets (three small kernels; 8-12 B/doc of traffic)        */
+/* ------------------------------------------------------------------------------------------- */
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t *total) {
+    __shared__ uint64_t warp_sums[SCAN_THREADS / 32];
+    __shared__ uint64_t block_total;
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t incl = v;
+    for (int o = 1; o < 32; o <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t w = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+        uint64_t wi = w;
+        for (int o = 1; o < 32; o <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= (uint32_t)o) wi += t; }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = wi - w;
+        if (lane == SCAN_THREADS / 32 - 1) block_total = wi;
+    }
+    __syncthreads();
+    uint64_t excl = incl - v + warp_sums[wid];
+    *total = block_total;
+    __syncthreads();
+    return excl;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_tiles(const uint32_t *__restrict__ counts, uint32_t n, uint64_t *__restrict__ off, uint64_t *__restrict__ tile_sums) {
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t c[SCAN_ITEMS]; uint64_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { c[k] = (base + k < n) ? counts[base + k] : 0; sum += c[k]; }
+    uint64_t total; uint64_t excl = block_exclusive_scan(sum, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) off[base + k] = excl; excl += c[k]; }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_sums(uint64_t *__restrict__ tile_sums, uint32_t ntiles, uint64_t *__restrict__ grand_total) {
+    uint64_t carry = 0;
+    for (uint32_t b = 0; b < ntiles; b += SCAN_THREADS) {
+        uint32_t i = b + threadIdx.x;
+        uint64_t v = i < ntiles ? tile_sums[i] : 0;
+        uint64_t total; uint64_t excl = block_exclusive_scan(v, &total);
+        if (i < ntiles) tile_sums[i] = carry + excl;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_add(uint64_t *__restrict__ off, uint32_t n, const uint64_t *__restrict__ tile_sums, uint64_t out_cap, uint32_t *__restrict__ status) {
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint64_t add = tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) off[base + k] += add;
+    /* off[n] was written by k_scan_sums (grand_total points at it) */
+    if (blockIdx.x == 0 && threadIdx.x == 0 && status && off[n] > out_cap) status[ST_OVERFLOW] = 1;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* synthetic corpus                                                                             */
+/* ------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(128)
+k_generate_corpus(uint8_t *__restrict__ bytes, uint64_t *__restrict__ doc_off, uint32_t ndocs, uint32_t doc_bytes,
+                  uint64_t first_doc, int flavour) {
+    uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d == 0 && doc_off) doc_off[ndocs] = (uint64_t)ndocs * doc_bytes;
+    if (d >= ndocs) return;
+    if (doc_off) doc_off[d] = (uint64_t)d * doc_bytes;
+    obmc::generate_doc(bytes + (uint64_t)d * doc_bytes, doc_bytes, first_doc + d, flavour);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* handle + error plumbing                                                                      */
+/* ------------------------------------------------------------------------------------------- */
+struct obm_handle {
+    int device;
+    cudaStream_t stream;
+    cudaEvent_t ev[4];
+    char err[512];
+    /* scratch kept across calls */
+    void *scratch; uint64_t scratch_bytes;
+    /* device staging for the host-buffer entry point */
+    uint8_t *d_bytes; uint64_t d_bytes_cap;
+    uint64_t *d_doc_off; uint64_t d_doc_off_cap; /* elements */
+    uint64_t *d_tuple_off; uint64_t d_tuple_off_cap;
+    obm_tuple *d_out; uint64_t d_out_cap;
+    uint32_t *d_status; unsigned long long *d_counts;
+    int mode; /* 0 = auto (fast path + exact for irregular docs), 1 = exact path only */
+    uint32_t launches; /* kernels launched by the last obm_lex_batch_device call */
+};
+
+static char g_static_err[256] = "no error";
+
+static void set_err(obm_handle *h, const char *fmt, ...) {
+    char *dst = h ? h->err : g_static_err; size_t cap = h ? sizeof h->err : sizeof g_static_err;
+    va_list ap; va_start(ap, fmt); vsnprintf(dst, cap, fmt, ap); va_end(ap);
+}
+
+#define OBM_CUDA(h, call)                                                                              \
+    do { cudaError_t e_ = (call);                                                                      \
+         if (e_ != cudaSuccess) { set_err((h), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+                                  return OBM_E_CUDA; } } while (0)
+
+extern "C" int obm_abi_version(void) { return OBM_ABI_VERSION; }
+
+extern "C" const char *obm_last_error(const obm_handle *h) { return h ? h->err : g_static_err; }
+
+extern "C" int obm_create(int device_ordinal, obm_handle **out) {
+    if (!out) return OBM_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_err(nullptr, "no usable CUDA device (%s); libobmarkers has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return OBM_E_NO_DEVICE;
+    }
+    if (device_ordinal < 0 || device_ordinal >= ndev) { set_err(nullptr, "device ordinal %d out of range (0..%d)", device_ordinal, ndev - 1); return OBM_E_ARG; }
+    obm_handle *h = new (std::nothrow) obm_handle();
+    if (!h) return OBM_E_NOMEM;
+    memset(h, 0, sizeof *h);
+    h->device = device_ordinal;
+    snprintf(h->err, sizeof h->err, "no error");
+    if (cudaSetDevice(device_ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_err(nullptr, "cannot initialise CUDA device %d: %s", device_ordinal, cudaGetErrorString(cudaGetLastError()));
+        delete h; return OBM_E_CUDA;
+    }
+    for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
+    if (cudaMalloc(&h->d_status, 4 * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&h->d_counts, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+        set_err(nullptr, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete h; return OBM_E_CUDA;
+    }
+    const char *m = getenv("OBM_FORCE_EXACT");
+    h->mode = (m && m[0] == '1') ? 1 : 0;
+    *out = h;
+    return OBM_OK;
+}
+
+extern "C" void obm_destroy(obm_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->scratch); cudaFree(h->d_bytes); cudaFree(h->d_doc_off); cudaFree(h->d_tuple_off); cudaFree(h->d_out);
+    cudaFree(h->d_status); cudaFree(h->d_counts);
+    for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+/* Number of this library's kernels the last obm_lex_batch_device / obm_lex_batch call launched. */
+extern "C" uint32_t obm_launches_last_call(const obm_handle *h) { return h ? h->launches : 0; }
+
+/* Selects the scanning strategy: 0 = auto (default), 1 = exact path only. Returns the previous mode. */
+extern "C" int obm_set_mode(obm_handle *h, int mode) { int old = h->mode; h->mode = mode; return old; }
+
+template <class T>
+static int ensure(obm_handle *h, T **p, uint64_t *cap, uint64_t need) {
+    if (*cap >= need && *p) return OBM_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    uint64_t want = need + need / 8 + 64;
+    OBM_CUDA(h, cudaMalloc((void **)p, want * sizeof(T)));
+    *cap = want;
+    return OBM_OK;
+}
+
+/* scratch layout: counts u32[ndocs] | tile_sums u64[ntiles] | fast-path workspace */
+static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+static uint32_t scan_tiles(uint32_t ndocs) { return (ndocs + SCAN_TILE - 1) / SCAN_TILE; }
+
+extern "C" uint64_t obm_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
+    uint64_t b = align_up((uint64_t)ndocs * 4 + 4, 256);
+    b += align_up((uint64_t)scan_tiles(ndocs) * 8 + 8, 256);
+    b += obm_fast_scratch_bytes(ndocs, total_bytes);
+    return b;
+}
+
+extern "C" int obm_lex_batch_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
+                                    uint64_t total_bytes, void *d_out, uint64_t out_cap, void *d_doc_tuple_off,
+                                    void *d_status, void *d_counts, void *stream_v) {
+    if (!h) return OBM_E_ARG;
+    if (!d_doc_off || !d_doc_tuple_off || (ndocs && total_bytes && !d_bytes)) { set_err(h, "null device pointer"); return OBM_E_ARG; }
+    OBM_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    uint64_t need = obm_scratch_bytes(ndocs, total_bytes);
+    if (h->scratch_bytes < need) {
+        if (h->scratch) { OBM_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->scratch); h->scratch = nullptr; h->scratch_bytes = 0; }
+        OBM_CUDA(h, cudaMalloc(&h->scratch, need));
+        h->scratch_bytes = need;
+    }
+    uint8_t *sc = (uint8_t *)h->scratch;
+    uint32_t *counts = (uint32_t *)sc; sc += align_up((uint64_t)ndocs * 4 + 4, 256);
+    uint64_t *tile_sums = (uint64_t *)sc; sc += align_up((uint64_t)scan_tiles(ndocs) * 8 + 8, 256);
+    void *fast_ws = sc;
+    uint32_t *status = (uint32_t *)(d_status ? d_status : (void *)h->d_status);
+    unsigned long long *totals = (unsigned long long *)(d_counts ? d_counts : (void *)h->d_counts);
+    uint64_t *toff = (uint64_t *)d_doc_tuple_off;
+    OBM_CUDA(h, cudaMemsetAsync(status, 0, 4 * sizeof(uint32_t), st));
+    OBM_CUDA(h, cudaMemsetAsync(totals, 0, 2 * sizeof(unsigned long long), st));
+    if (ndocs == 0) { OBM_CUDA(h, cudaMemsetAsync(toff, 0, sizeof(uint64_t), st)); return OBM_OK; }
+
+    if (h->mode == 0) {
+        int rc = obm_fast_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
+                                 (obm_tuple *)d_out, out_cap, toff, status, totals, counts, tile_sums, fast_ws, st);
+        if (rc != 1) return rc; /* 1 = fast path not available for this build: fall through to the exact kernels */
+    }
+    uint32_t nb = (ndocs + 127) / 128;
+    h->launches = 4 + ((d_out && out_cap) ? 1 : 0);
+    k_exact_count<<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, nullptr, ndocs, counts, totals, status);
+    uint32_t nt = scan_tiles(ndocs);
+    k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(counts, ndocs, toff, tile_sums);
+    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, toff + ndocs);
+    k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(toff, ndocs, tile_sums, out_cap, status);
+    if (d_out && out_cap)
+        k_exact_fill<<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, nullptr, ndocs, toff, (obm_tuple *)d_out, out_cap);
+    OBM_CUDA(h, cudaGetLastError());
+    return OBM_OK;
+}
+
+extern "C" int obm_lex_batch(obm_handle *h, const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs,
+                             obm_tuple *out, uint64_t out_cap, uint64_t *out_count, uint64_t *doc_tuple_off,
+                             obm_stats *stats) {
+    if (!h) return OBM_E_ARG;
+    if (!doc_off || !out_count || !doc_tuple_off) { set_err(h, "doc_off, out_count and doc_tuple_off must not be NULL"); return OBM_E_ARG; }
+    uint64_t total = doc_off[ndocs] - doc_off[0];
+    for (uint32_t d = 0; d < ndocs; d++) {
+        if (doc_off[d + 1] < doc_off[d]) { set_err(h, "doc_off is not ascending at document %u", d); return OBM_E_ARG; }
+        if (doc_off[d + 1] - doc_off[d] > OBM_MAX_DOC_BYTES) { set_err(h, "document %u exceeds %llu bytes", d, (unsigned long long)OBM_MAX_DOC_BYTES); return OBM_E_ARG; }
+    }
+    if (total && !bytes) { set_err(h, "bytes is NULL"); return OBM_E_ARG; }
+    OBM_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    int rc;
+    if ((rc = ensure(h, &h->d_bytes, &h->d_bytes_cap, total + 64)) != OBM_OK) return rc;
+    if ((rc = ensure(h, &h->d_doc_off, &h->d_doc_off_cap, (uint64_t)ndocs + 1)) != OBM_OK) return rc;
+    if ((rc = ensure(h, &h->d_tuple_off, &h->d_tuple_off_cap, (uint64_t)ndocs + 1)) != OBM_OK) return rc;
+    /* device output sized for the caller's capacity, but at least a typical 0.5 tuples/byte guess so
+     * that a sizing call followed by the real call does not reallocate */
+    uint64_t want_out = out_cap;
+    if ((rc = ensure(h, &h->d_out, &h->d_out_cap, want_out + 1)) != OBM_OK) return rc;
+
+    OBM_CUDA(h, cudaEventRecord(h->ev[0], st));
+    /* rebase offsets so that the device batch starts at 0 */
+    const uint64_t base = doc_off[0];
+    if (base == 0) {
+        OBM_CUDA(h, cudaMemcpyAsync(h->d_doc_off, doc_off, ((uint64_t)ndocs + 1) * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        uint64_t *tmp = (uint64_t *)malloc(((uint64_t)ndocs + 1) * 8);
+        if (!tmp) return OBM_E_NOMEM;
+        for (uint32_t d = 0; d <= ndocs; d++) tmp[d] = doc_off[d] - base;
+        cudaError_t e = cudaMemcpyAsync(h->d_doc_off, tmp, ((uint64_t)ndocs + 1) * 8, cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);
+        free(tmp);
+        OBM_CUDA(h, e);
+    }
+    if (total) OBM_CUDA(h, cudaMemcpyAsync(h->d_bytes, bytes + base, total, cudaMemcpyHostToDevice, st));
+    OBM_CUDA(h, cudaEventRecord(h->ev[1], st));
+    rc = obm_lex_batch_device(h, h->d_bytes, h->d_doc_off, ndocs, total, (out && out_cap) ? h->d_out : nullptr, out_cap,
+                              h->d_tuple_off, nullptr, nullptr, st);
+    if (rc != OBM_OK) return rc;
+    OBM_CUDA(h, cudaEventRecord(h->ev[2], st));
+    OBM_CUDA(h, cudaMemcpyAsync(doc_tuple_off, h->d_tuple_off, ((uint64_t)ndocs + 1) * 8, cudaMemcpyDeviceToHost, st));
+    uint32_t hstatus[4]; unsigned long long hcounts[2];
+    OBM_CUDA(h, cudaMemcpyAsync(hstatus, h->d_status, sizeof hstatus, cudaMemcpyDeviceToHost, st));
+    OBM_CUDA(h, cudaMemcpyAsync(hcounts, h->d_counts, sizeof hcounts, cudaMemcpyDeviceToHost, st));
+    OBM_CUDA(h, cudaStreamSynchronize(st));
+    uint64_t ntup = doc_tuple_off[ndocs];
+    *out_count = ntup;
+    int result = OBM_OK;
+    if (ntup > out_cap || (!out && ntup > 0)) {
+        set_err(h, "output capacity %llu < %llu tuples required", (unsigned long long)out_cap, (unsigned long long)ntup);
+        result = OBM_E_CAPACITY;
+    } else if (ntup) {
+        OBM_CUDA(h, cudaMemcpyAsync(out, h->d_out, ntup * sizeof(obm_tuple), cudaMemcpyDeviceToHost, st));
+    }
+    OBM_CUDA(h, cudaEventRecord(h->ev[3], st));
+    OBM_CUDA(h, cudaStreamSynchronize(st));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->n_tuples = ntup; stats->n_markers = hcounts[0]; stats->n_lexemes = hcounts[1];
+        stats->n_docs_exact = hstatus[ST_DOCS_EXACT]; stats->n_docs_fatal = hstatus[ST_DOCS_FATAL];
+        stats->bytes = total;
+        cudaEventElapsedTime(&stats->ms_kernels, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&stats->ms_total, h->ev[0], h->ev[3]);
+    }
+    return result;
+}
+
+extern "C" int obm_generate_corpus_device(obm_handle *h, void *d_bytes, void *d_doc_off, uint32_t ndocs,
+                                          uint32_t doc_bytes, uint64_t first_doc, int flavour, void *stream_v) {
+    if (!h || !d_bytes) return OBM_E_ARG;
+    OBM_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    if (ndocs == 0) return OBM_OK;
+    k_generate_corpus<<<(ndocs + 127) / 128, 128, 0, st>>>((uint8_t *)d_bytes, (uint64_t *)d_doc_off, ndocs, doc_bytes, first_doc, flavour);
+    OBM_CUDA(h, cudaGetLastError());
+    return OBM_OK;
+}
+
+/* Host copy of the same generator (test/bench utility; no lexing). */
+extern "C" int obm_generate_corpus_host(uint8_t *bytes, uint64_t *doc_off, uint32_t ndocs, uint32_t doc_bytes,
+                                        uint64_t first_doc, int flavour) {
+    if (!bytes) return OBM_E_ARG;
+    for (uint32_t d = 0; d < ndocs; d++) {
+        if (doc_off) doc_off[d] = (uint64_t)d * doc_bytes;
+        obmc::generate_doc(bytes + (uint64_t)d * doc_bytes, doc_bytes, first_doc + d, flavour);
+    }
+    if (doc_off) doc_off[ndocs] = (uint64_t)ndocs * doc_bytes;
+    return OBM_OK;
+}
+
+/* Pinned host memory for callers that want DMA-speed obm_lex_batch (the cgo shim keeps manifests in C memory). */
+extern "C" void *obm_pinned_alloc(uint64_t bytes) { void *p = nullptr; return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
+extern "C" void obm_pinned_free(void *p) { if (p) cudaFreeHost(p); }

@@ -490,11 +490,14 @@ static int32_t lx_peek(Lexer *l) { int32_t *rs; lx_peekN(l, 1, &rs); return rs[0
 
 /* strings.HasPrefix(string(runes), p): string([]rune) maps invalid runes (incl. -1) to U+FFFD */
 static int runes_have_prefix(const int32_t *rs, int cnt, const char *p) {
-    gstr tmp = {0};
-    for (int i = 0; i < cnt; i++) gs_append_rune(&tmp, rs[i]);
+    /* only the first strlen(p) bytes of string(runes) matter; each rune contributes >= 1 byte */
     size_t pl = strlen(p);
+    uint8_t stackbuf[64]; gstr tmp = {0};
+    int use = cnt < (int)pl ? cnt : (int)pl; /* runes needed to cover pl bytes */
+    if ((size_t)use * 4 <= sizeof stackbuf) { tmp.p = stackbuf; tmp.cap = sizeof stackbuf; }
+    for (int i = 0; i < use; i++) gs_append_rune(&tmp, rs[i]);
     int ok = tmp.len >= pl && memcmp(tmp.p, p, pl) == 0;
-    gs_free(&tmp);
+    if (tmp.p != stackbuf) gs_free(&tmp);
     return ok;
 }
 /* peek.go:92-96 hasPrefix -- len(p) is a BYTE length used as a rune count */

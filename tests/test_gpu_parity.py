@@ -1,0 +1,258 @@
+"""GPU parity tests proper: everything goes through the C ABI (obm_lex_batch / obm_lex_batch_device)
+and is compared lexeme-for-lexeme -- (Type, Value, Pos), stricter than lexer_test.go:429-432 --
+with the CPU oracle on the same inputs.  Bit-exact: this is integer/byte/index work."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from tests import corpus_util as cu
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "lexer_golden.json")))
+
+
+@pytest.fixture(scope="module")
+def scanner():
+    import operator_builder_b200 as ob
+    sc = ob.Scanner(0)
+    yield sc
+    sc.close()
+
+
+def pack(docs):
+    data = np.frombuffer(b"".join(docs) + b"\0", dtype=np.uint8)[:-1] if docs else np.zeros(0, np.uint8)
+    off = np.zeros(len(docs) + 1, dtype=np.uint64)
+    if docs:
+        off[1:] = np.cumsum([len(d) for d in docs])
+    return data, off
+
+
+def run_and_compare(scanner, oracle, docs, modes=(0, 1)):
+    import operator_builder_b200 as ob
+    data, off = pack(docs)
+    want_stream, want_off, want_n = oracle.lex_batch_raw(data if len(data) else np.zeros(1, np.uint8), off)
+    streams = []
+    for mode in modes:
+        scanner.set_mode(mode)
+        res = scanner.lex_batch(data, off)
+        streams.append(res.tuples.copy())
+        n_lex = 0
+        for i, doc in enumerate(docs):
+            t = res.tuples[int(res.doc_tuple_off[i]):int(res.doc_tuple_off[i + 1])]
+            got = ob.decode_doc_raw(doc, t)
+            want = want_stream[int(want_off[i]):int(want_off[i + 1])]
+            if got != want:
+                from tests import hostsim
+                raise AssertionError(f"mode {mode} doc {i} {doc[:200]!r}\n tuples={hostsim.fmt_tuples(t)[:60]}\n"
+                                     f" got ={oracle.parse_stream(got)[:40]}\n want={oracle.parse_stream(want)[:40]}")
+            n_lex += int(want_n[i])
+        assert res.stats["n_lexemes"] == n_lex
+        assert res.stats["n_tuples"] == len(res.tuples)
+    scanner.set_mode(0)
+    for s in streams[1:]:
+        assert np.array_equal(streams[0], s), "fast path and exact path tuple streams differ"
+    return streams[0]
+
+
+def test_golden_vectors(scanner, oracle):
+    """the reference's 24 vectors, lexer_test.go:28-402, as one batch"""
+    docs = [c["input"].encode() for c in GOLDEN["cases"]]
+    run_and_compare(scanner, oracle, docs)
+    # and with the reference test's own comparison: (Type, Value) until EOF
+    import operator_builder_b200 as ob
+    data, off = pack(docs)
+    res = scanner.lex_batch(data, off)
+    for c, lx in zip(GOLDEN["cases"], scanner.lexers(data.tobytes(), off, res)):
+        lx.run()
+        got = []
+        while True:
+            lexeme = lx.next_lexeme()
+            got.append([int(lexeme.type), lexeme.value.decode()])
+            if lexeme.type == ob.LexemeType.EOF:
+                break
+        assert got == c["expected"], c["name"]
+
+
+def test_targeted_and_edge_cases(scanner, oracle):
+    run_and_compare(scanner, oracle, list(cu.TARGETED))
+
+
+def test_non_ascii_and_invalid_utf8(scanner, oracle):
+    run_and_compare(scanner, oracle, list(cu.NON_ASCII))
+
+
+def test_reference_fixtures(scanner, oracle):
+    fx = cu.fixtures()
+    assert len(fx) == 33
+    run_and_compare(scanner, oracle, [d for _p, d in fx])
+
+
+def test_empty_and_ragged_batches(scanner, oracle):
+    run_and_compare(scanner, oracle, [])
+    run_and_compare(scanner, oracle, [b""])
+    run_and_compare(scanner, oracle, [b"", b"", b"+a:b", b"", b"#", b""])
+    rng = random.Random(3)
+    docs = [cu.fuzz_doc(rng, max_len=rng.choice([0, 1, 7, 63, 64, 65, 500, 5000])) for _ in range(300)]
+    run_and_compare(scanner, oracle, docs)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fuzz(scanner, oracle, seed):
+    rng = random.Random(900 + seed)
+    docs = [cu.fuzz_doc(rng, max_len=400, non_ascii=(seed % 2 == 1)) for _ in range(4000)]
+    run_and_compare(scanner, oracle, docs)
+
+
+def test_c2_10k_docs_bit_exact(scanner, oracle):
+    """BASELINE.json configs[1]: 10k synthetic 4 KiB manifests (40,960,000 B), 8 markers/file."""
+    import operator_builder_b200 as ob
+    data, off = ob.generate_corpus_host(10000, 4096)
+    want_stream, want_off, want_n = oracle.lex_batch_raw(data, off)
+    res = scanner.lex_batch(data, off)
+    assert res.stats["n_markers"] == 80000
+    assert res.stats["n_lexemes"] == int(want_n.sum())
+    raw = data.tobytes()
+    for i in range(10000):
+        doc = raw[i * 4096:(i + 1) * 4096]
+        got = ob.decode_doc_raw(doc, res.tuples[int(res.doc_tuple_off[i]):int(res.doc_tuple_off[i + 1])])
+        assert got == want_stream[int(want_off[i]):int(want_off[i + 1])], i
+    scanner.set_mode(1)
+    res1 = scanner.lex_batch(data, off)
+    scanner.set_mode(0)
+    assert np.array_equal(res.tuples, res1.tuples) and np.array_equal(res.doc_tuple_off, res1.doc_tuple_off)
+
+
+def test_collection_flavour_and_odd_doc_sizes(scanner, oracle):
+    import operator_builder_b200 as ob
+    for doc_bytes, n in ((4096, 500), (1000, 700), (37, 100), (16384, 40), (70000, 6)):
+        data, off = ob.generate_corpus_host(n, doc_bytes, flavour=1)
+        raw = data.tobytes()
+        run_and_compare(scanner, oracle, [raw[i * doc_bytes:(i + 1) * doc_bytes] for i in range(n)])
+
+
+def test_adversarial_sweep(scanner, oracle):
+    """BASELINE.json configs[4] (scaled to test size): markers/line 0..64 x line length 16 B..64 KiB."""
+    docs = []
+    for m in (0, 1, 2, 4, 8, 16, 32, 64):
+        for L in (16, 64, 256, 1024, 4096, 16384, 65536):
+            line = b"# " + b" ".join(b"+s:a%d=%d" % (k, k) for k in range(m))
+            if len(line) + 1 > L:
+                line = line[:L - 1]
+            pad = L - 1 - len(line)
+            variants = [line + b" " + b"x" * (pad - 1) if pad > 0 else line,
+                        line + (b" +q:v=\"" + b"y" * (pad - 9) + b"\"" if pad > 9 else b" " * pad),
+                        line + (b" +q:v=" + b"z" * (pad - 6) if pad > 6 else b" " * pad)]
+            for v in variants:
+                docs.append((v + b"\n") * max(1, min(8, 131072 // L)))
+    run_and_compare(scanner, oracle, docs)
+
+
+def test_large_documents(scanner, oracle):
+    """documents larger than any tile: 1 MiB and 9 MiB, many lines, markers sprinkled"""
+    rng = random.Random(11)
+    big = []
+    for target in (1 << 20, 9 << 20):
+        parts, n = [], 0
+        while n < target:
+            ln = rng.choice([b"key: value\n", b"  - item  # +operator-builder:field:name=a.b,type=int,default=3\n", b"\n",
+                             b"# +x:y=`multi\n  # line`\n", b"path: /a/b+c\n", b"x" * 300 + b"\n"])
+            parts.append(ln)
+            n += len(ln)
+        big.append(b"".join(parts))
+    run_and_compare(scanner, oracle, big + [b"+a:b"] + big[:1])
+
+
+def test_device_entry_point_and_capacity(scanner, oracle):
+    import torch
+    import operator_builder_b200 as ob
+    ndocs, doc_bytes = 4096, 4096
+    dev = torch.device("cuda:0")
+    d_bytes = torch.empty(ndocs * doc_bytes, dtype=torch.uint8, device=dev)
+    d_off = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
+    scanner.generate_corpus_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, doc_bytes, first_doc=0, flavour=0,
+                                   stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    host, hoff = ob.generate_corpus_host(ndocs, doc_bytes)
+    assert np.array_equal(d_bytes.cpu().numpy(), host), "device and host generators must agree byte for byte"
+    assert np.array_equal(d_off.cpu().numpy().astype(np.uint64), hoff)
+    cap = ndocs * doc_bytes // 8
+    d_out = torch.zeros(cap, dtype=torch.int64, device=dev)
+    d_toff = torch.zeros(ndocs + 1, dtype=torch.int64, device=dev)
+    d_status = torch.zeros(4, dtype=torch.int32, device=dev)
+    d_counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    scanner.lex_batch_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, ndocs * doc_bytes, d_out.data_ptr(), cap,
+                             d_toff.data_ptr(), d_status.data_ptr(), d_counts.data_ptr(), st)
+    torch.cuda.synchronize()
+    ref = scanner.lex_batch(host, hoff)
+    n = int(d_toff[-1].item())
+    assert n == len(ref.tuples) and int(d_status[0].item()) == 0
+    assert np.array_equal(d_out[:n].cpu().numpy().view(np.uint64), ref.tuples)
+    assert np.array_equal(d_toff.cpu().numpy().view(np.uint64), ref.doc_tuple_off)
+    assert int(d_counts[0].item()) == 8 * ndocs
+    # capacity overflow is reported, never written past
+    small = 1000
+    d_out2 = torch.full((small + 64,), -1, dtype=torch.int64, device=dev)
+    scanner.lex_batch_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, ndocs * doc_bytes, d_out2.data_ptr(), small,
+                             d_toff.data_ptr(), d_status.data_ptr(), d_counts.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert int(d_status[0].item()) == 1 and int(d_toff[-1].item()) == n
+    assert bool((d_out2[small:] == -1).all())
+    # host entry point: OBM_E_CAPACITY with the needed count
+    import ctypes
+    from operator_builder_b200 import _native
+    L = _native.lib()
+    cnt = ctypes.c_uint64()
+    toff = np.zeros(ndocs + 1, dtype=np.uint64)
+    tiny = np.zeros(10, dtype=np.uint64)
+    rc = L.obm_lex_batch(scanner.handle, host.ctypes.data, hoff.ctypes.data, ndocs, tiny.ctypes.data, 10, ctypes.byref(cnt),
+                         toff.ctypes.data, None)
+    assert rc == _native.OBM_E_CAPACITY and cnt.value == n and not tiny.any()
+
+
+def test_full_size_properties_on_device(scanner):
+    """Size-independent properties at a size the oracle cannot check in seconds (1 GiB resident):
+    fast path == exact path tuple-for-tuple; per-document counts are a function of the document only
+    (a shard generated at a different global index range reproduces the same tuples); totals add up."""
+    import torch
+    dev = torch.device("cuda:0")
+    ndocs, doc_bytes = 262144, 4096
+    st = torch.cuda.current_stream().cuda_stream
+    d_bytes = torch.empty(ndocs * doc_bytes, dtype=torch.uint8, device=dev)
+    d_off = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
+    scanner.generate_corpus_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, doc_bytes, 0, 1, st)
+    cap = ndocs * doc_bytes // 8
+    outs = []
+    for mode in (0, 1):
+        scanner.set_mode(mode)
+        d_out = torch.zeros(cap, dtype=torch.int64, device=dev)
+        d_toff = torch.zeros(ndocs + 1, dtype=torch.int64, device=dev)
+        d_status = torch.zeros(4, dtype=torch.int32, device=dev)
+        d_counts = torch.zeros(2, dtype=torch.int64, device=dev)
+        scanner.lex_batch_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, ndocs * doc_bytes, d_out.data_ptr(), cap,
+                                 d_toff.data_ptr(), d_status.data_ptr(), d_counts.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert int(d_status[0].item()) == 0
+        assert int(d_counts[0].item()) == 8 * ndocs
+        outs.append((d_out, d_toff, int(d_toff[-1].item()), int(d_counts[1].item())))
+    scanner.set_mode(0)
+    assert outs[0][2] == outs[1][2] and outs[0][3] == outs[1][3]
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
+    # shard property: documents [100000, 100000+4096) regenerated alone give the same tuples
+    sub = 4096
+    s_bytes = torch.empty(sub * doc_bytes, dtype=torch.uint8, device=dev)
+    s_off = torch.empty(sub + 1, dtype=torch.int64, device=dev)
+    scanner.generate_corpus_device(s_bytes.data_ptr(), s_off.data_ptr(), sub, doc_bytes, 100000, 1, st)
+    s_out = torch.zeros(sub * doc_bytes // 8, dtype=torch.int64, device=dev)
+    s_toff = torch.zeros(sub + 1, dtype=torch.int64, device=dev)
+    scanner.lex_batch_device(s_bytes.data_ptr(), s_off.data_ptr(), sub, sub * doc_bytes, s_out.data_ptr(), len(s_out),
+                             s_toff.data_ptr(), None, None, st)
+    torch.cuda.synchronize()
+    full_out, full_toff = outs[0][0], outs[0][1]
+    a, b = int(full_toff[100000].item()), int(full_toff[100000 + sub].item())
+    assert b - a == int(s_toff[-1].item())
+    assert torch.equal(full_out[a:b], s_out[:b - a])

@@ -129,8 +129,8 @@ int obm_lex_batch(obm_handle *h, const uint8_t *bytes, const uint64_t *doc_off, 
 
 /*
  * Same scan on DEVICE-resident buffers (benchmarking / pipelines that keep manifests in HBM).
- * All pointers are device pointers on the handle's device; `stream` is a cudaStream_t (NULL = the
- * handle's stream).  Asynchronous: returns after enqueueing.  d_doc_tuple_off[ndocs] holds the
+ * All pointers are device pointers on the handle's device; `stream` is a cudaStream_t used exactly as
+ * given (NULL = CUDA's default stream).  Asynchronous: returns after enqueueing.  d_doc_tuple_off[ndocs] holds the
  * total tuple count; if it exceeds out_cap the kernels write nothing past out_cap and set
  * d_status[0] = 1 (d_status is a device uint32[4]: {overflow, n_docs_exact, n_docs_fatal, reserved}).
  * d_counts (device uint64[2], may be NULL) receives {n_markers, n_lexemes}.

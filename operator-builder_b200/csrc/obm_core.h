@@ -236,7 +236,14 @@ struct WriteSink {
 enum RunStatus { RUN_EOF = 0, RUN_LINE_END = 1, RUN_FATAL = 2 };
 enum TopState { TOP_LEX = 0, TOP_COMMENT = 1, TOP_FATAL = 2 };
 
-template <class Sink>
+/* Scan accelerator hook: next_interesting(p) returns the smallest q >= p such that doc[q] may be a
+ * newline or one of # + / ' (or n).  The exact path uses NoAccel (q = p: no skipping); the tile path
+ * answers from its newline/special bitmaps.  Only valid for all-ASCII documents. */
+struct NoAccel {
+    OBM_HD uint32_t next_interesting(uint32_t p) const { return p; }
+};
+
+template <class Sink, class Accel = NoAccel>
 struct Lexer {
     const Tables &T;
     const uint8_t *d; uint32_t n;
@@ -248,13 +255,16 @@ struct Lexer {
     uint32_t last_w; int last_r;        /* l.width / rune of the last next() */
     uint32_t last_type;                 /* l.lastEmittedLexeme.Type */
     Sink &out;
+    Accel accel;
 
-    /* `first_line`/`line_start`: where this lexer instance begins (doc start: 1, 0). */
+    /* A lexer instance begins at byte `start_off` of line `first_line`, whose first byte is at
+     * `line_base` (document start: 0, 1, 0).  `announce_first`: the first located tuple must be
+     * preceded by a LINE tuple (true for every line-mode instance except the document's first line). */
     OBM_HD Lexer(const Tables &t, const uint8_t *doc, uint32_t len, Sink &sink, uint32_t start_off = 0,
-                 uint32_t first_line = 1, bool announce_first = false)
-        : T(t), d(doc), n(len), p(start_off), s(start_off), line_p(first_line), base_p(start_off), drift_p(0),
-          line_s(first_line), base_s(start_off), line_e(announce_first ? 0u : 1u), base_e(0),
-          sv_line(first_line), sv_base(start_off), sv_drift(0), last_w(0), last_r(RUNE_EOF), last_type(0), out(sink) {}
+                 uint32_t first_line = 1, uint32_t line_base = 0, bool announce_first = false, Accel acc = Accel())
+        : T(t), d(doc), n(len), p(start_off), s(start_off), line_p(first_line), base_p(line_base), drift_p(0),
+          line_s(first_line), base_s(line_base), line_e(announce_first ? 0u : 1u), base_e(0),
+          sv_line(first_line), sv_base(line_base), sv_drift(0), last_w(0), last_r(RUNE_EOF), last_type(0), out(sink), accel(acc) {}
 
     /* ---- tuple plumbing ---- */
     OBM_HD void ensure_line(uint32_t line, uint32_t base) {
@@ -326,6 +336,10 @@ struct Lexer {
         p += adv;
         if (r == '\n') { line_p++; base_p = p; drift_p = 0; }
         sync_start();
+    }
+    /* `q - p` discard() calls over bytes known to be ASCII, non-newline (Accel contract) */
+    OBM_HD void discard_to(uint32_t q) {
+        if (q > p) { part_tail(); p = q; sync_start(); }
     }
     OBM_HD bool has_prefix2(uint32_t a, uint32_t b) const { return p + 1 < n && d[p] == a && d[p + 1] == b; }
     /* consume.go:65-80 with an ASCII delimiter class; returns `consumed` */
@@ -461,20 +475,19 @@ struct Lexer {
         return TOP_FATAL;
     }
 
-    /* ---- top level: state.go:15-57.  LINE_MODE stops after discarding the first top-level '\n'
-     *      at or beyond `line_end` (the fast path's per-line owner); otherwise runs to EOF and
-     *      emits the EOF tuple itself. ---- */
+    /* ---- top level: state.go:15-57.  LINE_MODE (the tile path's per-line owner) stops right after
+     *      discarding the first top-level '\n'; otherwise runs to EOF and emits the EOF tuple. ---- */
     template <bool LINE_MODE>
-    OBM_HD int run(uint32_t line_end = 0) {
+    OBM_HD int run() {
         int st = TOP_LEX;
         for (;;) {
             if (st == TOP_LEX) {
+                discard_to(accel.next_interesting(p));
                 uint32_t w; int r = peek(w);
                 if (r == RUNE_EOF) { if (!LINE_MODE) out.put(OBM_K_EOF, n, 0); return RUN_EOF; }
                 if (is_space(r)) {
-                    bool stop = LINE_MODE && r == '\n' && p >= line_end;
                     discard1();
-                    if (stop) return RUN_LINE_END;
+                    if (LINE_MODE && r == '\n') return RUN_LINE_END;
                     continue;
                 }
                 if (has_prefix2('/', '/')) { next(); next(); emit(OBM_K_COMMENT); st = TOP_COMMENT; }
@@ -482,6 +495,7 @@ struct Lexer {
                 else if (r == '+') { next(); st = marker_start(); }
                 else discard1();
             } else if (st == TOP_COMMENT) {
+                discard_to(accel.next_interesting(p));
                 uint32_t c = peek_byte();
                 if (c == '+') { next(); st = marker_start(); }
                 else if (c == '\n' || c == 0x100u) st = TOP_LEX;

@@ -1,6 +1,294 @@
-/* obm_fast.cuh -- tile fast path (placeholder until the kernel lands; the exact path is used). */
+/*
+ * obm_fast.cuh -- the tile fast path: one persistent CTA per SM slot streams TILE-byte ranges of the
+ * packed batch through shared memory (TMA bulk copy, cp.async.bulk + mbarrier), lexes every
+ * document that starts in the range line-parallel (obm_tile.h) and writes the tuples at their final
+ * position in ONE pass over the input: per-tile tuple counts are chained with a decoupled
+ * look-back, so `doc_tuple_off` and the tuple stream come out ordered without a second read.
+ *
+ * HBM traffic per input byte: 1 B read (TMA) + ~0.32 B of tuples written + 8 B/document of offsets.
+ * Documents larger than MAXDOC are handed to the exact kernels (k_exact_count / k_exact_fill in
+ * obm_lib.cu) through a device-side list; their counts are folded into the same look-back chain.
+ */
 #pragma once
+#include "obm_tile.h"
+
 struct obm_handle;
-static inline uint64_t obm_fast_scratch_bytes(uint32_t, uint64_t) { return 0; }
-static inline int obm_fast_launch(obm_handle *, const uint8_t *, const uint64_t *, uint32_t, uint64_t, obm_tuple *, uint64_t,
-                                  uint64_t *, uint32_t *, unsigned long long *, uint32_t *, uint64_t *, void *, cudaStream_t) { return 1; }
+
+namespace obmf {
+
+using obmt::Smem;
+
+/* ---- PTX helpers: mbarrier + 1-D TMA bulk copy global -> shared ---------------------------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+/* ---- block-wide exclusive scan of one u32 per thread (NT threads); two barriers -------------------- */
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t *scratch /* NT/32+1 */, uint32_t &total) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+    if (lane == 31) scratch[wid] = incl;
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < obmt::NT / 32; w++) { uint32_t s = scratch[w]; if (w < wid) pre += s; tot += s; }
+    __syncthreads();
+    total = tot;
+    return pre + incl - v;
+}
+
+/* ---- look-back chain ----------------------------------------------------------------------------- */
+constexpr uint64_t LB_AGG = 1ull << 62, LB_INCL = 2ull << 62, LB_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t lookback(volatile uint64_t *state, uint32_t t, uint64_t my_total) {
+    /* publish the aggregate, then walk back until an inclusive prefix is found */
+    if (t == 0) { __threadfence(); state[0] = LB_INCL | my_total; return 0; }
+    state[t] = LB_AGG | my_total;
+    __threadfence();
+    uint64_t sum = 0;
+    int32_t i = (int32_t)t - 1;
+    for (;;) {
+        uint64_t s = state[i];
+        uint64_t f = s >> 62;
+        if (f == 0) { __nanosleep(20); continue; }
+        sum += s & LB_MASK;
+        if (f == 2) break;
+        i--;
+    }
+    state[t] = LB_INCL | (sum + my_total);
+    __threadfence();
+    return sum;
+}
+
+/* ---- pre-kernel: tile -> first document map, list of large documents ----------------------------- */
+__global__ void __launch_bounds__(256)
+k_tile_index(const uint64_t *__restrict__ doc_off, uint32_t ndocs, uint32_t ntiles, uint32_t *__restrict__ tile_first,
+             uint32_t *__restrict__ large_list, uint32_t *__restrict__ n_large) {
+    uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d > ndocs) return;
+    /* tiles t with  off[d-1] < t*TILE <= off[d]  have tile_first[t] = d; d == ndocs closes the table */
+    uint64_t tprev_plus1 = d == 0 ? 0 : doc_off[d - 1] / obmt::TILE + 1;
+    uint64_t tcur = d == ndocs ? (uint64_t)ntiles : doc_off[d] / obmt::TILE;
+    if (d == ndocs && ndocs > 0 && tprev_plus1 > tcur) return;
+    for (uint64_t t = tprev_plus1; t <= tcur && t <= ntiles; t++) tile_first[t] = d;
+    if (d < ndocs && doc_off[d + 1] - doc_off[d] > obmt::MAXDOC) large_list[atomicAdd(n_large, 1u)] = d;
+}
+
+/* ---- the tile kernel ------------------------------------------------------------------------------- */
+struct TileArgs {
+    const uint8_t *bytes; const uint64_t *doc_off; uint32_t ndocs; uint64_t total_bytes;
+    const uint32_t *tile_first; uint32_t ntiles;
+    const uint32_t *counts;            /* precomputed tuple counts of large documents */
+    obm_tuple *out; uint64_t out_cap; uint64_t *tuple_off;
+    uint64_t *tile_state; uint32_t *ticket;
+    uint32_t *status; unsigned long long *totals;
+};
+
+struct CtaShared {
+    Smem S;
+    alignas(8) uint64_t mbar;
+    uint64_t base;      /* look-back result */
+    uint32_t tile;
+    uint32_t sub_total; /* tuples of the current sub-batch */
+    uint32_t stats[4];  /* markers, lexemes, exact docs, fatal docs */
+};
+
+/* Stages documents [da, db) (all small) and runs P1..P6.  Leaves S ready for the fill pass and
+ * returns the sub-batch's tuple count (uniform across the CTA). */
+__device__ __forceinline__ uint32_t subbatch_count(CtaShared &C, const TileArgs &A, const obm::Tables &T, uint32_t da, uint32_t db,
+                                                   uint32_t &mbar_phase) {
+    Smem &S = C.S;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t nd = db - da;
+    const uint64_t b0 = A.doc_off[da], b1 = A.doc_off[db];
+    const uint64_t abs0 = (uint64_t)(uintptr_t)A.bytes + b0;
+    const uint64_t base_abs = abs0 & ~15ull;
+    const uint32_t skew = (uint32_t)(abs0 - base_abs);
+    const uint32_t span = (uint32_t)(b1 - b0) + skew;   /* bytes of `data` in use */
+    const uint32_t load = (span + 15u) & ~15u;
+    /* P1: TMA bulk copy of the byte range into shared memory */
+    if (tid == 0) {
+        S.nd = nd; S.lo_pos = skew; S.hi_pos = span; S.n_owners = 0;
+        if (load) {
+            fence_proxy_async();
+            mbar_expect_tx(&C.mbar, load);
+            tma_bulk_g2s(S.data, (const void *)(uintptr_t)base_abs, load, &C.mbar);
+        }
+    }
+    if (tid <= nd) S.dstart[tid] = (uint32_t)(A.doc_off[da + tid] - b0) + skew;
+    __syncthreads();
+    if (load) { mbar_wait(&C.mbar, mbar_phase); mbar_phase ^= 1; }
+    /* P2: classify 32-byte words (strided: conflict-free shared loads, warp = 32 consecutive words) */
+    const uint32_t nwords = (span + 31) >> 5;
+    for (uint32_t base = 0; base < nwords; base += obmt::NT) {
+        uint32_t wi = base + tid;
+        if (wi < ((nwords + 31u) & ~31u) && wi < obmt::NW) obmt::classify_word(S, wi); /* whole warps participate (ballot) */
+    }
+    for (uint32_t wi = ((nwords + 31u) & ~31u) + tid; wi < obmt::NW; wi += obmt::NT) { S.nlw[wi] = 0; S.spw[wi] = 0; }
+    __syncthreads();
+    /* P3: per-document preparation */
+    if (tid < nd) obmt::doc_prep(S, tid);
+    __syncthreads();
+    /* P4: line scan -- newline prefix + owner discovery (count, scan, write) */
+    uint32_t my_owners = 0;
+    uint32_t my_nl = obmt::line_scan(S, tid, [&](uint32_t, uint32_t) { my_owners++; });
+    uint32_t tot;
+    uint32_t pre = block_scan_excl(my_nl | (my_owners << 16), S.scan_tmp, tot);
+    {
+        uint32_t nlp = pre & 0xFFFFu, own = pre >> 16;
+#pragma unroll
+        for (uint32_t j = 0; j < obmt::WPT; j++) { S.nlpre[tid * obmt::WPT + j] = (uint16_t)nlp; nlp += (uint32_t)__popc(S.nlw[tid * obmt::WPT + j]); }
+        uint32_t n_owners = tot >> 16;
+        if (n_owners <= obmt::QMAX && my_owners)
+            obmt::line_scan(S, tid, [&](uint32_t first, uint32_t ls) { S.owner[own++] = first | (ls << 16); });
+        if (tid == 0) S.n_owners = n_owners <= obmt::QMAX ? n_owners : 0;
+        if (n_owners > obmt::QMAX && tid < nd) S.dflag[tid] |= obmt::DF_QOVERFLOW; /* too many special lines: exact path */
+    }
+    __syncthreads();
+    /* P5: owners, count pass */
+    const uint32_t n_owners = S.n_owners;
+    for (uint32_t o = tid; o < n_owners; o += obmt::NT) obmt::owner_count(S, T, o);
+    __syncthreads();
+    /* P6: E[] = exclusive scan of owner counts (owners of irregular documents contribute nothing) */
+    {
+        uint32_t v[4], sum = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+            uint32_t o = tid * 4 + j;
+            v[j] = (o < n_owners && !S.dflag[S.odoc[o]]) ? S.ocnt[o] : 0;
+            sum += v[j];
+        }
+        uint32_t etot;
+        uint32_t e = block_scan_excl(sum, S.scan_tmp, etot);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) { uint32_t o = tid * 4 + j; if (o < obmt::QMAX) S.ocnt[o] = e; e += v[j]; }
+        if (tid == 0) S.ocnt[obmt::QMAX] = etot;
+    }
+    if (tid <= nd) S.dfirst[tid] = tid == nd ? n_owners : obmt::first_owner_at(S, S.dstart[tid]);
+    __syncthreads();
+    if (n_owners < obmt::QMAX && tid == 0) S.ocnt[n_owners] = S.ocnt[obmt::QMAX]; /* E[n_owners] = total */
+    __syncthreads();
+    if (tid < nd) obmt::doc_count(S, T, tid);
+    __syncthreads();
+    {
+        uint32_t v = tid < nd ? S.dcnt[tid] : 0, dtot;
+        uint32_t e = block_scan_excl(v, S.scan_tmp, dtot);
+        if (tid < nd) S.dcnt[tid] = e;
+        if (tid == 0) { S.dcnt[nd] = dtot; C.sub_total = dtot; }
+    }
+    __syncthreads();
+    return C.sub_total;
+}
+
+__device__ __forceinline__ void subbatch_fill(CtaShared &C, const TileArgs &A, const obm::Tables &T, uint32_t da, uint32_t db, uint64_t base) {
+    Smem &S = C.S;
+    const uint32_t tid = threadIdx.x, nd = db - da;
+    obmt::FillStats fs = {0, 0, 0, 0};
+    const uint32_t n_owners = S.n_owners;
+    if (A.out) for (uint32_t o = tid; o < n_owners; o += obmt::NT) obmt::owner_fill(S, T, o, A.out, A.out_cap, base, fs);
+    if (tid < nd) {
+        A.tuple_off[da + tid] = base + S.dcnt[tid];
+        if (A.out) obmt::doc_fill(S, T, tid, A.out, A.out_cap, base, fs);
+    }
+    /* stats: warp reduce, then shared atomics */
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        fs.markers += __shfl_down_sync(0xffffffffu, fs.markers, o); fs.lexemes += __shfl_down_sync(0xffffffffu, fs.lexemes, o);
+        fs.exact_docs += __shfl_down_sync(0xffffffffu, fs.exact_docs, o); fs.fatal_docs += __shfl_down_sync(0xffffffffu, fs.fatal_docs, o);
+    }
+    if ((tid & 31) == 0) {
+        if (fs.markers) atomicAdd(&C.stats[0], fs.markers);
+        if (fs.lexemes) atomicAdd(&C.stats[1], fs.lexemes);
+        if (fs.exact_docs) atomicAdd(&C.stats[2], fs.exact_docs);
+        if (fs.fatal_docs) atomicAdd(&C.stats[3], fs.fatal_docs);
+    }
+}
+
+__global__ void __launch_bounds__(obmt::NT)
+k_tile_scan(TileArgs A) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    CtaShared &C = *reinterpret_cast<CtaShared *>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    obm::Tables T;
+    T.letter = D_GO_LETTER_RANGES; T.n_letter = D_GO_LETTER_RANGES_N;
+    T.number = D_GO_NUMBER_RANGES; T.n_number = D_GO_NUMBER_RANGES_N;
+    T.f64_overflow_digits = D_F64_OVERFLOW_DIGITS;
+    if (tid == 0) { mbar_init(&C.mbar, 1); fence_mbar_init(); }
+    if (tid < 4) C.stats[tid] = 0;
+    __syncthreads();
+    uint32_t mbar_phase = 0;
+    for (;;) {
+        if (tid == 0) C.tile = atomicAdd(A.ticket, 1u);
+        __syncthreads();
+        const uint32_t t = C.tile;
+        if (t >= A.ntiles) break;
+        const uint32_t d_first = A.tile_first[t], d_last = A.tile_first[t + 1];
+        /* every document starting here is small except possibly the last one */
+        uint32_t d_small_end = d_last;
+        uint32_t large_cnt = 0;
+        if (d_last > d_first && A.doc_off[d_last] - A.doc_off[d_last - 1] > obmt::MAXDOC) { d_small_end = d_last - 1; large_cnt = A.counts[d_last - 1]; }
+        const bool single = d_small_end - d_first <= obmt::DMAX;
+        uint64_t tile_total = large_cnt;
+        for (uint32_t da = d_first; da < d_small_end; da += obmt::DMAX) {
+            uint32_t db = min(da + obmt::DMAX, d_small_end);
+            tile_total += subbatch_count(C, A, T, da, db, mbar_phase);
+        }
+        if (tid == 0) {
+            uint64_t base = lookback(A.tile_state, t, tile_total);
+            C.base = base;
+            if (t == A.ntiles - 1) {
+                A.tuple_off[A.ndocs] = base + tile_total;
+                if (base + tile_total > A.out_cap) A.status[0] = 1;
+            }
+        }
+        __syncthreads();
+        uint64_t base = C.base;
+        for (uint32_t da = d_first; da < d_small_end; da += obmt::DMAX) {
+            uint32_t db = min(da + obmt::DMAX, d_small_end);
+            uint32_t sub = single ? C.sub_total : subbatch_count(C, A, T, da, db, mbar_phase);
+            subbatch_fill(C, A, T, da, db, base);
+            base += sub;
+            __syncthreads();
+        }
+        if (d_small_end < d_last && tid == 0) A.tuple_off[d_last - 1] = base;
+        __syncthreads();
+    }
+    if (tid < 4 && C.stats[tid]) {
+        if (tid < 2) atomicAdd(&A.totals[tid], (unsigned long long)C.stats[tid]);
+        else atomicAdd(&A.status[tid - 1], C.stats[tid]); /* status[1] = exact docs, status[2] = fatal docs */
+    }
+}
+
+} /* namespace obmf */
+
+/* scratch: tile_first u32[ntiles+2] | tile_state u64[ntiles+1] | large_list u32[max_large+1] | ctl u32[4] */
+static inline uint64_t obm_fast_ntiles(uint64_t total_bytes) { return total_bytes / obmt::TILE + 1; }
+static inline uint64_t obm_fast_max_large(uint64_t total_bytes) { return total_bytes / obmt::MAXDOC + 1; }
+static inline uint64_t obm_fast_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
+    (void)ndocs;
+    uint64_t nt = obm_fast_ntiles(total_bytes);
+    auto up = [](uint64_t v) { return (v + 255) / 256 * 256; };
+    return up((nt + 2) * 4) + up((nt + 1) * 8) + up((obm_fast_max_large(total_bytes) + 1) * 4) + 256;
+}

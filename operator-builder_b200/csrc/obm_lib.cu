@@ -55,8 +55,10 @@ enum { ST_OVERFLOW = 0, ST_DOCS_EXACT = 1, ST_DOCS_FATAL = 2, ST_RESERVED = 3 };
 /* doc_list == nullptr: documents [0, ndocs); otherwise the ids in doc_list[0..ndocs). */
 __global__ void __launch_bounds__(128)
 k_exact_count(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, const uint32_t *__restrict__ doc_list,
-              uint32_t ndocs, uint32_t *__restrict__ counts, unsigned long long *__restrict__ totals /* {markers, lexemes} */,
-              uint32_t *__restrict__ status) {
+              uint32_t ndocs, const uint32_t *__restrict__ ndocs_dev, uint32_t *__restrict__ counts,
+              unsigned long long *__restrict__ totals /* {markers, lexemes} */, uint32_t *__restrict__ status) {
+    if (ndocs_dev) ndocs = *ndocs_dev; /* list length decided on the device (large documents) */
+    if (blockIdx.x * blockDim.x >= ndocs) return;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t markers = 0, lexemes = 0, fatal = 0;
     if (i < ndocs) {
@@ -92,7 +94,9 @@ k_exact_count(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ do
 
 __global__ void __launch_bounds__(128)
 k_exact_fill(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, const uint32_t *__restrict__ doc_list,
-             uint32_t ndocs, const uint64_t *__restrict__ tuple_off, obm_tuple *__restrict__ out, uint64_t out_cap) {
+             uint32_t ndocs, const uint32_t *__restrict__ ndocs_dev, const uint64_t *__restrict__ tuple_off,
+             obm_tuple *__restrict__ out, uint64_t out_cap) {
+    if (ndocs_dev) ndocs = *ndocs_dev;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ndocs) return;
     uint32_t d = doc_list ? doc_list[i] : i;
@@ -273,6 +277,49 @@ static int ensure(obm_handle *h, T **p, uint64_t *cap, uint64_t need) {
     return OBM_OK;
 }
 
+/* Fast path: index kernel -> exact count of large documents -> tile kernel -> exact fill of large documents. */
+static int obm_fast_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t *d_doc_off, uint32_t ndocs, uint64_t total_bytes,
+                           obm_tuple *d_out, uint64_t out_cap, uint64_t *toff, uint32_t *status, unsigned long long *totals,
+                           uint32_t *counts, void *ws, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = sizeof(obmf::CtaShared);
+    if (!attr_set) {
+        OBM_CUDA(h, cudaFuncSetAttribute(obmf::k_tile_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const uint64_t nt64 = obm_fast_ntiles(total_bytes);
+    if (nt64 > 0xFFFFFFF0ull) { set_err(h, "batch too large for the tile index"); return OBM_E_ARG; }
+    const uint32_t ntiles = (uint32_t)nt64;
+    auto up = [](uint64_t v) { return (v + 255) / 256 * 256; };
+    uint8_t *w = (uint8_t *)ws;
+    uint32_t *tile_first = (uint32_t *)w; w += up(((uint64_t)ntiles + 2) * 4);
+    uint64_t *tile_state = (uint64_t *)w; w += up(((uint64_t)ntiles + 1) * 8);
+    const uint64_t max_large = obm_fast_max_large(total_bytes);
+    uint32_t *large_list = (uint32_t *)w; w += up((max_large + 1) * 4);
+    uint32_t *ctl = (uint32_t *)w; /* [0] ticket, [1] n_large */
+    OBM_CUDA(h, cudaMemsetAsync(tile_state, 0, ((uint64_t)ntiles + 1) * 8, st));
+    OBM_CUDA(h, cudaMemsetAsync(ctl, 0, 16, st));
+    obmf::k_tile_index<<<(ndocs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, ndocs, ntiles, tile_first, large_list, ctl + 1);
+    const uint32_t nb_large = (uint32_t)((max_large + 127) / 128);
+    k_exact_count<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, ctl + 1, counts, totals, status);
+    obmf::TileArgs A;
+    A.bytes = d_bytes; A.doc_off = d_doc_off; A.ndocs = ndocs; A.total_bytes = total_bytes;
+    A.tile_first = tile_first; A.ntiles = ntiles; A.counts = counts;
+    A.out = d_out; A.out_cap = d_out ? out_cap : 0; A.tuple_off = toff;
+    A.tile_state = tile_state; A.ticket = ctl; A.status = status; A.totals = totals;
+    int dev_sms = 0, per_sm = 0;
+    OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
+    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, obmf::k_tile_scan, (int)obmt::NT, smem));
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = (uint32_t)dev_sms * (uint32_t)per_sm; /* persistent CTAs: a multiple of the SM count */
+    if (grid > ntiles) grid = ntiles;
+    obmf::k_tile_scan<<<grid, obmt::NT, smem, st>>>(A);
+    if (d_out && out_cap) k_exact_fill<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, ctl + 1, toff, d_out, out_cap);
+    h->launches = 3 + ((d_out && out_cap) ? 1 : 0);
+    OBM_CUDA(h, cudaGetLastError());
+    return OBM_OK;
+}
+
 /* scratch layout: counts u32[ndocs] | tile_sums u64[ntiles] | fast-path workspace */
 static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 static uint32_t scan_tiles(uint32_t ndocs) { return (ndocs + SCAN_TILE - 1) / SCAN_TILE; }
@@ -284,13 +331,12 @@ extern "C" uint64_t obm_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
     return b;
 }
 
-extern "C" int obm_lex_batch_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
-                                    uint64_t total_bytes, void *d_out, uint64_t out_cap, void *d_doc_tuple_off,
-                                    void *d_status, void *d_counts, void *stream_v) {
+static int lex_device_impl(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
+                           uint64_t total_bytes, void *d_out, uint64_t out_cap, void *d_doc_tuple_off,
+                           void *d_status, void *d_counts, cudaStream_t st) {
     if (!h) return OBM_E_ARG;
     if (!d_doc_off || !d_doc_tuple_off || (ndocs && total_bytes && !d_bytes)) { set_err(h, "null device pointer"); return OBM_E_ARG; }
     OBM_CUDA(h, cudaSetDevice(h->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
     uint64_t need = obm_scratch_bytes(ndocs, total_bytes);
     if (h->scratch_bytes < need) {
         if (h->scratch) { OBM_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->scratch); h->scratch = nullptr; h->scratch_bytes = 0; }
@@ -309,21 +355,28 @@ extern "C" int obm_lex_batch_device(obm_handle *h, const void *d_bytes, const vo
     if (ndocs == 0) { OBM_CUDA(h, cudaMemsetAsync(toff, 0, sizeof(uint64_t), st)); return OBM_OK; }
 
     if (h->mode == 0) {
-        int rc = obm_fast_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
-                                 (obm_tuple *)d_out, out_cap, toff, status, totals, counts, tile_sums, fast_ws, st);
-        if (rc != 1) return rc; /* 1 = fast path not available for this build: fall through to the exact kernels */
+        return obm_fast_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
+                               (obm_tuple *)d_out, out_cap, toff, status, totals, counts, fast_ws, st);
     }
     uint32_t nb = (ndocs + 127) / 128;
     h->launches = 4 + ((d_out && out_cap) ? 1 : 0);
-    k_exact_count<<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, nullptr, ndocs, counts, totals, status);
+    k_exact_count<<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, nullptr, ndocs, nullptr, counts, totals, status);
     uint32_t nt = scan_tiles(ndocs);
     k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(counts, ndocs, toff, tile_sums);
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, toff + ndocs);
     k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(toff, ndocs, tile_sums, out_cap, status);
     if (d_out && out_cap)
-        k_exact_fill<<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, nullptr, ndocs, toff, (obm_tuple *)d_out, out_cap);
+        k_exact_fill<<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, nullptr, ndocs, nullptr, toff, (obm_tuple *)d_out, out_cap);
     OBM_CUDA(h, cudaGetLastError());
     return OBM_OK;
+}
+
+/* `stream` is used exactly as given: NULL is CUDA's (legacy) default stream, like any CUDA API. */
+extern "C" int obm_lex_batch_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
+                                    uint64_t total_bytes, void *d_out, uint64_t out_cap, void *d_doc_tuple_off,
+                                    void *d_status, void *d_counts, void *stream) {
+    return lex_device_impl(h, d_bytes, d_doc_off, ndocs, total_bytes, d_out, out_cap, d_doc_tuple_off, d_status, d_counts,
+                           (cudaStream_t)stream);
 }
 
 extern "C" int obm_lex_batch(obm_handle *h, const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs,
@@ -364,8 +417,8 @@ extern "C" int obm_lex_batch(obm_handle *h, const uint8_t *bytes, const uint64_t
     }
     if (total) OBM_CUDA(h, cudaMemcpyAsync(h->d_bytes, bytes + base, total, cudaMemcpyHostToDevice, st));
     OBM_CUDA(h, cudaEventRecord(h->ev[1], st));
-    rc = obm_lex_batch_device(h, h->d_bytes, h->d_doc_off, ndocs, total, (out && out_cap) ? h->d_out : nullptr, out_cap,
-                              h->d_tuple_off, nullptr, nullptr, st);
+    rc = lex_device_impl(h, h->d_bytes, h->d_doc_off, ndocs, total, (out && out_cap) ? h->d_out : nullptr, out_cap,
+                         h->d_tuple_off, nullptr, nullptr, st);
     if (rc != OBM_OK) return rc;
     OBM_CUDA(h, cudaEventRecord(h->ev[2], st));
     OBM_CUDA(h, cudaMemcpyAsync(doc_tuple_off, h->d_tuple_off, ((uint64_t)ndocs + 1) * 8, cudaMemcpyDeviceToHost, st));
@@ -399,7 +452,7 @@ extern "C" int obm_generate_corpus_device(obm_handle *h, void *d_bytes, void *d_
                                           uint32_t doc_bytes, uint64_t first_doc, int flavour, void *stream_v) {
     if (!h || !d_bytes) return OBM_E_ARG;
     OBM_CUDA(h, cudaSetDevice(h->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : h->stream;
+    cudaStream_t st = (cudaStream_t)stream_v;
     if (ndocs == 0) return OBM_OK;
     k_generate_corpus<<<(ndocs + 127) / 128, 128, 0, st>>>((uint8_t *)d_bytes, (uint64_t *)d_doc_off, ndocs, doc_bytes, first_doc, flavour);
     OBM_CUDA(h, cudaGetLastError());

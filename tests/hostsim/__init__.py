@@ -15,6 +15,7 @@ def build(force=False):
     srcs = [os.path.join(_HERE, "hostsim.cpp"),
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_decode.cpp"),
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_core.h"),
+            os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_tile.h"),
             os.path.join(_ROOT, "include", "obmarkers.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-shared", "-o", so,
@@ -31,6 +32,9 @@ def lib():
                                  ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
         L.hs_lex_doc_by_lines.restype = ctypes.c_uint64
         L.hs_lex_doc_by_lines.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64]
+        L.hs_tile_batch.restype = ctypes.c_uint64
+        L.hs_tile_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64,
+                                    ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
         L.hs_parse_float_err.argtypes = [ctypes.c_char_p, ctypes.c_uint32]
         L.hs_atoi_err.argtypes = [ctypes.c_char_p, ctypes.c_uint32]
         L.obm_decode_doc.restype = ctypes.c_int64
@@ -73,3 +77,19 @@ def fmt_tuples(tuples):
              21: "PART", 22: "FLUSH", 23: "DRIFT", 24: "LINE", 25: "LINEHI", 26: "WARN_NOSCOPE", 27: "WARN_INVALID",
              28: "ERR_MALFORMED", 29: "ERR_UNMATCHED", 30: "ERR_FLOAT", 31: "ERR_INT"}
     return [(names.get(int(t) >> 59, int(t) >> 59), int(t) & 0xFFFFFFFF, (int(t) >> 32) & 0x7FFFFFF) for t in tuples]
+
+
+def tile_batch(docs, skew=0):
+    """CTA emulation of the tile fast path over a list of documents -> (tuples, doc_tuple_off, stats)."""
+    L = lib()
+    data = np.frombuffer(b"".join(docs) + b"\0", dtype=np.uint8).copy()
+    off = np.zeros(len(docs) + 1, dtype=np.uint64)
+    if docs:
+        off[1:] = np.cumsum([len(d) for d in docs])
+    cap = 2 * int(off[-1]) + 2 * len(docs) + 16
+    out = np.zeros(cap, dtype=np.uint64)
+    toff = np.zeros(len(docs) + 1, dtype=np.uint64)
+    stats = np.zeros(4, dtype=np.uint64)
+    n = L.hs_tile_batch(data.ctypes.data, off.ctypes.data, len(docs), out.ctypes.data, cap, toff.ctypes.data, skew, stats.ctypes.data)
+    assert n <= cap
+    return out[:n].copy(), toff, stats

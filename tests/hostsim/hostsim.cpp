@@ -29,10 +29,8 @@ uint64_t hs_lex_doc_by_lines(const uint8_t *doc, uint32_t n, obm_tuple *out, uin
     uint32_t pos = 0, line = 1;
     bool fatal = false;
     while (pos < n) {
-        uint32_t le = pos;
-        while (le < n && doc[le] != '\n') le++;
-        obm::Lexer<obm::WriteSink> lx(TBL, doc, n, sink, pos, line, !(line == 1 && pos == 0));
-        int st = lx.run<true>(le);
+        obm::Lexer<obm::WriteSink> lx(TBL, doc, n, sink, pos, line, pos, !(line == 1 && pos == 0));
+        int st = lx.run<true>();
         if (st == obm::RUN_FATAL) { fatal = true; break; }
         if (st == obm::RUN_EOF) break;
         pos = lx.p; line = lx.line_p;
@@ -42,4 +40,102 @@ uint64_t hs_lex_doc_by_lines(const uint8_t *doc, uint32_t n, obm_tuple *out, uin
 }
 int hs_parse_float_err(const uint8_t *s, uint32_t n) { return obm::parse_float_err(TBL, s, n); }
 int hs_atoi_err(const uint8_t *s, uint32_t n) { return obm::atoi_err(s, n); }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * CTA emulation of the tile fast path (obm_fast.cuh's k_tile_scan): the same phase functions from
+ * obm_tile.h, run for tid = 0..NT-1 between "barriers", tiles visited in order (which is what the
+ * look-back chain enforces on the device).
+ * ------------------------------------------------------------------------------------------- */
+#include <vector>
+#include "../../operator-builder_b200/csrc/obm_tile.h"
+
+namespace {
+using obmt::Smem;
+
+struct Emu {
+    Smem S;
+    uint32_t sub_total = 0;
+    uint32_t count(const uint8_t *bytes, const uint64_t *doc_off, uint32_t da, uint32_t db, uint32_t fake_skew) {
+        const uint32_t nd = db - da;
+        const uint64_t b0 = doc_off[da], b1 = doc_off[db];
+        const uint32_t skew = fake_skew & 15u; /* the device derives it from the absolute address */
+        const uint32_t span = (uint32_t)(b1 - b0) + skew;
+        S.nd = nd; S.lo_pos = skew; S.hi_pos = span; S.n_owners = 0;
+        memset(S.data, 0x2B, sizeof S.data); /* '+' garbage outside the range must never matter */
+        memcpy(S.data + skew, bytes + b0, (size_t)(b1 - b0));
+        for (uint32_t t = 0; t <= nd; t++) S.dstart[t] = (uint32_t)(doc_off[da + t] - b0) + skew;
+        const uint32_t nwords = (span + 31) >> 5;
+        for (uint32_t wi = 0; wi < obmt::NW; wi++) {
+            if (wi < ((nwords + 31u) & ~31u)) obmt::classify_word(S, wi); else { S.nlw[wi] = 0; S.spw[wi] = 0; }
+        }
+        for (uint32_t t = 0; t < nd; t++) obmt::doc_prep(S, t);
+        std::vector<uint32_t> my_nl(obmt::NT), my_own(obmt::NT);
+        for (uint32_t t = 0; t < obmt::NT; t++) { uint32_t c = 0; my_nl[t] = obmt::line_scan(S, t, [&](uint32_t, uint32_t) { c++; }); my_own[t] = c; }
+        uint32_t nlp = 0, own = 0, n_owners = 0;
+        for (uint32_t t = 0; t < obmt::NT; t++) n_owners += my_own[t];
+        for (uint32_t t = 0; t < obmt::NT; t++) {
+            uint32_t q = nlp;
+            for (uint32_t j = 0; j < obmt::WPT; j++) { S.nlpre[t * obmt::WPT + j] = (uint16_t)q; q += (uint32_t)__builtin_popcount(S.nlw[t * obmt::WPT + j]); }
+            if (n_owners <= obmt::QMAX && my_own[t]) { uint32_t o = own; obmt::line_scan(S, t, [&](uint32_t first, uint32_t ls) { S.owner[o++] = first | (ls << 16); }); }
+            nlp += my_nl[t]; own += my_own[t];
+        }
+        S.n_owners = n_owners <= obmt::QMAX ? n_owners : 0;
+        if (n_owners > obmt::QMAX) for (uint32_t t = 0; t < nd; t++) S.dflag[t] |= obmt::DF_QOVERFLOW;
+        n_owners = S.n_owners;
+        for (uint32_t o = 0; o < n_owners; o++) obmt::owner_count(S, TBL, o);
+        uint32_t e = 0;
+        for (uint32_t o = 0; o < obmt::QMAX; o++) {
+            uint32_t v = (o < n_owners && !S.dflag[S.odoc[o]]) ? S.ocnt[o] : 0;
+            S.ocnt[o] = e; e += v;
+        }
+        S.ocnt[obmt::QMAX] = e;
+        if (n_owners < obmt::QMAX) S.ocnt[n_owners] = e;
+        for (uint32_t t = 0; t <= nd; t++) S.dfirst[t] = t == nd ? n_owners : obmt::first_owner_at(S, S.dstart[t]);
+        for (uint32_t t = 0; t < nd; t++) obmt::doc_count(S, TBL, t);
+        uint32_t acc = 0;
+        for (uint32_t t = 0; t < nd; t++) { uint32_t v = S.dcnt[t]; S.dcnt[t] = acc; acc += v; }
+        S.dcnt[nd] = acc; sub_total = acc;
+        return acc;
+    }
+    void fill(uint32_t da, uint32_t db, uint64_t base, obm_tuple *out, uint64_t cap, uint64_t *tuple_off, obmt::FillStats &fs) {
+        for (uint32_t o = 0; o < S.n_owners; o++) obmt::owner_fill(S, TBL, o, out, cap, base, fs);
+        for (uint32_t t = 0; t < db - da; t++) { tuple_off[da + t] = base + S.dcnt[t]; obmt::doc_fill(S, TBL, t, out, cap, base, fs); }
+    }
+};
+} // namespace
+
+extern "C" uint64_t hs_tile_batch(const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs, obm_tuple *out, uint64_t cap,
+                                  uint64_t *tuple_off, uint32_t fake_skew, uint64_t *stats /* markers, lexemes, exact, fatal */) {
+    static Emu emu;
+    const uint64_t total = doc_off[ndocs];
+    const uint64_t ntiles = total / obmt::TILE + 1;
+    uint64_t base = 0;
+    obmt::FillStats fs = {0, 0, 0, 0};
+    uint32_t d = 0;
+    for (uint64_t t = 0; t < ntiles; t++) {
+        uint32_t d_first = d;
+        while (d < ndocs && doc_off[d] < (t + 1) * (uint64_t)obmt::TILE) d++;
+        uint32_t d_last = d, d_small_end = d_last;
+        bool large = d_last > d_first && doc_off[d_last] - doc_off[d_last - 1] > obmt::MAXDOC;
+        if (large) d_small_end = d_last - 1;
+        for (uint32_t da = d_first; da < d_small_end; da += obmt::DMAX) {
+            uint32_t db = da + obmt::DMAX < d_small_end ? da + obmt::DMAX : d_small_end;
+            uint32_t sub = emu.count(bytes, doc_off, da, db, fake_skew);
+            emu.fill(da, db, base, out, cap, tuple_off, fs);
+            base += sub;
+        }
+        if (large) {
+            uint32_t dl = d_last - 1;
+            tuple_off[dl] = base;
+            obm::WriteSink sink(out + base, base < cap ? cap - base : 0);
+            obm::Lexer<obm::WriteSink> lx(TBL, bytes + doc_off[dl], (uint32_t)(doc_off[dl + 1] - doc_off[dl]), sink);
+            int st = lx.run<false>();
+            fs.markers += sink.n_markers; fs.lexemes += sink.n_lexemes; fs.exact_docs++; fs.fatal_docs += st == obm::RUN_FATAL;
+            base += sink.n_tuples;
+        }
+    }
+    tuple_off[ndocs] = base;
+    if (stats) { stats[0] = fs.markers; stats[1] = fs.lexemes; stats[2] = fs.exact_docs; stats[3] = fs.fatal_docs; }
+    return base;
 }

@@ -1,0 +1,69 @@
+"""CTA emulation of the tile fast path (obm_tile.h phase functions, tests/hostsim) vs the exact path:
+the two tuple streams must be identical, for every batch shape the kernel distinguishes
+(sub-batches, skewed starts, large documents, documents with non-ASCII bytes, interacting lines)."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from tests import corpus_util as cu
+from tests import hostsim
+
+
+def check_batch(docs, skew=0):
+    tup, toff, stats = hostsim.tile_batch(docs, skew)
+    for i, doc in enumerate(docs):
+        want = hostsim.lex_doc(doc)
+        got = tup[int(toff[i]):int(toff[i + 1])]
+        if not np.array_equal(got, want):
+            raise AssertionError(f"doc {i} (skew {skew}) {doc[:300]!r}\n tile ={hostsim.fmt_tuples(got)[:50]}\n exact={hostsim.fmt_tuples(want)[:50]}")
+    assert int(toff[-1]) == len(tup)
+    return stats
+
+
+def test_targeted_as_one_batch():
+    docs = list(cu.TARGETED)
+    for skew in (0, 1, 7, 15):
+        check_batch(docs, skew)
+
+
+def test_non_ascii_goes_exact():
+    stats = check_batch(list(cu.NON_ASCII) + [b"# +a:b\n"] * 5)
+    assert stats[2] >= len(cu.NON_ASCII) - 2
+
+
+def test_fixtures_and_golden():
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "lexer_golden.json")))
+    check_batch([c["input"].encode() for c in golden["cases"]])
+    check_batch([d for _p, d in cu.fixtures()], skew=5)
+
+
+def test_synthetic_corpus():
+    import operator_builder_b200 as ob
+    for flavour in (0, 1):
+        data, off = ob.generate_corpus_host(64, 4096, flavour=flavour)
+        raw = data.tobytes()
+        stats = check_batch([raw[i * 4096:(i + 1) * 4096] for i in range(64)])
+        assert stats[0] == 8 * 64 and stats[2] == 0
+    for doc_bytes, n in ((37, 300), (1000, 50), (16368, 3), (16369, 3), (70000, 2)):
+        data, off = ob.generate_corpus_host(n, doc_bytes)
+        raw = data.tobytes()
+        check_batch([raw[i * doc_bytes:(i + 1) * doc_bytes] for i in range(n)], skew=3)
+
+
+def test_many_tiny_and_empty_documents():
+    check_batch([b""] * 200)
+    check_batch([b"", b"+a:b", b"", b"", b"#", b"\n"] * 60)
+    check_batch([b"#\n" * 1500])           # more special lines than the owner queue holds -> exact
+    check_batch([b"+a:b\n" * 400, b"x" * 20000, b"# +c:d=1\n" * 100, b""])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_batches(seed):
+    rng = random.Random(4200 + seed)
+    for _ in range(40):
+        docs = [cu.fuzz_doc(rng, max_len=rng.choice([5, 60, 400, 3000]), non_ascii=rng.random() < 0.15)
+                for _ in range(rng.randint(1, 80))]
+        check_batch(docs, skew=rng.randint(0, 15))

@@ -27,9 +27,11 @@
 
 #if defined(__CUDACC__)
 #define OBM_HD __host__ __device__ __forceinline__
+#define OBM_FN __host__ __device__ inline
 #define OBM_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define OBM_HD inline
+#define OBM_FN inline
 #define OBM_HD_NOINLINE inline
 #endif
 
@@ -97,6 +99,8 @@ OBM_HD bool is_letter(const Tables &T, int r) {
     if (r < 0x80) { unsigned c = (unsigned)r | 0x20u; return c >= 'a' && c <= 'z'; }
     return in_ranges(T.letter, T.n_letter, r);
 }
+OBM_HD bool is_letter_ascii(int r) { unsigned c = (unsigned)r | 0x20u; return r >= 0 && r < 0x80 && c >= 'a' && c <= 'z'; }
+OBM_HD bool is_digit_ascii(int r) { return r >= '0' && r <= '9'; }
 OBM_HD bool is_number(const Tables &T, int r) {
     if (r < 0) return false;
     if (r < 0x80) return r >= '0' && r <= '9';
@@ -233,6 +237,18 @@ struct WriteSink {
     }
 };
 
+/* 32-bit sink for bounded documents (tile path): counts always, writes while n < cap (cap 0 = count only) */
+struct SmallSink {
+    obm_tuple *out; uint32_t cap; uint32_t n_tuples, n_markers, n_lexemes;
+    OBM_HD SmallSink(obm_tuple *o, uint32_t c) : out(o), cap(c), n_tuples(0), n_markers(0), n_lexemes(0) {}
+    OBM_HD void put(uint32_t kind, uint32_t off, uint32_t len) {
+        if (n_tuples < cap) out[n_tuples] = OBM_TUPLE(kind, off, len);
+        n_tuples++;
+        n_markers += (kind == OBM_K_MARKER_START);
+        n_lexemes += (kind <= OBM_K_EOF) || (kind >= OBM_K_WARN_NOSCOPE);
+    }
+};
+
 enum RunStatus { RUN_EOF = 0, RUN_LINE_END = 1, RUN_FATAL = 2 };
 enum TopState { TOP_LEX = 0, TOP_COMMENT = 1, TOP_FATAL = 2 };
 
@@ -243,7 +259,9 @@ struct NoAccel {
     OBM_HD uint32_t next_interesting(uint32_t p) const { return p; }
 };
 
-template <class Sink, class Accel = NoAccel>
+/* ASCII = true: the caller guarantees every byte of the document is < 0x80 (tile path); rune decoding,
+ * the Unicode tables and the U+FFFD over-discard drop out at compile time. */
+template <class Sink, class Accel = NoAccel, bool ASCII = false>
 struct Lexer {
     const Tables &T;
     const uint8_t *d; uint32_t n;
@@ -267,7 +285,7 @@ struct Lexer {
           sv_line(first_line), sv_base(line_base), sv_drift(0), last_w(0), last_r(RUNE_EOF), last_type(0), out(sink), accel(acc) {}
 
     /* ---- tuple plumbing ---- */
-    OBM_HD void ensure_line(uint32_t line, uint32_t base) {
+    OBM_FN void ensure_line(uint32_t line, uint32_t base) {
         if (line != line_e || base != base_e) {
             if (line >> OBM_LEN_BITS) out.put(OBM_K_LINEHI, line >> OBM_LEN_BITS, 0);
             out.put(OBM_K_LINE, base, line & OBM_MAX_LEN);
@@ -276,7 +294,7 @@ struct Lexer {
     }
     OBM_HD void sync_start() { s = p; line_s = line_p; base_s = base_p; }
     /* un-emitted text doc[s,p) becomes a PART (kept in the decoder's pending buffer) */
-    OBM_HD void part_tail() {
+    OBM_FN void part_tail() {
         if (p > s) {
             ensure_line(line_s, base_s);
             uint32_t off = s, len = p - s;
@@ -286,7 +304,7 @@ struct Lexer {
         }
     }
     /* emit.go:7-19 */
-    OBM_HD void emit(uint32_t kind) {
+    OBM_FN void emit(uint32_t kind) {
         ensure_line(line_s, base_s);
         uint32_t off = s, len = p - s;
         while (len > OBM_MAX_LEN) { out.put(OBM_K_PART, off, OBM_MAX_LEN); off += OBM_MAX_LEN; len -= OBM_MAX_LEN; }
@@ -299,16 +317,19 @@ struct Lexer {
     /* discard.go:68-71 */
     OBM_HD void flush() { out.put(OBM_K_FLUSH, p, 0); sync_start(); }
     /* error.go:37-45 (continues in lexComment) / error.go:15-34 (terminates) */
-    OBM_HD void located_at_pos(uint32_t kind) { part_tail(); ensure_line(line_p, base_p); out.put(kind, p, 0); }
+    OBM_FN void located_at_pos(uint32_t kind) { part_tail(); ensure_line(line_p, base_p); out.put(kind, p, 0); }
     OBM_HD void numeric_error(uint32_t kind) { ensure_line(line_s, base_s); out.put(kind, s, p - s); }
 
     /* ---- reader primitives ---- */
-    OBM_HD int peek(uint32_t &w) const { return decode_rune(d, p, n, w); }
-    OBM_HD int peek() const { uint32_t w; return decode_rune(d, p, n, w); }
+    OBM_HD int peek(uint32_t &w) const {
+        if (ASCII) { if (p < n) { w = 1; return (int)d[p]; } w = 0; return RUNE_EOF; }
+        return decode_rune(d, p, n, w);
+    }
+    OBM_HD int peek() const { uint32_t w; return peek(w); }
     OBM_HD uint32_t peek_byte() const { return p < n ? d[p] : 0x100u; } /* 0x100 = EOF sentinel */
     /* position.go:18-39 */
     OBM_HD int next() {
-        uint32_t w; int r = decode_rune(d, p, n, w);
+        uint32_t w; int r = peek(w);
         last_w = w; last_r = r;
         if (r == RUNE_EOF) return r;
         p += w;
@@ -323,28 +344,36 @@ struct Lexer {
         }
     }
     /* position.go:43-57, second call (state.go:79,126): UnreadRune fails, the column still moves */
-    OBM_HD void backup_again() {
+    OBM_FN void backup_again() {
         if (last_w != 0) { drift_p += last_w; ensure_line(line_p, base_p); out.put(OBM_K_DRIFT, p, 0); }
     }
     /* discard.go:12-38 discard() == discardN(1) */
-    OBM_HD void discard1() {
-        uint32_t w; int r = decode_rune(d, p, n, w);
+    OBM_FN void discard1() {
+        uint32_t w; int r = peek(w);
         if (r == RUNE_EOF) { flush(); return; }
         part_tail();
-        uint32_t adv = (r == RUNE_ERR && w == 1) ? 3u : w; /* utf8.RuneLen(U+FFFD) == 3, discard.go:27-28 */
+        uint32_t adv = (!ASCII && r == RUNE_ERR && w == 1) ? 3u : w; /* utf8.RuneLen(U+FFFD) == 3, discard.go:27-28 */
         if (adv > n - p) adv = n - p;
         p += adv;
         if (r == '\n') { line_p++; base_p = p; drift_p = 0; }
         sync_start();
     }
     /* `q - p` discard() calls over bytes known to be ASCII, non-newline (Accel contract) */
-    OBM_HD void discard_to(uint32_t q) {
+    OBM_FN void discard_to(uint32_t q) {
         if (q > p) { part_tail(); p = q; sync_start(); }
     }
     OBM_HD bool has_prefix2(uint32_t a, uint32_t b) const { return p + 1 < n && d[p] == a && d[p + 1] == b; }
     /* consume.go:65-80 with an ASCII delimiter class; returns `consumed` */
     template <bool NAKED>
-    OBM_HD bool consume_until() {
+    OBM_FN bool consume_until() {
+        if (ASCII) { /* '\n' is a delimiter: no line bookkeeping inside the run */
+            uint32_t q = p;
+            while (q < n) { uint32_t c = d[q]; if (NAKED ? is_naked_delim(c) : is_name_delim(c)) break; q++; }
+            bool any = q > p;
+            p = q;
+            if (q < n) { last_w = 1; last_r = (int)d[q]; } else { last_w = 0; last_r = RUNE_EOF; } /* state after next()+backup() */
+            return any;
+        }
         bool consumed = false;
         for (;;) {
             int r = next();
@@ -355,11 +384,13 @@ struct Lexer {
     }
     /* peek.go:65-89 for one ASCII token `tok[0..t)`: on success returns true and sets `width`
      * (= l.width after the final peekN: whitespace BYTES + token bytes). */
-    OBM_HD bool peeked_whitespaced(const char *tok, uint32_t t, uint32_t &width) const {
+    OBM_FN bool peeked_whitespaced(const char *tok, uint32_t t, uint32_t &width) const {
         uint32_t lim = (n - p > (uint32_t)BUFIO_WINDOW) ? p + (uint32_t)BUFIO_WINDOW : n;
         uint32_t o = p;
         for (;;) {
-            uint32_t w; int r = decode_rune(d, o, lim, w);
+            uint32_t w; int r;
+            if (ASCII) { if (o < lim) { r = (int)d[o]; w = 1; } else { r = RUNE_EOF; w = 0; } }
+            else r = decode_rune(d, o, lim, w);
             if (r == RUNE_EOF) return false; /* r[i] == eof (real end of input or end of the 4096-byte window) */
             if (!is_space(r)) break;
             o += w;
@@ -373,7 +404,7 @@ struct Lexer {
         return peeked_whitespaced("//", 2, width) || peeked_whitespaced("#", 1, width);
     }
     /* consume.go:37-47: consumes `width` RUNES (width is a byte count) */
-    OBM_HD bool consumed_whitespaced(const char *tok, uint32_t t) {
+    OBM_FN bool consumed_whitespaced(const char *tok, uint32_t t) {
         uint32_t width;
         if (!peeked_whitespaced(tok, t, width)) return false;
         for (uint32_t k = 0; k < width; k++) next();
@@ -382,12 +413,12 @@ struct Lexer {
 
     /* ---- marker states; each returns the top-level state to continue in ---- */
     /* state.go:60-68, entered with '+' just consumed */
-    OBM_HD int marker_start() {
-        if (is_letter(T, peek())) { emit(OBM_K_MARKER_START); return lex_marker(); }
+    OBM_FN int marker_start() {
+        if (ASCII ? is_letter_ascii(peek()) : is_letter(T, peek())) { emit(OBM_K_MARKER_START); return lex_marker(); }
         return TOP_COMMENT;
     }
     /* state.go:71-116 */
-    OBM_HD int lex_marker() {
+    OBM_FN int lex_marker() {
         for (;;) {
             if (!consume_until<false>()) { backup_again(); flush(); return TOP_COMMENT; }
             uint32_t c = peek_byte();
@@ -407,7 +438,7 @@ struct Lexer {
         }
     }
     /* state.go:118-154 (lexArgs) and state.go:304-317 (lexMoreArgs), as one loop */
-    OBM_HD int lex_more_args() {
+    OBM_FN int lex_more_args() {
         for (;;) {
             uint32_t c = peek_byte();
             if (c == ',') { next(); emit(OBM_K_ARG_DELIMITER); }
@@ -424,9 +455,9 @@ struct Lexer {
             return TOP_FATAL;
         }
     }
-    OBM_HD int lex_arg_value() { int st = lex_arg_value_inner(); return st != -1 ? st : lex_more_args(); }
+    OBM_FN int lex_arg_value() { int st = lex_arg_value_inner(); return st != -1 ? st : lex_more_args(); }
     /* state.go:156-302; returns -1 to continue in lexMoreArgs, else a TopState (fatal) */
-    OBM_HD int lex_arg_value_inner() {
+    OBM_FN int lex_arg_value_inner() {
         uint32_t c = peek_byte();
         /* lexStringLiteral, state.go:176-221 */
         if (c == '\'' || c == '"' || c == '`') {
@@ -453,13 +484,13 @@ struct Lexer {
         /* lexNumericLiteral, state.go:223-276 */
         {
             int r0 = peek();
-            if (r0 == '.' || r0 == '-' || is_number(T, r0)) {
+            if (r0 == '.' || r0 == '-' || (ASCII ? is_digit_ascii(r0) : is_number(T, r0))) {
                 bool isfloat = (r0 == '.');
                 for (;;) {
                     next();
                     uint32_t b = peek_byte();
                     if (b == '.' || b == 'e' || b == 'E' || b == '-') { isfloat = true; continue; }
-                    if (!is_number(T, peek())) break;
+                    if (!(ASCII ? is_digit_ascii(peek()) : is_number(T, peek()))) break;
                 }
                 int code = isfloat ? parse_float_err(T, d + s, p - s) : atoi_err(d + s, p - s);
                 if (code) { numeric_error(isfloat ? OBM_K_ERR_FLOAT : OBM_K_ERR_INT); return TOP_FATAL; }
@@ -478,7 +509,7 @@ struct Lexer {
     /* ---- top level: state.go:15-57.  LINE_MODE (the tile path's per-line owner) stops right after
      *      discarding the first top-level '\n'; otherwise runs to EOF and emits the EOF tuple. ---- */
     template <bool LINE_MODE>
-    OBM_HD int run() {
+    OBM_FN int run() {
         int st = TOP_LEX;
         for (;;) {
             if (st == TOP_LEX) {

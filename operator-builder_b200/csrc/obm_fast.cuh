@@ -60,25 +60,39 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t *scratc
 }
 
 /* ---- look-back chain ----------------------------------------------------------------------------- */
-constexpr uint64_t LB_AGG = 1ull << 62, LB_INCL = 2ull << 62, LB_MASK = (1ull << 62) - 1;
+#define LB_AGG (1ull << 62)
+#define LB_INCL (2ull << 62)
+#define LB_MASK ((1ull << 62) - 1)
 
-__device__ __forceinline__ uint64_t lookback(volatile uint64_t *state, uint32_t t, uint64_t my_total) {
-    /* publish the aggregate, then walk back until an inclusive prefix is found */
-    if (t == 0) { __threadfence(); state[0] = LB_INCL | my_total; return 0; }
-    state[t] = LB_AGG | my_total;
-    __threadfence();
-    uint64_t sum = 0;
-    int32_t i = (int32_t)t - 1;
-    for (;;) {
-        uint64_t s = state[i];
-        uint64_t f = s >> 62;
-        if (f == 0) { __nanosleep(20); continue; }
-        sum += s & LB_MASK;
-        if (f == 2) break;
-        i--;
+/* Executed by warp 0 (all 32 lanes).  Publishes this tile's aggregate, then inspects 32 predecessors
+ * per step (one coalesced load, two ballots) until an inclusive prefix is found.  Returns the
+ * exclusive prefix (sum of all earlier tiles) in every lane. */
+__device__ __forceinline__ uint64_t lookback_warp(volatile uint64_t *state, uint32_t t, uint64_t my_total) {
+    const uint32_t lane = threadIdx.x & 31;
+    if (t == 0) {
+        if (lane == 0) { state[0] = LB_INCL | my_total; __threadfence(); }
+        return 0;
     }
-    state[t] = LB_INCL | (sum + my_total);
-    __threadfence();
+    if (lane == 0) { state[t] = LB_AGG | my_total; __threadfence(); }
+    uint64_t sum = 0;
+    int64_t hi = (int64_t)t - 1; /* nearest predecessor not yet accounted for */
+    for (;;) {
+        int64_t idx = hi - (int64_t)lane;
+        uint64_t s = idx >= 0 ? state[idx] : LB_INCL; /* virtual inclusive 0 in front of tile 0 */
+        uint32_t f = (uint32_t)(s >> 62);
+        uint32_t incl = __ballot_sync(0xffffffffu, f == 2);
+        uint32_t zero = __ballot_sync(0xffffffffu, f == 0);
+        uint32_t upto = incl ? (uint32_t)__ffs((int)incl) - 1u : 31u;            /* last lane that contributes */
+        uint32_t need = upto == 31u ? 0xffffffffu : ((2u << upto) - 1u);
+        if (zero & need) { __nanosleep(40); continue; }                          /* a needed predecessor has not published yet */
+        uint64_t v = lane <= upto ? (s & LB_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        sum += v;
+        if (incl) break;
+        hi -= 32;
+    }
+    if (lane == 0) { state[t] = LB_INCL | (sum + my_total); __threadfence(); }
     return sum;
 }
 
@@ -151,9 +165,12 @@ __device__ __forceinline__ uint32_t subbatch_count(CtaShared &C, const TileArgs 
     /* P3: per-document preparation */
     if (tid < nd) obmt::doc_prep(S, tid);
     __syncthreads();
-    /* P4: line scan -- newline prefix + owner discovery (count, scan, write) */
-    uint32_t my_owners = 0;
-    uint32_t my_nl = obmt::line_scan(S, tid, [&](uint32_t, uint32_t) { my_owners++; });
+    /* P4: line scan -- newline prefix + owner discovery (records cached in registers, scan, write) */
+    uint32_t my_owners = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    uint32_t my_nl = obmt::line_scan(S, tid, [&](uint32_t rec) {
+        if (my_owners == 0) c0 = rec; else if (my_owners == 1) c1 = rec; else if (my_owners == 2) c2 = rec; else if (my_owners == 3) c3 = rec;
+        my_owners++;
+    });
     uint32_t tot;
     uint32_t pre = block_scan_excl(my_nl | (my_owners << 16), S.scan_tmp, tot);
     {
@@ -161,15 +178,29 @@ __device__ __forceinline__ uint32_t subbatch_count(CtaShared &C, const TileArgs 
 #pragma unroll
         for (uint32_t j = 0; j < obmt::WPT; j++) { S.nlpre[tid * obmt::WPT + j] = (uint16_t)nlp; nlp += (uint32_t)__popc(S.nlw[tid * obmt::WPT + j]); }
         uint32_t n_owners = tot >> 16;
-        if (n_owners <= obmt::QMAX && my_owners)
-            obmt::line_scan(S, tid, [&](uint32_t first, uint32_t ls) { S.owner[own++] = first | (ls << 16); });
-        if (tid == 0) S.n_owners = n_owners <= obmt::QMAX ? n_owners : 0;
+        if (n_owners <= obmt::QMAX && my_owners) {
+            if (my_owners <= 4) {
+                S.owner[own] = c0;
+                if (my_owners > 1) S.owner[own + 1] = c1;
+                if (my_owners > 2) S.owner[own + 2] = c2;
+                if (my_owners > 3) S.owner[own + 3] = c3;
+            } else {
+                obmt::line_scan(S, tid, [&](uint32_t rec) { S.owner[own++] = rec; });
+            }
+        }
+        if (tid == 0) { S.n_owners = n_owners <= obmt::QMAX ? n_owners : 0; S.n_markers_q = 0; }
         if (n_owners > obmt::QMAX && tid < nd) S.dflag[tid] |= obmt::DF_QOVERFLOW; /* too many special lines: exact path */
     }
     __syncthreads();
-    /* P5: owners, count pass */
+    /* P5a: every owner -> document, plain-line counts, dense list of marker lines */
     const uint32_t n_owners = S.n_owners;
-    for (uint32_t o = tid; o < n_owners; o += obmt::NT) obmt::owner_count(S, T, o);
+    for (uint32_t o = tid; o < n_owners; o += obmt::NT) obmt::owner_prepare(S, o);
+    __syncthreads();
+    /* P5b: marker lines, dense: tokenize once, stage the tuples in shared memory */
+    {
+        const uint32_t nm = S.n_markers_q;
+        for (uint32_t m = tid; m < nm; m += obmt::NT) obmt::marker_stage(S, T, m);
+    }
     __syncthreads();
     /* P6: E[] = exclusive scan of owner counts (owners of irregular documents contribute nothing) */
     {
@@ -207,7 +238,11 @@ __device__ __forceinline__ void subbatch_fill(CtaShared &C, const TileArgs &A, c
     const uint32_t tid = threadIdx.x, nd = db - da;
     obmt::FillStats fs = {0, 0, 0, 0};
     const uint32_t n_owners = S.n_owners;
-    if (A.out) for (uint32_t o = tid; o < n_owners; o += obmt::NT) obmt::owner_fill(S, T, o, A.out, A.out_cap, base, fs);
+    if (A.out) {
+        for (uint32_t o = tid; o < n_owners; o += obmt::NT) obmt::owner_fill_thread(S, T, o, S.ocnt[o + 1] - S.ocnt[o], A.out, A.out_cap, base, fs);
+        const uint32_t nm = S.n_markers_q < obmt::NSTAGE ? S.n_markers_q : obmt::NSTAGE;
+        for (uint32_t m = tid >> 5; m < nm; m += obmt::NT / 32) obmt::owner_fill_staged(S, m, tid & 31, 32, A.out, A.out_cap, base, fs);
+    }
     if (tid < nd) {
         A.tuple_off[da + tid] = base + S.dcnt[tid];
         if (A.out) obmt::doc_fill(S, T, tid, A.out, A.out_cap, base, fs);
@@ -255,12 +290,14 @@ k_tile_scan(TileArgs A) {
             uint32_t db = min(da + obmt::DMAX, d_small_end);
             tile_total += subbatch_count(C, A, T, da, db, mbar_phase);
         }
-        if (tid == 0) {
-            uint64_t base = lookback(A.tile_state, t, tile_total);
-            C.base = base;
-            if (t == A.ntiles - 1) {
-                A.tuple_off[A.ndocs] = base + tile_total;
-                if (base + tile_total > A.out_cap) A.status[0] = 1;
+        if (tid < 32) {
+            uint64_t base = lookback_warp(A.tile_state, t, tile_total);
+            if (tid == 0) {
+                C.base = base;
+                if (t == A.ntiles - 1) {
+                    A.tuple_off[A.ndocs] = base + tile_total;
+                    if (base + tile_total > A.out_cap) A.status[0] = 1;
+                }
             }
         }
         __syncthreads();

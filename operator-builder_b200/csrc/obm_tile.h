@@ -10,15 +10,18 @@
  *   P2 classify     every 32-byte word -> newline bitmap, special bitmap ({# ' + /}: everything that
  *                   can start a comment or a marker), non-ASCII flag
  *   P3 doc prep     a virtual newline in front of every document start; per-document non-ASCII flag
- *   P4 line scan    newline prefix counts (line numbers) + "owners": lines whose first special byte
- *                   exists, found by looking forward from every (virtual) newline
- *   P5 owners       one thread per owner runs obm::Lexer in LINE mode from the line's first special
- *                   byte (reference semantics: a line starts in state `lex`), skipping
- *                   dull bytes through the bitmaps
+ *   P4 line scan    newline prefix counts (line numbers) + "owners": looking forward from every
+ *                   (virtual) newline, a line that contains a '+' becomes a MARKER owner, a line with
+ *                   only a comment start becomes a PLAIN owner, any other line produces no tuple
+ *                   (reference semantics: a line starts in state `lex`)
+ *   P5 owners       plain owners: 1-2 tuples, computed in place.  Marker owners are compacted into a
+ *                   dense list; one thread per marker line runs the ASCII instantiation of obm::Lexer
+ *                   in LINE mode from the line's first special byte and stages its tuples in shared
+ *                   memory
  *   P6 resolve      documents whose lines interact (multi-line literal, fatal error) or that contain
  *                   non-ASCII bytes are re-lexed sequentially by one thread (exact path, same core);
  *                   tuple counts -> offsets
- *   P7 fill         owners re-run writing tuples at their final global positions
+ *   P7 fill         staged tuples are copied to their final global positions (a warp per owner)
  *
  * The tuple stream is identical to the exact path's by construction (same obm::Lexer, canonical
  * LINE/PART rules); tests compare the two streams tuple for tuple.
@@ -29,6 +32,14 @@
 #include <stdint.h>
 #include "obm_core.h"
 
+#if defined(__CUDA_ARCH__)
+#define OBMT_POPC(x) ((uint32_t)__popc(x))
+#define OBMT_CTZ(x) ((uint32_t)(__ffs((int)(x)) - 1))
+#else
+#define OBMT_POPC(x) ((uint32_t)__builtin_popcount(x))
+#define OBMT_CTZ(x) ((uint32_t)__builtin_ctz(x))
+#endif
+
 namespace obmt {
 
 constexpr uint32_t NT = 256;        /* threads per CTA */
@@ -38,24 +49,35 @@ constexpr uint32_t NW = 1024;       /* 32-byte words staged per sub-batch (32 Ki
 constexpr uint32_t WPT = NW / NT;   /* words per thread in the line scan (4) */
 constexpr uint32_t DMAX = 64;       /* documents per sub-batch */
 constexpr uint32_t QMAX = 1024;     /* owners per sub-batch */
+constexpr uint32_t NSTAGE = 48;     /* marker owners whose tuples are staged in shared memory */
+constexpr uint32_t STRIDE = 40;     /* staged tuples per marker owner */
 
 enum : uint32_t { DF_NONASCII = 1, DF_INTERACT = 2, DF_QOVERFLOW = 4 };
+
+/* owner record: bits 0..14 position of the first special ('+' lines) or of the comment start (plain
+ * lines), bit 15 = marker line, bits 16..30 line start, bit 31 = plain line whose comment is "//" */
+constexpr uint32_t OW_MARKER = 1u << 15, OW_SLASH2 = 1u << 31;
+OBM_HD uint32_t ow_pos(uint32_t r) { return r & 0x7FFFu; }
+OBM_HD uint32_t ow_ls(uint32_t r) { return (r >> 16) & 0x7FFFu; }
 
 struct Smem {
     alignas(16) uint8_t data[NW * 32];
     alignas(16) uint32_t nlw[NW];   /* bit i of word w: byte 32w+i is '\n' (or precedes a document start) */
     alignas(16) uint32_t spw[NW];   /* bit i of word w: byte 32w+i is one of # ' + / */
+    alignas(16) obm_tuple stage[NSTAGE * STRIDE];
     uint16_t nlpre[NW];             /* number of nlw bits in words [0, w) */
     uint32_t naw[NW / 32];          /* bit w%32 of naw[w/32]: word w holds a byte >= 0x80 */
-    uint32_t owner[QMAX];           /* first special position | line start << 16 (buffer-relative) */
+    uint32_t owner[QMAX];           /* owner records in position order */
     uint32_t ocnt[QMAX + 1];        /* tuple count of the owner; after the scan: exclusive prefix E[] */
+    uint16_t mlist[QMAX];           /* dense list of marker owners (indices into owner[]) */
+    uint16_t mslot[QMAX];           /* owner -> index in mlist (marker owners only) */
     uint8_t odoc[QMAX];             /* document (index in the sub-batch) of the owner */
     uint32_t dstart[DMAX + 1];      /* document start positions, buffer-relative; [nd] = end */
     uint32_t dflag[DMAX];
     uint32_t dcnt[DMAX + 1];        /* tuples per document; after the scan: exclusive offsets */
     uint32_t dfirst[DMAX + 1];      /* first owner of each document */
     uint32_t scan_tmp[NT / 32 + 1];
-    uint32_t n_owners;
+    uint32_t n_owners, n_markers_q; /* owners; marker owners in mlist */
     uint32_t nd;
     uint32_t lo_pos, hi_pos;        /* valid byte range of `data` */
 };
@@ -108,9 +130,16 @@ OBM_HD void atomic_or_u32(uint32_t *p, uint32_t v) {
     *p |= v;
 #endif
 }
+OBM_HD uint32_t atomic_inc_u32(uint32_t *p) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, 1u);
+#else
+    return (*p)++;
+#endif
+}
 
 /* ---- P3: per-document preparation (thread d < nd) ---------------------------------------------- */
-OBM_HD void doc_prep(Smem &S, uint32_t d) {
+OBM_FN void doc_prep(Smem &S, uint32_t d) {
     uint32_t q = S.dstart[d], e = S.dstart[d + 1];
     if (q > S.lo_pos) atomic_or_u32(&S.nlw[(q - 1) >> 5], 1u << ((q - 1) & 31)); /* virtual newline before the document */
     uint32_t flag = 0;
@@ -129,7 +158,7 @@ OBM_HD void doc_prep(Smem &S, uint32_t d) {
 
 /* ---- P4: line scan (thread t owns words [WPT*t, WPT*t+WPT)) -------------------------------------- */
 /* first position >= from whose (sp|nl) bit is set, or hi_pos if none */
-OBM_HD uint32_t next_event(const Smem &S, uint32_t from) {
+OBM_FN uint32_t next_event(const Smem &S, uint32_t from) {
     if (from >= S.hi_pos) return S.hi_pos;
     uint32_t w = from >> 5;
     uint32_t m = (S.spw[w] | S.nlw[w]) & (0xFFFFFFFFu << (from & 31));
@@ -138,43 +167,55 @@ OBM_HD uint32_t next_event(const Smem &S, uint32_t from) {
         if (++w >= wend) return S.hi_pos;
         m = S.spw[w] | S.nlw[w];
     }
-#if defined(__CUDA_ARCH__)
-    uint32_t pos = w * 32 + (uint32_t)(__ffs((int)m) - 1);
-#else
-    uint32_t pos = w * 32 + (uint32_t)__builtin_ctz(m);
-#endif
+    uint32_t pos = w * 32 + OBMT_CTZ(m);
     return pos < S.hi_pos ? pos : S.hi_pos;
+}
+OBM_HD bool is_sp(const Smem &S, uint32_t pos) { return (S.spw[pos >> 5] >> (pos & 31)) & 1u; }
+OBM_HD bool is_nl(const Smem &S, uint32_t pos) { return (S.nlw[pos >> 5] >> (pos & 31)) & 1u; }
+
+constexpr uint32_t OW_NONE = 0xFFFFFFFFu; /* not a valid record: it would be a MARKER line that is also flagged "//" */
+/* Examines the line starting at `start`: returns OW_NONE if it produces no tuple, else its owner record.
+ * A position carrying both bits (virtual newline on a document's last byte) is a special that also
+ * ends the line. */
+OBM_FN uint32_t line_owner(const Smem &S, uint32_t start) {
+    uint32_t ev = next_event(S, start);
+    if (ev >= S.hi_pos || !is_sp(S, ev)) return OW_NONE; /* no special before the end of the line */
+    const uint32_t first = ev;
+    uint32_t comment = 0xFFFFFFFFu; bool slash2 = false;
+    for (;;) {
+        uint32_t c = S.data[ev];
+        if (c == '+') return first | OW_MARKER | (start << 16);
+        if (comment == 0xFFFFFFFFu) {
+            if (c == '#') comment = ev;
+            else if (c == '/' && ev + 1 < S.hi_pos && S.data[ev + 1] == '/' && !is_nl(S, ev)) { comment = ev; slash2 = true; }
+        }
+        if (is_nl(S, ev)) break; /* the special sits on the line's last byte */
+        ev = next_event(S, ev + 1);
+        if (ev >= S.hi_pos || !is_sp(S, ev)) break;
+    }
+    if (comment == 0xFFFFFFFFu) return OW_NONE;
+    return comment | (start << 16) | (slash2 ? OW_SLASH2 : 0u);
 }
 
 /* Visits the owners whose line starts right after a newline bit in this thread's words (plus the
- * line starting at lo_pos).  f(first_special_pos, line_start) is called in position order.
- * Returns the number of nlw bits in the thread's words. */
+ * line starting at lo_pos), in position order.  Returns the number of nlw bits in the thread's words. */
 template <class F>
-OBM_HD uint32_t line_scan(const Smem &S, uint32_t t, F &&f) {
+OBM_FN uint32_t line_scan(const Smem &S, uint32_t t, F &&f) {
     uint32_t nls = 0;
 #pragma unroll
     for (uint32_t j = 0; j < WPT; j++) {
         uint32_t w = t * WPT + j;
         uint32_t nl = S.nlw[w];
         if (S.lo_pos < S.hi_pos && (S.lo_pos >> 5) == w) { /* the buffer's first line has no newline before it */
-            uint32_t ev = next_event(S, S.lo_pos);
-            if (ev < S.hi_pos && ((S.spw[ev >> 5] >> (ev & 31)) & 1u)) f(ev, S.lo_pos);
+            uint32_t rec = line_owner(S, S.lo_pos);
+            if (rec != OW_NONE) f(rec);
         }
-#if defined(__CUDA_ARCH__)
-        nls += (uint32_t)__popc(nl);
-#else
-        nls += (uint32_t)__builtin_popcount(nl);
-#endif
+        nls += OBMT_POPC(nl);
         while (nl) {
-#if defined(__CUDA_ARCH__)
-            uint32_t b = (uint32_t)(__ffs((int)nl) - 1);
-#else
-            uint32_t b = (uint32_t)__builtin_ctz(nl);
-#endif
+            uint32_t b = OBMT_CTZ(nl);
             nl &= nl - 1;
             uint32_t start = w * 32 + b + 1;
-            uint32_t ev = next_event(S, start);
-            if (ev < S.hi_pos && ((S.spw[ev >> 5] >> (ev & 31)) & 1u)) f(ev, start);
+            if (start < S.hi_pos) { uint32_t rec = line_owner(S, start); if (rec != OW_NONE) f(rec); }
         }
     }
     return nls;
@@ -183,18 +224,8 @@ OBM_HD uint32_t line_scan(const Smem &S, uint32_t t, F &&f) {
 /* number of nlw bits at positions < q */
 OBM_HD uint32_t nl_before(const Smem &S, uint32_t q) {
     uint32_t w = q >> 5;
-    if (w >= NW) return (uint32_t)S.nlpre[NW - 1] +
-#if defined(__CUDA_ARCH__)
-        (uint32_t)__popc(S.nlw[NW - 1]);
-#else
-        (uint32_t)__builtin_popcount(S.nlw[NW - 1]);
-#endif
-    uint32_t m = S.nlw[w] & ((1u << (q & 31)) - 1u);
-#if defined(__CUDA_ARCH__)
-    return (uint32_t)S.nlpre[w] + (uint32_t)__popc(m);
-#else
-    return (uint32_t)S.nlpre[w] + (uint32_t)__builtin_popcount(m);
-#endif
+    if (w >= NW) return (uint32_t)S.nlpre[NW - 1] + OBMT_POPC(S.nlw[NW - 1]);
+    return (uint32_t)S.nlpre[w] + OBMT_POPC(S.nlw[w] & ((1u << (q & 31)) - 1u));
 }
 
 /* ---- P5 / P7: owners ------------------------------------------------------------------------- */
@@ -208,8 +239,8 @@ struct BitmapAccel {
 };
 
 /* document (index in the sub-batch) containing buffer position `pos`: the last d with dstart[d] <= pos */
-OBM_HD uint32_t doc_of(const Smem &S, uint32_t pos) {
-    uint32_t lo = 0, hi = S.nd; /* invariant: dstart[lo] <= pos; answer in [lo, hi) */
+OBM_FN uint32_t doc_of(const Smem &S, uint32_t pos) {
+    uint32_t lo = 0, hi = S.nd;
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
         if (S.dstart[mid] <= pos) lo = mid; else hi = mid;
@@ -217,55 +248,90 @@ OBM_HD uint32_t doc_of(const Smem &S, uint32_t pos) {
     return lo;
 }
 
-struct OwnerResult { uint32_t tuples, markers, lexemes; bool interact; };
+/* The two lexer instantiations the tile kernel carries, each compiled once (noinline). */
+typedef obm::Lexer<obm::SmallSink, BitmapAccel, true> LineLexer;
+typedef obm::Lexer<obm::SmallSink, obm::NoAccel, false> DocLexer;
 
-/* Runs owner `o` with the given sink.  The sink sees document-relative offsets. */
-template <class Sink>
-OBM_HD OwnerResult owner_run(const Smem &S, const obm::Tables &T, uint32_t o, uint32_t d, Sink &sink) {
-    uint32_t rec = S.owner[o];
-    uint32_t first = rec & 0xFFFFu, ls = rec >> 16;
+/* marker line: LINE mode from the first special; returns true when the line interacted with others */
+OBM_HD_NOINLINE bool run_marker_line(const Smem &S, const obm::Tables &T, uint32_t rec, uint32_t d, obm::SmallSink &sink) {
+    uint32_t first = ow_pos(rec), ls = ow_ls(rec);
     uint32_t dpos = S.dstart[d], dend = S.dstart[d + 1];
     uint32_t line = 1 + nl_before(S, ls) - nl_before(S, dpos);
     BitmapAccel acc{&S, dpos, dend};
-    obm::Lexer<Sink, BitmapAccel> lx(T, S.data + dpos, dend - dpos, sink, first - dpos, line, ls - dpos,
-                                     !(line == 1 && ls == dpos), acc);
-    int st = lx.template run<true>();
-    OwnerResult r;
-    r.tuples = (uint32_t)sink.n_tuples; r.markers = sink.n_markers; r.lexemes = sink.n_lexemes;
+    LineLexer lx(T, S.data + dpos, dend - dpos, sink, first - dpos, line, ls - dpos, !(line == 1 && ls == dpos), acc);
+    int st = lx.run<true>();
     uint32_t end_line = lx.line_p - (st == obm::RUN_LINE_END ? 1u : 0u);
-    r.interact = (st == obm::RUN_FATAL) || (end_line != line);
-    return r;
+    return (st == obm::RUN_FATAL) || (end_line != line);
+}
+/* whole document through the exact (Unicode) lexer */
+OBM_HD_NOINLINE int run_doc_exact(const Smem &S, const obm::Tables &T, uint32_t d, obm::SmallSink &sink) {
+    uint32_t dpos = S.dstart[d], dend = S.dstart[d + 1];
+    DocLexer lx(T, S.data + dpos, dend - dpos, sink);
+    return lx.run<false>();
 }
 
-/* P5 body for owner o: count pass */
-OBM_HD void owner_count(Smem &S, const obm::Tables &T, uint32_t o) {
-    uint32_t d = doc_of(S, S.owner[o] >> 16);
+/* plain line: [LINE] Comment.  Returns the tuple count; writes when out != nullptr. */
+OBM_FN uint32_t plain_line(const Smem &S, uint32_t rec, uint32_t d, obm_tuple *out, uint64_t room) {
+    uint32_t cpos = ow_pos(rec), ls = ow_ls(rec), dpos = S.dstart[d];
+    bool need_line = true;
+    uint32_t line = 0;
+    if (ls == dpos) need_line = false;          /* first line of the document: basis (1, 0) is implied */
+    uint32_t k = 0;
+    if (out) {
+        if (need_line) {
+            line = 1 + nl_before(S, ls) - nl_before(S, dpos);
+            if (line >> OBM_LEN_BITS) { if (k < room) out[k] = OBM_TUPLE(OBM_K_LINEHI, line >> OBM_LEN_BITS, 0); k++; }
+            if (k < room) out[k] = OBM_TUPLE(OBM_K_LINE, ls - dpos, line & OBM_MAX_LEN);
+            k++;
+        }
+        if (k < room) out[k] = OBM_TUPLE(OBM_K_COMMENT, cpos - dpos, (rec & OW_SLASH2) ? 2 : 1);
+        k++;
+        return k;
+    }
+    return need_line ? 2u : 1u; /* line numbers inside a <= 16 KiB document never need LINEHI */
+}
+
+/* P5a body for owner o (every owner): document, plain counts, marker compaction */
+OBM_FN void owner_prepare(Smem &S, uint32_t o) {
+    uint32_t rec = S.owner[o];
+    uint32_t d = doc_of(S, ow_ls(rec));
     S.odoc[o] = (uint8_t)d;
+    if (rec & OW_MARKER) {
+        uint32_t m = atomic_inc_u32(&S.n_markers_q);
+        S.mlist[m] = (uint16_t)o; S.mslot[o] = (uint16_t)m;
+        S.ocnt[o] = 0;
+    } else {
+        S.ocnt[o] = S.dflag[d] ? 0u : plain_line(S, rec, d, nullptr, 0);
+    }
+}
+
+/* P5b body for marker owner m (dense): tokenize, stage */
+OBM_FN void marker_stage(Smem &S, const obm::Tables &T, uint32_t m) {
+    uint32_t o = S.mlist[m];
+    uint32_t d = S.odoc[o];
     if (S.dflag[d]) { S.ocnt[o] = 0; return; }
-    obm::CountSink sink;
-    OwnerResult r = owner_run(S, T, o, d, sink);
-    S.ocnt[o] = r.tuples;
-    if (r.interact) atomic_or_u32(&S.dflag[d], DF_INTERACT);
+    obm::SmallSink sink(m < NSTAGE ? S.stage + m * STRIDE : nullptr, m < NSTAGE ? STRIDE : 0u);
+    bool interact = run_marker_line(S, T, S.owner[o], d, sink);
+    S.ocnt[o] = sink.n_tuples;
+    if (interact) atomic_or_u32(&S.dflag[d], DF_INTERACT);
 }
 
 /* first owner whose line start is >= pos */
-OBM_HD uint32_t first_owner_at(const Smem &S, uint32_t pos) {
+OBM_FN uint32_t first_owner_at(const Smem &S, uint32_t pos) {
     uint32_t lo = 0, hi = S.n_owners;
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
-        if ((S.owner[mid] >> 16) < pos) lo = mid + 1; else hi = mid;
+        if (ow_ls(S.owner[mid]) < pos) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
 
 /* P6 body for document d (after the owner-count scan turned ocnt[] into E[]): tuples of the document */
-OBM_HD void doc_count(Smem &S, const obm::Tables &T, uint32_t d) {
-    uint32_t dpos = S.dstart[d], dend = S.dstart[d + 1];
+OBM_FN void doc_count(Smem &S, const obm::Tables &T, uint32_t d) {
     if (S.dflag[d]) { /* exact path, sequential, same core */
-        obm::CountSink sink;
-        obm::Lexer<obm::CountSink> lx(T, S.data + dpos, dend - dpos, sink);
-        lx.template run<false>();
-        S.dcnt[d] = (uint32_t)sink.n_tuples;
+        obm::SmallSink sink(nullptr, 0);
+        run_doc_exact(S, T, d, sink);
+        S.dcnt[d] = sink.n_tuples;
     } else {
         S.dcnt[d] = S.ocnt[S.dfirst[d + 1]] - S.ocnt[S.dfirst[d]] + 1; /* + EOF */
     }
@@ -273,30 +339,59 @@ OBM_HD void doc_count(Smem &S, const obm::Tables &T, uint32_t d) {
 
 struct FillStats { uint32_t markers, lexemes, exact_docs, fatal_docs; };
 
-/* P7 body for owner o: writes its tuples; `doc_base[d]` = global tuple index of the document's first tuple */
-OBM_HD void owner_fill(const Smem &S, const obm::Tables &T, uint32_t o, obm_tuple *out, uint64_t out_cap,
-                       uint64_t batch_base, FillStats &fs) {
+/* global tuple index of owner o's first tuple */
+OBM_HD uint64_t owner_at(const Smem &S, uint32_t o, uint64_t batch_base) {
+    uint32_t d = S.odoc[o];
+    return batch_base + S.dcnt[d] + (S.ocnt[o] - S.ocnt[S.dfirst[d]]);
+}
+
+/* P7 body for owner o handled by ONE thread: plain lines, and marker lines that were not staged */
+OBM_FN void owner_fill_thread(const Smem &S, const obm::Tables &T, uint32_t o, uint32_t cnt, obm_tuple *out, uint64_t out_cap,
+                              uint64_t batch_base, FillStats &fs) {
     uint32_t d = S.odoc[o];
     if (S.dflag[d]) return;
-    uint64_t at = batch_base + S.dcnt[d] + (S.ocnt[o] - S.ocnt[S.dfirst[d]]);
-    obm::WriteSink sink(out + at, at < out_cap ? out_cap - at : 0);
-    OwnerResult r = owner_run(S, T, o, d, sink);
-    fs.markers += r.markers; fs.lexemes += r.lexemes;
+    uint32_t rec = S.owner[o];
+    uint64_t at = owner_at(S, o, batch_base);
+    uint64_t room = at < out_cap ? out_cap - at : 0;
+    if (!(rec & OW_MARKER)) { plain_line(S, rec, d, out + at, room); fs.lexemes += 1; return; }
+    uint32_t m = S.mslot[o];
+    if (m < NSTAGE && cnt <= STRIDE) return; /* staged: copied by owner_fill_staged */
+    obm::SmallSink sink(out + at, room > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room);
+    run_marker_line(S, T, rec, d, sink);
+    fs.markers += sink.n_markers; fs.lexemes += sink.n_lexemes;
+}
+
+/* P7 body for staged marker owner m, lane `lane` of `nlanes` cooperating lanes */
+OBM_FN void owner_fill_staged(const Smem &S, uint32_t m, uint32_t lane, uint32_t nlanes, obm_tuple *out, uint64_t out_cap,
+                              uint64_t batch_base, FillStats &fs) {
+    uint32_t o = S.mlist[m];
+    uint32_t d = S.odoc[o];
+    if (S.dflag[d]) return;
+    uint32_t cnt = S.ocnt[o + 1] - S.ocnt[o]; /* E[] differences: owners are contiguous in E */
+    if (cnt > STRIDE) return;
+    uint64_t at = owner_at(S, o, batch_base);
+    const obm_tuple *src = S.stage + m * STRIDE;
+    for (uint32_t k = lane; k < cnt; k += nlanes) {
+        obm_tuple t = src[k];
+        if (at + k < out_cap) out[at + k] = t;
+        uint32_t kind = OBM_TUPLE_KIND(t);
+        fs.markers += (kind == OBM_K_MARKER_START);
+        fs.lexemes += (kind <= OBM_K_EOF) || (kind >= OBM_K_WARN_NOSCOPE);
+    }
 }
 
 /* P7 body for document d: EOF tuple of a regular document, or the whole irregular document */
-OBM_HD void doc_fill(const Smem &S, const obm::Tables &T, uint32_t d, obm_tuple *out, uint64_t out_cap,
+OBM_FN void doc_fill(const Smem &S, const obm::Tables &T, uint32_t d, obm_tuple *out, uint64_t out_cap,
                      uint64_t batch_base, FillStats &fs) {
-    uint32_t dpos = S.dstart[d], dend = S.dstart[d + 1];
     uint64_t at = batch_base + S.dcnt[d];
     if (S.dflag[d]) {
-        obm::WriteSink sink(out + at, at < out_cap ? out_cap - at : 0);
-        obm::Lexer<obm::WriteSink> lx(T, S.data + dpos, dend - dpos, sink);
-        int st = lx.template run<false>();
+        uint64_t room = at < out_cap ? out_cap - at : 0;
+        obm::SmallSink sink(out + at, room > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room);
+        int st = run_doc_exact(S, T, d, sink);
         fs.markers += sink.n_markers; fs.lexemes += sink.n_lexemes; fs.exact_docs += 1; fs.fatal_docs += (st == obm::RUN_FATAL);
     } else {
         uint64_t eof_at = batch_base + S.dcnt[d + 1] - 1;
-        if (eof_at < out_cap) out[eof_at] = OBM_TUPLE(OBM_K_EOF, dend - dpos, 0);
+        if (eof_at < out_cap) out[eof_at] = OBM_TUPLE(OBM_K_EOF, S.dstart[d + 1] - S.dstart[d], 0);
         fs.lexemes += 1;
     }
 }

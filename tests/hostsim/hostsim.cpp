@@ -71,19 +71,22 @@ struct Emu {
         }
         for (uint32_t t = 0; t < nd; t++) obmt::doc_prep(S, t);
         std::vector<uint32_t> my_nl(obmt::NT), my_own(obmt::NT);
-        for (uint32_t t = 0; t < obmt::NT; t++) { uint32_t c = 0; my_nl[t] = obmt::line_scan(S, t, [&](uint32_t, uint32_t) { c++; }); my_own[t] = c; }
+        for (uint32_t t = 0; t < obmt::NT; t++) { uint32_t c = 0; my_nl[t] = obmt::line_scan(S, t, [&](uint32_t) { c++; }); my_own[t] = c; }
         uint32_t nlp = 0, own = 0, n_owners = 0;
         for (uint32_t t = 0; t < obmt::NT; t++) n_owners += my_own[t];
         for (uint32_t t = 0; t < obmt::NT; t++) {
             uint32_t q = nlp;
             for (uint32_t j = 0; j < obmt::WPT; j++) { S.nlpre[t * obmt::WPT + j] = (uint16_t)q; q += (uint32_t)__builtin_popcount(S.nlw[t * obmt::WPT + j]); }
-            if (n_owners <= obmt::QMAX && my_own[t]) { uint32_t o = own; obmt::line_scan(S, t, [&](uint32_t first, uint32_t ls) { S.owner[o++] = first | (ls << 16); }); }
+            if (n_owners <= obmt::QMAX && my_own[t]) { uint32_t o = own; obmt::line_scan(S, t, [&](uint32_t rec) { S.owner[o++] = rec; }); }
             nlp += my_nl[t]; own += my_own[t];
         }
         S.n_owners = n_owners <= obmt::QMAX ? n_owners : 0;
+        S.n_markers_q = 0;
         if (n_owners > obmt::QMAX) for (uint32_t t = 0; t < nd; t++) S.dflag[t] |= obmt::DF_QOVERFLOW;
         n_owners = S.n_owners;
-        for (uint32_t o = 0; o < n_owners; o++) obmt::owner_count(S, TBL, o);
+        /* the device fills mlist in a nondeterministic order: emulate an adversarial one (reverse) */
+        for (uint32_t o = n_owners; o-- > 0;) obmt::owner_prepare(S, o);
+        for (uint32_t m = 0; m < S.n_markers_q; m++) obmt::marker_stage(S, TBL, m);
         uint32_t e = 0;
         for (uint32_t o = 0; o < obmt::QMAX; o++) {
             uint32_t v = (o < n_owners && !S.dflag[S.odoc[o]]) ? S.ocnt[o] : 0;
@@ -99,7 +102,9 @@ struct Emu {
         return acc;
     }
     void fill(uint32_t da, uint32_t db, uint64_t base, obm_tuple *out, uint64_t cap, uint64_t *tuple_off, obmt::FillStats &fs) {
-        for (uint32_t o = 0; o < S.n_owners; o++) obmt::owner_fill(S, TBL, o, out, cap, base, fs);
+        for (uint32_t o = 0; o < S.n_owners; o++) obmt::owner_fill_thread(S, TBL, o, S.ocnt[o + 1] - S.ocnt[o], out, cap, base, fs);
+        uint32_t nm = S.n_markers_q < obmt::NSTAGE ? S.n_markers_q : obmt::NSTAGE;
+        for (uint32_t m = 0; m < nm; m++) for (uint32_t lane = 0; lane < 32; lane++) obmt::owner_fill_staged(S, m, lane, 32, out, cap, base, fs);
         for (uint32_t t = 0; t < db - da; t++) { tuple_off[da + t] = base + S.dcnt[t]; obmt::doc_fill(S, TBL, t, out, cap, base, fs); }
     }
 };

@@ -110,17 +110,16 @@ OBM_HD bool is_number(const Tables &T, int r) {
 /* Delimiter sets of consumeUntil (state.go:72-76, 119-123, 289-293) as 128-bit ASCII masks.
  * name set:  : = SP " ' ` , + { } [ ] ( ) ; \n      naked-value set: the same without ';' */
 OBM_HD bool is_name_delim(uint32_t c) {
-    if (c >= 0x80) return false;
-    /* word0: \n(10)                               -> bit 10
-     * word1: SP(32) "(34) '(39) ((40) )(41) +(43) ,(44) :(58) ;(59) =(61)
-     * word2: [(91) ](93) `(96)
-     * word3: {(123) }(125) */
+    /* 128-bit membership mask, one 32-bit word per 32 code points:
+     * word0: \n(10)   word1: SP(32) "(34) '(39) ((40) )(41) +(43) ,(44) :(58) ;(59) =(61)
+     * word2: [(91) ](93)   word3: `(96) {(123) }(125) */
     const uint32_t m0 = 1u << 10;
     const uint32_t m1 = (1u << 0) | (1u << 2) | (1u << 7) | (1u << 8) | (1u << 9) | (1u << 11) | (1u << 12) | (1u << 26) | (1u << 27) | (1u << 29);
     const uint32_t m2 = (1u << (91 - 64)) | (1u << (93 - 64));
     const uint32_t m3 = (1u << 0) | (1u << (123 - 96)) | (1u << (125 - 96));
-    uint32_t m = (c < 32) ? m0 : (c < 64) ? m1 : (c < 96) ? m2 : m3;
-    return (m >> (c & 31)) & 1u;
+    /* letters, digits and '.', '-', '_', '/' (what names are made of) leave through the first test */
+    uint32_t lo = (c & 0x40u) ? ((c & 0x20u) ? m3 : m2) : ((c & 0x20u) ? m1 : m0);
+    return c < 0x80u && ((lo >> (c & 31u)) & 1u);
 }
 OBM_HD bool is_naked_delim(uint32_t c) { return c != ';' && is_name_delim(c); }
 
@@ -261,6 +260,32 @@ struct NoAccel {
 
 /* ASCII = true: the caller guarantees every byte of the document is < 0x80 (tile path); rune decoding,
  * the Unicode tables and the U+FFFD over-discard drop out at compile time. */
+/* cold path: a slice longer than OBM_MAX_LEN is sent as PART pieces; returns the remaining (off, len) */
+template <class Sink>
+OBM_HD_NOINLINE void put_long_prefix(Sink &out, uint32_t &off, uint32_t &len) {
+    while (len > OBM_MAX_LEN) { out.put(OBM_K_PART, off, OBM_MAX_LEN); off += OBM_MAX_LEN; len -= OBM_MAX_LEN; }
+}
+
+/* peek.go:65-89 for one ASCII token `tok[0..t)` at offset p of doc d[0..n): on success returns true and
+ * sets `width` (= l.width after the final peekN: whitespace BYTES + token bytes). */
+template <bool ASCII>
+OBM_HD_NOINLINE bool peeked_whitespaced_at(const uint8_t *d, uint32_t n, uint32_t p, const char *tok, uint32_t t, uint32_t &width) {
+    uint32_t lim = (n - p > (uint32_t)BUFIO_WINDOW) ? p + (uint32_t)BUFIO_WINDOW : n;
+    uint32_t o = p;
+    for (;;) {
+        uint32_t w; int r;
+        if (ASCII) { if (o < lim) { r = (int)d[o]; w = 1; } else { r = RUNE_EOF; w = 0; } }
+        else r = decode_rune(d, o, lim, w);
+        if (r == RUNE_EOF) return false; /* r[i] == eof (real end of input or end of the 4096-byte window) */
+        if (!is_space(r)) break;
+        o += w;
+    }
+    if (o + t > lim) return false;
+    for (uint32_t k = 0; k < t; k++) if (d[o + k] != (uint8_t)tok[k]) return false;
+    width = (o - p) + t;
+    return true;
+}
+
 template <class Sink, class Accel = NoAccel, bool ASCII = false>
 struct Lexer {
     const Tables &T;
@@ -274,6 +299,7 @@ struct Lexer {
     uint32_t last_type;                 /* l.lastEmittedLexeme.Type */
     Sink &out;
     Accel accel;
+    int32_t wbase; uint32_t wmask;      /* ASCII only: cached 32-byte window of "not a letter" bits */
 
     /* A lexer instance begins at byte `start_off` of line `first_line`, whose first byte is at
      * `line_base` (document start: 0, 1, 0).  `announce_first`: the first located tuple must be
@@ -282,10 +308,11 @@ struct Lexer {
                  uint32_t first_line = 1, uint32_t line_base = 0, bool announce_first = false, Accel acc = Accel())
         : T(t), d(doc), n(len), p(start_off), s(start_off), line_p(first_line), base_p(line_base), drift_p(0),
           line_s(first_line), base_s(line_base), line_e(announce_first ? 0u : 1u), base_e(0),
-          sv_line(first_line), sv_base(line_base), sv_drift(0), last_w(0), last_r(RUNE_EOF), last_type(0), out(sink), accel(acc) {}
+          sv_line(first_line), sv_base(line_base), sv_drift(0), last_w(0), last_r(RUNE_EOF), last_type(0), out(sink), accel(acc),
+          wbase(-0x40000000), wmask(0) {}
 
     /* ---- tuple plumbing ---- */
-    OBM_FN void ensure_line(uint32_t line, uint32_t base) {
+    OBM_HD void ensure_line(uint32_t line, uint32_t base) {
         if (line != line_e || base != base_e) {
             if (line >> OBM_LEN_BITS) out.put(OBM_K_LINEHI, line >> OBM_LEN_BITS, 0);
             out.put(OBM_K_LINE, base, line & OBM_MAX_LEN);
@@ -294,20 +321,20 @@ struct Lexer {
     }
     OBM_HD void sync_start() { s = p; line_s = line_p; base_s = base_p; }
     /* un-emitted text doc[s,p) becomes a PART (kept in the decoder's pending buffer) */
-    OBM_FN void part_tail() {
+    OBM_HD void part_tail() {
         if (p > s) {
             ensure_line(line_s, base_s);
             uint32_t off = s, len = p - s;
-            while (len > OBM_MAX_LEN) { out.put(OBM_K_PART, off, OBM_MAX_LEN); off += OBM_MAX_LEN; len -= OBM_MAX_LEN; }
+            if (len > OBM_MAX_LEN) put_long_prefix(out, off, len);
             out.put(OBM_K_PART, off, len);
             sync_start();
         }
     }
     /* emit.go:7-19 */
-    OBM_FN void emit(uint32_t kind) {
+    OBM_HD void emit(uint32_t kind) {
         ensure_line(line_s, base_s);
         uint32_t off = s, len = p - s;
-        while (len > OBM_MAX_LEN) { out.put(OBM_K_PART, off, OBM_MAX_LEN); off += OBM_MAX_LEN; len -= OBM_MAX_LEN; }
+        if (len > OBM_MAX_LEN) put_long_prefix(out, off, len);
         out.put(kind, off, len);
         last_type = kind;
         sync_start();
@@ -317,7 +344,7 @@ struct Lexer {
     /* discard.go:68-71 */
     OBM_HD void flush() { out.put(OBM_K_FLUSH, p, 0); sync_start(); }
     /* error.go:37-45 (continues in lexComment) / error.go:15-34 (terminates) */
-    OBM_FN void located_at_pos(uint32_t kind) { part_tail(); ensure_line(line_p, base_p); out.put(kind, p, 0); }
+    OBM_HD void located_at_pos(uint32_t kind) { part_tail(); ensure_line(line_p, base_p); out.put(kind, p, 0); }
     OBM_HD void numeric_error(uint32_t kind) { ensure_line(line_s, base_s); out.put(kind, s, p - s); }
 
     /* ---- reader primitives ---- */
@@ -344,11 +371,11 @@ struct Lexer {
         }
     }
     /* position.go:43-57, second call (state.go:79,126): UnreadRune fails, the column still moves */
-    OBM_FN void backup_again() {
+    OBM_HD void backup_again() {
         if (last_w != 0) { drift_p += last_w; ensure_line(line_p, base_p); out.put(OBM_K_DRIFT, p, 0); }
     }
     /* discard.go:12-38 discard() == discardN(1) */
-    OBM_FN void discard1() {
+    OBM_HD void discard1() {
         uint32_t w; int r = peek(w);
         if (r == RUNE_EOF) { flush(); return; }
         part_tail();
@@ -359,16 +386,62 @@ struct Lexer {
         sync_start();
     }
     /* `q - p` discard() calls over bytes known to be ASCII, non-newline (Accel contract) */
-    OBM_FN void discard_to(uint32_t q) {
+    OBM_HD void discard_to(uint32_t q) {
         if (q > p) { part_tail(); p = q; sync_start(); }
     }
     OBM_HD bool has_prefix2(uint32_t a, uint32_t b) const { return p + 1 < n && d[p] == a && d[p + 1] == b; }
+    /* ASCII only.  4-bit mask of the bytes of x that are NOT letters (x's bytes < 0x80):
+     * fold case (& 0x5F), then a letter is 0x41..0x5A -- two carry-free byte-wise range adds. */
+    static OBM_HD uint32_t nonletter4(uint32_t x) {
+        uint32_t y = x & 0x5F5F5F5Fu;
+        uint32_t gt = y + 0x25252525u;  /* bit 7 set: y > 0x5A  */
+        uint32_t ge = y + 0x3F3F3F3Fu;  /* bit 7 set: y >= 0x41 */
+        uint32_t non = (~(ge & ~gt) >> 7) & 0x01010101u;
+        return (non * 0x00204081u >> 21) & 0xFu;
+    }
+    /* first position >= q (capped at n) whose byte is not an ASCII letter.  Every byte the lexer has to
+     * look at (delimiters, quotes, digits, whitespace) is a non-letter, so identifier text is skipped 32
+     * bytes per step.  The window is read as aligned 32-bit words and may extend a few bytes around the
+     * document inside the staged buffer. */
+    OBM_HD uint32_t next_nonletter(uint32_t q) {
+        for (;;) {
+            if (q >= n) return n;
+            uint32_t sh = (uint32_t)((int32_t)q - wbase);
+            if (sh < 32u) {
+                uint32_t m = wmask >> sh;
+                if (m) {
+#if defined(__CUDA_ARCH__)
+                    q += (uint32_t)(__ffs((int)m) - 1);
+#else
+                    q += (uint32_t)__builtin_ctz(m);
+#endif
+                    return q < n ? q : n;
+                }
+                q = (uint32_t)(wbase + 32);
+                continue;
+            }
+            const uint8_t *a = d + q;
+            uint32_t mis = (uint32_t)((uintptr_t)a & 3u);
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(a - mis);
+            uint32_t mk = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) mk |= nonletter4(w[k]) << (4 * k);
+            wbase = (int32_t)q - (int32_t)mis; wmask = mk;
+        }
+    }
+
     /* consume.go:65-80 with an ASCII delimiter class; returns `consumed` */
     template <bool NAKED>
-    OBM_FN bool consume_until() {
+    OBM_HD bool consume_until() {
         if (ASCII) { /* '\n' is a delimiter: no line bookkeeping inside the run */
             uint32_t q = p;
-            while (q < n) { uint32_t c = d[q]; if (NAKED ? is_naked_delim(c) : is_name_delim(c)) break; q++; }
+            for (;;) {
+                q = next_nonletter(q);
+                if (q >= n) break;
+                uint32_t c = d[q];
+                if (NAKED ? is_naked_delim(c) : is_name_delim(c)) break;
+                q++; /* digit, '.', '-', '_', '/' ...: part of the name */
+            }
             bool any = q > p;
             p = q;
             if (q < n) { last_w = 1; last_r = (int)d[q]; } else { last_w = 0; last_r = RUNE_EOF; } /* state after next()+backup() */
@@ -382,29 +455,14 @@ struct Lexer {
             consumed = true;
         }
     }
-    /* peek.go:65-89 for one ASCII token `tok[0..t)`: on success returns true and sets `width`
-     * (= l.width after the final peekN: whitespace BYTES + token bytes). */
-    OBM_FN bool peeked_whitespaced(const char *tok, uint32_t t, uint32_t &width) const {
-        uint32_t lim = (n - p > (uint32_t)BUFIO_WINDOW) ? p + (uint32_t)BUFIO_WINDOW : n;
-        uint32_t o = p;
-        for (;;) {
-            uint32_t w; int r;
-            if (ASCII) { if (o < lim) { r = (int)d[o]; w = 1; } else { r = RUNE_EOF; w = 0; } }
-            else r = decode_rune(d, o, lim, w);
-            if (r == RUNE_EOF) return false; /* r[i] == eof (real end of input or end of the 4096-byte window) */
-            if (!is_space(r)) break;
-            o += w;
-        }
-        if (o + t > lim) return false;
-        for (uint32_t k = 0; k < t; k++) if (d[o + k] != (uint8_t)tok[k]) return false;
-        width = (o - p) + t;
-        return true;
+    OBM_HD bool peeked_whitespaced(const char *tok, uint32_t t, uint32_t &width) const {
+        return peeked_whitespaced_at<ASCII>(d, n, p, tok, t, width);
     }
     OBM_HD bool peeked_whitespaced_comment(uint32_t &width) const {
         return peeked_whitespaced("//", 2, width) || peeked_whitespaced("#", 1, width);
     }
     /* consume.go:37-47: consumes `width` RUNES (width is a byte count) */
-    OBM_FN bool consumed_whitespaced(const char *tok, uint32_t t) {
+    OBM_HD bool consumed_whitespaced(const char *tok, uint32_t t) {
         uint32_t width;
         if (!peeked_whitespaced(tok, t, width)) return false;
         for (uint32_t k = 0; k < width; k++) next();
@@ -413,12 +471,12 @@ struct Lexer {
 
     /* ---- marker states; each returns the top-level state to continue in ---- */
     /* state.go:60-68, entered with '+' just consumed */
-    OBM_FN int marker_start() {
+    OBM_HD int marker_start() {
         if (ASCII ? is_letter_ascii(peek()) : is_letter(T, peek())) { emit(OBM_K_MARKER_START); return lex_marker(); }
         return TOP_COMMENT;
     }
     /* state.go:71-116 */
-    OBM_FN int lex_marker() {
+    OBM_HD int lex_marker() {
         for (;;) {
             if (!consume_until<false>()) { backup_again(); flush(); return TOP_COMMENT; }
             uint32_t c = peek_byte();
@@ -438,7 +496,7 @@ struct Lexer {
         }
     }
     /* state.go:118-154 (lexArgs) and state.go:304-317 (lexMoreArgs), as one loop */
-    OBM_FN int lex_more_args() {
+    OBM_HD int lex_more_args() {
         for (;;) {
             uint32_t c = peek_byte();
             if (c == ',') { next(); emit(OBM_K_ARG_DELIMITER); }
@@ -455,14 +513,15 @@ struct Lexer {
             return TOP_FATAL;
         }
     }
-    OBM_FN int lex_arg_value() { int st = lex_arg_value_inner(); return st != -1 ? st : lex_more_args(); }
+    OBM_HD int lex_arg_value() { int st = lex_arg_value_inner(); return st != -1 ? st : lex_more_args(); }
     /* state.go:156-302; returns -1 to continue in lexMoreArgs, else a TopState (fatal) */
-    OBM_FN int lex_arg_value_inner() {
+    OBM_HD int lex_arg_value_inner() {
         uint32_t c = peek_byte();
         /* lexStringLiteral, state.go:176-221 */
         if (c == '\'' || c == '"' || c == '`') {
             next(); emit(OBM_K_QUOTE);
             for (;;) {
+                if (ASCII) p = next_nonletter(p); /* quotes and newlines are non-letters */
                 uint32_t b = peek_byte();
                 if (b == 0x100u) { located_at_pos(OBM_K_ERR_UNMATCHED); return TOP_FATAL; }
                 if (b == '\n') {
@@ -509,7 +568,7 @@ struct Lexer {
     /* ---- top level: state.go:15-57.  LINE_MODE (the tile path's per-line owner) stops right after
      *      discarding the first top-level '\n'; otherwise runs to EOF and emits the EOF tuple. ---- */
     template <bool LINE_MODE>
-    OBM_FN int run() {
+    OBM_HD int run() {
         int st = TOP_LEX;
         for (;;) {
             if (st == TOP_LEX) {

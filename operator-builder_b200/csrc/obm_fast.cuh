@@ -165,27 +165,47 @@ __device__ __forceinline__ uint32_t subbatch_count(CtaShared &C, const TileArgs 
     /* P3: per-document preparation */
     if (tid < nd) obmt::doc_prep(S, tid);
     __syncthreads();
-    /* P4: line scan -- newline prefix + owner discovery (records cached in registers, scan, write) */
-    uint32_t my_owners = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    uint32_t my_nl = obmt::line_scan(S, tid, [&](uint32_t rec) {
-        if (my_owners == 0) c0 = rec; else if (my_owners == 1) c1 = rec; else if (my_owners == 2) c2 = rec; else if (my_owners == 3) c3 = rec;
-        my_owners++;
-    });
+    /* P4: bit-parallel line scan.  Thread t owns words [4t, 4t+4): first event of every line via carry
+     * ripple, carries across threads/warps by generate/propagate look-ahead; then newline prefix counts
+     * and the ordered list of lines that own tuples (position of their first special byte). */
+    uint32_t nl[obmt::WPT], sp[obmt::WPT], lm[obmt::WPT];
+    {
+        const uint4 a = reinterpret_cast<const uint4 *>(S.nlw)[tid], b = reinterpret_cast<const uint4 *>(S.spw)[tid];
+        nl[0] = a.x; nl[1] = a.y; nl[2] = a.z; nl[3] = a.w; sp[0] = b.x; sp[1] = b.y; sp[2] = b.z; sp[3] = b.w;
+    }
+    obmt::line_starts(S, tid, nl, lm);
+    obmt::LineBits lb;
+    {
+        const uint32_t lane = tid & 31, wid = tid >> 5;
+        const uint32_t c0 = obmt::first_events(nl, sp, lm, 0, nullptr), c1 = obmt::first_events(nl, sp, lm, 1, nullptr);
+        const uint32_t Gb = __ballot_sync(0xffffffffu, c0 != 0), Pb = __ballot_sync(0xffffffffu, c1 != 0 && c0 == 0);
+        uint32_t w0, w1;
+        obmt::carry_lookahead32(Gb, Pb, 0, &w0);
+        obmt::carry_lookahead32(Gb, Pb, 1, &w1);
+        if (lane == 0) S.scan_tmp[wid] = w0 | ((w1 & ~w0 & 1u) << 1);
+        __syncthreads();
+        uint32_t cin = 0;
+        for (uint32_t w = 0; w < wid; w++) { uint32_t f = S.scan_tmp[w]; cin = (f & 1u) | ((f >> 1) & cin); }
+        __syncthreads();
+        uint32_t dummy;
+        const uint32_t C = obmt::carry_lookahead32(Gb, Pb, cin, &dummy);
+        obmt::first_events(nl, sp, lm, (C >> lane) & 1u, &lb);
+    }
+    uint32_t my_owners = 0, my_nl = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < obmt::WPT; j++) { my_owners += (uint32_t)__popc(lb.own[j]); my_nl += (uint32_t)__popc(nl[j]); }
     uint32_t tot;
     uint32_t pre = block_scan_excl(my_nl | (my_owners << 16), S.scan_tmp, tot);
     {
         uint32_t nlp = pre & 0xFFFFu, own = pre >> 16;
 #pragma unroll
-        for (uint32_t j = 0; j < obmt::WPT; j++) { S.nlpre[tid * obmt::WPT + j] = (uint16_t)nlp; nlp += (uint32_t)__popc(S.nlw[tid * obmt::WPT + j]); }
+        for (uint32_t j = 0; j < obmt::WPT; j++) { S.nlpre[tid * obmt::WPT + j] = (uint16_t)nlp; nlp += (uint32_t)__popc(nl[j]); }
         uint32_t n_owners = tot >> 16;
-        if (n_owners <= obmt::QMAX && my_owners) {
-            if (my_owners <= 4) {
-                S.owner[own] = c0;
-                if (my_owners > 1) S.owner[own + 1] = c1;
-                if (my_owners > 2) S.owner[own + 2] = c2;
-                if (my_owners > 3) S.owner[own + 3] = c3;
-            } else {
-                obmt::line_scan(S, tid, [&](uint32_t rec) { S.owner[own++] = rec; });
+        if (n_owners <= obmt::QMAX) {
+#pragma unroll
+            for (uint32_t j = 0; j < obmt::WPT; j++) {
+                uint32_t bits = lb.own[j];
+                while (bits) { S.owner[own++] = (tid * obmt::WPT + j) * 32 + (uint32_t)(__ffs((int)bits) - 1); bits &= bits - 1; }
             }
         }
         if (tid == 0) { S.n_owners = n_owners <= obmt::QMAX ? n_owners : 0; S.n_markers_q = 0; }
@@ -208,7 +228,7 @@ __device__ __forceinline__ uint32_t subbatch_count(CtaShared &C, const TileArgs 
 #pragma unroll
         for (uint32_t j = 0; j < 4; j++) {
             uint32_t o = tid * 4 + j;
-            v[j] = (o < n_owners && !S.dflag[S.odoc[o]]) ? S.ocnt[o] : 0;
+            v[j] = (o < n_owners && !S.dflag[S.odoc[o] & 0x7Fu]) ? S.ocnt[o] : 0;
             sum += v[j];
         }
         uint32_t etot;
@@ -261,7 +281,7 @@ __device__ __forceinline__ void subbatch_fill(CtaShared &C, const TileArgs &A, c
     }
 }
 
-__global__ void __launch_bounds__(obmt::NT)
+__global__ void __launch_bounds__(obmt::NT, 3)
 k_tile_scan(TileArgs A) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CtaShared &C = *reinterpret_cast<CtaShared *>(smem_raw);

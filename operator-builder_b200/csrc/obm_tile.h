@@ -173,14 +173,70 @@ OBM_FN uint32_t next_event(const Smem &S, uint32_t from) {
 OBM_HD bool is_sp(const Smem &S, uint32_t pos) { return (S.spw[pos >> 5] >> (pos & 31)) & 1u; }
 OBM_HD bool is_nl(const Smem &S, uint32_t pos) { return (S.nlw[pos >> 5] >> (pos & 31)) & 1u; }
 
+/* ---- P4a: which lines have a special byte, bit-parallel -------------------------------------------
+ * A line starts right after every newline bit (and at lo_pos).  Let X = nl|sp be the "event" bits and
+ * M the line-start bits.  Adding M to ~X lets each start bit ripple through the non-event bytes until it
+ * lands on the line's first event; (~X + M) & X therefore marks the FIRST event of every line, and
+ * & sp keeps the lines whose first event is a special byte -- those lines get an owner.  The carry
+ * that leaves a word (a line with no event yet) enters the next word; across threads and warps it is
+ * resolved with generate/propagate look-ahead (carry_lookahead32). */
+struct LineBits { uint32_t own[WPT]; uint32_t n_own, n_nl; };
+
+/* this thread's four words with carry-in `cin`; returns the carry out */
+OBM_HD uint32_t first_events(const uint32_t (&nl)[WPT], const uint32_t (&sp)[WPT], const uint32_t (&m)[WPT], uint32_t cin, LineBits *lb) {
+    uint32_t c = cin;
+#pragma unroll
+    for (uint32_t j = 0; j < WPT; j++) {
+        uint32_t x = nl[j] | sp[j];
+        uint64_t s = (uint64_t)(~x) + m[j] + c;
+        c = (uint32_t)(s >> 32);
+        if (lb) lb->own[j] = (uint32_t)s & x & sp[j];
+    }
+    return c;
+}
+/* line-start bits of the thread's words: after every newline, plus the buffer's first byte */
+OBM_HD void line_starts(const Smem &S, uint32_t t, const uint32_t (&nl)[WPT], uint32_t (&m)[WPT]) {
+    uint32_t prev = t ? (S.nlw[t * WPT - 1] >> 31) : 0u;
+#pragma unroll
+    for (uint32_t j = 0; j < WPT; j++) {
+        m[j] = (nl[j] << 1) | prev;
+        prev = nl[j] >> 31;
+        uint32_t w = t * WPT + j;
+        if (S.lo_pos < S.hi_pos && (S.lo_pos >> 5) == w) m[j] |= 1u << (S.lo_pos & 31);
+    }
+}
+/* 32 carry chains in one add: lane i generates (G bit) or propagates (P bit, disjoint from G) a carry.
+ * Returns the mask of lanes that RECEIVE a carry; *cout = carry out of lane 31. */
+OBM_HD uint32_t carry_lookahead32(uint32_t G, uint32_t P, uint32_t cin, uint32_t *cout) {
+    uint64_t s = (uint64_t)(G | P) + G + cin;
+    *cout = (uint32_t)(s >> 32);
+    return (uint32_t)s ^ P; /* sum ^ a ^ b with a = G|P, b = G, a ^ b = P */
+}
+
+/* previous line start: position after the last newline bit below `pos` (or lo_pos) */
+OBM_FN uint32_t line_start_of(const Smem &S, uint32_t pos) {
+    uint32_t w = pos >> 5;
+    uint32_t m = S.nlw[w] & ((1u << (pos & 31)) - 1u);
+    const uint32_t wlo = S.lo_pos >> 5;
+    while (m == 0) {
+        if (w == wlo) return S.lo_pos;
+        m = S.nlw[--w];
+    }
+#if defined(__CUDA_ARCH__)
+    uint32_t top = 31u - (uint32_t)__clz((int)m);
+#else
+    uint32_t top = 31u - (uint32_t)__builtin_clz(m);
+#endif
+    uint32_t ls = w * 32 + top + 1;
+    return ls > S.lo_pos ? ls : S.lo_pos;
+}
+
 constexpr uint32_t OW_NONE = 0xFFFFFFFFu; /* not a valid record: it would be a MARKER line that is also flagged "//" */
-/* Examines the line starting at `start`: returns OW_NONE if it produces no tuple, else its owner record.
- * A position carrying both bits (virtual newline on a document's last byte) is a special that also
- * ends the line. */
-OBM_FN uint32_t line_owner(const Smem &S, uint32_t start) {
-    uint32_t ev = next_event(S, start);
-    if (ev >= S.hi_pos || !is_sp(S, ev)) return OW_NONE; /* no special before the end of the line */
-    const uint32_t first = ev;
+/* Classifies the line whose first special byte is at `first`: marker line, plain comment line, or a line
+ * that produces no tuple (OW_NONE).  A position carrying both bits (virtual newline on a document's
+ * last byte) is a special that also ends the line. */
+OBM_FN uint32_t classify_line(const Smem &S, uint32_t first, uint32_t start) {
+    uint32_t ev = first;
     uint32_t comment = 0xFFFFFFFFu; bool slash2 = false;
     for (;;) {
         uint32_t c = S.data[ev];
@@ -195,30 +251,6 @@ OBM_FN uint32_t line_owner(const Smem &S, uint32_t start) {
     }
     if (comment == 0xFFFFFFFFu) return OW_NONE;
     return comment | (start << 16) | (slash2 ? OW_SLASH2 : 0u);
-}
-
-/* Visits the owners whose line starts right after a newline bit in this thread's words (plus the
- * line starting at lo_pos), in position order.  Returns the number of nlw bits in the thread's words. */
-template <class F>
-OBM_FN uint32_t line_scan(const Smem &S, uint32_t t, F &&f) {
-    uint32_t nls = 0;
-#pragma unroll
-    for (uint32_t j = 0; j < WPT; j++) {
-        uint32_t w = t * WPT + j;
-        uint32_t nl = S.nlw[w];
-        if (S.lo_pos < S.hi_pos && (S.lo_pos >> 5) == w) { /* the buffer's first line has no newline before it */
-            uint32_t rec = line_owner(S, S.lo_pos);
-            if (rec != OW_NONE) f(rec);
-        }
-        nls += OBMT_POPC(nl);
-        while (nl) {
-            uint32_t b = OBMT_CTZ(nl);
-            nl &= nl - 1;
-            uint32_t start = w * 32 + b + 1;
-            if (start < S.hi_pos) { uint32_t rec = line_owner(S, start); if (rec != OW_NONE) f(rec); }
-        }
-    }
-    return nls;
 }
 
 /* number of nlw bits at positions < q */
@@ -252,16 +284,22 @@ OBM_FN uint32_t doc_of(const Smem &S, uint32_t pos) {
 typedef obm::Lexer<obm::SmallSink, BitmapAccel, true> LineLexer;
 typedef obm::Lexer<obm::SmallSink, obm::NoAccel, false> DocLexer;
 
-/* marker line: LINE mode from the first special; returns true when the line interacted with others */
-OBM_HD_NOINLINE bool run_marker_line(const Smem &S, const obm::Tables &T, uint32_t rec, uint32_t d, obm::SmallSink &sink) {
+/* marker line: LINE mode from the first special.  Sink and lexer live in registers (everything inlines
+ * into this one function, which is compiled once and called from the stage and fill phases). */
+struct LineResult { uint32_t tuples, markers, lexemes; bool interact; };
+OBM_HD_NOINLINE LineResult run_marker_line(const Smem &S, const obm::Tables &T, uint32_t rec, uint32_t d, obm_tuple *out, uint32_t cap) {
     uint32_t first = ow_pos(rec), ls = ow_ls(rec);
     uint32_t dpos = S.dstart[d], dend = S.dstart[d + 1];
     uint32_t line = 1 + nl_before(S, ls) - nl_before(S, dpos);
     BitmapAccel acc{&S, dpos, dend};
+    obm::SmallSink sink(out, cap);
     LineLexer lx(T, S.data + dpos, dend - dpos, sink, first - dpos, line, ls - dpos, !(line == 1 && ls == dpos), acc);
     int st = lx.run<true>();
     uint32_t end_line = lx.line_p - (st == obm::RUN_LINE_END ? 1u : 0u);
-    return (st == obm::RUN_FATAL) || (end_line != line);
+    LineResult r;
+    r.tuples = sink.n_tuples; r.markers = sink.n_markers; r.lexemes = sink.n_lexemes;
+    r.interact = (st == obm::RUN_FATAL) || (end_line != line);
+    return r;
 }
 /* whole document through the exact (Unicode) lexer */
 OBM_HD_NOINLINE int run_doc_exact(const Smem &S, const obm::Tables &T, uint32_t d, obm::SmallSink &sink) {
@@ -291,29 +329,34 @@ OBM_FN uint32_t plain_line(const Smem &S, uint32_t rec, uint32_t d, obm_tuple *o
     return need_line ? 2u : 1u; /* line numbers inside a <= 16 KiB document never need LINEHI */
 }
 
-/* P5a body for owner o (every owner): document, plain counts, marker compaction */
+/* P5a body for owner o (every line that has a special byte): S.owner[o] holds the position of the line's
+ * first special; classify the line, find its document, count plain lines, compact marker lines.
+ * odoc bit 7 marks a line that produces no tuple. */
 OBM_FN void owner_prepare(Smem &S, uint32_t o) {
-    uint32_t rec = S.owner[o];
-    uint32_t d = doc_of(S, ow_ls(rec));
+    uint32_t first = S.owner[o];
+    uint32_t ls = line_start_of(S, first);
+    uint32_t d = doc_of(S, ls);
+    uint32_t rec = S.dflag[d] ? OW_NONE : classify_line(S, first, ls);
+    if (rec == OW_NONE) { S.owner[o] = first | (ls << 16); S.odoc[o] = (uint8_t)(d | 0x80u); S.ocnt[o] = 0; return; }
+    S.owner[o] = rec;
     S.odoc[o] = (uint8_t)d;
     if (rec & OW_MARKER) {
         uint32_t m = atomic_inc_u32(&S.n_markers_q);
         S.mlist[m] = (uint16_t)o; S.mslot[o] = (uint16_t)m;
         S.ocnt[o] = 0;
     } else {
-        S.ocnt[o] = S.dflag[d] ? 0u : plain_line(S, rec, d, nullptr, 0);
+        S.ocnt[o] = plain_line(S, rec, d, nullptr, 0);
     }
 }
 
 /* P5b body for marker owner m (dense): tokenize, stage */
 OBM_FN void marker_stage(Smem &S, const obm::Tables &T, uint32_t m) {
     uint32_t o = S.mlist[m];
-    uint32_t d = S.odoc[o];
+    uint32_t d = S.odoc[o]; /* marker owners never carry the dead flag */
     if (S.dflag[d]) { S.ocnt[o] = 0; return; }
-    obm::SmallSink sink(m < NSTAGE ? S.stage + m * STRIDE : nullptr, m < NSTAGE ? STRIDE : 0u);
-    bool interact = run_marker_line(S, T, S.owner[o], d, sink);
-    S.ocnt[o] = sink.n_tuples;
-    if (interact) atomic_or_u32(&S.dflag[d], DF_INTERACT);
+    LineResult r = run_marker_line(S, T, S.owner[o], d, m < NSTAGE ? S.stage + m * STRIDE : nullptr, m < NSTAGE ? STRIDE : 0u);
+    S.ocnt[o] = r.tuples;
+    if (r.interact) atomic_or_u32(&S.dflag[d], DF_INTERACT);
 }
 
 /* first owner whose line start is >= pos */
@@ -341,7 +384,7 @@ struct FillStats { uint32_t markers, lexemes, exact_docs, fatal_docs; };
 
 /* global tuple index of owner o's first tuple */
 OBM_HD uint64_t owner_at(const Smem &S, uint32_t o, uint64_t batch_base) {
-    uint32_t d = S.odoc[o];
+    uint32_t d = S.odoc[o] & 0x7Fu;
     return batch_base + S.dcnt[d] + (S.ocnt[o] - S.ocnt[S.dfirst[d]]);
 }
 
@@ -349,6 +392,7 @@ OBM_HD uint64_t owner_at(const Smem &S, uint32_t o, uint64_t batch_base) {
 OBM_FN void owner_fill_thread(const Smem &S, const obm::Tables &T, uint32_t o, uint32_t cnt, obm_tuple *out, uint64_t out_cap,
                               uint64_t batch_base, FillStats &fs) {
     uint32_t d = S.odoc[o];
+    if (d & 0x80u) return; /* the line produces no tuple */
     if (S.dflag[d]) return;
     uint32_t rec = S.owner[o];
     uint64_t at = owner_at(S, o, batch_base);
@@ -356,9 +400,8 @@ OBM_FN void owner_fill_thread(const Smem &S, const obm::Tables &T, uint32_t o, u
     if (!(rec & OW_MARKER)) { plain_line(S, rec, d, out + at, room); fs.lexemes += 1; return; }
     uint32_t m = S.mslot[o];
     if (m < NSTAGE && cnt <= STRIDE) return; /* staged: copied by owner_fill_staged */
-    obm::SmallSink sink(out + at, room > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room);
-    run_marker_line(S, T, rec, d, sink);
-    fs.markers += sink.n_markers; fs.lexemes += sink.n_lexemes;
+    LineResult r = run_marker_line(S, T, rec, d, out + at, room > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room);
+    fs.markers += r.markers; fs.lexemes += r.lexemes;
 }
 
 /* P7 body for staged marker owner m, lane `lane` of `nlanes` cooperating lanes */

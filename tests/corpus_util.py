@@ -69,3 +69,54 @@ def fuzz_doc(rng: random.Random, max_len=200, non_ascii=False):
         else:
             out += bytes(rng.choice(b"abcdefghijklmnopqrstuvwxyzABC0123456789") for _ in range(rng.randint(1, 6)))
     return bytes(out)
+
+
+def _ident(rng):
+    parts = []
+    for _ in range(rng.randint(1, 4)):
+        parts.append("".join(rng.choice("abcdefghijklmnopqrstuvwxyzABCXYZ0123456789_-") for _ in range(rng.randint(1, 14))))
+    return ".".join(parts)
+
+
+def _value(rng):
+    k = rng.random()
+    if k < 0.25:
+        return _ident(rng)
+    if k < 0.45:
+        q = rng.choice("\"'`")
+        body = "".join(rng.choice("abcdefghijklmnopqrstuvwxyz0123456789 .:/+-,;=#{}[]()") for _ in range(rng.randint(0, 40)))
+        return q + body.replace(q, "") + q
+    if k < 0.65:
+        return str(rng.randint(-500, 100000))
+    if k < 0.78:
+        return rng.choice(["1.5", "0.25", "-3.75e2", ".5", "1e3", "2.", "007"])
+    if k < 0.97:
+        return rng.choice(["true", "false", " true", "  false"])
+    return rng.choice(["nginx:1.17", "a;b;c", "x=y", "{a}", "", "v1,", "1e309", "`multi\n  # line`", "`a\n//b\nc`"])
+
+
+def fuzz_doc_valid(rng: random.Random, max_lines=30):
+    """Mostly well-formed manifests: YAML-ish lines, comments, markers with 1-3 scopes and 0-5 arguments;
+    a few malformed bits sprinkled in so that neighbouring regular lines are exercised too."""
+    lines = []
+    for _ in range(rng.randint(0, max_lines)):
+        k = rng.random()
+        indent = " " * rng.choice([0, 2, 4, 6, 8])
+        if k < 0.35:
+            lines.append(f"{indent}{_ident(rng)}: {rng.choice(['value', '3', '\"q\"', 'a/b', 'it' + chr(39) + 's', 'x+y', ''])}")
+        elif k < 0.45:
+            lines.append(f"{indent}# {rng.choice(['plain comment', 'see https://x/y', 'a # b', 'c // d', ''])}")
+        elif k < 0.5:
+            lines.append(rng.choice(["", "---", "  ", "\t", "// go comment", "/ not", "a//b: c"]))
+        else:
+            scopes = ":".join(_ident(rng).replace(".", "") or "s" for _ in range(rng.randint(1, 3)))
+            args = []
+            for _ in range(rng.randint(0, 5)):
+                a = _ident(rng).replace(".", "")
+                args.append(a if rng.random() < 0.2 else f"{a}={_value(rng)}")
+            m = "+" + scopes + (":" + ",".join(args) if args else "")
+            pre = rng.choice(["# ", "#", "// ", f"{_ident(rng)}: v  # ", "", "#   "])
+            post = rng.choice(["", "", "", "", " trailing words", " # +second:marker=1", " +x:y", "  "])
+            lines.append(indent + pre + m + post)
+    tail = rng.choice(["\n", "", "\n\n"])
+    return ("\n".join(lines) + tail).encode()

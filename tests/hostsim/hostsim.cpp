@@ -5,6 +5,8 @@
  * package; libobmarkers.so has no host lexing entry point.
  */
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "../../operator-builder_b200/csrc/go_unicode_tables.h"
 #include "../../operator-builder_b200/csrc/obm_core.h"
@@ -70,14 +72,56 @@ struct Emu {
             if (wi < ((nwords + 31u) & ~31u)) obmt::classify_word(S, wi); else { S.nlw[wi] = 0; S.spw[wi] = 0; }
         }
         for (uint32_t t = 0; t < nd; t++) obmt::doc_prep(S, t);
-        std::vector<uint32_t> my_nl(obmt::NT), my_own(obmt::NT);
-        for (uint32_t t = 0; t < obmt::NT; t++) { uint32_t c = 0; my_nl[t] = obmt::line_scan(S, t, [&](uint32_t) { c++; }); my_own[t] = c; }
-        uint32_t nlp = 0, own = 0, n_owners = 0;
-        for (uint32_t t = 0; t < obmt::NT; t++) n_owners += my_own[t];
+        /* P4: per-thread generate/propagate, warp look-ahead from emulated ballots, cross-warp resolve */
+        std::vector<uint32_t> my_nl(obmt::NT), my_own(obmt::NT), g(obmt::NT), pr(obmt::NT), cin_t(obmt::NT);
+        std::vector<obmt::LineBits> lbs(obmt::NT);
+        auto load = [&](uint32_t t, uint32_t (&nl)[obmt::WPT], uint32_t (&sp)[obmt::WPT], uint32_t (&lm)[obmt::WPT]) {
+            for (uint32_t j = 0; j < obmt::WPT; j++) { nl[j] = S.nlw[t * obmt::WPT + j]; sp[j] = S.spw[t * obmt::WPT + j]; }
+            obmt::line_starts(S, t, nl, lm);
+        };
+        for (uint32_t t = 0; t < obmt::NT; t++) {
+            uint32_t nl[obmt::WPT], sp[obmt::WPT], lm[obmt::WPT];
+            load(t, nl, sp, lm);
+            uint32_t c0 = obmt::first_events(nl, sp, lm, 0, nullptr), c1 = obmt::first_events(nl, sp, lm, 1, nullptr);
+            g[t] = c0 != 0; pr[t] = (c1 != 0 && c0 == 0);
+        }
+        uint32_t warp_cin = 0, naive = 0;
+        for (uint32_t w = 0; w < obmt::NT / 32; w++) {
+            uint32_t Gb = 0, Pb = 0;
+            for (uint32_t l = 0; l < 32; l++) { Gb |= g[w * 32 + l] << l; Pb |= pr[w * 32 + l] << l; }
+            uint32_t w0, w1, cout;
+            obmt::carry_lookahead32(Gb, Pb, 0, &w0);
+            obmt::carry_lookahead32(Gb, Pb, 1, &w1);
+            uint32_t C = obmt::carry_lookahead32(Gb, Pb, warp_cin, &cout);
+            for (uint32_t l = 0; l < 32; l++) {
+                cin_t[w * 32 + l] = (C >> l) & 1u;
+                if (cin_t[w * 32 + l] != naive) { fprintf(stderr, "hostsim: carry look-ahead mismatch at thread %u\n", w * 32 + l); abort(); }
+                naive = g[w * 32 + l] | (pr[w * 32 + l] & naive); /* sequential reference */
+            }
+            uint32_t f = w0 | ((w1 & ~w0 & 1u) << 1);
+            warp_cin = (f & 1u) | ((f >> 1) & warp_cin);
+            if (warp_cin != cout) { fprintf(stderr, "hostsim: warp carry mismatch\n"); abort(); }
+        }
+        uint32_t n_owners = 0;
+        for (uint32_t t = 0; t < obmt::NT; t++) {
+            uint32_t nl[obmt::WPT], sp[obmt::WPT], lm[obmt::WPT];
+            load(t, nl, sp, lm);
+            obmt::first_events(nl, sp, lm, cin_t[t], &lbs[t]);
+            my_nl[t] = my_own[t] = 0;
+            for (uint32_t j = 0; j < obmt::WPT; j++) { my_own[t] += (uint32_t)__builtin_popcount(lbs[t].own[j]); my_nl[t] += (uint32_t)__builtin_popcount(nl[j]); }
+            n_owners += my_own[t];
+        }
+        uint32_t nlp = 0, own = 0;
         for (uint32_t t = 0; t < obmt::NT; t++) {
             uint32_t q = nlp;
             for (uint32_t j = 0; j < obmt::WPT; j++) { S.nlpre[t * obmt::WPT + j] = (uint16_t)q; q += (uint32_t)__builtin_popcount(S.nlw[t * obmt::WPT + j]); }
-            if (n_owners <= obmt::QMAX && my_own[t]) { uint32_t o = own; obmt::line_scan(S, t, [&](uint32_t rec) { S.owner[o++] = rec; }); }
+            if (n_owners <= obmt::QMAX) {
+                uint32_t o = own;
+                for (uint32_t j = 0; j < obmt::WPT; j++) {
+                    uint32_t bits = lbs[t].own[j];
+                    while (bits) { S.owner[o++] = (t * obmt::WPT + j) * 32 + (uint32_t)__builtin_ctz(bits); bits &= bits - 1; }
+                }
+            }
             nlp += my_nl[t]; own += my_own[t];
         }
         S.n_owners = n_owners <= obmt::QMAX ? n_owners : 0;
@@ -89,7 +133,7 @@ struct Emu {
         for (uint32_t m = 0; m < S.n_markers_q; m++) obmt::marker_stage(S, TBL, m);
         uint32_t e = 0;
         for (uint32_t o = 0; o < obmt::QMAX; o++) {
-            uint32_t v = (o < n_owners && !S.dflag[S.odoc[o]]) ? S.ocnt[o] : 0;
+            uint32_t v = (o < n_owners && !S.dflag[S.odoc[o] & 0x7Fu]) ? S.ocnt[o] : 0;
             S.ocnt[o] = e; e += v;
         }
         S.ocnt[obmt::QMAX] = e;

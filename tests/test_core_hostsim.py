@@ -100,3 +100,10 @@ def test_strconv_helpers_agree(oracle):
             py = 1
         if "_" not in txt and "n" not in txt.lower() and "i" not in txt.lower():
             assert L.obo_parse_float_err(s, len(s)) == py, (s, py)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fuzz_valid(oracle, seed):
+    rng = random.Random(8800 + seed)
+    for _ in range(400):
+        check(oracle, cu.fuzz_doc_valid(rng))

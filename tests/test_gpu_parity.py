@@ -107,6 +107,13 @@ def test_fuzz(scanner, oracle, seed):
     run_and_compare(scanner, oracle, docs)
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_fuzz_valid_manifests(scanner, oracle, seed):
+    rng = random.Random(600 + seed)
+    docs = [cu.fuzz_doc_valid(rng) for _ in range(3000)]
+    run_and_compare(scanner, oracle, docs)
+
+
 def test_c2_10k_docs_bit_exact(scanner, oracle):
     """BASELINE.json configs[1]: 10k synthetic 4 KiB manifests (40,960,000 B), 8 markers/file."""
     import operator_builder_b200 as ob

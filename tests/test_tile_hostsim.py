@@ -67,3 +67,15 @@ def test_fuzz_batches(seed):
         docs = [cu.fuzz_doc(rng, max_len=rng.choice([5, 60, 400, 3000]), non_ascii=rng.random() < 0.15)
                 for _ in range(rng.randint(1, 80))]
         check_batch(docs, skew=rng.randint(0, 15))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_valid_batches(seed):
+    """well-formed manifests: almost every document stays on the line-parallel path"""
+    rng = random.Random(7700 + seed)
+    exact = total = 0
+    for _ in range(25):
+        docs = [cu.fuzz_doc_valid(rng) for _ in range(rng.randint(1, 40))]
+        stats = check_batch(docs, skew=rng.randint(0, 15))
+        exact += int(stats[2]); total += len(docs)
+    assert exact < total * 0.6

@@ -472,9 +472,89 @@ struct Lexer {
     /* ---- marker states; each returns the top-level state to continue in ---- */
     /* state.go:60-68, entered with '+' just consumed */
     OBM_HD int marker_start() {
-        if (ASCII ? is_letter_ascii(peek()) : is_letter(T, peek())) { emit(OBM_K_MARKER_START); return lex_marker(); }
+        if (ASCII ? is_letter_ascii(peek()) : is_letter(T, peek())) { emit(OBM_K_MARKER_START); return ASCII ? fast_marker() : lex_marker(); }
         return TOP_COMMENT;
     }
+    /* ---- ASCII fast machine: the well-formed marker grammar, ONE token (one emit site) per loop
+     * iteration so that the lanes of a warp, each lexing its own marker line, stay converged.  It keeps
+     * exactly the generic state (p, s, last_type, line basis) and hands over to the generic state
+     * functions at a token boundary the moment the input leaves the simple grammar (empty names,
+     * missing scope, multi-line / unterminated strings, unusual numbers, leading whitespace, errors),
+     * so the tuple stream is the generic one by construction (tests compare them). ---- */
+    OBM_HD uint32_t scan_delim(uint32_t q, bool naked) {
+        for (;;) {
+            q = next_nonletter(q);
+            if (q >= n) return n;
+            uint32_t c = d[q];
+            if (is_name_delim(c) && !(naked && c == ';')) return q;
+            q++;
+        }
+    }
+    OBM_HD int fast_marker() {
+        enum { F_NAME1, F_COLON, F_ASSIGN, F_VALUE, F_STRBODY, F_STRCLOSE, F_MORE, F_NAME2 };
+        uint32_t st = F_NAME1, send = 0;
+        for (;;) {
+            uint32_t kind, end, syn = 0, nst;
+            const uint32_t c0 = peek_byte();
+            if (st == F_NAME1 || st == F_NAME2) {
+                end = scan_delim(p, false);
+                const uint32_t c = end < n ? d[end] : 0x100u;
+                const bool term = (c == ' ' || c == '\n' || c == 0x100u);
+                if (end == p) return st == F_NAME1 ? lex_marker() : lex_more_args(true);
+                if (st == F_NAME1 && c == ':') { kind = OBM_K_SCOPE; nst = F_COLON; }
+                else {
+                    if (st == F_NAME1 && last_type != OBM_K_SEPARATOR) return lex_marker();
+                    kind = OBM_K_ARG;
+                    if (c == '=') nst = F_ASSIGN;
+                    else if (term) { syn = 3; nst = F_MORE; }
+                    else if (st == F_NAME2 && c == ',') { syn = 1; nst = F_MORE; }
+                    else return st == F_NAME1 ? lex_marker() : lex_more_args(true);
+                }
+            } else if (st == F_COLON) { kind = OBM_K_SEPARATOR; end = p + 1; nst = F_NAME1; }
+            else if (st == F_ASSIGN) { kind = OBM_K_ARG_ASSIGNMENT; end = p + 1; nst = F_VALUE; }
+            else if (st == F_VALUE) {
+                if (c0 == '\'' || c0 == '"' || c0 == '`') {
+                    uint32_t e = p + 1; /* closing quote on this line? */
+                    for (;;) { e = next_nonletter(e); if (e >= n) break; uint32_t b = d[e]; if (b == c0 || b == '\n') break; e++; }
+                    if (e >= n || d[e] != c0) return lex_arg_value();
+                    send = e; kind = OBM_K_QUOTE; end = p + 1; nst = F_STRBODY;
+                } else {
+                    end = scan_delim(p, true);
+                    const uint32_t len = end - p;
+                    if (len == 0 || is_space((int)c0)) return lex_arg_value(); /* \t \v \f \r may lead a bool literal (consume.go:37-47) */
+                    if (c0 == '.' || c0 == '-' || is_digit_ascii((int)c0)) {
+                        /* -?digits[.digits], at most 17 bytes: valid and in range for Atoi / ParseFloat */
+                        if (len > 17) return lex_arg_value();
+                        uint32_t dots = 0, digits = 0; bool ok = true;
+                        for (uint32_t k = (c0 == '-') ? 1u : 0u; k < len; k++) {
+                            uint32_t b = d[p + k];
+                            if (b == '.') dots++; else if (b >= '0' && b <= '9') digits++; else ok = false;
+                        }
+                        if (!ok || dots > 1 || digits == 0) return lex_arg_value();
+                        kind = dots ? OBM_K_FLOAT_LITERAL : OBM_K_INTEGER_LITERAL;
+                    } else {
+                        const bool t4 = len >= 4 && d[p] == 't' && d[p + 1] == 'r' && d[p + 2] == 'u' && d[p + 3] == 'e';
+                        const bool f5 = len >= 5 && d[p] == 'f' && d[p + 1] == 'a' && d[p + 2] == 'l' && d[p + 3] == 's' && d[p + 4] == 'e';
+                        if ((t4 && len > 4) || (f5 && len > 5)) return lex_arg_value();
+                        kind = (t4 || f5) ? OBM_K_BOOL_LITERAL : OBM_K_STRING_LITERAL;
+                    }
+                    nst = F_MORE;
+                }
+            } else if (st == F_STRBODY) { kind = OBM_K_STRING_LITERAL; end = send; nst = F_STRCLOSE; }
+            else if (st == F_STRCLOSE) { kind = OBM_K_QUOTE; end = p + 1; nst = F_MORE; }
+            else { /* F_MORE */
+                if (c0 == ',') { kind = OBM_K_ARG_DELIMITER; end = p + 1; nst = F_NAME2; }
+                else if (c0 == ' ' || c0 == '\n' || c0 == 0x100u) { emit_synthetic(OBM_K_MARKER_END); return TOP_COMMENT; }
+                else return lex_more_args();
+            }
+            p = end;
+            emit(kind);
+            if (syn & 1u) emit_synthetic(OBM_K_SYNTHETIC_BOOL);
+            if (syn & 2u) { emit_synthetic(OBM_K_MARKER_END); return TOP_COMMENT; }
+            st = nst;
+        }
+    }
+
     /* state.go:71-116 */
     OBM_HD int lex_marker() {
         for (;;) {
@@ -496,12 +576,16 @@ struct Lexer {
         }
     }
     /* state.go:118-154 (lexArgs) and state.go:304-317 (lexMoreArgs), as one loop */
-    OBM_HD int lex_more_args() {
+    OBM_HD int lex_more_args(bool at_args = false) {
         for (;;) {
-            uint32_t c = peek_byte();
-            if (c == ',') { next(); emit(OBM_K_ARG_DELIMITER); }
-            else if (c == ' ' || c == '\n' || c == 0x100u) { emit_synthetic(OBM_K_MARKER_END); return TOP_COMMENT; }
-            else { located_at_pos(OBM_K_ERR_MALFORMED); return TOP_FATAL; }
+            uint32_t c;
+            if (!at_args) {
+                c = peek_byte();
+                if (c == ',') { next(); emit(OBM_K_ARG_DELIMITER); }
+                else if (c == ' ' || c == '\n' || c == 0x100u) { emit_synthetic(OBM_K_MARKER_END); return TOP_COMMENT; }
+                else { located_at_pos(OBM_K_ERR_MALFORMED); return TOP_FATAL; }
+            }
+            at_args = false;
             /* lexArgs */
             if (!consume_until<false>()) { backup_again(); flush(); emit_synthetic(OBM_K_MARKER_END); return TOP_LEX; }
             emit(OBM_K_ARG);

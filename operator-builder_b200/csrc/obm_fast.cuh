@@ -118,6 +118,7 @@ struct TileArgs {
     obm_tuple *out; uint64_t out_cap; uint64_t *tuple_off;
     uint64_t *tile_state; uint32_t *ticket;
     uint32_t *status; unsigned long long *totals;
+    uint32_t msplit;                   /* marker lines are dealt to this many warps (1..NT/32) */
 };
 
 struct CtaShared {
@@ -218,8 +219,11 @@ __device__ __forceinline__ uint32_t subbatch_count(CtaShared &C, const TileArgs 
     __syncthreads();
     /* P5b: marker lines, dense: tokenize once, stage the tuples in shared memory */
     {
-        const uint32_t nm = S.n_markers_q;
-        for (uint32_t m = tid; m < nm; m += obmt::NT) obmt::marker_stage(S, T, m);
+        /* marker line m runs on warp (m % msplit), lane (m / msplit) % 32: divergent lanes of one warp
+         * serialise, so dealing the lines to several warps shortens this phase (the CTA's critical path) */
+        const uint32_t nm = S.n_markers_q, ms = A.msplit;
+        const uint32_t wid = tid >> 5, lane = tid & 31;
+        if (wid < ms) for (uint32_t m = wid + lane * ms; m < nm; m += 32 * ms) obmt::marker_stage(S, T, m);
     }
     __syncthreads();
     /* P6: E[] = exclusive scan of owner counts (owners of irregular documents contribute nothing) */

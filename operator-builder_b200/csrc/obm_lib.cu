@@ -307,6 +307,11 @@ static int obm_fast_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     A.tile_first = tile_first; A.ntiles = ntiles; A.counts = counts;
     A.out = d_out; A.out_cap = d_out ? out_cap : 0; A.tuple_off = toff;
     A.tile_state = tile_state; A.ticket = ctl; A.status = status; A.totals = totals;
+    {
+        static int msplit = -1;
+        if (msplit < 0) { const char *e = getenv("OBM_MSPLIT"); msplit = e ? atoi(e) : 4; if (msplit < 1) msplit = 1; if (msplit > (int)(obmt::NT / 32)) msplit = obmt::NT / 32; }
+        A.msplit = (uint32_t)msplit;
+    }
     int dev_sms = 0, per_sm = 0;
     OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
     OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, obmf::k_tile_scan, (int)obmt::NT, smem));

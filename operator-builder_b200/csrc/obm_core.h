@@ -492,67 +492,75 @@ struct Lexer {
     }
     OBM_HD int fast_marker() {
         enum { F_NAME1, F_COLON, F_ASSIGN, F_VALUE, F_STRBODY, F_STRCLOSE, F_MORE, F_NAME2 };
-        uint32_t st = F_NAME1, send = 0;
-        for (;;) {
-            uint32_t kind, end, syn = 0, nst;
+        enum { X_NONE, X_DONE, X_LEX_MARKER, X_LEX_ARGS, X_LEX_VALUE, X_LEX_MORE }; /* how the loop ends */
+        uint32_t st = F_NAME1, send = 0, exit_code = X_NONE;
+        do {
+            uint32_t kind = 0, end = p, syn = 0, nst = st;
             const uint32_t c0 = peek_byte();
             if (st == F_NAME1 || st == F_NAME2) {
                 end = scan_delim(p, false);
                 const uint32_t c = end < n ? d[end] : 0x100u;
                 const bool term = (c == ' ' || c == '\n' || c == 0x100u);
-                if (end == p) return st == F_NAME1 ? lex_marker() : lex_more_args(true);
-                if (st == F_NAME1 && c == ':') { kind = OBM_K_SCOPE; nst = F_COLON; }
+                const uint32_t fb = st == F_NAME1 ? X_LEX_MARKER : X_LEX_ARGS;
+                if (end == p) exit_code = fb;
+                else if (st == F_NAME1 && c == ':') { kind = OBM_K_SCOPE; nst = F_COLON; }
+                else if (st == F_NAME1 && last_type != OBM_K_SEPARATOR) exit_code = fb;
                 else {
-                    if (st == F_NAME1 && last_type != OBM_K_SEPARATOR) return lex_marker();
                     kind = OBM_K_ARG;
                     if (c == '=') nst = F_ASSIGN;
                     else if (term) { syn = 3; nst = F_MORE; }
                     else if (st == F_NAME2 && c == ',') { syn = 1; nst = F_MORE; }
-                    else return st == F_NAME1 ? lex_marker() : lex_more_args(true);
+                    else exit_code = fb;
                 }
-            } else if (st == F_COLON) { kind = OBM_K_SEPARATOR; end = p + 1; nst = F_NAME1; }
-            else if (st == F_ASSIGN) { kind = OBM_K_ARG_ASSIGNMENT; end = p + 1; nst = F_VALUE; }
-            else if (st == F_VALUE) {
+            } else if (st == F_VALUE) {
                 if (c0 == '\'' || c0 == '"' || c0 == '`') {
                     uint32_t e = p + 1; /* closing quote on this line? */
                     for (;;) { e = next_nonletter(e); if (e >= n) break; uint32_t b = d[e]; if (b == c0 || b == '\n') break; e++; }
-                    if (e >= n || d[e] != c0) return lex_arg_value();
-                    send = e; kind = OBM_K_QUOTE; end = p + 1; nst = F_STRBODY;
+                    if (e >= n || d[e] != c0) exit_code = X_LEX_VALUE;
+                    else { send = e; kind = OBM_K_QUOTE; end = p + 1; nst = F_STRBODY; }
                 } else {
                     end = scan_delim(p, true);
                     const uint32_t len = end - p;
-                    if (len == 0 || is_space((int)c0)) return lex_arg_value(); /* \t \v \f \r may lead a bool literal (consume.go:37-47) */
-                    if (c0 == '.' || c0 == '-' || is_digit_ascii((int)c0)) {
+                    nst = F_MORE;
+                    if (len == 0 || is_space((int)c0)) exit_code = X_LEX_VALUE; /* \t \v \f \r may lead a bool literal (consume.go:37-47) */
+                    else if (c0 == '.' || c0 == '-' || is_digit_ascii((int)c0)) {
                         /* -?digits[.digits], at most 17 bytes: valid and in range for Atoi / ParseFloat */
-                        if (len > 17) return lex_arg_value();
-                        uint32_t dots = 0, digits = 0; bool ok = true;
-                        for (uint32_t k = (c0 == '-') ? 1u : 0u; k < len; k++) {
+                        uint32_t dots = 0, digits = 0; bool ok = len <= 17;
+                        for (uint32_t k = (c0 == '-') ? 1u : 0u; ok && k < len; k++) {
                             uint32_t b = d[p + k];
                             if (b == '.') dots++; else if (b >= '0' && b <= '9') digits++; else ok = false;
                         }
-                        if (!ok || dots > 1 || digits == 0) return lex_arg_value();
+                        if (!ok || dots > 1 || digits == 0) exit_code = X_LEX_VALUE;
                         kind = dots ? OBM_K_FLOAT_LITERAL : OBM_K_INTEGER_LITERAL;
                     } else {
                         const bool t4 = len >= 4 && d[p] == 't' && d[p + 1] == 'r' && d[p + 2] == 'u' && d[p + 3] == 'e';
                         const bool f5 = len >= 5 && d[p] == 'f' && d[p + 1] == 'a' && d[p + 2] == 'l' && d[p + 3] == 's' && d[p + 4] == 'e';
-                        if ((t4 && len > 4) || (f5 && len > 5)) return lex_arg_value();
+                        if ((t4 && len > 4) || (f5 && len > 5)) exit_code = X_LEX_VALUE;
                         kind = (t4 || f5) ? OBM_K_BOOL_LITERAL : OBM_K_STRING_LITERAL;
                     }
-                    nst = F_MORE;
                 }
-            } else if (st == F_STRBODY) { kind = OBM_K_STRING_LITERAL; end = send; nst = F_STRCLOSE; }
-            else if (st == F_STRCLOSE) { kind = OBM_K_QUOTE; end = p + 1; nst = F_MORE; }
-            else { /* F_MORE */
+            } else if (st == F_MORE) {
                 if (c0 == ',') { kind = OBM_K_ARG_DELIMITER; end = p + 1; nst = F_NAME2; }
-                else if (c0 == ' ' || c0 == '\n' || c0 == 0x100u) { emit_synthetic(OBM_K_MARKER_END); return TOP_COMMENT; }
-                else return lex_more_args();
+                else if (c0 == ' ' || c0 == '\n' || c0 == 0x100u) { syn = 2; }
+                else exit_code = X_LEX_MORE;
+            } else if (st == F_STRBODY) { kind = OBM_K_STRING_LITERAL; end = send; nst = F_STRCLOSE; }
+            else { /* single-byte tokens: ':' '=' closing quote */
+                kind = st == F_COLON ? OBM_K_SEPARATOR : st == F_ASSIGN ? OBM_K_ARG_ASSIGNMENT : OBM_K_QUOTE;
+                end = p + 1;
+                nst = st == F_COLON ? F_NAME1 : st == F_ASSIGN ? F_VALUE : F_MORE;
             }
-            p = end;
-            emit(kind);
-            if (syn & 1u) emit_synthetic(OBM_K_SYNTHETIC_BOOL);
-            if (syn & 2u) { emit_synthetic(OBM_K_MARKER_END); return TOP_COMMENT; }
-            st = nst;
-        }
+            if (exit_code == X_NONE) {
+                if (kind) { p = end; emit(kind); }
+                if (syn & 1u) emit_synthetic(OBM_K_SYNTHETIC_BOOL);
+                if (syn & 2u) { emit_synthetic(OBM_K_MARKER_END); exit_code = X_DONE; }
+                st = nst;
+            }
+        } while (exit_code == X_NONE);
+        /* one hand-over point per generic entry (keeps the loop small and its lanes converged) */
+        if (exit_code == X_DONE) return TOP_COMMENT;
+        if (exit_code == X_LEX_MARKER) return lex_marker();
+        if (exit_code == X_LEX_VALUE) return lex_arg_value();
+        return lex_more_args(exit_code == X_LEX_ARGS);
     }
 
     /* state.go:71-116 */

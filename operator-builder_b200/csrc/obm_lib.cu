@@ -309,7 +309,7 @@ static int obm_fast_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     A.tile_state = tile_state; A.ticket = ctl; A.status = status; A.totals = totals;
     {
         static int msplit = -1;
-        if (msplit < 0) { const char *e = getenv("OBM_MSPLIT"); msplit = e ? atoi(e) : 4; if (msplit < 1) msplit = 1; if (msplit > (int)(obmt::NT / 32)) msplit = obmt::NT / 32; }
+        if (msplit < 0) { const char *e = getenv("OBM_MSPLIT"); msplit = e ? atoi(e) : 8; if (msplit < 1) msplit = 1; if (msplit > (int)(obmt::NT / 32)) msplit = obmt::NT / 32; }
         A.msplit = (uint32_t)msplit;
     }
     int dev_sms = 0, per_sm = 0;

@@ -163,6 +163,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     d0, d1 = args.docs * rank // world, args.docs * (rank + 1) // world
@@ -305,7 +306,8 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+            traffic = int(tj["dram_bytes_per_input_byte"] * (total_bytes // world))  # ncu capture scaled to this launch
     except Exception:
         pass
     cpu = None

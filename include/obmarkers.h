@@ -132,7 +132,10 @@ int obm_lex_batch(obm_handle *h, const uint8_t *bytes, const uint64_t *doc_off, 
  * All pointers are device pointers on the handle's device; `stream` is a cudaStream_t used exactly as
  * given (NULL = CUDA's default stream).  Asynchronous: returns after enqueueing.  d_doc_tuple_off[ndocs] holds the
  * total tuple count; if it exceeds out_cap the kernels write nothing past out_cap and set
- * d_status[0] = 1 (d_status is a device uint32[4]: {overflow, n_docs_exact, n_docs_fatal, reserved}).
+ * d_status[0] = 1 (d_status is a device uint32[4]: {overflow, n_docs_exact, n_docs_fatal, scratch_overflow}).
+ * scratch_overflow != 0 means the pipeline's internal work-record buffers were too small for this input
+ * (far denser in markers than manifests are): the output is invalid, rerun with obm_set_mode(h, 1).
+ * d_bytes must be readable up to the next 16-byte boundary past total_bytes (any cudaMalloc'd buffer is).
  * d_counts (device uint64[2], may be NULL) receives {n_markers, n_lexemes}.
  */
 int obm_lex_batch_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
@@ -154,8 +157,8 @@ int obm_generate_corpus_device(obm_handle *h, void *d_bytes, void *d_doc_off, ui
 int obm_generate_corpus_host(uint8_t *bytes, uint64_t *doc_off, uint32_t ndocs, uint32_t doc_bytes,
                              uint64_t first_doc, int flavour);
 
-/* Scanning strategy: 0 = auto (tile fast path, exact path for irregular documents; default),
- * 1 = exact path for every document.  Both produce the identical tuple stream. Returns the old mode. */
+/* Scanning strategy: 0 = three-stage pipeline (default), 1 = exact path for every document, 2 = fused tile
+ * kernel.  All produce the identical tuple stream.  Returns the old mode. */
 int obm_set_mode(obm_handle *h, int mode);
 
 /* Number of this library's kernels launched by the last scan call on this handle. */

@@ -424,8 +424,9 @@ struct Lexer {
             uint32_t mis = (uint32_t)((uintptr_t)a & 3u);
             const uint32_t *w = reinterpret_cast<const uint32_t *>(a - mis);
             uint32_t mk = 0;
+            const uint32_t wlim = n - q + mis; /* bytes from the window start to the end of the document */
 #pragma unroll
-            for (int k = 0; k < 8; k++) mk |= nonletter4(w[k]) << (4 * k);
+            for (int k = 0; k < 8; k++) mk |= nonletter4((uint32_t)(4 * k) < wlim ? w[k] : 0u) << (4 * k);
             wbase = (int32_t)q - (int32_t)mis; wmask = mk;
         }
     }

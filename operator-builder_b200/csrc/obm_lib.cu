@@ -48,6 +48,7 @@ __device__ __forceinline__ obm::Tables device_tables() {
 enum { ST_OVERFLOW = 0, ST_DOCS_EXACT = 1, ST_DOCS_FATAL = 2, ST_RESERVED = 3 };
 
 #include "obm_fast.cuh"
+#include "obm_pipe.cuh"
 
 /* ------------------------------------------------------------------------------------------- */
 /* exact path: one thread per document                                                          */
@@ -325,14 +326,92 @@ static int obm_fast_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     return OBM_OK;
 }
 
-/* scratch layout: counts u32[ndocs] | tile_sums u64[ntiles] | fast-path workspace */
+static uint64_t align_up(uint64_t v, uint64_t a);
+/* pipeline (mode 0) work records: capacities are generous multiples of what manifests produce (one owning
+ * line per ~68 B, one marker line per ~512 B); denser input sets the overflow flag and the scan is redone
+ * by the exact kernels. */
+static uint64_t pipe_items_cap(uint32_t ndocs, uint64_t total_bytes) { return total_bytes / 24 + ndocs + 1024; }
+static uint64_t pipe_mlines_cap(uint64_t total_bytes) { return total_bytes / 64 + 1024; }
+static uint64_t pipe_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
+    const uint64_t ic = pipe_items_cap(ndocs, total_bytes), mc = pipe_mlines_cap(total_bytes);
+    return align_up(ic * 8, 256) + align_up(ic * 4, 256) + align_up(mc * 16, 256) + align_up(mc * 4, 256) + align_up(mc * 8, 256) +
+           align_up(((uint64_t)ndocs + 1) * 8, 256) + 2 * align_up((uint64_t)ndocs * 4 + 4, 256) + 256;
+}
+
+/* Mode 0: index -> exact count of large documents -> k1_scan -> k2_markers<count> -> k3_assemble ->
+ * k2_markers<write> -> exact fill of large documents. */
+static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t *d_doc_off, uint32_t ndocs, uint64_t total_bytes,
+                           obm_tuple *d_out, uint64_t out_cap, uint64_t *toff, uint32_t *status, unsigned long long *totals,
+                           uint32_t *counts, void *fast_ws, void *pipe_ws, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem1 = sizeof(obmq::K1Shared);
+    if (!attr_set) {
+        OBM_CUDA(h, cudaFuncSetAttribute(obmq::k1_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        attr_set = true;
+    }
+    const uint64_t nt64 = obm_fast_ntiles(total_bytes);
+    if (nt64 > 0xFFFFFFF0ull) { set_err(h, "batch too large for the tile index"); return OBM_E_ARG; }
+    const uint32_t ntiles = (uint32_t)nt64;
+    auto up = [](uint64_t v) { return (v + 255) / 256 * 256; };
+    uint8_t *w = (uint8_t *)fast_ws;
+    uint32_t *tile_first = (uint32_t *)w; w += up(((uint64_t)ntiles + 2) * 4);
+    uint64_t *tile_state = (uint64_t *)w; w += up(((uint64_t)ntiles + 1) * 8);
+    const uint64_t max_large = obm_fast_max_large(total_bytes);
+    uint32_t *large_list = (uint32_t *)w; w += up((max_large + 1) * 4);
+    uint32_t *lctl = (uint32_t *)w; /* [1] n_large */
+    const uint64_t ic = pipe_items_cap(ndocs, total_bytes), mc = pipe_mlines_cap(total_bytes);
+    uint8_t *q = (uint8_t *)pipe_ws;
+    obmq::PipeArgs A;
+    A.bytes = d_bytes; A.doc_off = d_doc_off; A.ndocs = ndocs; A.total_bytes = total_bytes; A.tile_first = tile_first; A.ntiles = ntiles;
+    A.items = (obmp::item_t *)q; q += up(ic * 8); A.item_slot = (uint32_t *)q; q += up(ic * 4); A.items_cap = ic;
+    A.mlines = (obmp::MLine *)q; q += up(mc * 16); A.mres = (uint32_t *)q; q += up(mc * 4); A.moff = (uint64_t *)q; q += up(mc * 8); A.mlines_cap = mc;
+    A.doc_item_off = (uint64_t *)q; q += up(((uint64_t)ndocs + 1) * 8);
+    A.doc_item_n = (uint32_t *)q; q += up((uint64_t)ndocs * 4 + 4);
+    A.doc_flag = (uint32_t *)q; q += up((uint64_t)ndocs * 4 + 4);
+    A.ctl = (uint32_t *)q;
+    A.counts = counts; A.out = d_out; A.out_cap = d_out ? out_cap : 0; A.tuple_off = toff;
+    A.tile_state = tile_state; A.status = status; A.totals = totals;
+    OBM_CUDA(h, cudaMemsetAsync(tile_state, 0, ((uint64_t)ntiles + 1) * 8, st));
+    OBM_CUDA(h, cudaMemsetAsync(lctl, 0, 16, st));
+    OBM_CUDA(h, cudaMemsetAsync(A.ctl, 0, 64, st));
+    obmf::k_tile_index<<<(ndocs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, ndocs, ntiles, tile_first, large_list, lctl + 1);
+    const uint32_t nb_large = (uint32_t)((max_large + 127) / 128);
+    k_exact_count<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, lctl + 1, counts, totals, status);
+    int dev_sms = 0, per_sm1 = 0, per_sm3 = 0;
+    OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
+    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, obmq::k1_scan, (int)obmt::NT, smem1));
+    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, obmq::k3_assemble, (int)obmt::NT, 0));
+    if (per_sm1 < 1) per_sm1 = 1;
+    if (per_sm3 < 1) per_sm3 = 1;
+    uint32_t g1 = (uint32_t)dev_sms * (uint32_t)per_sm1, g3 = (uint32_t)dev_sms * (uint32_t)per_sm3;
+    if (g1 > ntiles) g1 = ntiles;
+    if (g3 > ntiles) g3 = ntiles;
+    const uint32_t g2 = (uint32_t)dev_sms * 8u; /* persistent, grid-stride over the device-side marker-line list */
+    obmq::k1_scan<<<g1, obmt::NT, smem1, st>>>(A);
+    obmq::k2_markers<false><<<g2, 256, 0, st>>>(A);
+    obmq::k3_assemble<<<g3, obmt::NT, 0, st>>>(A);
+    uint32_t launches = 5;
+    if (d_out && out_cap) {
+        obmq::k2_markers<true><<<g2, 256, 0, st>>>(A);
+        k_exact_fill<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, lctl + 1, toff, d_out, out_cap);
+        launches += 2;
+    }
+    /* work-record overflow -> status[3]: the caller must redo the scan with the exact kernels (mode 1) */
+    OBM_CUDA(h, cudaMemcpyAsync(status + ST_RESERVED, A.ctl + obmq::CT_OVF, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    h->launches = launches;
+    OBM_CUDA(h, cudaGetLastError());
+    return OBM_OK;
+}
+
+/* scratch layout: counts u32[ndocs] | tile_sums u64[ntiles] | fast-path workspace | pipeline workspace */
 static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 static uint32_t scan_tiles(uint32_t ndocs) { return (ndocs + SCAN_TILE - 1) / SCAN_TILE; }
 
 extern "C" uint64_t obm_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
     uint64_t b = align_up((uint64_t)ndocs * 4 + 4, 256);
     b += align_up((uint64_t)scan_tiles(ndocs) * 8 + 8, 256);
-    b += obm_fast_scratch_bytes(ndocs, total_bytes);
+    b += align_up(obm_fast_scratch_bytes(ndocs, total_bytes), 256);
+    b += pipe_scratch_bytes(ndocs, total_bytes);
     return b;
 }
 
@@ -351,7 +430,8 @@ static int lex_device_impl(obm_handle *h, const void *d_bytes, const void *d_doc
     uint8_t *sc = (uint8_t *)h->scratch;
     uint32_t *counts = (uint32_t *)sc; sc += align_up((uint64_t)ndocs * 4 + 4, 256);
     uint64_t *tile_sums = (uint64_t *)sc; sc += align_up((uint64_t)scan_tiles(ndocs) * 8 + 8, 256);
-    void *fast_ws = sc;
+    void *fast_ws = sc; sc += align_up(obm_fast_scratch_bytes(ndocs, total_bytes), 256);
+    void *pipe_ws = sc;
     uint32_t *status = (uint32_t *)(d_status ? d_status : (void *)h->d_status);
     unsigned long long *totals = (unsigned long long *)(d_counts ? d_counts : (void *)h->d_counts);
     uint64_t *toff = (uint64_t *)d_doc_tuple_off;
@@ -359,10 +439,12 @@ static int lex_device_impl(obm_handle *h, const void *d_bytes, const void *d_doc
     OBM_CUDA(h, cudaMemsetAsync(totals, 0, 2 * sizeof(unsigned long long), st));
     if (ndocs == 0) { OBM_CUDA(h, cudaMemsetAsync(toff, 0, sizeof(uint64_t), st)); return OBM_OK; }
 
-    if (h->mode == 0) {
+    if (h->mode == 0)
+        return obm_pipe_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
+                               (obm_tuple *)d_out, out_cap, toff, status, totals, counts, fast_ws, pipe_ws, st);
+    if (h->mode == 2)
         return obm_fast_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
                                (obm_tuple *)d_out, out_cap, toff, status, totals, counts, fast_ws, st);
-    }
     uint32_t nb = (ndocs + 127) / 128;
     h->launches = 4 + ((d_out && out_cap) ? 1 : 0);
     k_exact_count<<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, nullptr, ndocs, nullptr, counts, totals, status);
@@ -431,6 +513,21 @@ extern "C" int obm_lex_batch(obm_handle *h, const uint8_t *bytes, const uint64_t
     OBM_CUDA(h, cudaMemcpyAsync(hstatus, h->d_status, sizeof hstatus, cudaMemcpyDeviceToHost, st));
     OBM_CUDA(h, cudaMemcpyAsync(hcounts, h->d_counts, sizeof hcounts, cudaMemcpyDeviceToHost, st));
     OBM_CUDA(h, cudaStreamSynchronize(st));
+    if (hstatus[ST_RESERVED] && h->mode != 1) {
+        /* the pipeline's work-record buffers overflowed (input far denser in markers than manifests are):
+         * redo this batch with the exact kernels, which have no such limit */
+        const int saved = h->mode;
+        h->mode = 1;
+        rc = lex_device_impl(h, h->d_bytes, h->d_doc_off, ndocs, total, (out && out_cap) ? h->d_out : nullptr, out_cap,
+                             h->d_tuple_off, nullptr, nullptr, st);
+        h->mode = saved;
+        if (rc != OBM_OK) return rc;
+        OBM_CUDA(h, cudaEventRecord(h->ev[2], st));
+        OBM_CUDA(h, cudaMemcpyAsync(doc_tuple_off, h->d_tuple_off, ((uint64_t)ndocs + 1) * 8, cudaMemcpyDeviceToHost, st));
+        OBM_CUDA(h, cudaMemcpyAsync(hstatus, h->d_status, sizeof hstatus, cudaMemcpyDeviceToHost, st));
+        OBM_CUDA(h, cudaMemcpyAsync(hcounts, h->d_counts, sizeof hcounts, cudaMemcpyDeviceToHost, st));
+        OBM_CUDA(h, cudaStreamSynchronize(st));
+    }
     uint64_t ntup = doc_tuple_off[ndocs];
     *out_count = ntup;
     int result = OBM_OK;

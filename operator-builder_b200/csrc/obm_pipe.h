@@ -1,0 +1,151 @@
+/*
+ * obm_pipe.h -- host/device logic of the three-stage pipeline (mode 0), on top of obm_tile.h:
+ *
+ *   K1 scan      per 16 KiB tile, shared-memory resident: TMA stage, classify, bit-parallel line scan,
+ *                owner classification.  Emits compact work records to HBM instead of lexing:
+ *                  item  (8 B)  one per line that owns tuples, in position order
+ *                  mline (16 B) one per MARKER line (a line containing '+'), dense list for K2
+ *   K2 markers   one thread per marker line, any order, thousands of lines in flight per SM: the ASCII
+ *                instantiation of obm::Lexer runs straight off HBM/L2 (the line was streamed by K1 moments
+ *                ago).  Pass 1 counts the line's tuples; pass 2 (after K3) writes them at their final place
+ *   K3 assemble  per tile again, no input bytes needed: tuple counts -> decoupled look-back -> final
+ *                ordered positions; plain comment lines are materialised from their item, every marker line
+ *                gets its output offset, documents that K1/K2 flagged (non-ASCII, interacting lines) are
+ *                re-lexed sequentially by the exact (Unicode) instantiation
+ *
+ * Why three kernels: in the fused tile kernel (obm_fast.cuh, mode 2) the marker phase is a long dependent
+ * chain on a few warps while shared memory caps residency at 3 CTAs/SM (profiles/r01_*): latency-bound at
+ * 19 % issue utilisation.  Splitting lets every stage run dense at full occupancy; the price is ~0.25 B/B
+ * of extra HBM traffic (items, and marker lines re-read twice from L2/HBM) and lexing marker lines twice.
+ */
+#ifndef OBM_PIPE_H
+#define OBM_PIPE_H
+
+#include "obm_tile.h"
+
+namespace obmp {
+
+using obmt::Smem;
+
+
+/* ---- item: one line that owns tuples (8 bytes) ---------------------------------------------------
+ *  bits  0..13  ls    line start, document-relative (documents on this path are <= 16,368 B)
+ *  bits 14..27  pos   marker line: first special byte; plain line: comment start (document-relative)
+ *  bits 28..41  line  line number (1-based)
+ *  bit  42      marker line
+ *  bit  43      plain line whose comment is "//"
+ *  bit  44      dead (the line has specials but produces no tuple)
+ *  bits 45..50  doc   document index inside the sub-batch (< DMAX = 64)
+ *  marker lines: bits 51..63 unused; their slot number lives in item_slot[] */
+typedef uint64_t item_t;
+OBM_HD item_t make_item(uint32_t ls, uint32_t pos, uint32_t line, bool marker, bool slash2, bool dead, uint32_t d) {
+    return (item_t)ls | ((item_t)pos << 14) | ((item_t)line << 28) | ((item_t)marker << 42) | ((item_t)slash2 << 43) |
+           ((item_t)dead << 44) | ((item_t)d << 45);
+}
+OBM_HD uint32_t it_ls(item_t i) { return (uint32_t)(i & 0x3FFF); }
+OBM_HD uint32_t it_pos(item_t i) { return (uint32_t)((i >> 14) & 0x3FFF); }
+OBM_HD uint32_t it_line(item_t i) { return (uint32_t)((i >> 28) & 0x3FFF); }
+OBM_HD bool it_marker(item_t i) { return (i >> 42) & 1; }
+OBM_HD bool it_slash2(item_t i) { return (i >> 43) & 1; }
+OBM_HD bool it_dead(item_t i) { return (i >> 44) & 1; }
+OBM_HD uint32_t it_doc(item_t i) { return (uint32_t)((i >> 45) & 0x3F); }
+
+/* ---- mline: what K2 needs to lex one marker line (16 bytes) ---------------------------------------- */
+struct MLine { uint32_t doc; uint32_t ls_first; uint32_t line; uint32_t line_end; };
+/* ls_first = ls | first << 16 (document-relative, 14 bits each); line_end = offset of the line's '\n' (or doc length) */
+
+/* K2 result per marker line */
+OBM_HD uint32_t make_mres(uint32_t tuples, bool irregular) { return tuples | (irregular ? 0x80000000u : 0u); }
+OBM_HD uint32_t mres_tuples(uint32_t r) { return r & 0x7FFFFFFFu; }
+OBM_HD bool mres_irregular(uint32_t r) { return r >> 31; }
+
+/* document flags (u32 per document) */
+enum : uint32_t { GF_NONASCII = 1, GF_INTERACT = 2, GF_QOVERFLOW = 4, GF_LARGE = 8 };
+
+/* ---- K1: owner o of the sub-batch -> item (+ mline for marker lines) -----------------------------
+ * S.owner[o] holds the position of the line's first special byte (line scan output). */
+struct K1Out { item_t item; bool is_marker; MLine ml; };
+OBM_FN K1Out k1_owner(const Smem &S, uint32_t o, uint32_t doc_global_base) {
+    uint32_t first = S.owner[o];
+    uint32_t ls = obmt::line_start_of(S, first);
+    uint32_t d = obmt::doc_of(S, ls);
+    uint32_t dpos = S.dstart[d], dend = S.dstart[d + 1];
+    K1Out r; r.is_marker = false;
+    uint32_t rec = S.dflag[d] ? obmt::OW_NONE : obmt::classify_line(S, first, ls);
+    if (rec == obmt::OW_NONE) { r.item = make_item(ls - dpos, first - dpos, 0, false, false, true, d); return r; }
+    uint32_t line = 1 + obmt::nl_before(S, ls) - obmt::nl_before(S, dpos);
+    bool marker = (rec & obmt::OW_MARKER) != 0;
+    r.item = make_item(ls - dpos, obmt::ow_pos(rec) - dpos, line, marker, (rec & obmt::OW_SLASH2) != 0, false, d);
+    if (marker) {
+        /* end of the line: next newline bit at or after `first` (virtual newlines end the document's last line) */
+        uint32_t e = first;
+        for (;;) { if (e >= dend) { e = dend; break; } if (obmt::is_nl(S, e) && S.data[e] == '\n') break; uint32_t nx = obmt::next_event(S, e + 1); e = nx; }
+        r.is_marker = true;
+        r.ml.doc = doc_global_base + d;
+        r.ml.ls_first = (ls - dpos) | ((first - dpos) << 16);
+        r.ml.line = line;
+        r.ml.line_end = e - dpos;
+    }
+    return r;
+}
+
+/* ---- K2: one marker line straight from global memory -------------------------------------------- */
+/* lex / lexComment skipping without bitmaps: the next byte in [p, line_end] that is '\n' or one of # ' + /
+ * (same contract as obm::NoAccel but 4 bytes per step on the aligned words of the line) */
+struct LineAccel {
+    const uint8_t *d; uint32_t line_end;
+    OBM_HD uint32_t next_interesting(uint32_t p) const {
+        while (p < line_end) {
+            uint32_t mis = (uint32_t)((uintptr_t)(d + p) & 3u);
+            uint32_t w = *reinterpret_cast<const uint32_t *>(d + p - mis);
+            uint32_t sp = obmt::zero_bytes4((w & 0xF3F3F3F3u) ^ 0x23232323u) >> mis;
+            if (sp) {
+#if defined(__CUDA_ARCH__)
+                uint32_t q = p + (uint32_t)(__ffs((int)sp) - 1);
+#else
+                uint32_t q = p + (uint32_t)__builtin_ctz(sp);
+#endif
+                return q < line_end ? q : line_end;
+            }
+            p += 4 - mis;
+        }
+        return line_end;
+    }
+};
+typedef obm::Lexer<obm::SmallSink, LineAccel, true> GLineLexer;
+
+/* Lexes one marker line of the document doc[0..n) held in global memory (aligned 4-byte words around the
+ * line are readable: see the buffer contract in obmarkers.h).  out/cap: nullptr/0 to count only.
+ * Returns make_mres(count, irregular); adds the line's MarkerStart / lexeme counts when asked. */
+OBM_HD_NOINLINE uint32_t k2_marker_line(const obm::Tables &T, const uint8_t *doc, uint32_t n, const MLine &ml, obm_tuple *out,
+                                        uint32_t cap, uint32_t *markers = nullptr, uint32_t *lexemes = nullptr) {
+    uint32_t ls = ml.ls_first & 0xFFFFu, first = ml.ls_first >> 16;
+    LineAccel acc{doc, ml.line_end};
+    obm::SmallSink sink(out, cap);
+    GLineLexer lx(T, doc, n, sink, first, ml.line, ls, !(ml.line == 1 && ls == 0), acc);
+    int st = lx.run<true>();
+    uint32_t end_line = lx.line_p - (st == obm::RUN_LINE_END ? 1u : 0u);
+    bool irregular = (st == obm::RUN_FATAL) || (end_line != ml.line);
+    if (markers) *markers += sink.n_markers;
+    if (lexemes) *lexemes += sink.n_lexemes;
+    return make_mres(sink.n_tuples, irregular);
+}
+
+/* ---- K3 ------------------------------------------------------------------------------------------ */
+/* tuples of a plain item: [LINE] Comment */
+OBM_HD uint32_t plain_count(item_t it) { return it_line(it) == 1 ? 1u : 2u; }
+OBM_HD void plain_write(item_t it, obm_tuple *out, uint64_t at, uint64_t cap) {
+    uint32_t k = 0;
+    if (it_line(it) != 1) { if (at < cap) out[at] = OBM_TUPLE(OBM_K_LINE, it_ls(it), it_line(it)); k = 1; }
+    if (at + k < cap) out[at + k] = OBM_TUPLE(OBM_K_COMMENT, it_pos(it), it_slash2(it) ? 2 : 1);
+}
+
+/* whole document through the exact (Unicode) lexer, from global memory */
+typedef obm::Lexer<obm::SmallSink, obm::NoAccel, false> GDocLexer;
+OBM_HD_NOINLINE int k3_doc_exact(const obm::Tables &T, const uint8_t *doc, uint32_t n, obm::SmallSink &sink) {
+    GDocLexer lx(T, doc, n, sink);
+    return lx.run<false>();
+}
+
+} /* namespace obmp */
+#endif

@@ -16,6 +16,7 @@ def build(force=False):
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_decode.cpp"),
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_core.h"),
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_tile.h"),
+            os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_pipe.h"),
             os.path.join(_ROOT, "include", "obmarkers.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-shared", "-o", so,
@@ -35,6 +36,8 @@ def lib():
         L.hs_tile_batch.restype = ctypes.c_uint64
         L.hs_tile_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64,
                                     ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+        L.hs_pipe_batch.restype = ctypes.c_uint64
+        L.hs_pipe_batch.argtypes = L.hs_tile_batch.argtypes
         L.hs_parse_float_err.argtypes = [ctypes.c_char_p, ctypes.c_uint32]
         L.hs_atoi_err.argtypes = [ctypes.c_char_p, ctypes.c_uint32]
         L.obm_decode_doc.restype = ctypes.c_int64
@@ -79,8 +82,9 @@ def fmt_tuples(tuples):
     return [(names.get(int(t) >> 59, int(t) >> 59), int(t) & 0xFFFFFFFF, (int(t) >> 32) & 0x7FFFFFF) for t in tuples]
 
 
-def tile_batch(docs, skew=0):
-    """CTA emulation of the tile fast path over a list of documents -> (tuples, doc_tuple_off, stats)."""
+def tile_batch(docs, skew=0, pipeline=False):
+    """CTA emulation of the tile fast path (fused kernel, or the 3-stage pipeline) over a list of documents
+    -> (tuples, doc_tuple_off, stats)."""
     L = lib()
     data = np.frombuffer(b"".join(docs) + b"\0", dtype=np.uint8).copy()
     off = np.zeros(len(docs) + 1, dtype=np.uint64)
@@ -90,6 +94,7 @@ def tile_batch(docs, skew=0):
     out = np.zeros(cap, dtype=np.uint64)
     toff = np.zeros(len(docs) + 1, dtype=np.uint64)
     stats = np.zeros(4, dtype=np.uint64)
-    n = L.hs_tile_batch(data.ctypes.data, off.ctypes.data, len(docs), out.ctypes.data, cap, toff.ctypes.data, skew, stats.ctypes.data)
+    fn = L.hs_pipe_batch if pipeline else L.hs_tile_batch
+    n = fn(data.ctypes.data, off.ctypes.data, len(docs), out.ctypes.data, cap, toff.ctypes.data, skew, stats.ctypes.data)
     assert n <= cap
     return out[:n].copy(), toff, stats

@@ -13,13 +13,15 @@ from tests import hostsim
 
 
 def check_batch(docs, skew=0):
-    tup, toff, stats = hostsim.tile_batch(docs, skew)
-    for i, doc in enumerate(docs):
-        want = hostsim.lex_doc(doc)
-        got = tup[int(toff[i]):int(toff[i + 1])]
-        if not np.array_equal(got, want):
-            raise AssertionError(f"doc {i} (skew {skew}) {doc[:300]!r}\n tile ={hostsim.fmt_tuples(got)[:50]}\n exact={hostsim.fmt_tuples(want)[:50]}")
-    assert int(toff[-1]) == len(tup)
+    """both device organisations -- the fused tile kernel and the 3-stage pipeline -- against the exact path"""
+    for pipeline in (False, True):
+        tup, toff, stats = hostsim.tile_batch(docs, skew, pipeline=pipeline)
+        for i, doc in enumerate(docs):
+            want = hostsim.lex_doc(doc)
+            got = tup[int(toff[i]):int(toff[i + 1])]
+            if not np.array_equal(got, want):
+                raise AssertionError(f"pipeline={pipeline} doc {i} (skew {skew}) {doc[:300]!r}\n tile ={hostsim.fmt_tuples(got)[:50]}\n exact={hostsim.fmt_tuples(want)[:50]}")
+        assert int(toff[-1]) == len(tup)
     return stats
 
 

@@ -388,6 +388,14 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     if (g3 > ntiles) g3 = ntiles;
     const uint32_t g2 = (uint32_t)dev_sms * 8u; /* persistent, grid-stride over the device-side marker-line list */
     obmq::k1_scan<<<g1, obmt::NT, smem1, st>>>(A);
+    if (getenv("OBM_DEBUG_K1")) {
+        uint32_t hc[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hc, A.ctl, sizeof hc, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[obm debug] after k1: err=%s ticket=%u n_mlines=%u (cap %llu) items_top=%llu (cap %llu) ovf=%u ntiles=%u ndocs=%u\n",
+                cudaGetErrorString(cudaGetLastError()), hc[0], hc[1], (unsigned long long)mc,
+                (unsigned long long)hc[4] | ((unsigned long long)hc[5] << 32), (unsigned long long)ic, hc[6], ntiles, ndocs);
+    }
     obmq::k2_markers<false><<<g2, 256, 0, st>>>(A);
     obmq::k3_assemble<<<g3, obmt::NT, 0, st>>>(A);
     uint32_t launches = 5;
@@ -395,6 +403,13 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
         obmq::k2_markers<true><<<g2, 256, 0, st>>>(A);
         k_exact_fill<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, lctl + 1, toff, d_out, out_cap);
         launches += 2;
+    }
+    if (getenv("OBM_DEBUG_END")) {
+        uint32_t hc[16];
+        cudaError_t e1 = cudaStreamSynchronize(st);
+        cudaMemcpy(hc, A.ctl, sizeof hc, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[obm debug] end: sync=%s last=%s t1=%u n_mlines=%u t3=%u items_top=%u ovf=%u d_out=%p g1=%u g2=%u g3=%u smem1=%zu\n",
+                cudaGetErrorString(e1), cudaGetErrorString(cudaGetLastError()), hc[0], hc[1], hc[2], hc[4], hc[6], (void *)d_out, g1, g2, g3, smem1);
     }
     /* work-record overflow -> status[3]: the caller must redo the scan with the exact kernels (mode 1) */
     OBM_CUDA(h, cudaMemcpyAsync(status + ST_RESERVED, A.ctl + obmq::CT_OVF, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));

@@ -178,6 +178,7 @@ k1_scan(PipeArgs A) {
 template <bool WRITE>
 __global__ void __launch_bounds__(256)
 k2_markers(PipeArgs A) {
+    if (A.ctl[CT_OVF]) return; /* work records overflowed in k1: the host redoes the batch with the exact kernels */
     const obm::Tables T = dev_tables();
     const uint32_t n = min(A.ctl[CT_NML], (uint32_t)min(A.mlines_cap, (uint64_t)0xFFFFFFFFu));
     uint32_t markers = 0, lexemes = 0;
@@ -325,6 +326,7 @@ __global__ void __launch_bounds__(obmt::NT)
 k3_assemble(PipeArgs A) {
     __shared__ K3Shared K;
     const uint32_t tid = threadIdx.x;
+    if (A.ctl[CT_OVF]) return; /* see k2_markers */
     const obm::Tables T = dev_tables();
     if (tid < 4) K.stats[tid] = 0;
     __syncthreads();

@@ -244,7 +244,7 @@ struct SmallSink {
         if (n_tuples < cap) out[n_tuples] = OBM_TUPLE(kind, off, len);
         n_tuples++;
         n_markers += (kind == OBM_K_MARKER_START);
-        n_lexemes += (kind <= OBM_K_EOF) || (kind >= OBM_K_WARN_NOSCOPE);
+        n_lexemes += (kind - (uint32_t)OBM_K_PART) > 4u; /* everything but PART, FLUSH, DRIFT, LINE, LINEHI (21..25) */
     }
 };
 
@@ -299,7 +299,7 @@ struct Lexer {
     uint32_t last_type;                 /* l.lastEmittedLexeme.Type */
     Sink &out;
     Accel accel;
-    int32_t wbase; uint32_t wmask;      /* ASCII only: cached 32-byte window of "not a letter" bits */
+    int32_t wbase; uint32_t wm0, wm1, wm2, wm3; /* ASCII only: cached 128 bytes of "not a letter" bits from wbase */
 
     /* A lexer instance begins at byte `start_off` of line `first_line`, whose first byte is at
      * `line_base` (document start: 0, 1, 0).  `announce_first`: the first located tuple must be
@@ -309,7 +309,7 @@ struct Lexer {
         : T(t), d(doc), n(len), p(start_off), s(start_off), line_p(first_line), base_p(line_base), drift_p(0),
           line_s(first_line), base_s(line_base), line_e(announce_first ? 0u : 1u), base_e(0),
           sv_line(first_line), sv_base(line_base), sv_drift(0), last_w(0), last_r(RUNE_EOF), last_type(0), out(sink), accel(acc),
-          wbase(-0x40000000), wmask(0) {}
+          wbase(-0x40000000), wm0(0), wm1(0), wm2(0), wm3(0) {}
 
     /* ---- tuple plumbing ---- */
     OBM_HD void ensure_line(uint32_t line, uint32_t base) {
@@ -399,16 +399,36 @@ struct Lexer {
         uint32_t non = (~(ge & ~gt) >> 7) & 0x01010101u;
         return (non * 0x00204081u >> 21) & 0xFu;
     }
+    /* Computes the non-letter bits of the 128 bytes starting at the aligned word that holds byte q.  Done
+     * once per marker line, by every lane of the warp at the same time (converged): 32 independent word
+     * loads and ~10 ALU ops per word.  The window is read as aligned 32-bit words and may extend a few
+     * bytes around the document inside the staged buffer; words past the document end are not loaded. */
+    OBM_HD void fill_windows(uint32_t q) {
+        const uint8_t *a = d + q;
+        const uint32_t mis = (uint32_t)((uintptr_t)a & 3u);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(a - mis);
+        const uint32_t wlim = n - q + mis; /* bytes from the window start to the end of the document */
+        uint32_t m[4];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            uint32_t mk = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const uint32_t wi = (uint32_t)(g * 8 + k); mk |= nonletter4(wi * 4u < wlim ? w[wi] : 0u) << (4 * k); }
+            m[g] = mk;
+        }
+        wbase = (int32_t)q - (int32_t)mis; wm0 = m[0]; wm1 = m[1]; wm2 = m[2]; wm3 = m[3];
+    }
     /* first position >= q (capped at n) whose byte is not an ASCII letter.  Every byte the lexer has to
      * look at (delimiters, quotes, digits, whitespace) is a non-letter, so identifier text is skipped 32
-     * bytes per step.  The window is read as aligned 32-bit words and may extend a few bytes around the
-     * document inside the staged buffer. */
+     * bytes per step. */
     OBM_HD uint32_t next_nonletter(uint32_t q) {
         for (;;) {
             if (q >= n) return n;
-            uint32_t sh = (uint32_t)((int32_t)q - wbase);
-            if (sh < 32u) {
-                uint32_t m = wmask >> sh;
+            const uint32_t sh = (uint32_t)((int32_t)q - wbase);
+            if (sh < 128u) {
+                const uint32_t g = sh >> 5;
+                const uint32_t word = g == 0 ? wm0 : g == 1 ? wm1 : g == 2 ? wm2 : wm3;
+                const uint32_t m = word >> (sh & 31u);
                 if (m) {
 #if defined(__CUDA_ARCH__)
                     q += (uint32_t)(__ffs((int)m) - 1);
@@ -417,17 +437,10 @@ struct Lexer {
 #endif
                     return q < n ? q : n;
                 }
-                q = (uint32_t)(wbase + 32);
+                q = (uint32_t)(wbase + (int32_t)((g + 1u) * 32u));
                 continue;
             }
-            const uint8_t *a = d + q;
-            uint32_t mis = (uint32_t)((uintptr_t)a & 3u);
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(a - mis);
-            uint32_t mk = 0;
-            const uint32_t wlim = n - q + mis; /* bytes from the window start to the end of the document */
-#pragma unroll
-            for (int k = 0; k < 8; k++) mk |= nonletter4((uint32_t)(4 * k) < wlim ? w[k] : 0u) << (4 * k);
-            wbase = (int32_t)q - (int32_t)mis; wmask = mk;
+            fill_windows(q); /* beyond the cached 128 bytes (long line): refill from here */
         }
     }
 
@@ -473,7 +486,7 @@ struct Lexer {
     /* ---- marker states; each returns the top-level state to continue in ---- */
     /* state.go:60-68, entered with '+' just consumed */
     OBM_HD int marker_start() {
-        if (ASCII ? is_letter_ascii(peek()) : is_letter(T, peek())) { emit(OBM_K_MARKER_START); return ASCII ? fast_marker() : lex_marker(); }
+        if (ASCII ? is_letter_ascii(peek()) : is_letter(T, peek())) { emit(OBM_K_MARKER_START); return lex_marker(); }
         return TOP_COMMENT;
     }
     /* ---- ASCII fast machine: the well-formed marker grammar, ONE token (one emit site) per loop
@@ -491,77 +504,103 @@ struct Lexer {
             q++;
         }
     }
-    OBM_HD int fast_marker() {
-        enum { F_NAME1, F_COLON, F_ASSIGN, F_VALUE, F_STRBODY, F_STRCLOSE, F_MORE, F_NAME2 };
-        enum { X_NONE, X_DONE, X_LEX_MARKER, X_LEX_ARGS, X_LEX_VALUE, X_LEX_MORE }; /* how the loop ends */
-        uint32_t st = F_NAME1, send = 0, exit_code = X_NONE;
-        do {
-            uint32_t kind = 0, end = p, syn = 0, nst = st;
-            const uint32_t c0 = peek_byte();
-            if (st == F_NAME1 || st == F_NAME2) {
-                end = scan_delim(p, false);
-                const uint32_t c = end < n ? d[end] : 0x100u;
-                const bool term = (c == ' ' || c == '\n' || c == 0x100u);
-                const uint32_t fb = st == F_NAME1 ? X_LEX_MARKER : X_LEX_ARGS;
-                if (end == p) exit_code = fb;
-                else if (st == F_NAME1 && c == ':') { kind = OBM_K_SCOPE; nst = F_COLON; }
-                else if (st == F_NAME1 && last_type != OBM_K_SEPARATOR) exit_code = fb;
-                else {
-                    kind = OBM_K_ARG;
-                    if (c == '=') nst = F_ASSIGN;
-                    else if (term) { syn = 3; nst = F_MORE; }
-                    else if (st == F_NAME2 && c == ',') { syn = 1; nst = F_MORE; }
-                    else exit_code = fb;
-                }
-            } else if (st == F_VALUE) {
-                if (c0 == '\'' || c0 == '"' || c0 == '`') {
-                    uint32_t e = p + 1; /* closing quote on this line? */
-                    for (;;) { e = next_nonletter(e); if (e >= n) break; uint32_t b = d[e]; if (b == c0 || b == '\n') break; e++; }
-                    if (e >= n || d[e] != c0) exit_code = X_LEX_VALUE;
-                    else { send = e; kind = OBM_K_QUOTE; end = p + 1; nst = F_STRBODY; }
-                } else {
-                    end = scan_delim(p, true);
-                    const uint32_t len = end - p;
-                    nst = F_MORE;
-                    if (len == 0 || is_space((int)c0)) exit_code = X_LEX_VALUE; /* \t \v \f \r may lead a bool literal (consume.go:37-47) */
-                    else if (c0 == '.' || c0 == '-' || is_digit_ascii((int)c0)) {
-                        /* -?digits[.digits], at most 17 bytes: valid and in range for Atoi / ParseFloat */
-                        uint32_t dots = 0, digits = 0; bool ok = len <= 17;
-                        for (uint32_t k = (c0 == '-') ? 1u : 0u; ok && k < len; k++) {
-                            uint32_t b = d[p + k];
-                            if (b == '.') dots++; else if (b >= '0' && b <= '9') digits++; else ok = false;
-                        }
-                        if (!ok || dots > 1 || digits == 0) exit_code = X_LEX_VALUE;
-                        kind = dots ? OBM_K_FLOAT_LITERAL : OBM_K_INTEGER_LITERAL;
-                    } else {
-                        const bool t4 = len >= 4 && d[p] == 't' && d[p + 1] == 'r' && d[p + 2] == 'u' && d[p + 3] == 'e';
-                        const bool f5 = len >= 5 && d[p] == 'f' && d[p + 1] == 'a' && d[p + 2] == 'l' && d[p + 3] == 's' && d[p + 4] == 'e';
-                        if ((t4 && len > 4) || (f5 && len > 5)) exit_code = X_LEX_VALUE;
-                        kind = (t4 || f5) ? OBM_K_BOOL_LITERAL : OBM_K_STRING_LITERAL;
+    /* The whole ASCII line machine -- top level (state.go:15-57) and marker grammar -- as ONE loop: every
+     * lane of a warp (each lexing its own line) iterates the same loop from the first special byte to the
+     * end of its line, so divergence is confined to one iteration (the if-chain rejoins before the single
+     * emit site).  Anything outside the simple grammar is handed to the generic state functions at a token
+     * boundary; they return the top-level state to continue in. */
+    template <bool LINE_MODE>
+    OBM_HD int run_ascii() {
+        enum { T_LEX, T_COMMENT, F_NAME1, F_COLON, F_ASSIGN, F_VALUE, F_STRBODY, F_STRCLOSE, F_MORE, F_NAME2 };
+        enum { X_NONE, X_EOF, X_LINE_END, X_LEX_MARKER, X_LEX_ARGS, X_LEX_VALUE, X_LEX_MORE };
+        uint32_t st = T_LEX, send = 0;
+        for (;;) {
+            uint32_t xc = X_NONE;
+            do {
+                uint32_t kind = 0, end = p, syn = 0, nst = st;
+                bool disc = false;
+                if (st <= T_COMMENT) {
+                    discard_to(accel.next_interesting(p));
+                    end = p;
+                    const uint32_t c0 = peek_byte();
+                    if (c0 == 0x100u) { if (st == T_LEX) xc = X_EOF; else nst = T_LEX; }
+                    else if (c0 == '+') { /* consumed(markerStart) -> lexMarkerStart, state.go:29,48,60-68 */
+                        next(); end = p;
+                        if (is_letter_ascii((int)peek_byte())) { kind = OBM_K_MARKER_START; nst = F_NAME1; } else nst = T_COMMENT;
+                    } else if (st == T_COMMENT) { if (c0 == '\n') nst = T_LEX; else disc = true; }
+                    else if (is_space((int)c0)) { disc = true; if (LINE_MODE && c0 == '\n') xc = X_LINE_END; }
+                    else if (c0 == '#') { next(); end = p; kind = OBM_K_COMMENT; nst = T_COMMENT; }
+                    else if (c0 == '/' && has_prefix2('/', '/')) { next(); next(); end = p; kind = OBM_K_COMMENT; nst = T_COMMENT; }
+                    else disc = true;
+                } else if (st == F_NAME1 || st == F_NAME2) {
+                    end = scan_delim(p, false);
+                    const uint32_t c = end < n ? d[end] : 0x100u;
+                    const bool term = (c == ' ' || c == '\n' || c == 0x100u);
+                    const uint32_t fb = st == F_NAME1 ? X_LEX_MARKER : X_LEX_ARGS;
+                    if (end == p) xc = fb;
+                    else if (st == F_NAME1 && c == ':') { kind = OBM_K_SCOPE; nst = F_COLON; }
+                    else if (st == F_NAME1 && last_type != OBM_K_SEPARATOR) xc = fb;
+                    else {
+                        kind = OBM_K_ARG;
+                        if (c == '=') nst = F_ASSIGN;
+                        else if (term) { syn = 3; nst = T_COMMENT; }
+                        else if (st == F_NAME2 && c == ',') { syn = 1; nst = F_MORE; }
+                        else xc = fb;
                     }
+                } else if (st == F_VALUE) {
+                    const uint32_t c0 = peek_byte();
+                    if (c0 == '\'' || c0 == '"' || c0 == '`') {
+                        uint32_t e = p + 1; /* closing quote on this line? */
+                        for (;;) { e = next_nonletter(e); if (e >= n) break; uint32_t bb = d[e]; if (bb == c0 || bb == '\n') break; e++; }
+                        if (e >= n || d[e] != c0) xc = X_LEX_VALUE;
+                        else { send = e; kind = OBM_K_QUOTE; end = p + 1; nst = F_STRBODY; }
+                    } else {
+                        end = scan_delim(p, true);
+                        const uint32_t len = end - p;
+                        nst = F_MORE;
+                        if (len == 0 || is_space((int)c0)) xc = X_LEX_VALUE; /* \t \v \f \r may lead a bool literal (consume.go:37-47) */
+                        else if (c0 == '.' || c0 == '-' || is_digit_ascii((int)c0)) {
+                            /* -?digits[.digits], at most 17 bytes: valid and in range for Atoi / ParseFloat */
+                            uint32_t dots = 0, digits = 0; bool ok = len <= 17;
+                            for (uint32_t k = (c0 == '-') ? 1u : 0u; ok && k < len; k++) {
+                                uint32_t bb = d[p + k];
+                                if (bb == '.') dots++; else if (bb >= '0' && bb <= '9') digits++; else ok = false;
+                            }
+                            if (!ok || dots > 1 || digits == 0) xc = X_LEX_VALUE;
+                            kind = dots ? OBM_K_FLOAT_LITERAL : OBM_K_INTEGER_LITERAL;
+                        } else {
+                            const bool t4 = len >= 4 && d[p] == 't' && d[p + 1] == 'r' && d[p + 2] == 'u' && d[p + 3] == 'e';
+                            const bool f5 = len >= 5 && d[p] == 'f' && d[p + 1] == 'a' && d[p + 2] == 'l' && d[p + 3] == 's' && d[p + 4] == 'e';
+                            if ((t4 && len > 4) || (f5 && len > 5)) xc = X_LEX_VALUE;
+                            kind = (t4 || f5) ? OBM_K_BOOL_LITERAL : OBM_K_STRING_LITERAL;
+                        }
+                    }
+                } else if (st == F_MORE) {
+                    const uint32_t c0 = peek_byte();
+                    if (c0 == ',') { kind = OBM_K_ARG_DELIMITER; end = p + 1; nst = F_NAME2; }
+                    else if (c0 == ' ' || c0 == '\n' || c0 == 0x100u) { syn = 2; nst = T_COMMENT; }
+                    else xc = X_LEX_MORE;
+                } else if (st == F_STRBODY) { kind = OBM_K_STRING_LITERAL; end = send; nst = F_STRCLOSE; }
+                else { /* single-byte tokens: ':' '=' closing quote */
+                    kind = st == F_COLON ? OBM_K_SEPARATOR : st == F_ASSIGN ? OBM_K_ARG_ASSIGNMENT : OBM_K_QUOTE;
+                    end = p + 1;
+                    nst = st == F_COLON ? F_NAME1 : st == F_ASSIGN ? F_VALUE : F_MORE;
                 }
-            } else if (st == F_MORE) {
-                if (c0 == ',') { kind = OBM_K_ARG_DELIMITER; end = p + 1; nst = F_NAME2; }
-                else if (c0 == ' ' || c0 == '\n' || c0 == 0x100u) { syn = 2; }
-                else exit_code = X_LEX_MORE;
-            } else if (st == F_STRBODY) { kind = OBM_K_STRING_LITERAL; end = send; nst = F_STRCLOSE; }
-            else { /* single-byte tokens: ':' '=' closing quote */
-                kind = st == F_COLON ? OBM_K_SEPARATOR : st == F_ASSIGN ? OBM_K_ARG_ASSIGNMENT : OBM_K_QUOTE;
-                end = p + 1;
-                nst = st == F_COLON ? F_NAME1 : st == F_ASSIGN ? F_VALUE : F_MORE;
-            }
-            if (exit_code == X_NONE) {
-                if (kind) { p = end; emit(kind); }
-                if (syn & 1u) emit_synthetic(OBM_K_SYNTHETIC_BOOL);
-                if (syn & 2u) { emit_synthetic(OBM_K_MARKER_END); exit_code = X_DONE; }
-                st = nst;
-            }
-        } while (exit_code == X_NONE);
-        /* one hand-over point per generic entry (keeps the loop small and its lanes converged) */
-        if (exit_code == X_DONE) return TOP_COMMENT;
-        if (exit_code == X_LEX_MARKER) return lex_marker();
-        if (exit_code == X_LEX_VALUE) return lex_arg_value();
-        return lex_more_args(exit_code == X_LEX_ARGS);
+                if (xc == X_NONE || xc == X_LINE_END) {
+                    if (disc) discard1();
+                    if (kind) { p = end; emit(kind); }
+                    if (syn & 1u) emit_synthetic(OBM_K_SYNTHETIC_BOOL);
+                    if (syn & 2u) emit_synthetic(OBM_K_MARKER_END);
+                    st = nst;
+                }
+            } while (xc == X_NONE);
+            if (xc == X_EOF) { if (!LINE_MODE) out.put(OBM_K_EOF, n, 0); return RUN_EOF; }
+            if (xc == X_LINE_END) return RUN_LINE_END;
+            /* one hand-over point per generic entry */
+            int top = xc == X_LEX_MARKER ? lex_marker() : xc == X_LEX_VALUE ? lex_arg_value() : lex_more_args(xc == X_LEX_ARGS);
+            if (top == TOP_FATAL) return RUN_FATAL;
+            st = top == TOP_LEX ? T_LEX : T_COMMENT;
+        }
     }
 
     /* state.go:71-116 */
@@ -662,6 +701,7 @@ struct Lexer {
      *      discarding the first top-level '\n'; otherwise runs to EOF and emits the EOF tuple. ---- */
     template <bool LINE_MODE>
     OBM_HD int run() {
+        if (ASCII) return run_ascii<LINE_MODE>();
         int st = TOP_LEX;
         for (;;) {
             if (st == TOP_LEX) {

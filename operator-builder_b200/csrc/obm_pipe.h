@@ -123,6 +123,7 @@ OBM_HD_NOINLINE uint32_t k2_marker_line(const obm::Tables &T, const uint8_t *doc
     LineAccel acc{doc, ml.line_end};
     obm::SmallSink sink(out, cap);
     GLineLexer lx(T, doc, n, sink, first, ml.line, ls, !(ml.line == 1 && ls == 0), acc);
+    lx.fill_windows(lx.p);
     int st = lx.run<true>();
     uint32_t end_line = lx.line_p - (st == obm::RUN_LINE_END ? 1u : 0u);
     bool irregular = (st == obm::RUN_FATAL) || (end_line != ml.line);

@@ -294,6 +294,7 @@ OBM_HD_NOINLINE LineResult run_marker_line(const Smem &S, const obm::Tables &T, 
     BitmapAccel acc{&S, dpos, dend};
     obm::SmallSink sink(out, cap);
     LineLexer lx(T, S.data + dpos, dend - dpos, sink, first - dpos, line, ls - dpos, !(line == 1 && ls == dpos), acc);
+    lx.fill_windows(lx.p);
     int st = lx.run<true>();
     uint32_t end_line = lx.line_p - (st == obm::RUN_LINE_END ? 1u : 0u);
     LineResult r;

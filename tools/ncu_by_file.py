@@ -5,6 +5,7 @@ import csv, subprocess, collections, sys
 rep, ndocs = sys.argv[1], int(sys.argv[2])
 which = sys.argv[3] if len(sys.argv) > 3 else None
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+kfilter = sys.argv[5] if len(sys.argv) > 5 else None  # substring of the kernel name
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 files = {}
@@ -14,7 +15,13 @@ for f in ["obm_core.h", "obm_tile.h", "obm_fast.cuh", "obm_lib.cu"]:
 ie = None; cur = None
 agg = collections.defaultdict(lambda: [0, 0, 0]); tot = [0, 0]
 lines = collections.defaultdict(lambda: [0, 0, 0])
+kcur = True
 for r in rows:
+    if len(r) >= 2 and r[0] == "Kernel Name":
+        kcur = (kfilter is None) or (kfilter in r[1])
+        continue
+    if not kcur:
+        continue
     if "Instructions Executed" in r:
         ie, ti, sm = r.index("Instructions Executed"), r.index("Thread Instructions Executed"), r.index("# Samples"); continue
     if ie is None or len(r) <= ie: continue

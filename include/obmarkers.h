@@ -161,6 +161,11 @@ int obm_generate_corpus_host(uint8_t *bytes, uint64_t *doc_off, uint32_t ndocs, 
  * kernel.  All produce the identical tuple stream.  Returns the old mode. */
 int obm_set_mode(obm_handle *h, int mode);
 
+/* obm_lex_batch pipelines host batches of at least two chunks: H2D of chunk k+1, the scan of chunk k and D2H of
+ * chunk k-1 overlap on three streams (pass pinned buffers, obm_pinned_alloc, for the copies to be asynchronous).
+ * Default chunk: 64 MiB (env OBM_CHUNK_MB).  Returns the previous value. */
+uint64_t obm_set_chunk_bytes(obm_handle *h, uint64_t bytes);
+
 /* Number of this library's kernels launched by the last scan call on this handle. */
 uint32_t obm_launches_last_call(const obm_handle *h);
 

@@ -11,7 +11,7 @@ OBM_OK, OBM_E_NO_DEVICE, OBM_E_CUDA, OBM_E_CAPACITY, OBM_E_ARG, OBM_E_NOMEM = 0,
 # every symbol include/obmarkers.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "obm_abi_version", "obm_create", "obm_destroy", "obm_last_error", "obm_lex_batch", "obm_lex_batch_device",
-    "obm_scratch_bytes", "obm_generate_corpus_device", "obm_generate_corpus_host", "obm_set_mode", "obm_pinned_alloc", "obm_launches_last_call",
+    "obm_scratch_bytes", "obm_generate_corpus_device", "obm_generate_corpus_host", "obm_set_mode", "obm_pinned_alloc", "obm_launches_last_call", "obm_set_chunk_bytes",
     "obm_pinned_free", "obm_stream_new", "obm_stream_next", "obm_stream_free", "obm_decode_doc", "obm_free",
 ]
 
@@ -60,6 +60,8 @@ def lib():
     L.obm_set_mode.argtypes = [vp, ctypes.c_int]
     L.obm_launches_last_call.argtypes = [vp]
     L.obm_launches_last_call.restype = u32
+    L.obm_set_chunk_bytes.argtypes = [vp, u64]
+    L.obm_set_chunk_bytes.restype = u64
     L.obm_pinned_alloc.argtypes = [u64]
     L.obm_pinned_alloc.restype = vp
     L.obm_pinned_free.argtypes = [vp]

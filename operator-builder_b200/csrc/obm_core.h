@@ -29,10 +29,19 @@
 #define OBM_HD __host__ __device__ __forceinline__
 #define OBM_FN __host__ __device__ inline
 #define OBM_HD_NOINLINE __host__ __device__ __noinline__
+/* hides a value from the optimiser: keeps the state variable of the line machine a run-time value so that
+ * the compiler cannot thread jumps from one state's code straight into the next (which would leave the
+ * lanes of a warp in different copies of the loop body and never reconverged) */
+#if defined(__CUDA_ARCH__)
+#define OBM_OPAQUE(x) asm volatile("" : "+r"(x))
+#else
+#define OBM_OPAQUE(x) ((void)0)
+#endif
 #else
 #define OBM_HD inline
 #define OBM_FN inline
 #define OBM_HD_NOINLINE inline
+#define OBM_OPAQUE(x) ((void)0)
 #endif
 
 namespace obm {
@@ -593,6 +602,8 @@ struct Lexer {
                     if (syn & 2u) emit_synthetic(OBM_K_MARKER_END);
                     st = nst;
                 }
+                OBM_OPAQUE(st);
+                OBM_OPAQUE(xc);
             } while (xc == X_NONE);
             if (xc == X_EOF) { if (!LINE_MODE) out.put(OBM_K_EOF, n, 0); return RUN_EOF; }
             if (xc == X_LINE_END) return RUN_LINE_END;

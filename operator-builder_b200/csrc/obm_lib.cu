@@ -201,7 +201,23 @@ struct obm_handle {
     uint64_t *d_tuple_off; uint64_t d_tuple_off_cap;
     obm_tuple *d_out; uint64_t d_out_cap;
     uint32_t *d_status; unsigned long long *d_counts;
-    int mode; /* 0 = auto (fast path + exact for irregular docs), 1 = exact path only */
+    /* obm_lex_batch pipelines large host batches in chunks over three slots: H2D of chunk k+1, scan of
+     * chunk k and D2H of chunk k-1 overlap (each slot has its own stream, staging and scratch) */
+    struct Slot {
+        cudaStream_t st; cudaEvent_t ev_scan;
+        uint8_t *d_bytes; uint64_t d_bytes_cap;
+        uint64_t *d_doc_off; uint64_t d_doc_off_cap;
+        uint64_t *d_tuple_off; uint64_t d_tuple_off_cap;
+        obm_tuple *d_out; uint64_t d_out_cap;
+        void *scratch; uint64_t scratch_bytes;
+        uint32_t *d_status; unsigned long long *d_counts;
+        uint64_t *h_doc_off; uint64_t h_doc_off_cap; /* pinned: rebased offsets of the chunk */
+        uint64_t *h_info;                             /* pinned: [0] total, [1..2] status words, [3..4] counts */
+        uint32_t d0, d1; uint64_t b0; bool busy;
+    } slots[3];
+    bool slots_ready;
+    uint64_t chunk_bytes; /* host batches of at least twice this size are pipelined in chunks */
+    int mode; /* 0 = three-stage pipeline, 1 = exact path only, 2 = fused tile kernel */
     uint32_t launches; /* kernels launched by the last obm_lex_batch_device call */
 };
 
@@ -245,6 +261,7 @@ extern "C" int obm_create(int device_ordinal, obm_handle **out) {
         set_err(nullptr, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete h; return OBM_E_CUDA;
     }
+    { const char *e = getenv("OBM_CHUNK_MB"); h->chunk_bytes = (uint64_t)(e && atoi(e) > 0 ? atoi(e) : 64) << 20; }
     const char *m = getenv("OBM_FORCE_EXACT");
     h->mode = (m && m[0] == '1') ? 1 : 0;
     *out = h;
@@ -257,6 +274,12 @@ extern "C" void obm_destroy(obm_handle *h) {
     cudaStreamSynchronize(h->stream);
     cudaFree(h->scratch); cudaFree(h->d_bytes); cudaFree(h->d_doc_off); cudaFree(h->d_tuple_off); cudaFree(h->d_out);
     cudaFree(h->d_status); cudaFree(h->d_counts);
+    if (h->slots_ready) for (auto &sl : h->slots) {
+        cudaStreamSynchronize(sl.st);
+        cudaFree(sl.d_bytes); cudaFree(sl.d_doc_off); cudaFree(sl.d_tuple_off); cudaFree(sl.d_out); cudaFree(sl.scratch);
+        cudaFree(sl.d_status); cudaFree(sl.d_counts); cudaFreeHost(sl.h_doc_off); cudaFreeHost(sl.h_info);
+        cudaEventDestroy(sl.ev_scan); cudaStreamDestroy(sl.st);
+    }
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -264,6 +287,9 @@ extern "C" void obm_destroy(obm_handle *h) {
 
 /* Number of this library's kernels the last obm_lex_batch_device / obm_lex_batch call launched. */
 extern "C" uint32_t obm_launches_last_call(const obm_handle *h) { return h ? h->launches : 0; }
+
+/* Chunk size of the overlapped host path (obm_lex_batch pipelines batches of >= 2 chunks). Returns the old value. */
+extern "C" uint64_t obm_set_chunk_bytes(obm_handle *h, uint64_t bytes) { uint64_t old = h->chunk_bytes; if (bytes >= 4096) h->chunk_bytes = bytes; return old; }
 
 /* Selects the scanning strategy: 0 = auto (default), 1 = exact path only. Returns the previous mode. */
 extern "C" int obm_set_mode(obm_handle *h, int mode) { int old = h->mode; h->mode = mode; return old; }
@@ -432,17 +458,18 @@ extern "C" uint64_t obm_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
 
 static int lex_device_impl(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
                            uint64_t total_bytes, void *d_out, uint64_t out_cap, void *d_doc_tuple_off,
-                           void *d_status, void *d_counts, cudaStream_t st) {
+                           void *d_status, void *d_counts, cudaStream_t st, void **scratch_p = nullptr, uint64_t *scratch_bytes_p = nullptr) {
     if (!h) return OBM_E_ARG;
     if (!d_doc_off || !d_doc_tuple_off || (ndocs && total_bytes && !d_bytes)) { set_err(h, "null device pointer"); return OBM_E_ARG; }
     OBM_CUDA(h, cudaSetDevice(h->device));
+    if (!scratch_p) { scratch_p = &h->scratch; scratch_bytes_p = &h->scratch_bytes; }
     uint64_t need = obm_scratch_bytes(ndocs, total_bytes);
-    if (h->scratch_bytes < need) {
-        if (h->scratch) { OBM_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->scratch); h->scratch = nullptr; h->scratch_bytes = 0; }
-        OBM_CUDA(h, cudaMalloc(&h->scratch, need));
-        h->scratch_bytes = need;
+    if (*scratch_bytes_p < need) {
+        if (*scratch_p) { OBM_CUDA(h, cudaStreamSynchronize(st)); cudaFree(*scratch_p); *scratch_p = nullptr; *scratch_bytes_p = 0; }
+        OBM_CUDA(h, cudaMalloc(scratch_p, need));
+        *scratch_bytes_p = need;
     }
-    uint8_t *sc = (uint8_t *)h->scratch;
+    uint8_t *sc = (uint8_t *)*scratch_p;
     uint32_t *counts = (uint32_t *)sc; sc += align_up((uint64_t)ndocs * 4 + 4, 256);
     uint64_t *tile_sums = (uint64_t *)sc; sc += align_up((uint64_t)scan_tiles(ndocs) * 8 + 8, 256);
     void *fast_ws = sc; sc += align_up(obm_fast_scratch_bytes(ndocs, total_bytes), 256);
@@ -481,6 +508,131 @@ extern "C" int obm_lex_batch_device(obm_handle *h, const void *d_bytes, const vo
                            (cudaStream_t)stream);
 }
 
+
+/* ---- chunked, overlapped host path ------------------------------------------------------------------- */
+static int slots_init(obm_handle *h) {
+    if (h->slots_ready) return OBM_OK;
+    for (auto &sl : h->slots) {
+        memset(&sl, 0, sizeof sl);
+        OBM_CUDA(h, cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));
+        OBM_CUDA(h, cudaEventCreateWithFlags(&sl.ev_scan, cudaEventDisableTiming));
+        OBM_CUDA(h, cudaMalloc(&sl.d_status, 4 * sizeof(uint32_t)));
+        OBM_CUDA(h, cudaMalloc(&sl.d_counts, 2 * sizeof(unsigned long long)));
+        OBM_CUDA(h, cudaHostAlloc((void **)&sl.h_info, 8 * sizeof(uint64_t), cudaHostAllocDefault));
+    }
+    h->slots_ready = true;
+    return OBM_OK;
+}
+
+/* enqueue H2D + scan + info D2H of documents [d0, d1) on slot sl */
+static int chunk_issue(obm_handle *h, obm_handle::Slot &sl, const uint8_t *bytes, const uint64_t *doc_off, uint32_t d0, uint32_t d1,
+                       bool want_out) {
+    const uint32_t nd = d1 - d0;
+    const uint64_t b0 = doc_off[d0], nb = doc_off[d1] - b0;
+    int rc;
+    if ((rc = ensure(h, &sl.d_bytes, &sl.d_bytes_cap, nb + 64)) != OBM_OK) return rc;
+    if ((rc = ensure(h, &sl.d_doc_off, &sl.d_doc_off_cap, (uint64_t)nd + 1)) != OBM_OK) return rc;
+    if ((rc = ensure(h, &sl.d_tuple_off, &sl.d_tuple_off_cap, (uint64_t)nd + 1)) != OBM_OK) return rc;
+    const uint64_t cap = want_out ? nb / 4 + 2ull * nd + 1024 : 0; /* 2 B of tuples per input byte: ~6x what manifests need */
+    if (want_out && (rc = ensure(h, &sl.d_out, &sl.d_out_cap, cap)) != OBM_OK) return rc;
+    if (sl.h_doc_off_cap < (uint64_t)nd + 1) {
+        if (sl.h_doc_off) cudaFreeHost(sl.h_doc_off);
+        sl.h_doc_off = nullptr; sl.h_doc_off_cap = 0;
+        uint64_t want = (uint64_t)nd + 1 + nd / 8 + 64;
+        OBM_CUDA(h, cudaHostAlloc((void **)&sl.h_doc_off, want * 8, cudaHostAllocDefault));
+        sl.h_doc_off_cap = want;
+    }
+    for (uint32_t d = 0; d <= nd; d++) sl.h_doc_off[d] = doc_off[d0 + d] - b0;
+    OBM_CUDA(h, cudaMemcpyAsync(sl.d_doc_off, sl.h_doc_off, ((uint64_t)nd + 1) * 8, cudaMemcpyHostToDevice, sl.st));
+    if (nb) OBM_CUDA(h, cudaMemcpyAsync(sl.d_bytes, bytes + b0, nb, cudaMemcpyHostToDevice, sl.st));
+    rc = lex_device_impl(h, sl.d_bytes, sl.d_doc_off, nd, nb, want_out ? sl.d_out : nullptr, want_out ? sl.d_out_cap : 0, sl.d_tuple_off,
+                         sl.d_status, sl.d_counts, sl.st, &sl.scratch, &sl.scratch_bytes);
+    if (rc != OBM_OK) return rc;
+    OBM_CUDA(h, cudaMemcpyAsync(&sl.h_info[0], sl.d_tuple_off + nd, 8, cudaMemcpyDeviceToHost, sl.st));
+    OBM_CUDA(h, cudaMemcpyAsync(&sl.h_info[1], sl.d_status, 16, cudaMemcpyDeviceToHost, sl.st));
+    OBM_CUDA(h, cudaMemcpyAsync(&sl.h_info[3], sl.d_counts, 16, cudaMemcpyDeviceToHost, sl.st));
+    OBM_CUDA(h, cudaEventRecord(sl.ev_scan, sl.st));
+    sl.d0 = d0; sl.d1 = d1; sl.b0 = b0; sl.busy = true;
+    return OBM_OK;
+}
+
+struct ChunkTotals { uint64_t tuples, markers, lexemes, exact, fatal; bool overflow, need_exact; };
+
+/* wait for the slot's scan, then enqueue the D2H of its tuples / offsets at their final host positions */
+static int chunk_retire(obm_handle *h, obm_handle::Slot &sl, obm_tuple *out, uint64_t out_cap, uint64_t *doc_tuple_off,
+                        uint64_t *chunk_base /* per document's chunk base, filled for the fix-up */, ChunkTotals &T) {
+    OBM_CUDA(h, cudaEventSynchronize(sl.ev_scan));
+    const uint32_t nd = sl.d1 - sl.d0;
+    const uint64_t total = sl.h_info[0];
+    const uint32_t *st = (const uint32_t *)&sl.h_info[1];
+    if (st[ST_RESERVED]) T.need_exact = true;       /* work-record overflow: the caller redoes the batch with the exact kernels */
+    if (st[ST_OVERFLOW] && out) T.overflow = true;  /* the slot's tuple buffer was too small for this chunk */
+    const uint64_t base = T.tuples;
+    *chunk_base = base;
+    OBM_CUDA(h, cudaMemcpyAsync(doc_tuple_off + sl.d0, sl.d_tuple_off, (uint64_t)nd * 8, cudaMemcpyDeviceToHost, sl.st));
+    if (out && !T.overflow && !T.need_exact && base + total <= out_cap && total)
+        OBM_CUDA(h, cudaMemcpyAsync(out + base, sl.d_out, total * sizeof(obm_tuple), cudaMemcpyDeviceToHost, sl.st));
+    T.tuples += total; T.markers += sl.h_info[3]; T.lexemes += sl.h_info[4]; T.exact += st[ST_DOCS_EXACT]; T.fatal += st[ST_DOCS_FATAL];
+    sl.busy = false;
+    return OBM_OK;
+}
+
+/* returns 1 when the batch was handled here, 0 to let the caller use the single-shot path, <0 on error */
+static int lex_batch_chunked(obm_handle *h, const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs, obm_tuple *out, uint64_t out_cap,
+                             uint64_t *out_count, uint64_t *doc_tuple_off, obm_stats *stats, int *result) {
+    const uint64_t chunk_bytes = h->chunk_bytes;
+    const uint64_t total = doc_off[ndocs] - doc_off[0];
+    if (total < 2 * chunk_bytes || ndocs < 4) return 0;
+    int rc;
+    if ((rc = slots_init(h)) != OBM_OK) return rc;
+    OBM_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    ChunkTotals T = {0, 0, 0, 0, 0, false, false};
+    /* chunk boundaries (document aligned) and the per-chunk tuple base for the final offset fix-up */
+    struct Ck { uint32_t d0, d1; uint64_t base; };
+    Ck *cks = nullptr; uint32_t nck = 0, capck = 0;
+    for (uint32_t d = 0; d < ndocs;) {
+        uint32_t e = d; const uint64_t lim = doc_off[d] + chunk_bytes;
+        while (e < ndocs && (doc_off[e + 1] <= lim || e == d)) e++;
+        if (nck == capck) { capck = capck ? capck * 2 : 64; cks = (Ck *)realloc(cks, capck * sizeof(Ck)); if (!cks) return OBM_E_NOMEM; }
+        cks[nck++] = Ck{d, e, 0};
+        d = e;
+    }
+    int err = OBM_OK;
+    for (uint32_t k = 0; k < nck + 2 && err == OBM_OK; k++) {
+        if (k < nck) {
+            obm_handle::Slot &sl = h->slots[k % 3];
+            /* the slot's previous chunk (k-3) was retired two iterations ago; its D2H copies are still queued on the
+             * slot's stream, in order, ahead of this chunk's H2D -- only the pinned offsets staging needs the host to wait */
+            if (k >= 3) { cudaError_t e_ = cudaStreamSynchronize(sl.st); if (e_ != cudaSuccess) { set_err(h, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e_)); err = OBM_E_CUDA; break; } }
+            err = chunk_issue(h, sl, bytes, doc_off, cks[k].d0, cks[k].d1, out != nullptr && out_cap > 0);
+            if (err != OBM_OK) break;
+        }
+        if (k >= 2 && k - 2 < nck) err = chunk_retire(h, h->slots[(k - 2) % 3], out, out_cap, doc_tuple_off, &cks[k - 2].base, T);
+    }
+    for (auto &sl : h->slots) cudaStreamSynchronize(sl.st);
+    if (err != OBM_OK) { free(cks); return err; }
+    if (T.need_exact || T.overflow) { free(cks); return 0; } /* rare: let the single-shot path (with its own fallbacks) redo the batch */
+    for (uint32_t k = 0; k < nck; k++) { const uint64_t b = cks[k].base; if (b) for (uint32_t d = cks[k].d0; d < cks[k].d1; d++) doc_tuple_off[d] += b; }
+    free(cks);
+    doc_tuple_off[ndocs] = T.tuples;
+    *out_count = T.tuples;
+    *result = OBM_OK;
+    if (T.tuples > out_cap || (!out && T.tuples > 0)) {
+        set_err(h, "output capacity %llu < %llu tuples required", (unsigned long long)out_cap, (unsigned long long)T.tuples);
+        *result = OBM_E_CAPACITY;
+    }
+    OBM_CUDA(h, cudaEventRecord(h->ev[3], h->stream));
+    OBM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->n_tuples = T.tuples; stats->n_markers = T.markers; stats->n_lexemes = T.lexemes;
+        stats->n_docs_exact = T.exact; stats->n_docs_fatal = T.fatal; stats->bytes = total;
+        cudaEventElapsedTime(&stats->ms_total, h->ev[0], h->ev[3]);
+        stats->ms_kernels = 0.f; /* scans overlap the copies in this path; see the device entry point for kernel time */
+    }
+    return 1;
+}
+
 extern "C" int obm_lex_batch(obm_handle *h, const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs,
                              obm_tuple *out, uint64_t out_cap, uint64_t *out_count, uint64_t *doc_tuple_off,
                              obm_stats *stats) {
@@ -495,6 +647,12 @@ extern "C" int obm_lex_batch(obm_handle *h, const uint8_t *bytes, const uint64_t
     OBM_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     int rc;
+    {
+        int result = OBM_OK;
+        rc = lex_batch_chunked(h, bytes, doc_off, ndocs, out, out_cap, out_count, doc_tuple_off, stats, &result);
+        if (rc < 0) return rc;
+        if (rc == 1) return result;
+    }
     if ((rc = ensure(h, &h->d_bytes, &h->d_bytes_cap, total + 64)) != OBM_OK) return rc;
     if ((rc = ensure(h, &h->d_doc_off, &h->d_doc_off_cap, (uint64_t)ndocs + 1)) != OBM_OK) return rc;
     if ((rc = ensure(h, &h->d_tuple_off, &h->d_tuple_off_cap, (uint64_t)ndocs + 1)) != OBM_OK) return rc;

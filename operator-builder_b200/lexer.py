@@ -141,6 +141,9 @@ class Scanner:
     def set_mode(self, mode: int) -> int:
         return self._L.obm_set_mode(self._h, mode)
 
+    def set_chunk_bytes(self, nbytes: int) -> int:
+        return self._L.obm_set_chunk_bytes(self._h, nbytes)
+
     def lex_batch(self, data, doc_off, out: np.ndarray = None) -> BatchResult:
         """data: bytes-like / uint8 array of packed documents; doc_off: uint64[ndocs+1]."""
         buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data

@@ -134,6 +134,28 @@ def test_c2_10k_docs_bit_exact(scanner, oracle):
     scanner.set_mode(0)
 
 
+def test_chunked_overlapped_host_path(scanner, oracle):
+    """obm_lex_batch pipelines big host batches in chunks (H2D / scan / D2H overlapped): same result as one shot"""
+    import operator_builder_b200 as ob
+    data, off = ob.generate_corpus_host(3000, 4096)
+    rng = random.Random(5)
+    extra = [cu.fuzz_doc_valid(rng) for _ in range(500)] + [b"", b"+a:b=1e309\n# +c:d", "# +\u00e9:x=1\n".encode()]
+    docs = [data.tobytes()[i * 4096:(i + 1) * 4096] for i in range(3000)] + extra
+    pdata, poff = pack(docs)
+    one = scanner.lex_batch(pdata, poff)
+    old = scanner.set_chunk_bytes(1 << 20)
+    try:
+        for mode in (0, 1):
+            scanner.set_mode(mode)
+            res = scanner.lex_batch(pdata, poff)
+            assert np.array_equal(res.tuples, one.tuples) and np.array_equal(res.doc_tuple_off, one.doc_tuple_off), mode
+            assert res.stats["n_markers"] == one.stats["n_markers"] and res.stats["n_lexemes"] == one.stats["n_lexemes"]
+    finally:
+        scanner.set_mode(0)
+        scanner.set_chunk_bytes(old)
+    run_and_compare(scanner, oracle, docs[-600:], modes=(0,))
+
+
 def test_collection_flavour_and_odd_doc_sizes(scanner, oracle):
     import operator_builder_b200 as ob
     for doc_bytes, n in ((4096, 500), (1000, 700), (37, 100), (16384, 40), (70000, 6)):

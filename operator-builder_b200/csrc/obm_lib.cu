@@ -353,6 +353,7 @@ static int obm_fast_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
 }
 
 static uint64_t align_up(uint64_t v, uint64_t a);
+static uint32_t scan_tiles(uint32_t ndocs);
 /* pipeline (mode 0) work records: capacities are generous multiples of what manifests produce (one owning
  * line per ~68 B, one marker line per ~512 B); denser input sets the overflow flag and the scan is redone
  * by the exact kernels. */
@@ -368,7 +369,7 @@ static uint64_t pipe_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
  * k2_markers<write> -> exact fill of large documents. */
 static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t *d_doc_off, uint32_t ndocs, uint64_t total_bytes,
                            obm_tuple *d_out, uint64_t out_cap, uint64_t *toff, uint32_t *status, unsigned long long *totals,
-                           uint32_t *counts, void *fast_ws, void *pipe_ws, cudaStream_t st) {
+                           uint32_t *counts, uint64_t *tile_sums, void *fast_ws, void *pipe_ws, cudaStream_t st) {
     static bool attr_set = false;
     const size_t smem1 = sizeof(obmq::K1Shared);
     if (!attr_set) {
@@ -403,16 +404,15 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     obmf::k_tile_index<<<(ndocs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, ndocs, ntiles, tile_first, large_list, lctl + 1);
     const uint32_t nb_large = (uint32_t)((max_large + 127) / 128);
     k_exact_count<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, lctl + 1, counts, totals, status);
-    int dev_sms = 0, per_sm1 = 0, per_sm3 = 0;
+    int dev_sms = 0, per_sm1 = 0;
     OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
     OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, obmq::k1_scan, (int)obmt::NT, smem1));
-    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, obmq::k3_assemble, (int)obmt::NT, 0));
     if (per_sm1 < 1) per_sm1 = 1;
-    if (per_sm3 < 1) per_sm3 = 1;
-    uint32_t g1 = (uint32_t)dev_sms * (uint32_t)per_sm1, g3 = (uint32_t)dev_sms * (uint32_t)per_sm3;
+    uint32_t g1 = (uint32_t)dev_sms * (uint32_t)per_sm1;
     if (g1 > ntiles) g1 = ntiles;
-    if (g3 > ntiles) g3 = ntiles;
     const uint32_t g2 = (uint32_t)dev_sms * 8u; /* persistent, grid-stride over the device-side marker-line list */
+    const uint32_t gd = (ndocs + 255) / 256;
+    const uint32_t nt = scan_tiles(ndocs);
     obmq::k1_scan<<<g1, obmt::NT, smem1, st>>>(A);
     if (getenv("OBM_DEBUG_K1")) {
         uint32_t hc[16];
@@ -423,8 +423,12 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
                 (unsigned long long)hc[4] | ((unsigned long long)hc[5] << 32), (unsigned long long)ic, hc[6], ntiles, ndocs);
     }
     obmq::k2_markers<false><<<g2, 256, 0, st>>>(A);
-    obmq::k3_assemble<<<g3, obmt::NT, 0, st>>>(A);
-    uint32_t launches = 5;
+    obmq::k3_doc_count<<<gd, 256, 0, st>>>(A, counts);
+    k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(counts, ndocs, toff, tile_sums);
+    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, toff + ndocs);
+    k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(toff, ndocs, tile_sums, d_out ? out_cap : ~0ull, status);
+    obmq::k3_doc_write<<<gd, 256, 0, st>>>(A);
+    uint32_t launches = 9;
     if (d_out && out_cap) {
         obmq::k2_markers<true><<<g2, 256, 0, st>>>(A);
         k_exact_fill<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, lctl + 1, toff, d_out, out_cap);
@@ -434,8 +438,8 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
         uint32_t hc[16];
         cudaError_t e1 = cudaStreamSynchronize(st);
         cudaMemcpy(hc, A.ctl, sizeof hc, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[obm debug] end: sync=%s last=%s t1=%u n_mlines=%u t3=%u items_top=%u ovf=%u d_out=%p g1=%u g2=%u g3=%u smem1=%zu\n",
-                cudaGetErrorString(e1), cudaGetErrorString(cudaGetLastError()), hc[0], hc[1], hc[2], hc[4], hc[6], (void *)d_out, g1, g2, g3, smem1);
+        fprintf(stderr, "[obm debug] end: sync=%s last=%s t1=%u n_mlines=%u items_top=%u ovf=%u d_out=%p g1=%u g2=%u smem1=%zu\n",
+                cudaGetErrorString(e1), cudaGetErrorString(cudaGetLastError()), hc[0], hc[1], hc[4], hc[6], (void *)d_out, g1, g2, smem1);
     }
     /* work-record overflow -> status[3]: the caller must redo the scan with the exact kernels (mode 1) */
     OBM_CUDA(h, cudaMemcpyAsync(status + ST_RESERVED, A.ctl + obmq::CT_OVF, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
@@ -483,7 +487,7 @@ static int lex_device_impl(obm_handle *h, const void *d_bytes, const void *d_doc
 
     if (h->mode == 0)
         return obm_pipe_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
-                               (obm_tuple *)d_out, out_cap, toff, status, totals, counts, fast_ws, pipe_ws, st);
+                               (obm_tuple *)d_out, out_cap, toff, status, totals, counts, tile_sums, fast_ws, pipe_ws, st);
     if (h->mode == 2)
         return obm_fast_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
                                (obm_tuple *)d_out, out_cap, toff, status, totals, counts, fast_ws, st);

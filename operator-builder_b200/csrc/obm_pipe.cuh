@@ -5,8 +5,8 @@
  *   k2_markers  one thread per marker line, grid-stride over the device-side list: <WRITE=false> counts the
  *               line's tuples (and flags documents whose lines interact), <WRITE=true> runs after k3 and
  *               writes the tuples at their final position
- *   k3_assemble per tile: counts -> decoupled look-back -> doc_tuple_off; writes LINE/Comment of plain lines,
- *               EOF tuples, irregular documents (exact lexer), and each marker line's final offset
+ *   k3_doc_count / k3_doc_write   one thread per document: tuple counts (-> device-wide scan -> doc_tuple_off), then
+ *               LINE/Comment of plain lines, EOF tuples, irregular documents (exact lexer), marker-line offsets
  */
 #pragma once
 #include "obm_fast.cuh"
@@ -14,7 +14,7 @@
 
 namespace obmq {
 
-using obmt::Smem;
+using obmt::SmemScan;
 using obmp::item_t;
 using obmp::MLine;
 
@@ -45,22 +45,23 @@ __device__ __forceinline__ obm::Tables dev_tables() {
 
 /* ---------------------------------------------------------------------------------------------- K1 -- */
 struct K1Shared {
-    Smem S;
+    SmemScan S;
+    alignas(8) item_t sitems[obmt::QMAX]; /* items of the sub-batch (coalesced to HBM, searched per document) */
     alignas(8) uint64_t mbar;
     uint64_t item_base;
     uint32_t tile;
 };
 
-__global__ void __launch_bounds__(obmt::NT, 3)
+__global__ void __launch_bounds__(obmt::NT, 4)
 k1_scan(PipeArgs A) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     K1Shared &C = *reinterpret_cast<K1Shared *>(smem_raw);
-    Smem &S = C.S;
+    SmemScan &S = C.S;
     const uint32_t tid = threadIdx.x;
     if (tid == 0) { obmf::mbar_init(&C.mbar, 1); obmf::fence_mbar_init(); }
     __syncthreads();
     uint32_t mbar_phase = 0;
-    item_t *sitems = reinterpret_cast<item_t *>(S.stage); /* QMAX items fit in the staging area */
+    item_t *sitems = C.sitems;
     for (;;) {
         if (tid == 0) C.tile = atomicAdd(&A.ctl[CT_T1], 1u);
         __syncthreads();
@@ -209,104 +210,68 @@ k2_markers(PipeArgs A) {
 }
 
 /* ---------------------------------------------------------------------------------------------- K3 -- */
-struct K3Shared {
-    item_t items[obmt::QMAX];
-    uint32_t slot[obmt::QMAX];
-    uint32_t E[obmt::QMAX + 1];      /* exclusive prefix of item tuple counts */
-    uint64_t ioff[obmt::DMAX + 1];   /* doc_item_off */
-    uint32_t dn[obmt::DMAX];         /* doc_item_n */
-    uint32_t dfirst[obmt::DMAX + 1]; /* first item of each document, relative to the sub-batch */
-    uint32_t dflag[obmt::DMAX];
-    uint32_t dcnt[obmt::DMAX + 1];
-    uint32_t scan_tmp[obmt::NT / 32 + 1];
-    uint64_t base;
-    uint32_t tile, sub_total, n_items;
-    uint32_t stats[4];
-};
-
-/* loads the sub-batch's items and computes E[], per-document counts and offsets; returns the tuple total */
-__device__ __forceinline__ uint32_t k3_count(K3Shared &K, const PipeArgs &A, const obm::Tables &T, uint32_t da, uint32_t db) {
-    const uint32_t tid = threadIdx.x, nd = db - da;
-    if (tid < nd) { K.ioff[tid] = A.doc_item_off[da + tid]; K.dn[tid] = A.doc_item_n[da + tid]; K.dflag[tid] = A.doc_flag[da + tid]; }
-    __syncthreads();
-    {
-        uint32_t v = tid < nd ? K.dn[tid] : 0, tot;
-        uint32_t e = obmf::block_scan_excl(v, K.scan_tmp, tot);
-        if (tid < nd) K.dfirst[tid] = e;
-        if (tid == 0) { K.dfirst[nd] = tot; K.n_items = tot; }
-    }
-    __syncthreads();
-    const uint32_t n_items = K.n_items;
-    const uint64_t ibase = nd ? K.ioff[0] : 0; /* the sub-batch's items are contiguous in HBM */
-    for (uint32_t i = tid; i < n_items; i += obmt::NT) { K.items[i] = A.items[ibase + i]; K.slot[i] = A.item_slot[ibase + i]; }
-    __syncthreads();
-    {
-        uint32_t v[4], sum = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < 4; j++) {
-            uint32_t i = tid * 4 + j; v[j] = 0;
-            if (i < n_items) {
-                item_t it = K.items[i];
-                if (!obmp::it_dead(it) && !K.dflag[obmp::it_doc(it)])
-                    v[j] = obmp::it_marker(it) ? obmp::mres_tuples(A.mres[K.slot[i]]) : obmp::plain_count(it);
-            }
-            sum += v[j];
-        }
-        uint32_t etot;
-        uint32_t e = obmf::block_scan_excl(sum, K.scan_tmp, etot);
-#pragma unroll
-        for (uint32_t j = 0; j < 4; j++) { uint32_t i = tid * 4 + j; if (i < obmt::QMAX) K.E[i] = e; e += v[j]; }
-        if (tid == 0) K.E[obmt::QMAX] = etot;
-    }
-    __syncthreads();
-    if (tid == 0 && n_items < obmt::QMAX) K.E[n_items] = K.E[obmt::QMAX];
-    __syncthreads();
-    if (tid < nd) {
-        if (K.dflag[tid]) {
-            const uint64_t o0 = A.doc_off[da + tid];
-            obm::SmallSink sink(nullptr, 0);
-            obmp::k3_doc_exact(T, A.bytes + o0, (uint32_t)(A.doc_off[da + tid + 1] - o0), sink);
-            K.dcnt[tid] = sink.n_tuples;
-        } else {
-            K.dcnt[tid] = K.E[K.dfirst[tid + 1]] - K.E[K.dfirst[tid]] + 1; /* + EOF */
+/* One thread per DOCUMENT, no shared memory, no barriers: a document's items are contiguous in HBM, so the
+ * thread walks them twice -- k3_doc_count sums the tuple counts (the device-wide exclusive scan of those
+ * counts, k_scan_* in obm_lib.cu, then yields doc_tuple_off), k3_doc_write materialises plain comment lines
+ * and the EOF tuple and hands every marker line its final offset.  Flagged documents (non-ASCII, interacting
+ * lines) run the exact lexer here; large documents keep the count k_exact_count wrote. */
+__global__ void __launch_bounds__(256)
+k3_doc_count(PipeArgs A, uint32_t *__restrict__ counts) {
+    if (A.ctl[CT_OVF]) return; /* see k2_markers */
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= A.ndocs) return;
+    const uint32_t flag = A.doc_flag[d];
+    if (flag & obmp::GF_LARGE) return; /* counts[d] already holds the exact count */
+    uint32_t c;
+    if (flag) {
+        const obm::Tables T = dev_tables();
+        const uint64_t o0 = A.doc_off[d];
+        obm::SmallSink sink(nullptr, 0);
+        obmp::k3_doc_exact(T, A.bytes + o0, (uint32_t)(A.doc_off[d + 1] - o0), sink);
+        c = sink.n_tuples;
+    } else {
+        const uint64_t i0 = A.doc_item_off[d];
+        const uint32_t n = A.doc_item_n[d];
+        c = 1; /* EOF */
+        for (uint32_t i = 0; i < n; i++) {
+            const item_t it = A.items[i0 + i];
+            if (obmp::it_dead(it)) continue;
+            c += obmp::it_marker(it) ? obmp::mres_tuples(A.mres[A.item_slot[i0 + i]]) : obmp::plain_count(it);
         }
     }
-    __syncthreads();
-    {
-        uint32_t v = tid < nd ? K.dcnt[tid] : 0, dtot;
-        uint32_t e = obmf::block_scan_excl(v, K.scan_tmp, dtot);
-        if (tid < nd) K.dcnt[tid] = e;
-        if (tid == 0) { K.dcnt[nd] = dtot; K.sub_total = dtot; }
-    }
-    __syncthreads();
-    return K.sub_total;
+    counts[d] = c;
 }
 
-__device__ __forceinline__ void k3_fill(K3Shared &K, const PipeArgs &A, const obm::Tables &T, uint32_t da, uint32_t db, uint64_t base) {
-    const uint32_t tid = threadIdx.x, nd = db - da, n_items = K.n_items;
+__global__ void __launch_bounds__(256)
+k3_doc_write(PipeArgs A) {
+    if (A.ctl[CT_OVF]) return;
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t markers = 0, lexemes = 0, exact = 0, fatal = 0;
-    for (uint32_t i = tid; i < n_items; i += obmt::NT) {
-        item_t it = K.items[i];
-        uint32_t d = obmp::it_doc(it);
-        if (obmp::it_dead(it) || K.dflag[d]) continue;
-        uint64_t at = base + K.dcnt[d] + (K.E[i] - K.E[K.dfirst[d]]);
-        if (obmp::it_marker(it)) A.moff[K.slot[i]] = at;
-        else { if (A.out) obmp::plain_write(it, A.out, at, A.out_cap); lexemes += 1; }
-    }
-    if (tid < nd) {
-        const uint64_t at = base + K.dcnt[tid];
-        A.tuple_off[da + tid] = at;
-        const uint64_t o0 = A.doc_off[da + tid];
-        const uint32_t len = (uint32_t)(A.doc_off[da + tid + 1] - o0);
-        if (K.dflag[tid]) {
-            const uint64_t roomv = (A.out && at < A.out_cap) ? A.out_cap - at : 0;
-            obm::SmallSink sink(A.out + at, roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv);
+    if (d < A.ndocs) {
+        const uint32_t flag = A.doc_flag[d];
+        const uint64_t base = A.tuple_off[d];
+        const uint64_t o0 = A.doc_off[d];
+        const uint32_t len = (uint32_t)(A.doc_off[d + 1] - o0);
+        if (flag & obmp::GF_LARGE) {
+            /* written by k_exact_fill */
+        } else if (flag) {
+            const obm::Tables T = dev_tables();
+            const uint64_t roomv = (A.out && base < A.out_cap) ? A.out_cap - base : 0;
+            obm::SmallSink sink(A.out + base, roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv);
             int st = obmp::k3_doc_exact(T, A.bytes + o0, len, sink);
-            markers += sink.n_markers; lexemes += sink.n_lexemes; exact += 1; fatal += (st == obm::RUN_FATAL);
+            markers = sink.n_markers; lexemes = sink.n_lexemes; exact = 1; fatal = (st == obm::RUN_FATAL);
         } else {
-            const uint64_t eof_at = base + K.dcnt[tid + 1] - 1;
-            if (A.out && eof_at < A.out_cap) A.out[eof_at] = OBM_TUPLE(OBM_K_EOF, len, 0);
-            lexemes += 1;
+            const uint64_t i0 = A.doc_item_off[d];
+            const uint32_t n = A.doc_item_n[d];
+            uint64_t at = base;
+            for (uint32_t i = 0; i < n; i++) {
+                const item_t it = A.items[i0 + i];
+                if (obmp::it_dead(it)) continue;
+                if (obmp::it_marker(it)) { const uint32_t slot = A.item_slot[i0 + i]; A.moff[slot] = at; at += obmp::mres_tuples(A.mres[slot]); }
+                else { if (A.out) obmp::plain_write(it, A.out, at, A.out_cap); at += obmp::plain_count(it); lexemes++; }
+            }
+            if (A.out && at < A.out_cap) A.out[at] = OBM_TUPLE(OBM_K_EOF, len, 0);
+            lexemes++;
         }
     }
 #pragma unroll
@@ -314,55 +279,11 @@ __device__ __forceinline__ void k3_fill(K3Shared &K, const PipeArgs &A, const ob
         markers += __shfl_down_sync(0xffffffffu, markers, o); lexemes += __shfl_down_sync(0xffffffffu, lexemes, o);
         exact += __shfl_down_sync(0xffffffffu, exact, o); fatal += __shfl_down_sync(0xffffffffu, fatal, o);
     }
-    if ((tid & 31) == 0) {
-        if (markers) atomicAdd(&K.stats[0], markers);
-        if (lexemes) atomicAdd(&K.stats[1], lexemes);
-        if (exact) atomicAdd(&K.stats[2], exact);
-        if (fatal) atomicAdd(&K.stats[3], fatal);
-    }
-}
-
-__global__ void __launch_bounds__(obmt::NT)
-k3_assemble(PipeArgs A) {
-    __shared__ K3Shared K;
-    const uint32_t tid = threadIdx.x;
-    if (A.ctl[CT_OVF]) return; /* see k2_markers */
-    const obm::Tables T = dev_tables();
-    if (tid < 4) K.stats[tid] = 0;
-    __syncthreads();
-    for (;;) {
-        if (tid == 0) K.tile = atomicAdd(&A.ctl[CT_T3], 1u);
-        __syncthreads();
-        const uint32_t t = K.tile;
-        if (t >= A.ntiles) break;
-        const uint32_t d_first = A.tile_first[t], d_last = A.tile_first[t + 1];
-        uint32_t d_small_end = d_last, large_cnt = 0;
-        if (d_last > d_first && A.doc_off[d_last] - A.doc_off[d_last - 1] > obmt::MAXDOC) { d_small_end = d_last - 1; large_cnt = A.counts[d_last - 1]; }
-        const bool single = d_small_end - d_first <= obmt::DMAX;
-        uint64_t tile_total = large_cnt;
-        for (uint32_t da = d_first; da < d_small_end; da += obmt::DMAX) tile_total += k3_count(K, A, T, da, min(da + obmt::DMAX, d_small_end));
-        if (tid < 32) {
-            uint64_t base = obmf::lookback_warp(A.tile_state, t, tile_total);
-            if (tid == 0) {
-                K.base = base;
-                if (t == A.ntiles - 1) { A.tuple_off[A.ndocs] = base + tile_total; if (base + tile_total > A.out_cap) A.status[0] = 1; }
-            }
-        }
-        __syncthreads();
-        uint64_t base = K.base;
-        for (uint32_t da = d_first; da < d_small_end; da += obmt::DMAX) {
-            const uint32_t db = min(da + obmt::DMAX, d_small_end);
-            const uint32_t sub = single ? K.sub_total : k3_count(K, A, T, da, db);
-            k3_fill(K, A, T, da, db, base);
-            base += sub;
-            __syncthreads();
-        }
-        if (d_small_end < d_last && tid == 0) A.tuple_off[d_last - 1] = base;
-        __syncthreads();
-    }
-    if (tid < 4 && K.stats[tid]) {
-        if (tid < 2) atomicAdd(&A.totals[tid], (unsigned long long)K.stats[tid]);
-        else atomicAdd(&A.status[tid - 1], K.stats[tid]);
+    if ((threadIdx.x & 31) == 0) {
+        if (markers) atomicAdd(&A.totals[0], (unsigned long long)markers);
+        if (lexemes) atomicAdd(&A.totals[1], (unsigned long long)lexemes);
+        if (exact) atomicAdd(&A.status[1], exact);
+        if (fatal) atomicAdd(&A.status[2], fatal);
     }
 }
 

@@ -25,7 +25,7 @@
 
 namespace obmp {
 
-using obmt::Smem;
+using obmt::SmemScan;
 
 
 /* ---- item: one line that owns tuples (8 bytes) ---------------------------------------------------
@@ -65,7 +65,7 @@ enum : uint32_t { GF_NONASCII = 1, GF_INTERACT = 2, GF_QOVERFLOW = 4, GF_LARGE =
 /* ---- K1: owner o of the sub-batch -> item (+ mline for marker lines) -----------------------------
  * S.owner[o] holds the position of the line's first special byte (line scan output). */
 struct K1Out { item_t item; bool is_marker; MLine ml; };
-OBM_FN K1Out k1_owner(const Smem &S, uint32_t o, uint32_t doc_global_base) {
+OBM_FN K1Out k1_owner(const SmemScan &S, uint32_t o, uint32_t doc_global_base) {
     uint32_t first = S.owner[o];
     uint32_t ls = obmt::line_start_of(S, first);
     uint32_t d = obmt::doc_of(S, ls);

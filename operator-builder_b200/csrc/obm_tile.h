@@ -60,26 +60,30 @@ constexpr uint32_t OW_MARKER = 1u << 15, OW_SLASH2 = 1u << 31;
 OBM_HD uint32_t ow_pos(uint32_t r) { return r & 0x7FFFu; }
 OBM_HD uint32_t ow_ls(uint32_t r) { return (r >> 16) & 0x7FFFu; }
 
-struct Smem {
+/* what the scan phases (P1..P4, owner classification) need; k1_scan stages exactly this */
+struct SmemScan {
     alignas(16) uint8_t data[NW * 32];
     alignas(16) uint32_t nlw[NW];   /* bit i of word w: byte 32w+i is '\n' (or precedes a document start) */
     alignas(16) uint32_t spw[NW];   /* bit i of word w: byte 32w+i is one of # ' + / */
-    alignas(16) obm_tuple stage[NSTAGE * STRIDE];
     uint16_t nlpre[NW];             /* number of nlw bits in words [0, w) */
     uint32_t naw[NW / 32];          /* bit w%32 of naw[w/32]: word w holds a byte >= 0x80 */
     uint32_t owner[QMAX];           /* owner records in position order */
-    uint32_t ocnt[QMAX + 1];        /* tuple count of the owner; after the scan: exclusive prefix E[] */
-    uint16_t mlist[QMAX];           /* dense list of marker owners (indices into owner[]) */
-    uint16_t mslot[QMAX];           /* owner -> index in mlist (marker owners only) */
-    uint8_t odoc[QMAX];             /* document (index in the sub-batch) of the owner */
     uint32_t dstart[DMAX + 1];      /* document start positions, buffer-relative; [nd] = end */
     uint32_t dflag[DMAX];
-    uint32_t dcnt[DMAX + 1];        /* tuples per document; after the scan: exclusive offsets */
-    uint32_t dfirst[DMAX + 1];      /* first owner of each document */
     uint32_t scan_tmp[NT / 32 + 1];
     uint32_t n_owners, n_markers_q; /* owners; marker owners in mlist */
     uint32_t nd;
     uint32_t lo_pos, hi_pos;        /* valid byte range of `data` */
+};
+/* the fused tile kernel (mode 2) additionally lexes, stages and resolves inside the CTA */
+struct Smem : SmemScan {
+    alignas(16) obm_tuple stage[NSTAGE * STRIDE];
+    uint32_t ocnt[QMAX + 1];        /* tuple count of the owner; after the scan: exclusive prefix E[] */
+    uint16_t mlist[QMAX];           /* dense list of marker owners (indices into owner[]) */
+    uint16_t mslot[QMAX];           /* owner -> index in mlist (marker owners only) */
+    uint8_t odoc[QMAX];             /* document (index in the sub-batch) of the owner */
+    uint32_t dcnt[DMAX + 1];        /* tuples per document; after the scan: exclusive offsets */
+    uint32_t dfirst[DMAX + 1];      /* first owner of each document */
 };
 
 /* ---- P2: classification ---------------------------------------------------------------------- */
@@ -90,7 +94,7 @@ OBM_HD uint32_t zero_bytes4(uint32_t t) {
     return (eq * 0x00204081u >> 21) & 0xFu;
 }
 
-OBM_HD void classify_word(Smem &S, uint32_t wi) {
+OBM_HD void classify_word(SmemScan &S, uint32_t wi) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(S.data) + wi * 8;
     uint32_t nl = 0, sp = 0, hi = 0;
 #if defined(__CUDA_ARCH__)
@@ -139,7 +143,7 @@ OBM_HD uint32_t atomic_inc_u32(uint32_t *p) {
 }
 
 /* ---- P3: per-document preparation (thread d < nd) ---------------------------------------------- */
-OBM_FN void doc_prep(Smem &S, uint32_t d) {
+OBM_FN void doc_prep(SmemScan &S, uint32_t d) {
     uint32_t q = S.dstart[d], e = S.dstart[d + 1];
     if (q > S.lo_pos) atomic_or_u32(&S.nlw[(q - 1) >> 5], 1u << ((q - 1) & 31)); /* virtual newline before the document */
     uint32_t flag = 0;
@@ -158,7 +162,7 @@ OBM_FN void doc_prep(Smem &S, uint32_t d) {
 
 /* ---- P4: line scan (thread t owns words [WPT*t, WPT*t+WPT)) -------------------------------------- */
 /* first position >= from whose (sp|nl) bit is set, or hi_pos if none */
-OBM_FN uint32_t next_event(const Smem &S, uint32_t from) {
+OBM_FN uint32_t next_event(const SmemScan &S, uint32_t from) {
     if (from >= S.hi_pos) return S.hi_pos;
     uint32_t w = from >> 5;
     uint32_t m = (S.spw[w] | S.nlw[w]) & (0xFFFFFFFFu << (from & 31));
@@ -170,8 +174,8 @@ OBM_FN uint32_t next_event(const Smem &S, uint32_t from) {
     uint32_t pos = w * 32 + OBMT_CTZ(m);
     return pos < S.hi_pos ? pos : S.hi_pos;
 }
-OBM_HD bool is_sp(const Smem &S, uint32_t pos) { return (S.spw[pos >> 5] >> (pos & 31)) & 1u; }
-OBM_HD bool is_nl(const Smem &S, uint32_t pos) { return (S.nlw[pos >> 5] >> (pos & 31)) & 1u; }
+OBM_HD bool is_sp(const SmemScan &S, uint32_t pos) { return (S.spw[pos >> 5] >> (pos & 31)) & 1u; }
+OBM_HD bool is_nl(const SmemScan &S, uint32_t pos) { return (S.nlw[pos >> 5] >> (pos & 31)) & 1u; }
 
 /* ---- P4a: which lines have a special byte, bit-parallel -------------------------------------------
  * A line starts right after every newline bit (and at lo_pos).  Let X = nl|sp be the "event" bits and
@@ -195,7 +199,7 @@ OBM_HD uint32_t first_events(const uint32_t (&nl)[WPT], const uint32_t (&sp)[WPT
     return c;
 }
 /* line-start bits of the thread's words: after every newline, plus the buffer's first byte */
-OBM_HD void line_starts(const Smem &S, uint32_t t, const uint32_t (&nl)[WPT], uint32_t (&m)[WPT]) {
+OBM_HD void line_starts(const SmemScan &S, uint32_t t, const uint32_t (&nl)[WPT], uint32_t (&m)[WPT]) {
     uint32_t prev = t ? (S.nlw[t * WPT - 1] >> 31) : 0u;
 #pragma unroll
     for (uint32_t j = 0; j < WPT; j++) {
@@ -214,7 +218,7 @@ OBM_HD uint32_t carry_lookahead32(uint32_t G, uint32_t P, uint32_t cin, uint32_t
 }
 
 /* previous line start: position after the last newline bit below `pos` (or lo_pos) */
-OBM_FN uint32_t line_start_of(const Smem &S, uint32_t pos) {
+OBM_FN uint32_t line_start_of(const SmemScan &S, uint32_t pos) {
     uint32_t w = pos >> 5;
     uint32_t m = S.nlw[w] & ((1u << (pos & 31)) - 1u);
     const uint32_t wlo = S.lo_pos >> 5;
@@ -235,7 +239,7 @@ constexpr uint32_t OW_NONE = 0xFFFFFFFFu; /* not a valid record: it would be a M
 /* Classifies the line whose first special byte is at `first`: marker line, plain comment line, or a line
  * that produces no tuple (OW_NONE).  A position carrying both bits (virtual newline on a document's
  * last byte) is a special that also ends the line. */
-OBM_FN uint32_t classify_line(const Smem &S, uint32_t first, uint32_t start) {
+OBM_FN uint32_t classify_line(const SmemScan &S, uint32_t first, uint32_t start) {
     uint32_t ev = first;
     uint32_t comment = 0xFFFFFFFFu; bool slash2 = false;
     for (;;) {
@@ -254,7 +258,7 @@ OBM_FN uint32_t classify_line(const Smem &S, uint32_t first, uint32_t start) {
 }
 
 /* number of nlw bits at positions < q */
-OBM_HD uint32_t nl_before(const Smem &S, uint32_t q) {
+OBM_HD uint32_t nl_before(const SmemScan &S, uint32_t q) {
     uint32_t w = q >> 5;
     if (w >= NW) return (uint32_t)S.nlpre[NW - 1] + OBMT_POPC(S.nlw[NW - 1]);
     return (uint32_t)S.nlpre[w] + OBMT_POPC(S.nlw[w] & ((1u << (q & 31)) - 1u));
@@ -262,7 +266,7 @@ OBM_HD uint32_t nl_before(const Smem &S, uint32_t q) {
 
 /* ---- P5 / P7: owners ------------------------------------------------------------------------- */
 struct BitmapAccel {
-    const Smem *S; uint32_t dpos, dend; /* document start / end, buffer-relative */
+    const SmemScan *S; uint32_t dpos, dend; /* document start / end, buffer-relative */
     OBM_HD uint32_t next_interesting(uint32_t p) const {
         uint32_t q = next_event(*S, dpos + p);
         if (q > dend) q = dend;
@@ -271,7 +275,7 @@ struct BitmapAccel {
 };
 
 /* document (index in the sub-batch) containing buffer position `pos`: the last d with dstart[d] <= pos */
-OBM_FN uint32_t doc_of(const Smem &S, uint32_t pos) {
+OBM_FN uint32_t doc_of(const SmemScan &S, uint32_t pos) {
     uint32_t lo = 0, hi = S.nd;
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;

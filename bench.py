@@ -163,7 +163,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        os.environ.pop("NCCL_DEBUG", None)  # NCCL_DEBUG=VERSION|WARN|INFO prints a banner on stdout; rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     d0, d1 = args.docs * rank // world, args.docs * (rank + 1) // world

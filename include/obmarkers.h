@@ -199,6 +199,21 @@ int64_t obm_decode_doc(const uint8_t *doc, uint64_t doc_len, const obm_tuple *tu
                        uint8_t **out, uint64_t *out_len);
 void obm_free(void *p);
 
+/*
+ * The lexer's only consumer on the same tuple stream: mirrors internal/markers/parser
+ * (state.go:13-175, definition.go:13-21, emit.go:8-24, error.go:8-22) over obm_stream_*.  A registry lists the
+ * marker names (with their leading '+', e.g. "+operator-builder:field") and the argument names each accepts
+ * (marker/marker.go LookupArgument).  obm_parse_doc returns the number of Results and a malloc'd record
+ * buffer (format: csrc/obm_parse.cpp); Argument.SetValue / InflateObject type checks are not modelled.
+ */
+typedef struct obm_registry obm_registry;
+obm_registry *obm_registry_new(void);
+obm_registry *obm_registry_operator_builder(void); /* field / collection:field / resource markers */
+int obm_registry_add(obm_registry *r, const char *marker_name, const char *const *arg_names, uint32_t nargs);
+void obm_registry_free(obm_registry *r);
+int64_t obm_parse_doc(const obm_registry *reg, const uint8_t *doc, uint64_t doc_len, const obm_tuple *tuples, uint64_t ntuples,
+                      uint8_t **out, uint64_t *out_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -202,3 +202,44 @@ def generate_corpus_host(ndocs: int, doc_bytes: int = 4096, first_doc: int = 0, 
     if rc != 0:
         raise NativeError(rc, "obm_generate_corpus_host")
     return data, off
+
+
+# ---- the lexer's consumer: internal/markers/parser over the same tuple stream ----
+class Registry:
+    """marker.Registry stand-in (marker/registry.go:8-42): marker names (with '+') -> accepted argument names."""
+
+    def __init__(self, markers=None):
+        self._L = _native.lib()
+        if markers is None:
+            self._r = self._L.obm_registry_operator_builder()  # field / collection:field / resource
+        else:
+            self._r = self._L.obm_registry_new()
+            for name, args in markers.items():
+                arr = (ctypes.c_char_p * max(1, len(args)))(*[a if isinstance(a, bytes) else a.encode() for a in args])
+                self._L.obm_registry_add(self._r, name if isinstance(name, bytes) else name.encode(), arr, len(args))
+
+    @property
+    def handle(self):
+        return self._r
+
+    def __del__(self):
+        try:
+            if self._r:
+                self._L.obm_registry_free(self._r)
+                self._r = None
+        except Exception:
+            pass
+
+
+def parse_doc_raw(registry: Registry, doc: bytes, tuples: np.ndarray) -> bytes:
+    """parser.NewParser(...).Parse() over one document's tuples -> serialised Results (csrc/obm_parse.cpp)."""
+    L = _native.lib()
+    tuples = np.ascontiguousarray(tuples, dtype=np.uint64)
+    out = ctypes.POINTER(ctypes.c_uint8)()
+    outlen = ctypes.c_uint64()
+    n = L.obm_parse_doc(registry.handle, doc, len(doc), tuples.ctypes.data, len(tuples), ctypes.byref(out), ctypes.byref(outlen))
+    if n < 0:
+        raise NativeError(n, "obm_parse_doc")
+    data = ctypes.string_at(out, outlen.value)
+    L.obm_free(out)
+    return data

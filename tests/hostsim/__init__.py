@@ -14,13 +14,14 @@ def build(force=False):
     so = os.path.join(_HERE, "libhostsim.so")
     srcs = [os.path.join(_HERE, "hostsim.cpp"),
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_decode.cpp"),
+            os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_parse.cpp"),
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_core.h"),
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_tile.h"),
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_pipe.h"),
             os.path.join(_ROOT, "include", "obmarkers.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-shared", "-o", so,
-                               srcs[0], srcs[1]])
+                               srcs[0], srcs[1], srcs[2]])
     return so
 
 

@@ -211,6 +211,17 @@ obm_registry *obm_registry_new(void);
 obm_registry *obm_registry_operator_builder(void); /* field / collection:field / resource markers */
 int obm_registry_add(obm_registry *r, const char *marker_name, const char *const *arg_names, uint32_t nargs);
 void obm_registry_free(obm_registry *r);
+/*
+ * Device side of the same row: a compact index of the REGISTERED markers in a tuple stream that is still in
+ * HBM -- one 16-byte record {u32 doc, u32 tuple index in the document, u32 offset of '+', u16 registry id,
+ * u16 scope count} per marker whose name parser/definition.go:13-21 would find in the registry (at most 8
+ * names, 512 bytes).  d_doc_rec_off[ndocs+1] receives the per-document record offsets (last = total).  With
+ * d_records == NULL only the offsets are computed.  This index (~3 % of the input), not the tuple stream
+ * (~35 %), is what ranks exchange over NVLink.
+ */
+int obm_marker_index_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
+                            const void *d_tuples, const void *d_doc_tuple_off, void *d_records, uint64_t cap,
+                            void *d_doc_rec_off, void *stream);
 int64_t obm_parse_doc(const obm_registry *reg, const uint8_t *doc, uint64_t doc_len, const obm_tuple *tuples, uint64_t ntuples,
                       uint8_t **out, uint64_t *out_len);
 

@@ -55,6 +55,13 @@ extern "C" obm_registry *obm_registry_operator_builder(void) {
     return r;
 }
 
+/* names of the registry (internal use by the device index, obm_lib.cu) */
+extern "C" uint32_t obm_registry_names(const obm_registry *r, const char **names, uint32_t *lens, uint32_t cap) {
+    uint32_t n = 0;
+    for (const auto &d : r->defs) { if (n >= cap) break; names[n] = d.name.data(); lens[n] = (uint32_t)d.name.size(); n++; }
+    return n;
+}
+
 namespace {
 
 struct Lx { int32_t type; std::string value; int64_t line, col; };

@@ -58,6 +58,7 @@ class Parser:
         self.current = (ERROR, b"", 0, 0)
         self.definition = None  # (name, argset)
         self.results = []
+        self.loaded = []  # names for which loadDefinition succeeded, in order (definition.go:13-21)
 
     # lexer.NextLexeme on a channel that is closed after the last lexeme
     def _next_lexeme(self):
@@ -166,6 +167,7 @@ class Parser:
             name = self.scope_buffer[:-1]  # definition.go:14: strip the trailing ':'
             if name in self.registry:
                 self.definition = (name, self.registry[name])
+                self.loaded.append(name)
                 self.args = []
                 return self.parse_arg
         self.flush()

@@ -96,3 +96,56 @@ def test_parser_on_gpu_tuples(oracle):
         n_ok += want.count(b"+operator-builder:")
     assert n_ok > 1500
     sc.close()
+
+
+@pytest.mark.gpu
+def test_marker_index_kernel(oracle):
+    """k_marker_index: one record per marker whose definition the parser would load (definition.go:13-21)"""
+    import ctypes
+    import numpy as np
+    import torch
+    import operator_builder_b200 as ob
+    from operator_builder_b200 import _native
+    from oracle import parser_oracle as po
+    rng = random.Random(77)
+    docs = [d for _p, d in cu.fixtures()] + list(cu.TARGETED) + [cu.fuzz_doc_valid(rng) for _ in range(800)]
+    docs += [b"# a+1 +operator-builder:field:name=x\n", b"++operator-builder:field:name=x", b"+operator-builder:fieldx:name=y\n+operator-builder:field:name=z",
+             b"+operator-builder:field:\n+operator-builder:resource:include +operator-builder:collection:field:name=q"]
+    data0, _ = ob.generate_corpus_host(300, 4096, flavour=1)
+    docs += [data0.tobytes()[i * 4096:(i + 1) * 4096] for i in range(300)]
+    data = np.frombuffer(b"".join(docs), dtype=np.uint8)
+    off = np.zeros(len(docs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(d) for d in docs])
+    sc = ob.Scanner(0)
+    res = sc.lex_batch(data, off)
+    dev = torch.device("cuda:0")
+    d_bytes = torch.from_numpy(data.copy()).to(dev)
+    d_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+    d_tup = torch.from_numpy(res.tuples.view(np.int64).copy()).to(dev)
+    d_toff = torch.from_numpy(res.doc_tuple_off.view(np.int64).copy()).to(dev)
+    cap = len(res.tuples)
+    d_rec = torch.zeros(cap * 4, dtype=torch.int32, device=dev)
+    d_roff = torch.zeros(len(docs) + 1, dtype=torch.int64, device=dev)
+    L = _native.lib()
+    reg = ob.Registry()
+    st = torch.cuda.current_stream().cuda_stream
+    rc = L.obm_marker_index_device(sc.handle, reg.handle, d_bytes.data_ptr(), d_off.data_ptr(), len(docs), d_tup.data_ptr(), d_toff.data_ptr(),
+                                   d_rec.data_ptr(), cap, d_roff.data_ptr(), st)
+    assert rc == 0
+    torch.cuda.synchronize()
+    roff = d_roff.cpu().numpy()
+    rec = d_rec.cpu().numpy().view(np.uint32).reshape(-1, 4)
+    names = [b"+operator-builder:field", b"+operator-builder:collection:field", b"+operator-builder:resource"]
+    total = 0
+    for i, doc in enumerate(docs):
+        prs = po.Parser(oracle.lex(doc), po.OPERATOR_BUILDER_REGISTRY)
+        prs.run()
+        got = rec[int(roff[i]):int(roff[i + 1])]
+        assert [names[int(r[3]) & 0xFFFF] for r in got] == prs.loaded, (doc[:200], got, prs.loaded)
+        for r in got:
+            assert int(r[0]) == i and doc[int(r[2])] == ord("+")
+            t = int(res.tuples[int(res.doc_tuple_off[i]) + int(r[1])])
+            assert t >> 59 == 2 and (t & 0xFFFFFFFF) == int(r[2])
+        total += len(got)
+    assert total == int(roff[-1]) and total > 2400
+    sc.close()

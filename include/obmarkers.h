@@ -174,6 +174,24 @@ uint32_t obm_launches_last_call(const obm_handle *h);
 void *obm_pinned_alloc(uint64_t bytes);
 void obm_pinned_free(void *p);
 
+/* --- the data formats either side of the scan, device resident ------------ */
+/*
+ * Manifest.LoadContent's collection rewrite (internal/workload/v1/manifests/manifest.go:89-95):
+ *     ReplaceAll(content, "+operator-builder:collection:field", "+operator-builder:field")
+ *     ReplaceAll(content, "collectionField", "field")
+ * applied to every document of a packed batch in HBM.  Writes the rewritten batch (never longer than the
+ * input) and its ndocs+1 offsets; with d_out_bytes == NULL only the offsets are produced.
+ */
+int obm_rewrite_collection_markers_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
+                                          void *d_out_bytes, uint64_t out_cap, void *d_out_doc_off, void *stream);
+/*
+ * Manifest.ExtractManifests (manifests/manifest.go:57-80): split every document on lines that equal "---" after
+ * trimming trailing spaces.  One 16-byte record {u32 doc, u32 a, u32 b, u32 0} per extracted manifest, whose text
+ * is "\n" + content[a:b) exactly as the reference rebuilds it; d_doc_rec_off[ndocs+1] = per-document offsets.
+ */
+int obm_split_docs_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs, void *d_records, uint64_t cap,
+                          void *d_doc_rec_off, void *stream);
+
 /* --- host-side consumers of the tuple stream (no GPU needed; no lexing happens here) ------- */
 /*
  * Replays one document's tuples as the reference's Lexeme sequence.  Mirrors

@@ -837,6 +837,128 @@ extern "C" int obm_marker_index_device(obm_handle *h, const obm_registry *reg, c
     return OBM_OK;
 }
 
+/* ------------------------------------------------------------------------------------------- */
+/* collection prefix rewrite (manifests/manifest.go:89-95) on the device  */
+/* manifest splitting on "---" lines (manifests/manifest.go:57-80)         */
+/* First versions: one thread per document, two passes (count, exclusive scan, write).  Correct and */
+/* measured; not yet bandwidth-shaped (DESIGN.md lists the chunked, coalesced form as next).        */
+/* ------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ bool dev_match(const uint8_t *p, uint32_t avail, const char *pat, uint32_t len) {
+    if (avail < len) return false;
+    for (uint32_t k = 0; k < len; k++) if (p[k] != (uint8_t)pat[k]) return false;
+    return true;
+}
+/* strings.ReplaceAll(ReplaceAll(content, "+operator-builder:collection:field", "+operator-builder:field"),
+ *                    "collectionField", "field"): the two patterns cannot overlap each other or themselves and the
+ * first replacement cannot create an occurrence of the second, so one left-to-right pass is equivalent. */
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+k_rewrite_collection(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs,
+                     uint32_t *__restrict__ new_len, const uint64_t *__restrict__ new_off, uint8_t *__restrict__ out) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndocs) return;
+    const uint8_t *src = bytes + doc_off[d];
+    const uint32_t n = (uint32_t)(doc_off[d + 1] - doc_off[d]);
+    uint8_t *dst = WRITE ? out + new_off[d] : nullptr;
+    const char P1[] = "+operator-builder:collection:field", R1[] = "+operator-builder:field", P2[] = "collectionField", R2[] = "field";
+    uint32_t o = 0;
+    for (uint32_t i = 0; i < n;) {
+        const uint8_t c = src[i];
+        if (c == '+' && dev_match(src + i, n - i, P1, 34)) { if (WRITE) for (uint32_t k = 0; k < 23; k++) dst[o + k] = (uint8_t)R1[k]; o += 23; i += 34; }
+        else if (c == 'c' && dev_match(src + i, n - i, P2, 15)) { if (WRITE) for (uint32_t k = 0; k < 5; k++) dst[o + k] = (uint8_t)R2[k]; o += 5; i += 15; }
+        else { if (WRITE) dst[o] = c; o++; i++; }
+    }
+    if (!WRITE) new_len[d] = o;
+}
+
+/* Each record: { u32 doc, u32 a, u32 b, u32 0 }: extracted manifest = "\n" + content[a:b) (ExtractManifests
+ * rebuilds it as "\n" + line for every line between separators; a separator is a line that equals "---" after
+ * trimming trailing spaces; empty groups are dropped). */
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+k_split_docs(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs, uint32_t *__restrict__ counts,
+             const uint64_t *__restrict__ rec_off, uint4 *__restrict__ records, uint64_t cap) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndocs) return;
+    const uint8_t *src = bytes + doc_off[d];
+    const uint32_t n = (uint32_t)(doc_off[d + 1] - doc_off[d]);
+    uint32_t found = 0;
+    uint64_t at = WRITE ? rec_off[d] : 0;
+    /* strings.Split(content, "\n") yields lines [ls, le) for every '\n' plus a final (possibly empty) line */
+    bool open = false; uint32_t a = 0, last_end = 0;
+    uint32_t ls = 0;
+    for (;;) {
+        uint32_t le = ls;
+        while (le < n && src[le] != '\n') le++;
+        /* separator? */
+        uint32_t te = le;
+        while (te > ls && src[te - 1] == ' ') te--;
+        const bool sep = (te - ls == 3) && src[ls] == '-' && src[ls + 1] == '-' && src[ls + 2] == '-';
+        if (sep) {
+            if (open) { if (WRITE) { if (at < cap) records[at] = make_uint4(d, a, last_end, 0); at++; } found++; open = false; }
+        } else {
+            if (!open) { open = true; a = ls; }
+            last_end = le;
+        }
+        if (le >= n) break;
+        ls = le + 1;
+    }
+    if (open) { if (WRITE) { if (at < cap) records[at] = make_uint4(d, a, last_end, 0); at++; } found++; }
+    if (!WRITE) counts[d] = found;
+}
+
+static int two_pass_scratch(obm_handle *h, uint32_t ndocs, cudaStream_t st, uint32_t **counts, uint64_t **tile_sums) {
+    uint64_t need = align_up((uint64_t)ndocs * 4 + 4, 256) + align_up((uint64_t)scan_tiles(ndocs) * 8 + 8, 256);
+    if (h->scratch_bytes < need) {
+        if (h->scratch) { OBM_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->scratch); h->scratch = nullptr; h->scratch_bytes = 0; }
+        OBM_CUDA(h, cudaMalloc(&h->scratch, need)); h->scratch_bytes = need;
+    }
+    *counts = (uint32_t *)h->scratch;
+    *tile_sums = (uint64_t *)((uint8_t *)h->scratch + align_up((uint64_t)ndocs * 4 + 4, 256));
+    return OBM_OK;
+}
+
+extern "C" int obm_rewrite_collection_markers_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
+                                                     void *d_out_bytes, uint64_t out_cap, void *d_out_doc_off, void *stream) {
+    if (!h || !d_doc_off || !d_out_doc_off) return OBM_E_ARG;
+    OBM_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ndocs == 0) { OBM_CUDA(h, cudaMemsetAsync(d_out_doc_off, 0, 8, st)); return OBM_OK; }
+    uint32_t *counts; uint64_t *tile_sums; int rc;
+    if ((rc = two_pass_scratch(h, ndocs, st, &counts, &tile_sums)) != OBM_OK) return rc;
+    uint64_t *noff = (uint64_t *)d_out_doc_off;
+    const uint32_t nb = (ndocs + 127) / 128, nt = scan_tiles(ndocs);
+    k_rewrite_collection<false><<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, counts, nullptr, nullptr);
+    k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(counts, ndocs, noff, tile_sums);
+    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, noff + ndocs);
+    k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(noff, ndocs, tile_sums, ~0ull, nullptr);
+    (void)out_cap; /* the rewrite only shrinks: a buffer of the input size always suffices */
+    if (d_out_bytes)
+        k_rewrite_collection<true><<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, nullptr, noff, (uint8_t *)d_out_bytes);
+    OBM_CUDA(h, cudaGetLastError());
+    return OBM_OK;
+}
+
+extern "C" int obm_split_docs_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs, void *d_records, uint64_t cap,
+                                     void *d_doc_rec_off, void *stream) {
+    if (!h || !d_doc_off || !d_doc_rec_off) return OBM_E_ARG;
+    OBM_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ndocs == 0) { OBM_CUDA(h, cudaMemsetAsync(d_doc_rec_off, 0, 8, st)); return OBM_OK; }
+    uint32_t *counts; uint64_t *tile_sums; int rc;
+    if ((rc = two_pass_scratch(h, ndocs, st, &counts, &tile_sums)) != OBM_OK) return rc;
+    uint64_t *roff = (uint64_t *)d_doc_rec_off;
+    const uint32_t nb = (ndocs + 127) / 128, nt = scan_tiles(ndocs);
+    k_split_docs<false><<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, counts, nullptr, nullptr, 0);
+    k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(counts, ndocs, roff, tile_sums);
+    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, roff + ndocs);
+    k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(roff, ndocs, tile_sums, ~0ull, nullptr);
+    if (d_records && cap)
+        k_split_docs<true><<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, nullptr, roff, (uint4 *)d_records, cap);
+    OBM_CUDA(h, cudaGetLastError());
+    return OBM_OK;
+}
+
 /* Host copy of the same generator (test/bench utility; no lexing). */
 extern "C" int obm_generate_corpus_host(uint8_t *bytes, uint64_t *doc_off, uint32_t ndocs, uint32_t doc_bytes,
                                         uint64_t first_doc, int flavour) {

@@ -166,7 +166,8 @@ def main():
         os.environ.pop("NCCL_DEBUG", None)  # NCCL_DEBUG=VERSION|WARN|INFO prints a banner on stdout; rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
-    d0, d1 = args.docs * rank // world, args.docs * (rank + 1) // world
+    from operator_builder_b200 import shard
+    d0, d1 = shard.shard_range(args.docs, rank, world)
     ndocs = d1 - d0
     nbytes = ndocs * DOC_BYTES
     sc = ob.Scanner(local_rank)
@@ -185,14 +186,14 @@ def main():
     # N>1: the one exchange step -- every rank learns every document's tuple count (the global
     # doc_tuple_off index), 4 B/document, one all-gather.  Full-tuple all-gather is timed separately.
     counts_local = torch.empty(ndocs, dtype=torch.int32, device=dev) if world > 1 else None
-    counts_all = torch.empty(ndocs * world, dtype=torch.int32, device=dev) if world > 1 and args.docs % world == 0 else None
+    counts_all = torch.empty(args.docs, dtype=torch.int32, device=dev) if world > 1 else None
 
     def step():
         sc.lex_batch_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, nbytes, d_out.data_ptr(), cap, d_toff.data_ptr(),
                             d_status.data_ptr(), d_counts.data_ptr(), sp)
         if counts_all is not None:
-            torch.sub(d_toff[1:], d_toff[:-1], out=counts_local)
-            dist.all_gather_into_tensor(counts_all, counts_local)
+            shard.counts_from_offsets(d_toff, out=counts_local)
+            shard.exchange_counts(counts_local, args.docs, rank, world, counts_all=counts_all)
 
     def barrier():
         if world > 1:

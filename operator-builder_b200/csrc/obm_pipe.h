@@ -132,6 +132,75 @@ OBM_HD_NOINLINE uint32_t k2_marker_line(const obm::Tables &T, const uint8_t *doc
     return make_mres(sink.n_tuples, irregular);
 }
 
+OBM_HD uint32_t plain_count_fwd(item_t it) { return it_line(it) == 1 ? 1u : 2u; }
+
+/* ==== ordered pipeline (mode 0): K1 emits ONE ordered item stream, K2 lexes + assembles per group ======
+ * Items are written in global position order (K1 allocates through a decoupled look-back over static
+ * unit ids).  Besides one item per tuple-owning line, every document closes with an EOF item, so tuple
+ * positions are a plain prefix sum over item counts.  A marker item carries everything K2 needs to lex
+ * its line (there is no separate marker-line list):
+ *   marker item : ls | first<<14 | line<<28 | 1<<42 | line_end[13]<<43 | doc6<<45 | line_end[0..12]<<51
+ *   plain item  : ls | comment<<14 | line<<28 | slash2<<43 | dead<<44 | doc6<<45
+ *   EOF item    : doc length | doc6<<45 | 1<<51 | exact<<52      (exact: K1 flagged the document)
+ *   LARGE item  : 1<<51 | 1<<53                                  (document = last of the unit; > MAXDOC)
+ * A unit is one K1 sub-batch (<= DMAX documents, <= QMAX owning lines).  Unit records: exclusive item
+ * prefix and first document.  K2 groups are runs of units of ~equal weight (GROUP_W). */
+OBM_HD item_t make_marker_item(uint32_t ls, uint32_t first, uint32_t line, uint32_t d, uint32_t line_end) {
+    return (item_t)ls | ((item_t)first << 14) | ((item_t)line << 28) | ((item_t)1 << 42) | ((item_t)((line_end >> 13) & 1u) << 43) |
+           ((item_t)d << 45) | ((item_t)(line_end & 0x1FFFu) << 51);
+}
+OBM_HD uint32_t it_line_end(item_t i) { return (uint32_t)((i >> 51) & 0x1FFF) | ((uint32_t)((i >> 43) & 1) << 13); }
+OBM_HD item_t make_eof_item(uint32_t len, uint32_t d, bool exact) { return (item_t)len | ((item_t)d << 45) | ((item_t)1 << 51) | ((item_t)exact << 52); }
+OBM_HD item_t make_large_item() { return ((item_t)1 << 51) | ((item_t)1 << 53); }
+OBM_HD bool it_eof(item_t i) { return !it_marker(i) && ((i >> 51) & 1); }
+OBM_HD bool it_exact(item_t i) { return !it_marker(i) && ((i >> 52) & 1); }
+OBM_HD bool it_large(item_t i) { return !it_marker(i) && ((i >> 53) & 1); }
+
+constexpr uint32_t GROUP_W = 768;       /* weight of a K2 group */
+constexpr uint32_t UNIT_W = 8;          /* weight of a unit = UNIT_W + 4 * marker lines + items */
+constexpr uint32_t G_NT = 128;          /* threads of a K2 group CTA */
+constexpr uint32_t G_MLCAP = 128;       /* marker lines whose tuples are staged in shared memory */
+constexpr uint32_t G_LTS = 25;          /* staged tuples per marker line (odd stride: no bank clash) */
+constexpr uint32_t G_UCAP = GROUP_W / UNIT_W + 2;   /* units per group */
+constexpr uint32_t G_IMAX = GROUP_W + obmt::QMAX + obmt::DMAX + 2; /* items per group */
+constexpr uint16_t G_CNT_LOOKUP = 0xFFFF; /* item count lives in counts[doc] (exact / large documents) */
+OBM_HD uint32_t unit_weight(uint32_t n_items, uint32_t n_ml) { return UNIT_W + 4u * n_ml + n_items; }
+
+/* K1: owner o of the sub-batch -> item (ordered pipeline) */
+OBM_FN item_t k1_owner_item(const SmemScan &S, uint32_t o) {
+    uint32_t first = S.owner[o];
+    uint32_t ls = obmt::line_start_of(S, first);
+    uint32_t d = obmt::doc_of(S, ls);
+    uint32_t dpos = S.dstart[d], dend = S.dstart[d + 1];
+    uint32_t rec = S.dflag[d] ? obmt::OW_NONE : obmt::classify_line(S, first, ls);
+    if (rec == obmt::OW_NONE) return make_item(ls - dpos, first - dpos, 0, false, false, true, d);
+    uint32_t line = 1 + obmt::nl_before(S, ls) - obmt::nl_before(S, dpos);
+    if (!(rec & obmt::OW_MARKER)) return make_item(ls - dpos, obmt::ow_pos(rec) - dpos, line, false, (rec & obmt::OW_SLASH2) != 0, false, d);
+    uint32_t e = first;
+    for (;;) { if (e >= dend) { e = dend; break; } if (obmt::is_nl(S, e) && S.data[e] == '\n') break; e = obmt::next_event(S, e + 1); }
+    return make_marker_item(ls - dpos, first - dpos, line, d, e - dpos);
+}
+
+/* K2: lex the line of a marker item of document doc[0..n) (global memory) */
+OBM_HD_NOINLINE uint32_t k2_marker_item(const obm::Tables &T, const uint8_t *doc, uint32_t n, item_t it, obm_tuple *out, uint32_t cap,
+                                        uint32_t *markers = nullptr, uint32_t *lexemes = nullptr) {
+    MLine ml; ml.doc = 0; ml.ls_first = it_ls(it) | (it_pos(it) << 16); ml.line = it_line(it); ml.line_end = it_line_end(it);
+    uint32_t ls = it_ls(it), first = it_pos(it);
+    LineAccel acc{doc, ml.line_end};
+    obm::SmallSink sink(out, cap);
+    GLineLexer lx(T, doc, n, sink, first, ml.line, ls, !(ml.line == 1 && ls == 0), acc);
+    lx.fill_windows(lx.p);
+    int st = lx.run<true>();
+    uint32_t end_line = lx.line_p - (st == obm::RUN_LINE_END ? 1u : 0u);
+    bool irregular = (st == obm::RUN_FATAL) || (end_line != ml.line);
+    if (markers) *markers += sink.n_markers;
+    if (lexemes) *lexemes += sink.n_lexemes;
+    return make_mres(sink.n_tuples, irregular);
+}
+
+/* tuples of a non-marker item of a regular document */
+OBM_HD uint32_t simple_count(item_t it) { return it_dead(it) ? 0u : it_eof(it) ? 1u : plain_count_fwd(it); }
+
 /* ---- K3 ------------------------------------------------------------------------------------------ */
 /* tuples of a plain item: [LINE] Comment */
 OBM_HD uint32_t plain_count(item_t it) { return it_line(it) == 1 ? 1u : 2u; }

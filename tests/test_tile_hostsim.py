@@ -13,8 +13,8 @@ from tests import hostsim
 
 
 def check_batch(docs, skew=0):
-    """both device organisations -- the fused tile kernel and the 3-stage pipeline -- against the exact path"""
-    for pipeline in (False, True):
+    """both device organisations -- the fused tile kernel, the 3-stage and the ordered 2-stage pipeline -- against the exact path"""
+    for pipeline in (0, 1, 2):
         tup, toff, stats = hostsim.tile_batch(docs, skew, pipeline=pipeline)
         for i, doc in enumerate(docs):
             want = hostsim.lex_doc(doc)
@@ -22,7 +22,30 @@ def check_batch(docs, skew=0):
             if not np.array_equal(got, want):
                 raise AssertionError(f"pipeline={pipeline} doc {i} (skew {skew}) {doc[:300]!r}\n tile ={hostsim.fmt_tuples(got)[:50]}\n exact={hostsim.fmt_tuples(want)[:50]}")
         assert int(toff[-1]) == len(tup)
+        # marker / lexeme totals are recomputed from the stream: they must agree for every organisation
+        kinds = (tup >> np.uint64(59)).astype(np.int64)
+        assert int(stats[0]) == int((kinds == 2).sum()), (pipeline, stats)
+        assert int(stats[1]) == int(((kinds < 21) | (kinds > 25)).sum()), (pipeline, stats)
     return stats
+
+
+def test_dense_marker_lines_long_lines_and_large_documents():
+    """shapes that stress the ordered pipeline's group logic: more marker lines than the staging area holds,
+    lines with more tuples than a staging slot, large documents between small ones, interacting lines and
+    non-ASCII documents inside dense groups, tiles with more than DMAX documents"""
+    long_line = b"# +operator-builder:field:" + b",".join(b"a%d=%d" % (i, i) for i in range(40)) + b"\n"
+    dense = b"".join(b"# +a:b:c=%d\n" % i for i in range(700))
+    big = b"kind: X\n" + b"".join(b"  key%d: v # +operator-builder:field:name=k%d,type=string\n" % (i, i) for i in range(600))
+    assert len(big) > 16368
+    multi = b"# +a:b:c=`x\ny`\n# +d:e\n"
+    docs = [dense, long_line * 3, big, b"", multi, dense[:3000] + "é".encode() + dense[3000:6000], long_line, big + long_line, b"#x\n" * 2000]
+    docs += [b"# +t:%d\n" % i for i in range(300)]  # > DMAX documents in one tile
+    docs += [dense, multi * 40, b"+" * 50 + b"\n"]
+    for skew in (0, 9):
+        check_batch(docs, skew)
+    check_batch([long_line * 200])  # every line overflows its staging slot
+    check_batch([big])  # a batch that is one large document
+    check_batch([b""] * 200 + [big] + [b""] * 3)
 
 
 def test_targeted_as_one_batch():

@@ -1,18 +1,18 @@
 /*
- * obm_group.cuh -- kernels of the ordered two-stage pipeline (mode 0); logic in obm_pipe.h / obm_tile.h.
+ * obm_group.cuh -- kernels of the two-stage pipeline (mode 0); logic in obm_pipe.h / obm_tile.h.
  *
- *   k_tile_units  units (K1 sub-batches) per 16 KiB tile; an exclusive scan gives every unit a static id
- *   k1_scan       tile-resident classification + bit-parallel line logic (no lexing).  Emits ONE item stream
- *                 in global position order: a decoupled look-back over unit ids hands every unit its item
- *                 base, so the stream needs no per-document index.  Every document closes with an EOF item.
- *                 Units are cut into K2 groups of ~equal weight on the fly (second look-back chain).
- *   k2_group      one CTA per group (a few consecutive units = whole documents): marker items are compacted
- *                 and lexed ONCE, one thread per line, tuples staged in shared memory; item counts -> group
- *                 total -> decoupled look-back over groups -> final positions; comment / EOF tuples are
- *                 written in place, staged marker tuples copied out by warps.  Lines that do not fit the
- *                 staging area are lexed a second time straight to their final place; documents whose lines
- *                 interact (or that K1 flagged: non-ASCII, too many owning lines) are lexed by the exact
- *                 Unicode instantiation, all inside the group.  Writes doc_tuple_off as it goes.
+ *   k_tile_units  units (K1 sub-batches: <= DMAX whole documents of one 16 KiB tile) per tile; an exclusive
+ *                 scan gives every unit a static id in document order
+ *   k1_scan       tile-resident classification + bit-parallel line logic (no lexing).  Per unit: one item per
+ *                 tuple-owning line in position order, every document closed by an EOF item, plus a 16-byte
+ *                 unit record.  No cross-CTA dependency.
+ *   k2_units      ONE WARP per unit, no block barriers: marker items are compacted (ballots) and lexed ONCE,
+ *                 one lane per line, tuples staged in the warp's shared-memory area; item counts -> unit total
+ *                 -> decoupled look-back over units -> final positions; comment / EOF tuples are written in
+ *                 place, staged marker tuples copied out lane-per-tuple.  Lines that do not fit the staging area
+ *                 are lexed again straight to their final place; documents whose lines interact (or that K1
+ *                 flagged: non-ASCII, too many owning lines) are lexed by the exact Unicode instantiation, all
+ *                 inside the warp.  Writes doc_tuple_off as it goes.
  */
 #pragma once
 #include "obm_fast.cuh"
@@ -29,17 +29,15 @@ struct GroupArgs {
     const uint64_t *ubase;      /* [ntiles+1] exclusive scan of units per tile; [ntiles] = number of units */
     /* K1 -> K2 */
     item_t *items; uint64_t items_cap;
-    uint64_t *uitem;            /* [nunits+1] exclusive item prefix of the unit */
-    uint32_t *udoc;             /* [nunits+1] first document of the unit */
-    uint32_t *gstart; uint64_t gcap; /* first unit of group j */
+    obmp::Unit *units;          /* [nunits] */
     uint32_t *doc_flag;
-    uint64_t *st_items, *st_weight, *st_tuples; /* look-back chains: units (items, weight), groups (tuples) */
+    uint64_t *st_tuples;        /* look-back chain over units */
     /* results */
     uint32_t *counts; obm_tuple *out; uint64_t out_cap; uint64_t *tuple_off;
     uint32_t *status; unsigned long long *totals;
     uint32_t *ctl;
 };
-enum { CT_T1 = 0, CT_T2 = 1, CT_NG = 2, CT_OVF = 6 };
+enum { CT_T1 = 0, CT_T2 = 1, CT_ITOP = 4 /* u64 at ctl[4..5] */, CT_OVF = 6 };
 
 __device__ __forceinline__ obm::Tables dev_tables() {
     obm::Tables T;
@@ -70,8 +68,8 @@ struct K1Shared {
     alignas(8) item_t sitems[obmt::QMAX]; /* items of the sub-batch in owner order */
     uint16_t dlast[obmt::DMAX + 1];       /* index after the last owner of document k */
     alignas(8) uint64_t mbar;
-    uint64_t item_base, w_base;
-    uint32_t tile, n_ml;
+    uint64_t item_base;
+    uint32_t tile;
 };
 
 __global__ void __launch_bounds__(obmt::NT, 4)
@@ -84,7 +82,6 @@ k1_scan(GroupArgs A) {
     __syncthreads();
     uint32_t mbar_phase = 0;
     item_t *sitems = C.sitems;
-    const uint64_t nunits = A.ubase[A.ntiles];
     for (;;) {
         if (tid == 0) C.tile = atomicAdd(&A.ctl[CT_T1], 1u);
         __syncthreads();
@@ -103,7 +100,6 @@ k1_scan(GroupArgs A) {
             const uint32_t extra = (k == nsub - 1 && has_large) ? 1u : 0u;
             const uint64_t u = u0 + k;
             uint32_t n_owners = 0;
-            if (tid == 0) C.n_ml = 0;
             if (nd) {
                 const uint64_t b0 = A.doc_off[da], b1 = A.doc_off[db];
                 const uint64_t abs0 = (uint64_t)(uintptr_t)A.bytes + b0, base_abs = abs0 & ~15ull;
@@ -170,15 +166,7 @@ k1_scan(GroupArgs A) {
                 }
                 __syncthreads();
                 /* P5 owners -> items (shared memory, owner order) */
-                uint32_t my_ml = 0;
-                for (uint32_t o = tid; o < n_owners; o += obmt::NT) {
-                    const item_t it = obmp::k1_owner_item(S, o);
-                    sitems[o] = it;
-                    my_ml += obmp::it_marker(it) ? 1u : 0u;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) my_ml += __shfl_down_sync(0xffffffffu, my_ml, o);
-                if ((tid & 31) == 0 && my_ml) atomicAdd(&C.n_ml, my_ml);
+                for (uint32_t o = tid; o < n_owners; o += obmt::NT) sitems[o] = obmp::k1_owner_item(S, o);
                 __syncthreads();
                 /* per document: index after its last owner (owners are in position order, hence grouped by document) */
                 if (tid < nd) {
@@ -190,16 +178,9 @@ k1_scan(GroupArgs A) {
                 }
             }
             __syncthreads();
-            /* ordered allocation: exclusive prefixes of items and weight over all earlier units */
-            const uint32_t n_items = n_owners + nd + extra, n_ml = C.n_ml;
-            const uint32_t weight = obmp::unit_weight(n_items, n_ml);
-            if (tid < 32) {
-                const uint64_t b = obmf::lookback_warp(A.st_items, (uint32_t)u, n_items);
-                if (tid == 0) C.item_base = b;
-            } else if (tid < 64) {
-                const uint64_t b = obmf::lookback_warp(A.st_weight, (uint32_t)u, weight);
-                if (tid == 32) C.w_base = b;
-            }
+            /* the unit's items are contiguous; units are placed by a bump allocator (any order) */
+            const uint32_t n_items = n_owners + nd + extra;
+            if (tid == 0) C.item_base = atomicAdd(reinterpret_cast<unsigned long long *>(&A.ctl[CT_ITOP]), (unsigned long long)n_items);
             __syncthreads();
             const uint64_t ibase = C.item_base;
             const bool room = ibase + n_items <= A.items_cap;
@@ -210,10 +191,7 @@ k1_scan(GroupArgs A) {
             }
             if (tid == 0) {
                 if (!room) A.ctl[CT_OVF] = 1;
-                A.uitem[u] = ibase; A.udoc[u] = da;
-                const uint64_t w0 = C.w_base, w1 = w0 + weight;
-                for (uint64_t j = w0 / obmp::GROUP_W + 1; j <= w1 / obmp::GROUP_W; j++) { if (j < A.gcap) A.gstart[j] = (uint32_t)(u + 1); else A.ctl[CT_OVF] = 1; }
-                if (u == nunits - 1) { A.uitem[nunits] = ibase + n_items; A.udoc[nunits] = A.ndocs; A.ctl[CT_NG] = (uint32_t)(w1 / obmp::GROUP_W + 1); }
+                A.units[u] = obmp::Unit{ibase, da, n_items | (nd << 16)};
             }
             __syncthreads();
         }
@@ -221,202 +199,223 @@ k1_scan(GroupArgs A) {
 }
 
 /* ---------------------------------------------------------------------------------------------- K2 -- */
-struct K2Shared {
-    alignas(16) obm_tuple stage[obmp::G_MLCAP * obmp::G_LTS];
-    uint64_t moff[obmp::G_MLCAP];       /* staged line -> final output position (~0: not copied) */
-    uint16_t icnt[obmp::G_IMAX];        /* tuples per item (G_CNT_LOOKUP: counts[doc]) */
-    uint16_t mlist[obmp::G_IMAX];       /* marker rank -> item index */
-    uint32_t ut_item[obmp::G_UCAP + 1]; /* unit -> first item (group-relative) */
-    uint32_t ut_doc[obmp::G_UCAP + 1];  /* unit -> first document */
-    uint64_t red[obmp::G_NT / 32 + 1];
-    uint32_t red2[obmp::G_NT / 32 + 1];
-    uint64_t base;
-    uint32_t group, any_flag;
+struct K2Warp {
+    alignas(16) obm_tuple stage[obmp::W_MLCAP * obmp::W_LTS];
+    uint64_t moff[obmp::W_MLCAP];   /* staged line -> final output position (~0: not copied) */
+    uint16_t icnt[obmp::W_ICAP];    /* tuples per item of the block (G_CNT_LOOKUP: counts[doc]) */
+    uint8_t mlist[obmp::W_ICAP];    /* marker rank -> item index inside the block */
 };
 
-/* exclusive scan over the CTA of (v, f) with totals; v 64-bit, f small */
-__device__ __forceinline__ void group_scan(K2Shared &C, uint64_t v, uint32_t f, uint64_t &v_excl, uint32_t &f_excl, uint64_t &v_tot, uint32_t &f_tot) {
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint64_t vi = v; uint32_t fi = f;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t tv = __shfl_up_sync(0xffffffffu, vi, o); const uint32_t tf = __shfl_up_sync(0xffffffffu, fi, o);
-        if (lane >= (uint32_t)o) { vi += tv; fi += tf; }
+struct K2Ctx {
+    const GroupArgs &A; K2Warp &C; const obm::Tables &T;
+    uint64_t i0; uint32_t d0, nd, lane; bool writing;
+    uint32_t markers, lexemes, exact, fatal;
+    __device__ __forceinline__ uint32_t doc_of(item_t it) const { return obmp::it_large(it) ? d0 + nd : d0 + obmp::it_doc(it); }
+};
+
+/* Block [b0, b1) of the unit's items: compact the marker items, lex each line once (lane per line, the first
+ * W_MLCAP lines stage their tuples), counts of everything else.  stable: document flags are final (large
+ * units, second sweep) -- lines of flagged documents are skipped.  Returns lane-local "needs the flag pass". */
+__device__ __forceinline__ bool k2_lex_block(K2Ctx &X, uint32_t b0, uint32_t b1, bool stable, uint32_t &n_ml_out) {
+    K2Warp &C = X.C; const GroupArgs &A = X.A; const uint32_t lane = X.lane;
+    uint32_t n_ml = 0; bool any = false;
+    C.moff[lane] = ~0ull;
+    for (uint32_t c0 = b0; c0 < b1; c0 += 32) {
+        const uint32_t i = c0 + lane; const bool valid = i < b1;
+        const item_t it = valid ? A.items[X.i0 + i] : 0;
+        bool m = valid && obmp::it_marker(it);
+        if (stable && valid && A.doc_flag[X.doc_of(it)]) { m = false; C.icnt[i - b0] = obmp::it_eof(it) ? obmp::G_CNT_LOOKUP : (uint16_t)0; }
+        else if (valid && !m) {
+            if (obmp::it_exact(it) || obmp::it_large(it)) { C.icnt[i - b0] = obmp::G_CNT_LOOKUP; any = true; }
+            else C.icnt[i - b0] = (uint16_t)obmp::simple_count(it);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, m);
+        if (m) C.mlist[n_ml + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = (uint8_t)(i - b0);
+        n_ml += (uint32_t)__popc(bal);
     }
-    if (lane == 31) { C.red[wid] = vi; C.red2[wid] = fi; }
-    __syncthreads();
-    uint64_t pv = 0, tv = 0; uint32_t pf = 0, tf = 0;
+    __syncwarp();
+    for (uint32_t k = lane; k < n_ml; k += 32) {
+        const uint32_t ib = C.mlist[k];
+        const item_t it = A.items[X.i0 + b0 + ib];
+        const uint32_t d = X.doc_of(it);
+        const uint64_t o0 = A.doc_off[d];
+        const bool staged = k < obmp::W_MLCAP;
+        const uint32_t r = obmp::k2_marker_item(X.T, A.bytes + o0, (uint32_t)(A.doc_off[d + 1] - o0), it,
+                                                staged ? C.stage + k * obmp::W_LTS : nullptr, staged ? obmp::W_LTS : 0u);
+        C.icnt[ib] = (uint16_t)obmp::mres_tuples(r);
+        if (obmp::mres_irregular(r)) { atomicOr(&A.doc_flag[d], obmp::GF_INTERACT); any = true; }
+    }
+    __syncwarp();
+    n_ml_out = n_ml;
+    return any;
+}
+
+/* exact tuple counts of the unit's flagged documents -> counts[] (large documents were counted by k_exact_count) */
+__device__ __forceinline__ void k2_count_flagged_docs(K2Ctx &X) {
+    for (uint32_t q = X.lane; q < X.nd; q += 32) {
+        const uint32_t d = X.d0 + q, f = X.A.doc_flag[d];
+        if (f && !(f & obmp::GF_LARGE)) {
+            const uint64_t o0 = X.A.doc_off[d];
+            obm::SmallSink sink(nullptr, 0);
+            obmp::k3_doc_exact(X.T, X.A.bytes + o0, (uint32_t)(X.A.doc_off[d + 1] - o0), sink);
+            X.A.counts[d] = sink.n_tuples;
+        }
+    }
+    __syncwarp();
+}
+
+/* items of flagged documents: everything counts 0 except the closing item, which stands for the whole document */
+__device__ __forceinline__ void k2_apply_flags(K2Ctx &X, uint32_t b0, uint32_t b1) {
+    for (uint32_t i = b0 + X.lane; i < b1; i += 32) {
+        const item_t it = X.A.items[X.i0 + i];
+        if (X.A.doc_flag[X.doc_of(it)]) X.C.icnt[i - b0] = obmp::it_eof(it) ? obmp::G_CNT_LOOKUP : (uint16_t)0;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint64_t k2_block_total(K2Ctx &X, uint32_t b0, uint32_t b1) {
+    uint64_t sum = 0;
+    for (uint32_t i = b0 + X.lane; i < b1; i += 32) {
+        uint32_t c = X.C.icnt[i - b0];
+        if (c == obmp::G_CNT_LOOKUP) c = X.A.counts[X.doc_of(X.A.items[X.i0 + i])];
+        sum += c;
+    }
 #pragma unroll
-    for (uint32_t w = 0; w < obmp::G_NT / 32; w++) { const uint64_t a = C.red[w]; const uint32_t b = C.red2[w]; if (w < wid) { pv += a; pf += b; } tv += a; tf += b; }
-    __syncthreads();
-    v_excl = pv + vi - v; f_excl = pf + fi - f; v_tot = tv; f_tot = tf;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    return sum;
 }
 
-__device__ __forceinline__ uint32_t unit_of(const K2Shared &C, uint32_t nu, uint32_t i) {
-    uint32_t lo = 0, hi = nu; /* last k with ut_item[k] <= i */
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (C.ut_item[mid] <= i) lo = mid; else hi = mid; }
-    return lo;
-}
-__device__ __forceinline__ uint32_t doc_of_item(const K2Shared &C, uint32_t nu, uint32_t i, item_t it) {
-    const uint32_t u = unit_of(C, nu, i);
-    return obmp::it_large(it) ? C.ut_doc[u + 1] - 1u : C.ut_doc[u] + obmp::it_doc(it);
-}
-
-__global__ void __launch_bounds__(obmp::G_NT)
-k2_group(GroupArgs A) {
-    if (A.ctl[CT_OVF]) return; /* work records overflowed in k1: the host redoes the batch with the exact kernels */
-    __shared__ K2Shared C;
-    const obm::Tables T = dev_tables();
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t NG = A.ctl[CT_NG];
-    const uint64_t nunits = A.ubase[A.ntiles];
-    const bool writing = A.out != nullptr && A.out_cap != 0;
-    uint32_t markers = 0, lexemes = 0, exact = 0, fatal = 0;
-    for (;;) {
-        if (tid == 0) C.group = atomicAdd(&A.ctl[CT_T2], 1u);
-        __syncthreads();
-        const uint32_t j = C.group;
-        if (j >= NG) break;
-        const uint64_t ua = A.gstart[j], ub = (j + 1 < NG) ? A.gstart[j + 1] : nunits;
-        const uint32_t nu = (uint32_t)(ub - ua);
-        const uint64_t i0 = A.uitem[ua];
-        const uint32_t n_items = (uint32_t)(A.uitem[ub] - i0);
-        for (uint32_t k = tid; k <= nu; k += obmp::G_NT) { C.ut_item[k] = (uint32_t)(A.uitem[ua + k] - i0); C.ut_doc[k] = A.udoc[ua + k]; }
-        if (tid == 0) C.any_flag = 0;
-        C.moff[tid] = ~0ull; /* G_MLCAP == G_NT */
-        __syncthreads();
-        /* pass A: compact the marker items, counts of everything else */
-        uint32_t n_ml = 0;
-        for (uint32_t c0 = 0; c0 < n_items; c0 += obmp::G_NT) {
-            const uint32_t i = c0 + tid; const bool valid = i < n_items;
-            const item_t it = valid ? A.items[i0 + i] : 0;
-            const bool m = valid && obmp::it_marker(it);
-            uint64_t ve, vt; uint32_t fe, ft;
-            group_scan(C, 0, m ? 1u : 0u, ve, fe, vt, ft);
-            if (m) C.mlist[n_ml + fe] = (uint16_t)i;
-            else if (valid) {
-                if (obmp::it_exact(it) || obmp::it_large(it)) { C.icnt[i] = obmp::G_CNT_LOOKUP; C.any_flag = 1; }
-                else C.icnt[i] = (uint16_t)obmp::simple_count(it);
-            }
-            n_ml += ft;
-        }
-        __syncthreads();
-        /* lex every marker line once; the first G_MLCAP lines stage their tuples in shared memory */
-        for (uint32_t k = tid; k < n_ml; k += obmp::G_NT) {
-            const uint32_t i = C.mlist[k];
-            const item_t it = A.items[i0 + i];
-            const uint32_t d = doc_of_item(C, nu, i, it);
-            const uint64_t o0 = A.doc_off[d];
-            const uint32_t len = (uint32_t)(A.doc_off[d + 1] - o0);
-            const bool staged = k < obmp::G_MLCAP;
-            const uint32_t r = obmp::k2_marker_item(T, A.bytes + o0, len, it, staged ? C.stage + k * obmp::G_LTS : nullptr, staged ? obmp::G_LTS : 0u);
-            C.icnt[i] = (uint16_t)obmp::mres_tuples(r);
-            if (obmp::mres_irregular(r)) { atomicOr(&A.doc_flag[d], obmp::GF_INTERACT); C.any_flag = 1; }
-        }
-        __syncthreads();
-        const bool any = C.any_flag != 0;
-        if (any) {
-            /* documents that need the exact lexer: count them here (large documents were counted by k_exact_count) */
-            const uint32_t dA = C.ut_doc[0], dB = C.ut_doc[nu];
-            for (uint32_t d = dA + tid; d < dB; d += obmp::G_NT) {
-                const uint32_t f = A.doc_flag[d];
-                if (f && !(f & obmp::GF_LARGE)) {
+/* final positions of the block starting at `at0`: comment / EOF tuples in place, exact documents, unstaged
+ * lines; then the staged marker tuples, a lane per tuple.  Returns the block's tuple count. */
+__device__ __forceinline__ uint64_t k2_write_block(K2Ctx &X, uint32_t b0, uint32_t b1, uint32_t n_ml, uint64_t at0, bool stable) {
+    K2Warp &C = X.C; const GroupArgs &A = X.A; const uint32_t lane = X.lane;
+    uint64_t run = 0; uint32_t mrun = 0;
+    for (uint32_t c0 = b0; c0 < b1; c0 += 32) {
+        const uint32_t i = c0 + lane; const bool valid = i < b1;
+        const item_t it = valid ? A.items[X.i0 + i] : 0;
+        const uint32_t d = valid ? X.doc_of(it) : 0u;
+        const bool m = valid && obmp::it_marker(it) && !(stable && A.doc_flag[d]); /* same membership rule as the block's mlist */
+        const bool eof = valid && obmp::it_eof(it);
+        uint32_t c = valid ? C.icnt[i - b0] : 0u;
+        const bool lookup = c == obmp::G_CNT_LOOKUP;
+        if (lookup) c = A.counts[d];
+        uint64_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+        const uint64_t at = at0 + run + incl - c;
+        const uint32_t bal = __ballot_sync(0xffffffffu, m);
+        if (m) {
+            const uint32_t k = mrun + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+            if (c) {
+                if (k < obmp::W_MLCAP && c <= obmp::W_LTS) C.moff[k] = at;
+                else if (X.writing) {
                     const uint64_t o0 = A.doc_off[d];
-                    obm::SmallSink sink(nullptr, 0);
-                    obmp::k3_doc_exact(T, A.bytes + o0, (uint32_t)(A.doc_off[d + 1] - o0), sink);
-                    A.counts[d] = sink.n_tuples;
+                    const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
+                    uint32_t mk = 0, lx = 0; /* locals: taking the context's address would push it to the stack */
+                    obmp::k2_marker_item(X.T, A.bytes + o0, (uint32_t)(A.doc_off[d + 1] - o0), it, A.out + at,
+                                         roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv, &mk, &lx);
+                    X.markers += mk; X.lexemes += lx;
                 }
             }
-            __syncthreads();
-            for (uint32_t i = tid; i < n_items; i += obmp::G_NT) {
-                const item_t it = A.items[i0 + i];
-                if (A.doc_flag[doc_of_item(C, nu, i, it)]) C.icnt[i] = obmp::it_eof(it) ? obmp::G_CNT_LOOKUP : (uint16_t)0;
-            }
-            __syncthreads();
-        }
-        /* group total -> look-back -> base */
-        uint64_t sum = 0;
-        for (uint32_t i = tid; i < n_items; i += obmp::G_NT) {
-            uint32_t c = C.icnt[i];
-            if (c == obmp::G_CNT_LOOKUP) c = A.counts[doc_of_item(C, nu, i, A.items[i0 + i])];
-            sum += c;
-        }
-        uint64_t se, gtotal; uint32_t fe0, ft0;
-        group_scan(C, sum, 0, se, fe0, gtotal, ft0);
-        if (tid < 32) {
-            const uint64_t b = obmf::lookback_warp(A.st_tuples, j, gtotal);
-            if (tid == 0) {
-                C.base = b;
-                if (j == 0) A.tuple_off[0] = 0;
-                if (j == NG - 1) { A.tuple_off[A.ndocs] = b + gtotal; if (A.out && b + gtotal > A.out_cap) A.status[0] = 1; }
-            }
-        }
-        __syncthreads();
-        const uint64_t base = C.base;
-        /* pass B: final positions; comment / EOF tuples in place, exact documents, unstaged lines */
-        uint64_t run = 0; uint32_t mrun = 0;
-        for (uint32_t c0 = 0; c0 < n_items; c0 += obmp::G_NT) {
-            const uint32_t i = c0 + tid; const bool valid = i < n_items;
-            const item_t it = valid ? A.items[i0 + i] : 0;
-            const bool m = valid && obmp::it_marker(it);
-            const bool eof = valid && obmp::it_eof(it);
-            uint32_t c = valid ? C.icnt[i] : 0u;
-            const bool lookup = c == obmp::G_CNT_LOOKUP;
-            uint32_t d = 0;
-            if (eof || lookup) d = doc_of_item(C, nu, i, it);
-            if (lookup) c = A.counts[d];
-            uint64_t ve, vt; uint32_t fe, ft;
-            group_scan(C, c, m ? 1u : 0u, ve, fe, vt, ft);
-            const uint64_t at = base + run + ve;
-            if (m) {
-                const uint32_t k = mrun + fe;
-                if (c) {
-                    if (k < obmp::G_MLCAP && c <= obmp::G_LTS) C.moff[k] = at;
-                    else if (writing) {
-                        const uint32_t dd = doc_of_item(C, nu, i, it);
-                        const uint64_t o0 = A.doc_off[dd];
-                        const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
-                        obmp::k2_marker_item(T, A.bytes + o0, (uint32_t)(A.doc_off[dd + 1] - o0), it, A.out + at,
-                                             roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv, &markers, &lexemes);
-                    }
-                }
-            } else if (eof) {
-                A.tuple_off[d + 1] = at + c;
-                if (!lookup) {
-                    if (writing && at < A.out_cap) A.out[at] = OBM_TUPLE(OBM_K_EOF, obmp::it_ls(it), 0);
-                    lexemes++;
-                } else if (!obmp::it_large(it)) {
+        } else if (eof) {
+            A.tuple_off[d + 1] = at + c;
+            if (!lookup) {
+                if (X.writing && at < A.out_cap) A.out[at] = OBM_TUPLE(OBM_K_EOF, obmp::it_ls(it), 0);
+                X.lexemes++;
+            } else if (!obmp::it_large(it)) {
+                X.exact++;
+                if (X.writing) {
                     const uint64_t o0 = A.doc_off[d];
-                    const uint64_t roomv = (writing && at < A.out_cap) ? A.out_cap - at : 0;
+                    const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
                     obm::SmallSink sink(A.out + at, roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv);
-                    const int st = obmp::k3_doc_exact(T, A.bytes + o0, (uint32_t)(A.doc_off[d + 1] - o0), sink);
-                    markers += sink.n_markers; lexemes += sink.n_lexemes; exact++; fatal += (st == obm::RUN_FATAL) ? 1u : 0u;
+                    const int st = obmp::k3_doc_exact(X.T, A.bytes + o0, (uint32_t)(A.doc_off[d + 1] - o0), sink);
+                    X.markers += sink.n_markers; X.lexemes += sink.n_lexemes; X.fatal += (st == obm::RUN_FATAL) ? 1u : 0u;
                 }
-            } else if (valid && c) {
-                if (writing) obmp::plain_write(it, A.out, at, A.out_cap);
-                lexemes++;
             }
-            run += vt; mrun += ft;
+        } else if (valid && c) {
+            if (X.writing) obmp::plain_write(it, A.out, at, A.out_cap);
+            X.lexemes++;
         }
-        __syncthreads();
-        /* staged marker tuples -> final position, a warp per line */
-        if (writing) {
-            const uint32_t ns = n_ml < obmp::G_MLCAP ? n_ml : obmp::G_MLCAP;
-            for (uint32_t k = wid; k < ns; k += obmp::G_NT / 32) {
-                const uint64_t at = C.moff[k];
-                if (at == ~0ull) continue;
-                const uint32_t c = C.icnt[C.mlist[k]];
-                const bool on = lane < c;
-                const obm_tuple tup = on ? C.stage[k * obmp::G_LTS + lane] : 0;
-                if (on && at + lane < A.out_cap) A.out[at + lane] = tup;
-                const uint32_t kind = OBM_TUPLE_KIND(tup);
-                const uint32_t mk = __ballot_sync(0xffffffffu, on && kind == OBM_K_MARKER_START);
-                const uint32_t lx = __ballot_sync(0xffffffffu, on && (kind - (uint32_t)OBM_K_PART) > 4u);
-                if (lane == 0) { markers += (uint32_t)__popc(mk); lexemes += (uint32_t)__popc(lx); }
-            }
-        }
-        __syncthreads();
+        run += __shfl_sync(0xffffffffu, incl, 31);
+        mrun += (uint32_t)__popc(bal);
     }
+    __syncwarp();
+    if (X.writing) {
+        const uint32_t ns = n_ml < obmp::W_MLCAP ? n_ml : obmp::W_MLCAP;
+        for (uint32_t k = 0; k < ns; k++) {
+            const uint64_t at = C.moff[k];
+            if (at == ~0ull) continue;
+            const uint32_t c = C.icnt[C.mlist[k]];
+            const bool on = lane < c;
+            const obm_tuple tup = on ? C.stage[k * obmp::W_LTS + lane] : 0;
+            if (on && at + lane < A.out_cap) A.out[at + lane] = tup;
+            const uint32_t kind = OBM_TUPLE_KIND(tup);
+            const uint32_t mk = __ballot_sync(0xffffffffu, on && kind == OBM_K_MARKER_START);
+            const uint32_t lx = __ballot_sync(0xffffffffu, on && (kind - (uint32_t)OBM_K_PART) > 4u);
+            if (lane == 0) { X.markers += (uint32_t)__popc(mk); X.lexemes += (uint32_t)__popc(lx); }
+        }
+    }
+    __syncwarp();
+    return run;
+}
+
+__global__ void __launch_bounds__(obmp::W_WARPS * 32)
+k2_units(GroupArgs A) {
+    if (A.ctl[CT_OVF]) return; /* work records overflowed in k1: the host redoes the batch with the exact kernels */
+    __shared__ K2Warp WS[obmp::W_WARPS];
+    const obm::Tables T = dev_tables();
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nunits = (uint32_t)A.ubase[A.ntiles];
+    K2Ctx X{A, WS[threadIdx.x >> 5], T, 0, 0, 0, lane, A.out != nullptr && A.out_cap != 0, 0, 0, 0, 0};
+    for (;;) {
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(&A.ctl[CT_T2], 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= nunits) break;
+        const obmp::Unit U = A.units[u];
+        const uint32_t n_items = obmp::unit_items(U);
+        X.i0 = U.item_base; X.d0 = U.doc_base; X.nd = obmp::unit_nd(U);
+        uint64_t total; uint32_t n_ml = 0;
+        const bool one_block = n_items <= obmp::W_ICAP;
+        if (one_block) {
+            const bool any = __any_sync(0xffffffffu, k2_lex_block(X, 0, n_items, false, n_ml));
+            if (any) { k2_count_flagged_docs(X); k2_apply_flags(X, 0, n_items); }
+            total = k2_block_total(X, 0, n_items);
+        } else {
+            /* large unit: count sweep in 32-item blocks (repeated once if it discovered interacting lines),
+             * then the write sweep lexes block by block again */
+            bool stable = false;
+            for (;;) {
+                total = 0; bool any = false;
+                for (uint32_t b0 = 0; b0 < n_items; b0 += 32) {
+                    const uint32_t b1 = min(b0 + 32u, n_items);
+                    uint32_t nm;
+                    any |= k2_lex_block(X, b0, b1, stable, nm);
+                    if (stable) total += k2_block_total(X, b0, b1);
+                }
+                if (stable) break;
+                (void)__any_sync(0xffffffffu, any);
+                k2_count_flagged_docs(X); /* flags are final now: no line of an unflagged document is irregular */
+                stable = true;
+            }
+        }
+        const uint64_t base = obmf::lookback_warp(A.st_tuples, u, total);
+        if (lane == 0) {
+            if (u == 0) A.tuple_off[0] = 0;
+            if (u == nunits - 1 && A.out && base + total > A.out_cap) A.status[0] = 1;
+        }
+        if (one_block) k2_write_block(X, 0, n_items, n_ml, base, false);
+        else {
+            uint64_t at = base;
+            for (uint32_t b0 = 0; b0 < n_items; b0 += 32) {
+                const uint32_t b1 = min(b0 + 32u, n_items);
+                uint32_t nm;
+                k2_lex_block(X, b0, b1, true, nm);
+                at += k2_write_block(X, b0, b1, nm, at, true);
+            }
+        }
+    }
+    uint32_t markers = X.markers, lexemes = X.lexemes, exact = X.exact, fatal = X.fatal;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         markers += __shfl_down_sync(0xffffffffu, markers, o); lexemes += __shfl_down_sync(0xffffffffu, lexemes, o);

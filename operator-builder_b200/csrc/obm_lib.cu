@@ -220,7 +220,7 @@ struct obm_handle {
     } slots[3];
     bool slots_ready;
     uint64_t chunk_bytes; /* host batches of at least twice this size are pipelined in chunks */
-    int mode; /* 0 = ordered two-stage pipeline, 1 = exact path only, 2 = fused tile kernel, 3 = three-stage pipeline */
+    int mode; /* 0 = two-stage pipeline, 1 = exact path only, 2 = fused tile kernel, 3 = three-stage pipeline */
     uint32_t launches; /* kernels launched by the last obm_lex_batch_device call */
 };
 
@@ -456,20 +456,17 @@ static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 static uint32_t scan_tiles(uint32_t ndocs) { return (ndocs + SCAN_TILE - 1) / SCAN_TILE; }
 
 
-/* ---- ordered two-stage pipeline (mode 0) ------------------------------------------------------------- */
+/* ---- two-stage pipeline (mode 0) --------------------------------------------------------------------- */
 static uint64_t group_items_cap(uint32_t ndocs, uint64_t total_bytes) { return total_bytes / 24 + 2ull * ndocs + obm_fast_ntiles(total_bytes) + 1024; }
 static uint64_t group_units_max(uint32_t ndocs, uint64_t total_bytes) { return obm_fast_ntiles(total_bytes) + ndocs / obmt::DMAX + 2; }
-static uint64_t group_gcap(uint32_t ndocs, uint64_t total_bytes) {
-    return (obmp::UNIT_W * group_units_max(ndocs, total_bytes) + 5 * group_items_cap(ndocs, total_bytes)) / obmp::GROUP_W + 4;
-}
 static uint64_t group_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
-    const uint64_t nt = obm_fast_ntiles(total_bytes), um = group_units_max(ndocs, total_bytes), gc = group_gcap(ndocs, total_bytes);
+    const uint64_t nt = obm_fast_ntiles(total_bytes), um = group_units_max(ndocs, total_bytes);
     return align_up(group_items_cap(ndocs, total_bytes) * 8, 256) + align_up(nt * 4 + 4, 256) + align_up((nt + 1) * 8, 256) +
-           align_up(((uint64_t)scan_tiles((uint32_t)nt) + 1) * 8, 256) + align_up((um + 1) * 8, 256) + align_up((um + 1) * 4, 256) +
-           align_up(gc * 4, 256) + align_up((uint64_t)ndocs * 4 + 4, 256) + 2 * align_up((um + 1) * 8, 256) + align_up(gc * 8, 256) + 256;
+           align_up(((uint64_t)scan_tiles((uint32_t)nt) + 1) * 8, 256) + align_up((um + 1) * 16, 256) +
+           align_up((uint64_t)ndocs * 4 + 4, 256) + align_up((um + 1) * 8, 256) + 256;
 }
 
-/* index -> exact count of large documents -> units per tile (+ scan) -> k1_scan -> k2_group -> exact fill of
+/* index -> exact count of large documents -> units per tile (+ scan) -> k1_scan -> k2_units -> exact fill of
  * large documents. */
 static int obm_group_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t *d_doc_off, uint32_t ndocs, uint64_t total_bytes,
                             obm_tuple *d_out, uint64_t out_cap, uint64_t *toff, uint32_t *status, unsigned long long *totals,
@@ -481,7 +478,7 @@ static int obm_group_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_
         attr_set = true;
     }
     const uint64_t nt64 = obm_fast_ntiles(total_bytes);
-    if (nt64 > 0xFFFFFFF0ull || group_items_cap(ndocs, total_bytes) > 0xFFFFFFF0ull) { set_err(h, "batch too large for the tile index"); return OBM_E_ARG; }
+    if (nt64 > 0xFFFFFFF0ull || group_units_max(ndocs, total_bytes) > 0xFFFFFFF0ull) { set_err(h, "batch too large for the tile index"); return OBM_E_ARG; }
     const uint32_t ntiles = (uint32_t)nt64;
     auto up = [](uint64_t v) { return (v + 255) / 256 * 256; };
     uint8_t *w = (uint8_t *)fast_ws;
@@ -490,7 +487,7 @@ static int obm_group_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_
     const uint64_t max_large = obm_fast_max_large(total_bytes);
     uint32_t *large_list = (uint32_t *)w; w += up((max_large + 1) * 4);
     uint32_t *lctl = (uint32_t *)w; /* [1] n_large */
-    const uint64_t ic = group_items_cap(ndocs, total_bytes), um = group_units_max(ndocs, total_bytes), gc = group_gcap(ndocs, total_bytes);
+    const uint64_t ic = group_items_cap(ndocs, total_bytes), um = group_units_max(ndocs, total_bytes);
     const uint32_t nt_u = scan_tiles(ntiles);
     uint8_t *q = (uint8_t *)group_ws;
     obmg::GroupArgs A;
@@ -499,21 +496,14 @@ static int obm_group_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_
     uint32_t *nsub = (uint32_t *)q; q += up((uint64_t)ntiles * 4 + 4);
     uint64_t *ubase = (uint64_t *)q; q += up(((uint64_t)ntiles + 1) * 8); A.ubase = ubase;
     uint64_t *usums = (uint64_t *)q; q += up(((uint64_t)nt_u + 1) * 8);
-    A.uitem = (uint64_t *)q; q += up((um + 1) * 8);
-    A.udoc = (uint32_t *)q; q += up((um + 1) * 4);
-    A.gstart = (uint32_t *)q; q += up(gc * 4); A.gcap = gc;
+    A.units = (obmp::Unit *)q; q += up((um + 1) * 16);
     A.doc_flag = (uint32_t *)q; q += up((uint64_t)ndocs * 4 + 4);
-    uint8_t *chains = q;
-    A.st_items = (uint64_t *)q; q += up((um + 1) * 8);
-    A.st_weight = (uint64_t *)q; q += up((um + 1) * 8);
-    A.st_tuples = (uint64_t *)q; q += up(gc * 8);
-    const size_t chain_bytes = (size_t)(q - chains);
+    A.st_tuples = (uint64_t *)q; q += up((um + 1) * 8);
     A.ctl = (uint32_t *)q;
     A.counts = counts; A.out = d_out; A.out_cap = d_out ? out_cap : 0; A.tuple_off = toff;
     A.status = status; A.totals = totals;
-    OBM_CUDA(h, cudaMemsetAsync(chains, 0, chain_bytes + 64, st)); /* look-back chains + control words */
+    OBM_CUDA(h, cudaMemsetAsync(A.st_tuples, 0, up((um + 1) * 8) + 64, st)); /* look-back chain + control words */
     OBM_CUDA(h, cudaMemsetAsync(lctl, 0, 16, st));
-    OBM_CUDA(h, cudaMemsetAsync(A.gstart, 0, 4, st));
     obmf::k_tile_index<<<(ndocs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, ndocs, ntiles, tile_first, large_list, lctl + 1);
     const uint32_t nb_large = (uint32_t)((max_large + 127) / 128);
     k_exact_count<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, lctl + 1, counts, totals, status);
@@ -524,16 +514,16 @@ static int obm_group_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_
     int dev_sms = 0, per_sm1 = 0, per_sm2 = 0;
     OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
     OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, obmg::k1_scan, (int)obmt::NT, smem1));
-    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, obmg::k2_group, (int)obmp::G_NT, 0));
+    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, obmg::k2_units, (int)(obmp::W_WARPS * 32), 0));
     if (per_sm1 < 1) per_sm1 = 1;
     if (per_sm2 < 1) per_sm2 = 1;
     uint32_t g1 = (uint32_t)dev_sms * (uint32_t)per_sm1; /* persistent CTAs: multiples of the SM count */
     if (g1 > ntiles) g1 = ntiles;
     uint32_t g2 = (uint32_t)dev_sms * (uint32_t)per_sm2;
-    const uint64_t g2max = total_bytes / (4 * obmt::TILE) + 2;
+    const uint64_t g2max = (um + obmp::W_WARPS - 1) / obmp::W_WARPS;
     if (g2 > g2max) g2 = (uint32_t)g2max;
     obmg::k1_scan<<<g1, obmt::NT, smem1, st>>>(A);
-    obmg::k2_group<<<g2, obmp::G_NT, 0, st>>>(A);
+    obmg::k2_units<<<g2, obmp::W_WARPS * 32, 0, st>>>(A);
     uint32_t launches = 8;
     if (d_out && out_cap) {
         k_exact_fill<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, lctl + 1, toff, d_out, out_cap);

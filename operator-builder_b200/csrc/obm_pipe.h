@@ -134,17 +134,16 @@ OBM_HD_NOINLINE uint32_t k2_marker_line(const obm::Tables &T, const uint8_t *doc
 
 OBM_HD uint32_t plain_count_fwd(item_t it) { return it_line(it) == 1 ? 1u : 2u; }
 
-/* ==== ordered pipeline (mode 0): K1 emits ONE ordered item stream, K2 lexes + assembles per group ======
- * Items are written in global position order (K1 allocates through a decoupled look-back over static
- * unit ids).  Besides one item per tuple-owning line, every document closes with an EOF item, so tuple
- * positions are a plain prefix sum over item counts.  A marker item carries everything K2 needs to lex
- * its line (there is no separate marker-line list):
+/* ==== two-stage pipeline (mode 0): K1 emits per-unit item runs, K2 lexes + assembles one unit per warp ====
+ * Within a unit the items are in position order.  Besides one item per tuple-owning line, every document
+ * closes with an EOF item, so tuple positions are a plain prefix sum over item counts.  A marker item
+ * carries everything K2 needs to lex its line (there is no separate marker-line list):
  *   marker item : ls | first<<14 | line<<28 | 1<<42 | line_end[13]<<43 | doc6<<45 | line_end[0..12]<<51
  *   plain item  : ls | comment<<14 | line<<28 | slash2<<43 | dead<<44 | doc6<<45
  *   EOF item    : doc length | doc6<<45 | 1<<51 | exact<<52      (exact: K1 flagged the document)
  *   LARGE item  : 1<<51 | 1<<53                                  (document = last of the unit; > MAXDOC)
- * A unit is one K1 sub-batch (<= DMAX documents, <= QMAX owning lines).  Unit records: exclusive item
- * prefix and first document.  K2 groups are runs of units of ~equal weight (GROUP_W). */
+ * A unit is one K1 sub-batch (<= DMAX whole documents of one tile, <= QMAX owning lines); unit ids are
+ * static and in document order, so a decoupled look-back over units orders the output. */
 OBM_HD item_t make_marker_item(uint32_t ls, uint32_t first, uint32_t line, uint32_t d, uint32_t line_end) {
     return (item_t)ls | ((item_t)first << 14) | ((item_t)line << 28) | ((item_t)1 << 42) | ((item_t)((line_end >> 13) & 1u) << 43) |
            ((item_t)d << 45) | ((item_t)(line_end & 0x1FFFu) << 51);
@@ -156,17 +155,18 @@ OBM_HD bool it_eof(item_t i) { return !it_marker(i) && ((i >> 51) & 1); }
 OBM_HD bool it_exact(item_t i) { return !it_marker(i) && ((i >> 52) & 1); }
 OBM_HD bool it_large(item_t i) { return !it_marker(i) && ((i >> 53) & 1); }
 
-constexpr uint32_t GROUP_W = 768;       /* weight of a K2 group */
-constexpr uint32_t UNIT_W = 8;          /* weight of a unit = UNIT_W + 4 * marker lines + items */
-constexpr uint32_t G_NT = 128;          /* threads of a K2 group CTA */
-constexpr uint32_t G_MLCAP = 128;       /* marker lines whose tuples are staged in shared memory */
-constexpr uint32_t G_LTS = 25;          /* staged tuples per marker line (odd stride: no bank clash) */
-constexpr uint32_t G_UCAP = GROUP_W / UNIT_W + 2;   /* units per group */
-constexpr uint32_t G_IMAX = GROUP_W + obmt::QMAX + obmt::DMAX + 2; /* items per group */
-constexpr uint16_t G_CNT_LOOKUP = 0xFFFF; /* item count lives in counts[doc] (exact / large documents) */
-OBM_HD uint32_t unit_weight(uint32_t n_items, uint32_t n_ml) { return UNIT_W + 4u * n_ml + n_items; }
+/* unit record (16 B): where the unit's items are, its first document, item / small-document counts */
+struct Unit { uint64_t item_base; uint32_t doc_base; uint32_t n; /* n_items | nd << 16 */ };
+OBM_HD uint32_t unit_items(const Unit &u) { return u.n & 0xFFFFu; }
+OBM_HD uint32_t unit_nd(const Unit &u) { return u.n >> 16; }
 
-/* K1: owner o of the sub-batch -> item (ordered pipeline) */
+constexpr uint32_t W_WARPS = 4;         /* warps per K2 CTA (each works alone) */
+constexpr uint32_t W_MLCAP = 32;        /* marker lines staged per block = one per lane */
+constexpr uint32_t W_LTS = 25;          /* staged tuples per marker line (odd stride: no bank clash) */
+constexpr uint32_t W_ICAP = 256;        /* items of a unit handled as one block (larger units: 32-item blocks) */
+constexpr uint16_t G_CNT_LOOKUP = 0xFFFF; /* item count lives in counts[doc] (exact / large documents) */
+
+/* K1: owner o of the sub-batch -> item */
 OBM_FN item_t k1_owner_item(const SmemScan &S, uint32_t o) {
     uint32_t first = S.owner[o];
     uint32_t ls = obmt::line_start_of(S, first);

@@ -315,19 +315,113 @@ extern "C" uint64_t hs_pipe_batch(const uint8_t *bytes, const uint64_t *doc_off,
 }
 
 /* ---------------------------------------------------------------------------------------------
- * Emulation of the ordered two-stage pipeline (obm_group.cuh): k1_scan builds the ordered item
- * stream with EOF items, unit records and weight-cut groups; k2_group is replayed per group with
- * the same staging capacity, look-up sentinel, flag handling and pass structure as the kernel.
+ * Emulation of the two-stage pipeline (obm_group.cuh): k1_scan builds per-unit item runs with EOF
+ * items and unit records; k2_units is replayed unit by unit (one warp each on the device) with the
+ * same block structure, staging capacity, look-up sentinel and flag handling as the kernel.
  * ------------------------------------------------------------------------------------------- */
+namespace {
+struct GroupEmu {
+    const uint8_t *bytes; const uint64_t *doc_off; obm_tuple *out; uint64_t cap; uint64_t *tuple_off;
+    std::vector<obmp::item_t> items; std::vector<obmp::Unit> units; std::vector<uint32_t> doc_flag, counts;
+    uint64_t st_m = 0, st_l = 0, st_e = 0, st_f = 0;
+    /* per-warp shared memory */
+    obm_tuple stage[obmp::W_MLCAP * obmp::W_LTS]; uint64_t moff[obmp::W_MLCAP]; uint16_t icnt[obmp::W_ICAP]; uint8_t mlist[obmp::W_ICAP];
+    uint64_t i0; uint32_t d0, nd;
+    uint32_t doc_of(obmp::item_t it) const { return obmp::it_large(it) ? d0 + nd : d0 + obmp::it_doc(it); }
+    uint32_t dlen(uint32_t d) const { return (uint32_t)(doc_off[d + 1] - doc_off[d]); }
+    bool lex_block(uint32_t b0, uint32_t b1, bool stable, uint32_t &n_ml_out) {
+        using namespace obmp;
+        uint32_t n_ml = 0; bool any = false;
+        for (uint32_t k = 0; k < W_MLCAP; k++) moff[k] = ~0ull;
+        for (uint32_t i = b0; i < b1; i++) {
+            item_t it = items[i0 + i];
+            bool m = it_marker(it);
+            if (stable && doc_flag[doc_of(it)]) { m = false; icnt[i - b0] = it_eof(it) ? G_CNT_LOOKUP : (uint16_t)0; }
+            else if (!m) {
+                if (it_exact(it) || it_large(it)) { icnt[i - b0] = G_CNT_LOOKUP; any = true; }
+                else icnt[i - b0] = (uint16_t)simple_count(it);
+            }
+            if (m) mlist[n_ml++] = (uint8_t)(i - b0);
+        }
+        for (uint32_t k = 0; k < n_ml; k++) {
+            const uint32_t ib = mlist[k]; item_t it = items[i0 + b0 + ib];
+            const uint32_t d = doc_of(it);
+            const bool staged = k < W_MLCAP;
+            uint32_t r = k2_marker_item(TBL, bytes + doc_off[d], dlen(d), it, staged ? stage + k * W_LTS : nullptr, staged ? W_LTS : 0u);
+            icnt[ib] = (uint16_t)mres_tuples(r);
+            if (mres_irregular(r)) { doc_flag[d] |= GF_INTERACT; any = true; }
+        }
+        n_ml_out = n_ml;
+        return any;
+    }
+    void count_flagged_docs() {
+        for (uint32_t q = 0; q < nd; q++) {
+            const uint32_t d = d0 + q, f = doc_flag[d];
+            if (f && !(f & obmp::GF_LARGE)) { obm::SmallSink s(nullptr, 0); obmp::k3_doc_exact(TBL, bytes + doc_off[d], dlen(d), s); counts[d] = s.n_tuples; }
+        }
+    }
+    void apply_flags(uint32_t b0, uint32_t b1) {
+        for (uint32_t i = b0; i < b1; i++) { obmp::item_t it = items[i0 + i]; if (doc_flag[doc_of(it)]) icnt[i - b0] = obmp::it_eof(it) ? obmp::G_CNT_LOOKUP : (uint16_t)0; }
+    }
+    uint64_t block_total(uint32_t b0, uint32_t b1) {
+        uint64_t sum = 0;
+        for (uint32_t i = b0; i < b1; i++) { uint32_t c = icnt[i - b0]; if (c == obmp::G_CNT_LOOKUP) c = counts[doc_of(items[i0 + i])]; sum += c; }
+        return sum;
+    }
+    uint64_t write_block(uint32_t b0, uint32_t b1, uint32_t n_ml, uint64_t at0, bool stable) {
+        using namespace obmp;
+        uint64_t at = at0; uint32_t k = 0;
+        for (uint32_t i = b0; i < b1; i++) {
+            item_t it = items[i0 + i];
+            uint32_t c = icnt[i - b0]; const bool lookup = c == G_CNT_LOOKUP;
+            const uint32_t d = doc_of(it);
+            if (lookup) c = counts[d];
+            if (it_marker(it) && !(stable && doc_flag[d])) { /* same membership rule as lex_block's mlist */
+                if (c) {
+                    if (k < W_MLCAP && c <= W_LTS) moff[k] = at;
+                    else { uint32_t mk = 0, lx = 0; k2_marker_item(TBL, bytes + doc_off[d], dlen(d), it, out + at, at < cap ? (uint32_t)(cap - at) : 0u, &mk, &lx); st_m += mk; st_l += lx; }
+                }
+                k++;
+            } else if (it_marker(it)) {
+                /* line of a flagged document: nothing to write */
+            } else if (it_eof(it)) {
+                tuple_off[d + 1] = at + c;
+                if (!lookup) { if (at < cap) out[at] = OBM_TUPLE(OBM_K_EOF, it_ls(it), 0); st_l++; }
+                else if (it_large(it)) { /* k_exact_fill on the device */
+                    obm::WriteSink sink(out + at, at < cap ? cap - at : 0);
+                    obm::Lexer<obm::WriteSink> lx(TBL, bytes + doc_off[d], dlen(d), sink);
+                    lx.run<false>();
+                } else {
+                    obm::SmallSink s(out + at, at < cap ? (uint32_t)(cap - at) : 0u);
+                    int st = k3_doc_exact(TBL, bytes + doc_off[d], dlen(d), s);
+                    st_m += s.n_markers; st_l += s.n_lexemes; st_e++; st_f += st == obm::RUN_FATAL;
+                }
+            } else if (c) { plain_write(it, out, at, cap); st_l++; }
+            at += c;
+        }
+        for (uint32_t q = 0; q < (n_ml < W_MLCAP ? n_ml : W_MLCAP); q++) {
+            if (moff[q] == ~0ull) continue;
+            const uint32_t c = icnt[mlist[q]];
+            for (uint32_t l = 0; l < c; l++) {
+                obm_tuple tup = stage[q * W_LTS + l];
+                if (moff[q] + l < cap) out[moff[q] + l] = tup;
+                uint32_t kind = OBM_TUPLE_KIND(tup);
+                st_m += kind == OBM_K_MARKER_START; st_l += (kind - (uint32_t)OBM_K_PART) > 4u;
+            }
+        }
+        return at - at0;
+    }
+};
+} // namespace
+
 extern "C" uint64_t hs_group_batch(const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs, obm_tuple *out, uint64_t cap,
                                    uint64_t *tuple_off, uint32_t fake_skew, uint64_t *stats) {
     static Emu emu;
     using namespace obmp;
+    GroupEmu G; G.bytes = bytes; G.doc_off = doc_off; G.out = out; G.cap = cap; G.tuple_off = tuple_off;
+    G.doc_flag.assign(ndocs, 0); G.counts.assign(ndocs, 0);
     const uint64_t total = doc_off[ndocs];
     const uint64_t ntiles = total / obmt::TILE + 1;
-    std::vector<item_t> items; std::vector<uint64_t> uitem; std::vector<uint32_t> udoc, gstart(1, 0), doc_flag(ndocs, 0), counts(ndocs, 0);
-    uint64_t st_m = 0, st_l = 0, st_e = 0, st_f = 0;
-    uint64_t wsum = 0;
     /* K1 */
     uint32_t d = 0;
     for (uint64_t t = 0; t < ntiles; t++) {
@@ -339,124 +433,58 @@ extern "C" uint64_t hs_group_batch(const uint8_t *bytes, const uint64_t *doc_off
         const uint32_t d_small_end = d_last - (has_large ? 1u : 0u);
         uint32_t nsub = (d_small_end - d_first + obmt::DMAX - 1) / obmt::DMAX; if (nsub == 0) nsub = 1;
         if (has_large) {
-            const uint32_t dl = d_last - 1; doc_flag[dl] = GF_LARGE;
+            const uint32_t dl = d_last - 1; G.doc_flag[dl] = GF_LARGE;
             obm::SmallSink s(nullptr, 0); obm::Lexer<obm::SmallSink> lx(TBL, bytes + doc_off[dl], (uint32_t)(doc_off[dl + 1] - doc_off[dl]), s);
-            int st = lx.run<false>(); counts[dl] = s.n_tuples; st_m += s.n_markers; st_l += s.n_lexemes; st_e++; st_f += st == obm::RUN_FATAL;
+            int st = lx.run<false>(); G.counts[dl] = s.n_tuples; G.st_m += s.n_markers; G.st_l += s.n_lexemes; G.st_e++; G.st_f += st == obm::RUN_FATAL;
         }
         for (uint32_t k = 0; k < nsub; k++) {
             const uint32_t da = d_first + k * obmt::DMAX, db = da + obmt::DMAX < d_small_end ? da + obmt::DMAX : d_small_end, nd = db - da;
             const uint32_t extra = (k == nsub - 1 && has_large) ? 1u : 0u;
-            uint32_t n_owners = 0, n_ml = 0;
+            uint32_t n_owners = 0;
             std::vector<item_t> sit;
             if (nd) {
                 emu.scan(bytes, doc_off, da, db, fake_skew);
                 n_owners = emu.S.n_owners;
                 sit.resize(n_owners);
-                for (uint32_t o = 0; o < n_owners; o++) { sit[o] = k1_owner_item(emu.S, o); n_ml += it_marker(sit[o]); }
+                for (uint32_t o = 0; o < n_owners; o++) sit[o] = k1_owner_item(emu.S, o);
             }
             const uint32_t n_items = n_owners + nd + extra;
-            const uint64_t ibase = items.size();
-            items.resize(ibase + n_items, ~0ull);
-            for (uint32_t o = 0; o < n_owners; o++) items[ibase + o + it_doc(sit[o])] = sit[o];
+            const uint64_t ibase = G.items.size();
+            G.items.resize(ibase + n_items, ~0ull);
+            for (uint32_t o = 0; o < n_owners; o++) G.items[ibase + o + it_doc(sit[o])] = sit[o];
             for (uint32_t q = 0; q < nd; q++) {
                 uint32_t lo = 0; while (lo < n_owners && it_doc(sit[lo]) <= q) lo++;
                 const uint32_t f = emu.S.dflag[q];
-                doc_flag[da + q] = ((f & obmt::DF_NONASCII) ? GF_NONASCII : 0u) | ((f & obmt::DF_QOVERFLOW) ? GF_QOVERFLOW : 0u);
-                items[ibase + lo + q] = make_eof_item(emu.S.dstart[q + 1] - emu.S.dstart[q], q, f != 0);
+                G.doc_flag[da + q] = ((f & obmt::DF_NONASCII) ? GF_NONASCII : 0u) | ((f & obmt::DF_QOVERFLOW) ? GF_QOVERFLOW : 0u);
+                G.items[ibase + lo + q] = make_eof_item(emu.S.dstart[q + 1] - emu.S.dstart[q], q, f != 0);
             }
-            if (extra) items[ibase + n_items - 1] = make_large_item();
-            for (uint64_t i = ibase; i < ibase + n_items; i++) if (items[i] == ~0ull) { fprintf(stderr, "hostsim: item hole\n"); abort(); }
-            const uint32_t u = (uint32_t)uitem.size();
-            uitem.push_back(ibase); udoc.push_back(da);
-            const uint64_t w0 = wsum, w1 = wsum + unit_weight(n_items, n_ml);
-            for (uint64_t j = w0 / GROUP_W + 1; j <= w1 / GROUP_W; j++) { if (gstart.size() != j) { fprintf(stderr, "hostsim: group order\n"); abort(); } gstart.push_back(u + 1); }
-            wsum = w1;
+            if (extra) G.items[ibase + n_items - 1] = make_large_item();
+            for (uint64_t i = ibase; i < ibase + n_items; i++) if (G.items[i] == ~0ull) { fprintf(stderr, "hostsim: item hole\n"); abort(); }
+            G.units.push_back(Unit{ibase, da, n_items | (nd << 16)});
         }
     }
-    const uint32_t nunits = (uint32_t)uitem.size();
-    uitem.push_back(items.size()); udoc.push_back(ndocs);
-    const uint32_t NG = nunits ? (uint32_t)(wsum / GROUP_W + 1) : 0;
-    if (nunits && gstart.size() != NG) { fprintf(stderr, "hostsim: group count %zu vs %u\n", gstart.size(), NG); abort(); }
-    /* K2 */
+    /* K2: units in id order (the look-back chain) */
     uint64_t base = 0;
     tuple_off[0] = 0;
-    std::vector<obm_tuple> stage(G_MLCAP * G_LTS);
-    for (uint32_t j = 0; j < NG; j++) {
-        const uint32_t ua = gstart[j], ub = (j + 1 < NG) ? gstart[j + 1] : nunits, nu = ub - ua;
-        if (nu > G_UCAP) { fprintf(stderr, "hostsim: group has %u units\n", nu); abort(); }
-        const uint64_t i0 = uitem[ua];
-        const uint32_t n_items = (uint32_t)(uitem[ub] - i0);
-        if (n_items > G_IMAX) { fprintf(stderr, "hostsim: group has %u items\n", n_items); abort(); }
-        auto unit_of = [&](uint32_t i) { uint32_t lo = 0, hi = nu; while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (uitem[ua + mid] - i0 <= i) lo = mid; else hi = mid; } return lo; };
-        auto doc_of_item = [&](uint32_t i, item_t it) { uint32_t u = unit_of(i); return it_large(it) ? udoc[ua + u + 1] - 1u : udoc[ua + u] + it_doc(it); };
-        std::vector<uint16_t> icnt(n_items, 0), mlist; std::vector<uint64_t> moff(G_MLCAP, ~0ull);
-        bool any = false;
-        for (uint32_t i = 0; i < n_items; i++) {
-            item_t it = items[i0 + i];
-            if (it_marker(it)) mlist.push_back((uint16_t)i);
-            else if (it_exact(it) || it_large(it)) { icnt[i] = G_CNT_LOOKUP; any = true; }
-            else icnt[i] = (uint16_t)simple_count(it);
+    for (const Unit &U : G.units) {
+        const uint32_t n_items = unit_items(U);
+        G.i0 = U.item_base; G.d0 = U.doc_base; G.nd = unit_nd(U);
+        uint32_t n_ml = 0;
+        if (n_items <= W_ICAP) {
+            if (G.lex_block(0, n_items, false, n_ml)) { G.count_flagged_docs(); G.apply_flags(0, n_items); }
+            base += G.write_block(0, n_items, n_ml, base, false);
+        } else {
+            for (uint32_t b0 = 0; b0 < n_items; b0 += 32) { uint32_t nm; G.lex_block(b0, b0 + 32 < n_items ? b0 + 32 : n_items, false, nm); }
+            G.count_flagged_docs();
+            uint64_t total_u = 0;
+            for (uint32_t b0 = 0; b0 < n_items; b0 += 32) { uint32_t nm, b1 = b0 + 32 < n_items ? b0 + 32 : n_items; G.lex_block(b0, b1, true, nm); total_u += G.block_total(b0, b1); }
+            uint64_t at = base;
+            for (uint32_t b0 = 0; b0 < n_items; b0 += 32) { uint32_t nm, b1 = b0 + 32 < n_items ? b0 + 32 : n_items; G.lex_block(b0, b1, true, nm); at += G.write_block(b0, b1, nm, at, true); }
+            if (at - base != total_u) { fprintf(stderr, "hostsim: large-unit sweeps disagree (%llu vs %llu)\n", (unsigned long long)(at - base), (unsigned long long)total_u); abort(); }
+            base = at;
         }
-        const uint32_t n_ml = (uint32_t)mlist.size();
-        for (uint32_t k = 0; k < n_ml; k++) {
-            const uint32_t i = mlist[k]; item_t it = items[i0 + i];
-            const uint32_t dd = doc_of_item(i, it);
-            const bool staged = k < G_MLCAP;
-            uint32_t r = k2_marker_item(TBL, bytes + doc_off[dd], (uint32_t)(doc_off[dd + 1] - doc_off[dd]), it, staged ? &stage[k * G_LTS] : nullptr, staged ? G_LTS : 0u);
-            icnt[i] = (uint16_t)mres_tuples(r);
-            if (mres_irregular(r)) { doc_flag[dd] |= GF_INTERACT; any = true; }
-        }
-        if (any) {
-            for (uint32_t dd = udoc[ua]; dd < udoc[ub]; dd++) {
-                if (doc_flag[dd] && !(doc_flag[dd] & GF_LARGE)) { obm::SmallSink s(nullptr, 0); k3_doc_exact(TBL, bytes + doc_off[dd], (uint32_t)(doc_off[dd + 1] - doc_off[dd]), s); counts[dd] = s.n_tuples; }
-            }
-            for (uint32_t i = 0; i < n_items; i++) { item_t it = items[i0 + i]; if (doc_flag[doc_of_item(i, it)]) icnt[i] = it_eof(it) ? G_CNT_LOOKUP : (uint16_t)0; }
-        }
-        uint64_t at = base; uint32_t k = 0;
-        for (uint32_t i = 0; i < n_items; i++) {
-            item_t it = items[i0 + i];
-            uint32_t c = icnt[i]; const bool lookup = c == G_CNT_LOOKUP;
-            uint32_t dd = 0;
-            if (it_eof(it) || lookup) dd = doc_of_item(i, it);
-            if (lookup) c = counts[dd];
-            if (it_marker(it)) {
-                if (c) {
-                    if (k < G_MLCAP && c <= G_LTS) moff[k] = at;
-                    else {
-                        uint32_t d2 = doc_of_item(i, it), mk = 0, lx = 0;
-                        k2_marker_item(TBL, bytes + doc_off[d2], (uint32_t)(doc_off[d2 + 1] - doc_off[d2]), it, out + at, at < cap ? (uint32_t)(cap - at) : 0u, &mk, &lx);
-                        st_m += mk; st_l += lx;
-                    }
-                }
-                k++;
-            } else if (it_eof(it)) {
-                tuple_off[dd + 1] = at + c;
-                if (!lookup) { if (at < cap) out[at] = OBM_TUPLE(OBM_K_EOF, it_ls(it), 0); st_l++; }
-                else if (it_large(it)) {
-                    obm::WriteSink sink(out + at, at < cap ? cap - at : 0);
-                    obm::Lexer<obm::WriteSink> lx(TBL, bytes + doc_off[dd], (uint32_t)(doc_off[dd + 1] - doc_off[dd]), sink);
-                    lx.run<false>();
-                } else {
-                    obm::SmallSink s(out + at, at < cap ? (uint32_t)(cap - at) : 0u);
-                    int st = k3_doc_exact(TBL, bytes + doc_off[dd], (uint32_t)(doc_off[dd + 1] - doc_off[dd]), s);
-                    st_m += s.n_markers; st_l += s.n_lexemes; st_e++; st_f += st == obm::RUN_FATAL;
-                }
-            } else if (c) { plain_write(it, out, at, cap); st_l++; }
-            at += c;
-        }
-        for (uint32_t q = 0; q < (n_ml < G_MLCAP ? n_ml : G_MLCAP); q++) {
-            if (moff[q] == ~0ull) continue;
-            const uint32_t c = icnt[mlist[q]];
-            for (uint32_t l = 0; l < c; l++) {
-                obm_tuple tup = stage[q * G_LTS + l];
-                if (moff[q] + l < cap) out[moff[q] + l] = tup;
-                uint32_t kind = OBM_TUPLE_KIND(tup);
-                st_m += kind == OBM_K_MARKER_START; st_l += (kind - (uint32_t)OBM_K_PART) > 4u;
-            }
-        }
-        base = at;
     }
     tuple_off[ndocs] = base;
-    if (stats) { stats[0] = st_m; stats[1] = st_l; stats[2] = st_e; stats[3] = st_f; }
+    if (stats) { stats[0] = G.st_m; stats[1] = G.st_l; stats[2] = G.st_e; stats[3] = G.st_f; }
     return base;
 }

@@ -270,7 +270,7 @@ def test_full_size_properties_on_device(scanner):
         assert int(d_counts[0].item()) == 8 * ndocs
         outs.append((d_out, d_toff, int(d_toff[-1].item()), int(d_counts[1].item())))
     scanner.set_mode(0)
-    for k in (1, 2):
+    for k in (1, 2, 3):
         assert outs[0][2] == outs[k][2] and outs[0][3] == outs[k][3]
         assert torch.equal(outs[0][1], outs[k][1]) and torch.equal(outs[0][0], outs[k][0])
     # shard property: documents [100000, 100000+4096) regenerated alone give the same tuples

@@ -5,11 +5,12 @@ import csv, subprocess, collections, sys
 rep, ndocs = sys.argv[1], int(sys.argv[2])
 which = sys.argv[3] if len(sys.argv) > 3 else None
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+by_samples = bool(int(__import__("os").environ.get("BY_SAMPLES", "0")))
 kfilter = sys.argv[5] if len(sys.argv) > 5 else None  # substring of the kernel name
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 files = {}
-for f in ["obm_core.h", "obm_tile.h", "obm_fast.cuh", "obm_lib.cu", "obm_pipe.h", "obm_pipe.cuh"]:
+for f in ["obm_core.h", "obm_tile.h", "obm_fast.cuh", "obm_lib.cu", "obm_pipe.h", "obm_pipe.cuh", "obm_group.cuh"]:
     for i, l in enumerate(open("operator-builder_b200/csrc/" + f).read().split("\n"), 1):
         files.setdefault((i, l.strip()[:60]), f)
 ie = None; cur = None
@@ -35,5 +36,5 @@ for k, a in agg.items():
     print(f"{k:14s} {a[0]/tot[0]:6.1%} inst  lanes {a[1]/max(a[0],1):5.1f}  {a[0]/ndocs:7.0f} warp-inst/doc  {a[2]/max(tot[1],1):6.1%} samples")
 print(f"total {tot[0]/ndocs:.0f} warp-inst/doc")
 if which:
-    for k, a in sorted([(k, a) for k, a in lines.items() if k[0] == which], key=lambda kv: -kv[1][0])[:topn]:
+    for k, a in sorted([(k, a) for k, a in lines.items() if k[0] == which], key=lambda kv: -(kv[1][2] if by_samples else kv[1][0]))[:topn]:
         print(f"{a[0]/ndocs:7.1f}/doc lanes {a[1]/max(a[0],1):5.1f} smp {a[2]/max(tot[1],1):5.1%} :{k[1]} {k[2]}")

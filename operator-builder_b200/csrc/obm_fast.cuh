@@ -96,6 +96,55 @@ __device__ __forceinline__ uint64_t lookback_warp(volatile uint64_t *state, uint
     return sum;
 }
 
+/* Read-only walk (all 32 lanes of a warp): exclusive prefix of chain element t, i.e. the sum of all elements
+ * before it, from whatever mixture of aggregates and inclusive prefixes their owners have published so far. */
+__device__ __forceinline__ uint64_t lookback_read_warp(volatile uint64_t *state, uint32_t t) {
+    const uint32_t lane = threadIdx.x & 31;
+    if (t == 0) return 0;
+    uint64_t sum = 0;
+    int64_t hi = (int64_t)t - 1;
+    for (;;) {
+        int64_t idx = hi - (int64_t)lane;
+        uint64_t s = idx >= 0 ? state[idx] : LB_INCL;
+        uint32_t f = (uint32_t)(s >> 62);
+        uint32_t incl = __ballot_sync(0xffffffffu, f == 2);
+        uint32_t zero = __ballot_sync(0xffffffffu, f == 0);
+        uint32_t upto = incl ? (uint32_t)__ffs((int)incl) - 1u : 31u;
+        uint32_t need = upto == 31u ? 0xffffffffu : ((2u << upto) - 1u);
+        if (zero & need) { __nanosleep(100); continue; }
+        uint64_t v = lane <= upto ? (s & LB_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        sum += v;
+        if (incl) break;
+        hi -= 32;
+    }
+    return sum;
+}
+
+/* Two-level chain for many small elements (one per warp): level 0 holds plain aggregates, level 1 one
+ * aggregate / inclusive prefix per block of 32 elements.  An element waits only for the aggregates of the
+ * earlier elements of its own block and for a 32-wide walk over blocks, so one round trip advances the
+ * resolved frontier by up to 1024 elements instead of 32.  Executed by all 32 lanes; returns the exclusive
+ * prefix of element t (n = number of elements). */
+__device__ __forceinline__ uint64_t lookback2_warp(volatile uint64_t *st0, volatile uint64_t *st1, uint32_t t, uint32_t n, uint64_t my_total) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t b = t >> 5, r = t & 31;
+    const uint32_t bs = min(32u, n - (b << 5));
+    if (lane == 0) { st0[t] = LB_AGG | my_total; __threadfence(); }
+    uint64_t s;
+    for (;;) {
+        s = lane < r ? st0[(b << 5) + lane] : LB_AGG;
+        if (__ballot_sync(0xffffffffu, (s >> 62) == 0) == 0) break;
+        __nanosleep(100);
+    }
+    uint64_t partial = s & LB_MASK;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) partial += __shfl_xor_sync(0xffffffffu, partial, o);
+    const uint64_t P = (r == bs - 1) ? lookback_warp(st1, b, partial + my_total) : lookback_read_warp(st1, b);
+    return P + partial;
+}
+
 /* ---- pre-kernel: tile -> first document map, list of large documents ----------------------------- */
 __global__ void __launch_bounds__(256)
 k_tile_index(const uint64_t *__restrict__ doc_off, uint32_t ndocs, uint32_t ntiles, uint32_t *__restrict__ tile_first,

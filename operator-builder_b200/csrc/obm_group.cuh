@@ -31,7 +31,7 @@ struct GroupArgs {
     item_t *items; uint64_t items_cap;
     obmp::Unit *units;          /* [nunits] */
     uint32_t *doc_flag;
-    uint64_t *st_tuples;        /* look-back chain over units */
+    uint64_t *st_tuples, *st_blocks; /* two-level look-back chain over units (obmf::lookback2_warp) */
     /* results */
     uint32_t *counts; obm_tuple *out; uint64_t out_cap; uint64_t *tuple_off;
     uint32_t *status; unsigned long long *totals;
@@ -99,7 +99,7 @@ k1_scan(GroupArgs A) {
             const uint32_t da = d_first + k * obmt::DMAX, db = min(da + obmt::DMAX, d_small_end), nd = db - da;
             const uint32_t extra = (k == nsub - 1 && has_large) ? 1u : 0u;
             const uint64_t u = u0 + k;
-            uint32_t n_owners = 0;
+            uint32_t n_owners = 0, n_live = 0;
             if (nd) {
                 const uint64_t b0 = A.doc_off[da], b1 = A.doc_off[db];
                 const uint64_t abs0 = (uint64_t)(uintptr_t)A.bytes + b0, base_abs = abs0 & ~15ull;
@@ -165,27 +165,42 @@ k1_scan(GroupArgs A) {
                     }
                 }
                 __syncthreads();
-                /* P5 owners -> items (shared memory, owner order) */
-                for (uint32_t o = tid; o < n_owners; o += obmt::NT) sitems[o] = obmp::k1_owner_item(S, o);
-                __syncthreads();
+                /* P5 owners -> items (shared memory, owner order); lines that own no tuple ("dead": a quote or slash
+                 * outside any comment) are dropped here: S.owner[o] becomes the number of live owners before o */
+                uint32_t live_run = 0;
+                for (uint32_t o0 = 0; o0 < n_owners; o0 += obmt::NT) {
+                    const uint32_t o = o0 + tid;
+                    bool live = false;
+                    if (o < n_owners) { const item_t it = obmp::k1_owner_item(S, o); sitems[o] = it; live = !obmp::it_dead(it); }
+                    const uint32_t bal = __ballot_sync(0xffffffffu, live);
+                    if ((tid & 31) == 0) S.scan_tmp[tid >> 5] = (uint32_t)__popc(bal);
+                    __syncthreads();
+                    uint32_t pre = 0, tot = 0;
+#pragma unroll
+                    for (uint32_t w = 0; w < obmt::NT / 32; w++) { const uint32_t c = S.scan_tmp[w]; if (w < (tid >> 5)) pre += c; tot += c; }
+                    if (o < n_owners) S.owner[o] = live_run + pre + (uint32_t)__popc(bal & ((1u << (tid & 31)) - 1u));
+                    live_run += tot;
+                    __syncthreads();
+                }
+                n_live = live_run;
                 /* per document: index after its last owner (owners are in position order, hence grouped by document) */
                 if (tid < nd) {
                     uint32_t lo = 0, hi = n_owners;
                     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (obmp::it_doc(sitems[mid]) <= tid) lo = mid + 1; else hi = mid; }
-                    C.dlast[tid] = (uint16_t)lo;
+                    C.dlast[tid] = (uint16_t)(lo < n_owners ? S.owner[lo] : n_live); /* live items before the next document */
                     const uint32_t f = S.dflag[tid];
                     A.doc_flag[da + tid] = ((f & obmt::DF_NONASCII) ? obmp::GF_NONASCII : 0u) | ((f & obmt::DF_QOVERFLOW) ? obmp::GF_QOVERFLOW : 0u);
                 }
             }
             __syncthreads();
             /* the unit's items are contiguous; units are placed by a bump allocator (any order) */
-            const uint32_t n_items = n_owners + nd + extra;
+            const uint32_t n_items = n_live + nd + extra;
             if (tid == 0) C.item_base = atomicAdd(reinterpret_cast<unsigned long long *>(&A.ctl[CT_ITOP]), (unsigned long long)n_items);
             __syncthreads();
             const uint64_t ibase = C.item_base;
             const bool room = ibase + n_items <= A.items_cap;
             if (room) {
-                for (uint32_t o = tid; o < n_owners; o += obmt::NT) { const item_t it = sitems[o]; A.items[ibase + o + obmp::it_doc(it)] = it; }
+                for (uint32_t o = tid; o < n_owners; o += obmt::NT) { const item_t it = sitems[o]; if (!obmp::it_dead(it)) A.items[ibase + S.owner[o] + obmp::it_doc(it)] = it; }
                 if (tid < nd) A.items[ibase + C.dlast[tid] + tid] = obmp::make_eof_item(S.dstart[tid + 1] - S.dstart[tid], tid, S.dflag[tid] != 0);
                 if (extra && tid == 0) A.items[ibase + n_items - 1] = obmp::make_large_item();
             }
@@ -202,6 +217,7 @@ k1_scan(GroupArgs A) {
 struct K2Warp {
     alignas(16) obm_tuple stage[obmp::W_MLCAP * obmp::W_LTS];
     uint64_t moff[obmp::W_MLCAP];   /* staged line -> final output position (~0: not copied) */
+    alignas(16) uint8_t pool[obmp::W_POOL * 16]; /* staged line text (obm_pipe.h: LineView) */
     uint16_t icnt[obmp::W_ICAP];    /* tuples per item of the block (G_CNT_LOOKUP: counts[doc]) */
     uint8_t mlist[obmp::W_ICAP];    /* marker rank -> item index inside the block */
 };
@@ -234,16 +250,46 @@ __device__ __forceinline__ bool k2_lex_block(K2Ctx &X, uint32_t b0, uint32_t b1,
         n_ml += (uint32_t)__popc(bal);
     }
     __syncwarp();
-    for (uint32_t k = lane; k < n_ml; k += 32) {
-        const uint32_t ib = C.mlist[k];
-        const item_t it = A.items[X.i0 + b0 + ib];
-        const uint32_t d = X.doc_of(it);
-        const uint64_t o0 = A.doc_off[d];
-        const bool staged = k < obmp::W_MLCAP;
-        const uint32_t r = obmp::k2_marker_item(X.T, A.bytes + o0, (uint32_t)(A.doc_off[d + 1] - o0), it,
-                                                staged ? C.stage + k * obmp::W_LTS : nullptr, staged ? obmp::W_LTS : 0u);
-        C.icnt[ib] = (uint16_t)obmp::mres_tuples(r);
-        if (obmp::mres_irregular(r)) { atomicOr(&A.doc_flag[d], obmp::GF_INTERACT); any = true; }
+    for (uint32_t k0 = 0; k0 < n_ml; k0 += 32) {
+        const uint32_t k = k0 + lane; const bool on = k < n_ml;
+        const bool staged = k0 == 0; /* the first W_MLCAP lines: text and tuples staged in shared memory */
+        uint32_t ib = 0, d = 0, len = 0; item_t it = 0; const uint8_t *gdoc = nullptr;
+        obmp::LineView v{0, 0, 0};
+        if (on) {
+            ib = C.mlist[k]; it = A.items[X.i0 + b0 + ib]; d = X.doc_of(it);
+            const uint64_t o0 = A.doc_off[d];
+            len = (uint32_t)(A.doc_off[d + 1] - o0); gdoc = A.bytes + o0;
+            if (staged) v = obmp::line_view(gdoc, len, it, A.bytes, A.total_bytes);
+        }
+        const uint8_t *doc = gdoc; uint32_t n_view = len;
+        if (staged) {
+            /* pack the lines' chunk runs into the pool (exclusive scan of chunk counts), cp.async them all, wait once */
+            uint32_t want = (on && v.nch <= 32u) ? v.nch : 0u, incl = want;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+            const bool fits = want != 0 && incl <= obmp::W_POOL;
+            const uint32_t off = incl - want;
+            for (uint32_t q = 0; q < 32 && q < n_ml; q++) {
+                const uint32_t nq = __shfl_sync(0xffffffffu, fits ? want : 0u, q), oq = __shfl_sync(0xffffffffu, off, q);
+                const unsigned long long gq = __shfl_sync(0xffffffffu, (unsigned long long)v.g0, q);
+                if (lane < nq) {
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(C.pool + (size_t)(oq + lane) * 16u);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gq + (unsigned long long)lane * 16ull) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            if (fits) {
+                const uint8_t *sm = C.pool + (size_t)off * 16u;
+                const uint32_t nv = obmp::line_view_safe(sm, v, gdoc, len, it);
+                if (nv) { doc = sm + (intptr_t)((uintptr_t)gdoc - v.g0); n_view = nv; }
+            }
+        }
+        if (on) {
+            const uint32_t r = obmp::k2_marker_item(X.T, doc, n_view, it, staged ? C.stage + k * obmp::W_LTS : nullptr, staged ? obmp::W_LTS : 0u);
+            C.icnt[ib] = (uint16_t)obmp::mres_tuples(r);
+            if (obmp::mres_irregular(r)) { atomicOr(&A.doc_flag[d], obmp::GF_INTERACT); any = true; }
+        }
     }
     __syncwarp();
     n_ml_out = n_ml;
@@ -359,7 +405,7 @@ __device__ __forceinline__ uint64_t k2_write_block(K2Ctx &X, uint32_t b0, uint32
     return run;
 }
 
-__global__ void __launch_bounds__(obmp::W_WARPS * 32)
+__global__ void __launch_bounds__(obmp::W_WARPS * 32, 5)
 k2_units(GroupArgs A) {
     if (A.ctl[CT_OVF]) return; /* work records overflowed in k1: the host redoes the batch with the exact kernels */
     __shared__ K2Warp WS[obmp::W_WARPS];
@@ -399,7 +445,7 @@ k2_units(GroupArgs A) {
                 stable = true;
             }
         }
-        const uint64_t base = obmf::lookback_warp(A.st_tuples, u, total);
+        const uint64_t base = obmf::lookback2_warp(A.st_tuples, A.st_blocks, u, nunits, total);
         if (lane == 0) {
             if (u == 0) A.tuple_off[0] = 0;
             if (u == nunits - 1 && A.out && base + total > A.out_cap) A.status[0] = 1;

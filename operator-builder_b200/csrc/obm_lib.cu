@@ -463,7 +463,7 @@ static uint64_t group_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
     const uint64_t nt = obm_fast_ntiles(total_bytes), um = group_units_max(ndocs, total_bytes);
     return align_up(group_items_cap(ndocs, total_bytes) * 8, 256) + align_up(nt * 4 + 4, 256) + align_up((nt + 1) * 8, 256) +
            align_up(((uint64_t)scan_tiles((uint32_t)nt) + 1) * 8, 256) + align_up((um + 1) * 16, 256) +
-           align_up((uint64_t)ndocs * 4 + 4, 256) + align_up((um + 1) * 8, 256) + 256;
+           align_up((uint64_t)ndocs * 4 + 4, 256) + align_up((um + 1) * 8, 256) + align_up((um / 32 + 2) * 8, 256) + 256;
 }
 
 /* index -> exact count of large documents -> units per tile (+ scan) -> k1_scan -> k2_units -> exact fill of
@@ -499,10 +499,11 @@ static int obm_group_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_
     A.units = (obmp::Unit *)q; q += up((um + 1) * 16);
     A.doc_flag = (uint32_t *)q; q += up((uint64_t)ndocs * 4 + 4);
     A.st_tuples = (uint64_t *)q; q += up((um + 1) * 8);
+    A.st_blocks = (uint64_t *)q; q += up((um / 32 + 2) * 8);
     A.ctl = (uint32_t *)q;
     A.counts = counts; A.out = d_out; A.out_cap = d_out ? out_cap : 0; A.tuple_off = toff;
     A.status = status; A.totals = totals;
-    OBM_CUDA(h, cudaMemsetAsync(A.st_tuples, 0, up((um + 1) * 8) + 64, st)); /* look-back chain + control words */
+    OBM_CUDA(h, cudaMemsetAsync(A.st_tuples, 0, up((um + 1) * 8) + up((um / 32 + 2) * 8) + 64, st)); /* look-back chains + control words */
     OBM_CUDA(h, cudaMemsetAsync(lctl, 0, 16, st));
     obmf::k_tile_index<<<(ndocs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, ndocs, ntiles, tile_first, large_list, lctl + 1);
     const uint32_t nb_large = (uint32_t)((max_large + 127) / 128);

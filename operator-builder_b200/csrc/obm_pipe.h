@@ -162,7 +162,10 @@ OBM_HD uint32_t unit_nd(const Unit &u) { return u.n >> 16; }
 
 constexpr uint32_t W_WARPS = 4;         /* warps per K2 CTA (each works alone) */
 constexpr uint32_t W_MLCAP = 32;        /* marker lines staged per block = one per lane */
-constexpr uint32_t W_LTS = 25;          /* staged tuples per marker line (odd stride: no bank clash) */
+constexpr uint32_t W_LTS = 23;          /* staged tuples per marker line (odd stride: no bank clash) */
+constexpr uint32_t W_POOL = 192;        /* 16-byte chunks of line text staged per warp (3 KiB) */
+constexpr uint32_t W_LOOK = 24;         /* bytes staged past a line's newline: whitespace run + longest peeked token */
+constexpr uint32_t W_TOKEN = 8;         /* >= the longest token a whitespace-skipping peek compares ("false") */
 constexpr uint32_t W_ICAP = 256;        /* items of a unit handled as one block (larger units: 32-item blocks) */
 constexpr uint16_t G_CNT_LOOKUP = 0xFFFF; /* item count lives in counts[doc] (exact / large documents) */
 
@@ -196,6 +199,39 @@ OBM_HD_NOINLINE uint32_t k2_marker_item(const obm::Tables &T, const uint8_t *doc
     if (markers) *markers += sink.n_markers;
     if (lexemes) *lexemes += sink.n_lexemes;
     return make_mres(sink.n_tuples, irregular);
+}
+
+/* ---- staged line text ------------------------------------------------------------------------------
+ * K2 copies a marker line (first special byte .. newline + W_LOOK bytes, 16-byte chunks at the global
+ * alignment) into shared memory and lexes it from there: all chunk loads of a warp are in flight at once
+ * instead of one dependent miss per sector.  The lexer is handed a document pointer rebased onto the copy
+ * and a document length cut at the end of the copy (`n_view`); that is exact as long as nothing past the
+ * copy can matter:
+ *   - bytes are only CONSUMED past the newline by constructs that make the line irregular (the document is
+ *     then re-lexed exactly, whatever was read);
+ *   - bytes are only PEEKED past the newline by whitespace-skipping token checks (peek.go:65-89: "true",
+ *     "false", "//", "#"), which stop at the first non-whitespace byte + the token length.
+ * line_view_safe() checks the second condition on the staged bytes; lines that fail it (or do not fit)
+ * are lexed from global memory. */
+struct LineView { uintptr_t g0, g1; uint32_t nch; };   /* staged address range [g0, g1), 16-byte chunks */
+OBM_HD LineView line_view(const uint8_t *gdoc, uint32_t len, item_t it, const uint8_t *bytes, uint64_t total_bytes) {
+    LineView v;
+    const uintptr_t a_first = (uintptr_t)(gdoc + it_pos(it));
+    uint32_t e = it_line_end(it) + 1u + W_LOOK; if (e > len) e = len;
+    const uintptr_t lim = ((uintptr_t)(bytes + total_bytes) + 15u) & ~(uintptr_t)15u; /* readable end of the batch (obmarkers.h) */
+    uintptr_t g1 = ((uintptr_t)(gdoc + e) + 15u) & ~(uintptr_t)15u; if (g1 > lim) g1 = lim;
+    v.g0 = a_first & ~(uintptr_t)15u; v.g1 = g1; v.nch = (uint32_t)((g1 - v.g0) >> 4);
+    return v;
+}
+/* sm: the staged copy of [g0, g1).  Returns n_view (> 0) when lexing from the copy is exact, else 0. */
+OBM_HD uint32_t line_view_safe(const uint8_t *sm, const LineView &v, const uint8_t *gdoc, uint32_t len, item_t it) {
+    const uintptr_t endrel = v.g1 - (uintptr_t)gdoc;
+    const uint32_t n_view = endrel < len ? (uint32_t)endrel : len;
+    if (n_view == len) return n_view;                      /* the copy reaches the real end of the document */
+    uint32_t w = it_line_end(it) + 1u;                     /* first byte after the newline */
+    const uint8_t *base = sm + (intptr_t)((uintptr_t)gdoc - v.g0); /* base[p] = document byte p (wraps: g0 is usually past gdoc) */
+    while (w < n_view && obm::is_space(base[w])) w++;
+    return (w + W_TOKEN <= n_view) ? n_view : 0u;
 }
 
 /* tuples of a non-marker item of a regular document */

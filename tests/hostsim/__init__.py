@@ -90,7 +90,7 @@ def tile_batch(docs, skew=0, pipeline=False):
     pipeline) over a list of documents
     -> (tuples, doc_tuple_off, stats)."""
     L = lib()
-    data = np.frombuffer(b"".join(docs) + b"\0", dtype=np.uint8).copy()
+    data = np.frombuffer(b"".join(docs) + b"+" * 32, dtype=np.uint8).copy()  # readable (poisoned) past the end, like the device buffer contract
     off = np.zeros(len(docs) + 1, dtype=np.uint64)
     if docs:
         off[1:] = np.cumsum([len(d) for d in docs])

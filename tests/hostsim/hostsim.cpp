@@ -326,7 +326,7 @@ struct GroupEmu {
     uint64_t st_m = 0, st_l = 0, st_e = 0, st_f = 0;
     /* per-warp shared memory */
     obm_tuple stage[obmp::W_MLCAP * obmp::W_LTS]; uint64_t moff[obmp::W_MLCAP]; uint16_t icnt[obmp::W_ICAP]; uint8_t mlist[obmp::W_ICAP];
-    uint64_t i0; uint32_t d0, nd;
+    uint64_t i0; uint32_t d0, nd; uint64_t total_bytes = 0; uint64_t views = 0, unsafe_views = 0;
     uint32_t doc_of(obmp::item_t it) const { return obmp::it_large(it) ? d0 + nd : d0 + obmp::it_doc(it); }
     uint32_t dlen(uint32_t d) const { return (uint32_t)(doc_off[d + 1] - doc_off[d]); }
     bool lex_block(uint32_t b0, uint32_t b1, bool stable, uint32_t &n_ml_out) {
@@ -343,11 +343,28 @@ struct GroupEmu {
             }
             if (m) mlist[n_ml++] = (uint8_t)(i - b0);
         }
+        /* staged line text: same packing rule as the kernel (exclusive scan of chunk counts over the first 32 lines);
+         * everything outside the copied chunks is poison, so any dependence on bytes past a view shows up */
+        alignas(16) static uint8_t pool[W_POOL * 16];
+        memset(pool, 0x2B, sizeof pool);
+        uint32_t pool_used = 0;
         for (uint32_t k = 0; k < n_ml; k++) {
             const uint32_t ib = mlist[k]; item_t it = items[i0 + b0 + ib];
             const uint32_t d = doc_of(it);
             const bool staged = k < W_MLCAP;
-            uint32_t r = k2_marker_item(TBL, bytes + doc_off[d], dlen(d), it, staged ? stage + k * W_LTS : nullptr, staged ? W_LTS : 0u);
+            const uint8_t *doc = bytes + doc_off[d]; uint32_t n_view = dlen(d);
+            if (staged) {
+                LineView v = line_view(bytes + doc_off[d], dlen(d), it, bytes, total_bytes);
+                const uint32_t want = v.nch <= 32u ? v.nch : 0u;
+                pool_used += want; /* the scan is over all lines, fitting or not, exactly like the warp scan */
+                if (want && pool_used <= W_POOL) {
+                    uint8_t *sm = pool + (size_t)(pool_used - want) * 16u;
+                    memcpy(sm, (const void *)v.g0, (size_t)want * 16u);
+                    const uint32_t nv = line_view_safe(sm, v, bytes + doc_off[d], dlen(d), it);
+                    if (nv) { doc = sm + (intptr_t)((uintptr_t)(bytes + doc_off[d]) - v.g0); n_view = nv; views++; } else unsafe_views++;
+                }
+            }
+            uint32_t r = k2_marker_item(TBL, doc, n_view, it, staged ? stage + k * W_LTS : nullptr, staged ? W_LTS : 0u);
             icnt[ib] = (uint16_t)mres_tuples(r);
             if (mres_irregular(r)) { doc_flag[d] |= GF_INTERACT; any = true; }
         }
@@ -421,6 +438,7 @@ extern "C" uint64_t hs_group_batch(const uint8_t *bytes, const uint64_t *doc_off
     GroupEmu G; G.bytes = bytes; G.doc_off = doc_off; G.out = out; G.cap = cap; G.tuple_off = tuple_off;
     G.doc_flag.assign(ndocs, 0); G.counts.assign(ndocs, 0);
     const uint64_t total = doc_off[ndocs];
+    G.total_bytes = total;
     const uint64_t ntiles = total / obmt::TILE + 1;
     /* K1 */
     uint32_t d = 0;
@@ -448,12 +466,15 @@ extern "C" uint64_t hs_group_batch(const uint8_t *bytes, const uint64_t *doc_off
                 sit.resize(n_owners);
                 for (uint32_t o = 0; o < n_owners; o++) sit[o] = k1_owner_item(emu.S, o);
             }
-            const uint32_t n_items = n_owners + nd + extra;
+            std::vector<uint32_t> lp(n_owners + 1, 0); /* live owners before o (dead lines own no tuple and are dropped) */
+            for (uint32_t o = 0; o < n_owners; o++) lp[o + 1] = lp[o] + (it_dead(sit[o]) ? 0u : 1u);
+            const uint32_t n_items = lp[n_owners] + nd + extra;
             const uint64_t ibase = G.items.size();
             G.items.resize(ibase + n_items, ~0ull);
-            for (uint32_t o = 0; o < n_owners; o++) G.items[ibase + o + it_doc(sit[o])] = sit[o];
+            for (uint32_t o = 0; o < n_owners; o++) if (!it_dead(sit[o])) G.items[ibase + lp[o] + it_doc(sit[o])] = sit[o];
             for (uint32_t q = 0; q < nd; q++) {
                 uint32_t lo = 0; while (lo < n_owners && it_doc(sit[lo]) <= q) lo++;
+                lo = lp[lo];
                 const uint32_t f = emu.S.dflag[q];
                 G.doc_flag[da + q] = ((f & obmt::DF_NONASCII) ? GF_NONASCII : 0u) | ((f & obmt::DF_QOVERFLOW) ? GF_QOVERFLOW : 0u);
                 G.items[ibase + lo + q] = make_eof_item(emu.S.dstart[q + 1] - emu.S.dstart[q], q, f != 0);
@@ -486,5 +507,6 @@ extern "C" uint64_t hs_group_batch(const uint8_t *bytes, const uint64_t *doc_off
     }
     tuple_off[ndocs] = base;
     if (stats) { stats[0] = G.st_m; stats[1] = G.st_l; stats[2] = G.st_e; stats[3] = G.st_f; }
+    if (getenv("HS_VIEW_STATS")) fprintf(stderr, "hostsim: %llu staged line views, %llu rejected\n", (unsigned long long)G.views, (unsigned long long)G.unsafe_views);
     return base;
 }

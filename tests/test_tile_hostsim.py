@@ -104,3 +104,23 @@ def test_fuzz_valid_batches(seed):
         stats = check_batch(docs, skew=rng.randint(0, 15))
         exact += int(stats[2]); total += len(docs)
     assert exact < total * 0.6
+
+
+def test_staged_line_views_lookahead_across_the_newline():
+    """K2 lexes marker lines from a shared-memory copy that ends W_LOOK bytes after the newline (obm_pipe.h LineView).
+    Whitespace-skipping peeks (peek.go:65-89) may look across the newline: every distance around the end of the copy,
+    every peeked token, and line tails that leave the lexer in each value / argument state."""
+    tails = [b"+a:b:c=", b"+a:b:c= ", b"+a:b:c", b"+a:b:c,", b"+a:b:c=1,", b"+a:b:c=1,d", b"+a:b:c=1,d=", b"+a:b", b"+a:b:", b"+a",
+             b"+a:b:c=\"x", b"+a:b:c=`x", b"+a:b:c='x", b"+a:b:c=tru", b"+a:b:c=t", b"# +a:b:c=", b"  x: y # +a:b:c=", b"+a:b:c=1 ", b"+a:b:c=1\t"]
+    nexts = [b"true", b"false", b"//x", b"#y", b"x", b"truex", b"tru", b"=1", b",d=2", b"`", b"\"", b""]
+    docs = []
+    for tail in tails:
+        for nxt in nexts:
+            for ws in (0, 1, 2, 7, 15, 16, 17, 18, 19, 20, 23, 24, 25, 31, 40, 70):
+                for sep in (b" ", b"\t", b"\n"):
+                    docs.append(b"k: v\n" + tail + b"\n" + sep * ws + nxt + b"\nrest: 1 # +z:y=2\n")
+    random.Random(7).shuffle(docs)
+    for lo in range(0, len(docs), 400):
+        check_batch(docs[lo:lo + 400], skew=lo % 16)
+    # the same at the very end of a document / of the batch (the copy is cut at the document end)
+    check_batch([t + b"\n" + b" " * w for t in tails for w in (0, 1, 5, 30)] + [tails[0]])

@@ -51,7 +51,6 @@ enum { ST_OVERFLOW = 0, ST_DOCS_EXACT = 1, ST_DOCS_FATAL = 2, ST_RESERVED = 3 };
 
 #include "obm_fast.cuh"
 #include "obm_pipe.cuh"
-#include "obm_group.cuh"
 
 /* ------------------------------------------------------------------------------------------- */
 /* exact path: one thread per document                                                          */
@@ -220,7 +219,7 @@ struct obm_handle {
     } slots[3];
     bool slots_ready;
     uint64_t chunk_bytes; /* host batches of at least twice this size are pipelined in chunks */
-    int mode; /* 0 = two-stage pipeline, 1 = exact path only, 2 = fused tile kernel, 3 = three-stage pipeline */
+    int mode; /* 0 = two-stage pipeline, 1 = exact path only, 2 = fused tile kernel */
     uint32_t launches; /* kernels launched by the last obm_lex_batch_device call */
 };
 
@@ -357,99 +356,6 @@ static int obm_fast_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
 
 static uint64_t align_up(uint64_t v, uint64_t a);
 static uint32_t scan_tiles(uint32_t ndocs);
-/* pipeline (mode 0) work records: capacities are generous multiples of what manifests produce (one owning
- * line per ~68 B, one marker line per ~512 B); denser input sets the overflow flag and the scan is redone
- * by the exact kernels. */
-static uint64_t pipe_items_cap(uint32_t ndocs, uint64_t total_bytes) { return total_bytes / 24 + ndocs + 1024; }
-static uint64_t pipe_mlines_cap(uint64_t total_bytes) { return total_bytes / 64 + 1024; }
-static uint64_t pipe_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
-    const uint64_t ic = pipe_items_cap(ndocs, total_bytes), mc = pipe_mlines_cap(total_bytes);
-    return align_up(ic * 8, 256) + align_up(ic * 4, 256) + align_up(mc * 16, 256) + align_up(mc * 4, 256) + align_up(mc * 8, 256) +
-           align_up(((uint64_t)ndocs + 1) * 8, 256) + 2 * align_up((uint64_t)ndocs * 4 + 4, 256) + 256;
-}
-
-/* Mode 0: index -> exact count of large documents -> k1_scan -> k2_markers<count> -> k3_assemble ->
- * k2_markers<write> -> exact fill of large documents. */
-static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t *d_doc_off, uint32_t ndocs, uint64_t total_bytes,
-                           obm_tuple *d_out, uint64_t out_cap, uint64_t *toff, uint32_t *status, unsigned long long *totals,
-                           uint32_t *counts, uint64_t *tile_sums, void *fast_ws, void *pipe_ws, cudaStream_t st) {
-    static bool attr_set = false;
-    const size_t smem1 = sizeof(obmq::K1Shared);
-    if (!attr_set) {
-        OBM_CUDA(h, cudaFuncSetAttribute(obmq::k1_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        attr_set = true;
-    }
-    const uint64_t nt64 = obm_fast_ntiles(total_bytes);
-    if (nt64 > 0xFFFFFFF0ull) { set_err(h, "batch too large for the tile index"); return OBM_E_ARG; }
-    const uint32_t ntiles = (uint32_t)nt64;
-    auto up = [](uint64_t v) { return (v + 255) / 256 * 256; };
-    uint8_t *w = (uint8_t *)fast_ws;
-    uint32_t *tile_first = (uint32_t *)w; w += up(((uint64_t)ntiles + 2) * 4);
-    uint64_t *tile_state = (uint64_t *)w; w += up(((uint64_t)ntiles + 1) * 8);
-    const uint64_t max_large = obm_fast_max_large(total_bytes);
-    uint32_t *large_list = (uint32_t *)w; w += up((max_large + 1) * 4);
-    uint32_t *lctl = (uint32_t *)w; /* [1] n_large */
-    const uint64_t ic = pipe_items_cap(ndocs, total_bytes), mc = pipe_mlines_cap(total_bytes);
-    uint8_t *q = (uint8_t *)pipe_ws;
-    obmq::PipeArgs A;
-    A.bytes = d_bytes; A.doc_off = d_doc_off; A.ndocs = ndocs; A.total_bytes = total_bytes; A.tile_first = tile_first; A.ntiles = ntiles;
-    A.items = (obmp::item_t *)q; q += up(ic * 8); A.item_slot = (uint32_t *)q; q += up(ic * 4); A.items_cap = ic;
-    A.mlines = (obmp::MLine *)q; q += up(mc * 16); A.mres = (uint32_t *)q; q += up(mc * 4); A.moff = (uint64_t *)q; q += up(mc * 8); A.mlines_cap = mc;
-    A.doc_item_off = (uint64_t *)q; q += up(((uint64_t)ndocs + 1) * 8);
-    A.doc_item_n = (uint32_t *)q; q += up((uint64_t)ndocs * 4 + 4);
-    A.doc_flag = (uint32_t *)q; q += up((uint64_t)ndocs * 4 + 4);
-    A.ctl = (uint32_t *)q;
-    A.counts = counts; A.out = d_out; A.out_cap = d_out ? out_cap : 0; A.tuple_off = toff;
-    A.tile_state = tile_state; A.status = status; A.totals = totals;
-    OBM_CUDA(h, cudaMemsetAsync(tile_state, 0, ((uint64_t)ntiles + 1) * 8, st));
-    OBM_CUDA(h, cudaMemsetAsync(lctl, 0, 16, st));
-    OBM_CUDA(h, cudaMemsetAsync(A.ctl, 0, 64, st));
-    obmf::k_tile_index<<<(ndocs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, ndocs, ntiles, tile_first, large_list, lctl + 1);
-    const uint32_t nb_large = (uint32_t)((max_large + 127) / 128);
-    k_exact_count<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, lctl + 1, counts, totals, status);
-    int dev_sms = 0, per_sm1 = 0;
-    OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
-    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, obmq::k1_scan, (int)obmt::NT, smem1));
-    if (per_sm1 < 1) per_sm1 = 1;
-    uint32_t g1 = (uint32_t)dev_sms * (uint32_t)per_sm1;
-    if (g1 > ntiles) g1 = ntiles;
-    const uint32_t g2 = (uint32_t)dev_sms * 8u; /* persistent, grid-stride over the device-side marker-line list */
-    const uint32_t gd = (ndocs + 255) / 256;
-    const uint32_t nt = scan_tiles(ndocs);
-    obmq::k1_scan<<<g1, obmt::NT, smem1, st>>>(A);
-    if (getenv("OBM_DEBUG_K1")) {
-        uint32_t hc[16];
-        cudaStreamSynchronize(st);
-        cudaMemcpy(hc, A.ctl, sizeof hc, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[obm debug] after k1: err=%s ticket=%u n_mlines=%u (cap %llu) items_top=%llu (cap %llu) ovf=%u ntiles=%u ndocs=%u\n",
-                cudaGetErrorString(cudaGetLastError()), hc[0], hc[1], (unsigned long long)mc,
-                (unsigned long long)hc[4] | ((unsigned long long)hc[5] << 32), (unsigned long long)ic, hc[6], ntiles, ndocs);
-    }
-    obmq::k2_markers<false><<<g2, 256, 0, st>>>(A);
-    obmq::k3_doc_count<<<gd, 256, 0, st>>>(A, counts);
-    k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(counts, ndocs, toff, tile_sums);
-    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, toff + ndocs);
-    k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(toff, ndocs, tile_sums, d_out ? out_cap : ~0ull, status);
-    obmq::k3_doc_write<<<gd, 256, 0, st>>>(A);
-    uint32_t launches = 9;
-    if (d_out && out_cap) {
-        obmq::k2_markers<true><<<g2, 256, 0, st>>>(A);
-        k_exact_fill<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, lctl + 1, toff, d_out, out_cap);
-        launches += 2;
-    }
-    if (getenv("OBM_DEBUG_END")) {
-        uint32_t hc[16];
-        cudaError_t e1 = cudaStreamSynchronize(st);
-        cudaMemcpy(hc, A.ctl, sizeof hc, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[obm debug] end: sync=%s last=%s t1=%u n_mlines=%u items_top=%u ovf=%u d_out=%p g1=%u g2=%u smem1=%zu\n",
-                cudaGetErrorString(e1), cudaGetErrorString(cudaGetLastError()), hc[0], hc[1], hc[4], hc[6], (void *)d_out, g1, g2, smem1);
-    }
-    /* work-record overflow -> status[3]: the caller must redo the scan with the exact kernels (mode 1) */
-    OBM_CUDA(h, cudaMemcpyAsync(status + ST_RESERVED, A.ctl + obmq::CT_OVF, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-    h->launches = launches;
-    OBM_CUDA(h, cudaGetLastError());
-    return OBM_OK;
-}
 
 /* scratch layout: counts u32[ndocs] | tile_sums u64[ntiles] | fast-path workspace | pipeline workspace */
 static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
@@ -457,28 +363,28 @@ static uint32_t scan_tiles(uint32_t ndocs) { return (ndocs + SCAN_TILE - 1) / SC
 
 
 /* ---- two-stage pipeline (mode 0) --------------------------------------------------------------------- */
-static uint64_t group_items_cap(uint32_t ndocs, uint64_t total_bytes) { return total_bytes / 24 + 2ull * ndocs + obm_fast_ntiles(total_bytes) + 1024; }
-static uint64_t group_units_max(uint32_t ndocs, uint64_t total_bytes) { return obm_fast_ntiles(total_bytes) + ndocs / obmt::DMAX + 2; }
-static uint64_t group_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
-    const uint64_t nt = obm_fast_ntiles(total_bytes), um = group_units_max(ndocs, total_bytes);
-    return align_up(group_items_cap(ndocs, total_bytes) * 8, 256) + align_up(nt * 4 + 4, 256) + align_up((nt + 1) * 8, 256) +
+static uint64_t pipe_items_cap(uint32_t ndocs, uint64_t total_bytes) { return total_bytes / 24 + 2ull * ndocs + obm_fast_ntiles(total_bytes) + 1024; }
+static uint64_t pipe_units_max(uint32_t ndocs, uint64_t total_bytes) { return obm_fast_ntiles(total_bytes) + ndocs / obmt::DMAX + 2; }
+static uint64_t pipe_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
+    const uint64_t nt = obm_fast_ntiles(total_bytes), um = pipe_units_max(ndocs, total_bytes);
+    return align_up(pipe_items_cap(ndocs, total_bytes) * 8, 256) + align_up(nt * 4 + 4, 256) + align_up((nt + 1) * 8, 256) +
            align_up(((uint64_t)scan_tiles((uint32_t)nt) + 1) * 8, 256) + align_up((um + 1) * 16, 256) +
            align_up((uint64_t)ndocs * 4 + 4, 256) + align_up((um + 1) * 8, 256) + align_up((um / 32 + 2) * 8, 256) + 256;
 }
 
 /* index -> exact count of large documents -> units per tile (+ scan) -> k1_scan -> k2_units -> exact fill of
  * large documents. */
-static int obm_group_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t *d_doc_off, uint32_t ndocs, uint64_t total_bytes,
+static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t *d_doc_off, uint32_t ndocs, uint64_t total_bytes,
                             obm_tuple *d_out, uint64_t out_cap, uint64_t *toff, uint32_t *status, unsigned long long *totals,
-                            uint32_t *counts, void *fast_ws, void *group_ws, cudaStream_t st) {
+                            uint32_t *counts, void *fast_ws, void *pipe_ws, cudaStream_t st) {
     static bool attr_set = false;
-    const size_t smem1 = sizeof(obmg::K1Shared);
+    const size_t smem1 = sizeof(obmq::K1Shared);
     if (!attr_set) {
-        OBM_CUDA(h, cudaFuncSetAttribute(obmg::k1_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        OBM_CUDA(h, cudaFuncSetAttribute(obmq::k1_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
         attr_set = true;
     }
     const uint64_t nt64 = obm_fast_ntiles(total_bytes);
-    if (nt64 > 0xFFFFFFF0ull || group_units_max(ndocs, total_bytes) > 0xFFFFFFF0ull) { set_err(h, "batch too large for the tile index"); return OBM_E_ARG; }
+    if (nt64 > 0xFFFFFFF0ull || pipe_units_max(ndocs, total_bytes) > 0xFFFFFFF0ull) { set_err(h, "batch too large for the tile index"); return OBM_E_ARG; }
     const uint32_t ntiles = (uint32_t)nt64;
     auto up = [](uint64_t v) { return (v + 255) / 256 * 256; };
     uint8_t *w = (uint8_t *)fast_ws;
@@ -487,10 +393,10 @@ static int obm_group_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_
     const uint64_t max_large = obm_fast_max_large(total_bytes);
     uint32_t *large_list = (uint32_t *)w; w += up((max_large + 1) * 4);
     uint32_t *lctl = (uint32_t *)w; /* [1] n_large */
-    const uint64_t ic = group_items_cap(ndocs, total_bytes), um = group_units_max(ndocs, total_bytes);
+    const uint64_t ic = pipe_items_cap(ndocs, total_bytes), um = pipe_units_max(ndocs, total_bytes);
     const uint32_t nt_u = scan_tiles(ntiles);
-    uint8_t *q = (uint8_t *)group_ws;
-    obmg::GroupArgs A;
+    uint8_t *q = (uint8_t *)pipe_ws;
+    obmq::PipeArgs A;
     A.bytes = d_bytes; A.doc_off = d_doc_off; A.ndocs = ndocs; A.total_bytes = total_bytes; A.tile_first = tile_first; A.ntiles = ntiles;
     A.items = (obmp::item_t *)q; q += up(ic * 8); A.items_cap = ic;
     uint32_t *nsub = (uint32_t *)q; q += up((uint64_t)ntiles * 4 + 4);
@@ -508,14 +414,14 @@ static int obm_group_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_
     obmf::k_tile_index<<<(ndocs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, ndocs, ntiles, tile_first, large_list, lctl + 1);
     const uint32_t nb_large = (uint32_t)((max_large + 127) / 128);
     k_exact_count<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, lctl + 1, counts, totals, status);
-    obmg::k_tile_units<<<(ntiles + 255) / 256, 256, 0, st>>>(d_doc_off, tile_first, ntiles, nsub);
+    obmq::k_tile_units<<<(ntiles + 255) / 256, 256, 0, st>>>(d_doc_off, tile_first, ntiles, nsub);
     k_scan_tiles<<<nt_u, SCAN_THREADS, 0, st>>>(nsub, ntiles, ubase, usums);
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(usums, nt_u, ubase + ntiles);
     k_scan_add<<<nt_u, SCAN_THREADS, 0, st>>>(ubase, ntiles, usums, ~0ull, nullptr);
     int dev_sms = 0, per_sm1 = 0, per_sm2 = 0;
     OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
-    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, obmg::k1_scan, (int)obmt::NT, smem1));
-    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, obmg::k2_units, (int)(obmp::W_WARPS * 32), 0));
+    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, obmq::k1_scan, (int)obmt::NT, smem1));
+    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, obmq::k2_units, (int)(obmp::W_WARPS * 32), 0));
     if (per_sm1 < 1) per_sm1 = 1;
     if (per_sm2 < 1) per_sm2 = 1;
     uint32_t g1 = (uint32_t)dev_sms * (uint32_t)per_sm1; /* persistent CTAs: multiples of the SM count */
@@ -523,15 +429,15 @@ static int obm_group_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_
     uint32_t g2 = (uint32_t)dev_sms * (uint32_t)per_sm2;
     const uint64_t g2max = (um + obmp::W_WARPS - 1) / obmp::W_WARPS;
     if (g2 > g2max) g2 = (uint32_t)g2max;
-    obmg::k1_scan<<<g1, obmt::NT, smem1, st>>>(A);
-    obmg::k2_units<<<g2, obmp::W_WARPS * 32, 0, st>>>(A);
+    obmq::k1_scan<<<g1, obmt::NT, smem1, st>>>(A);
+    obmq::k2_units<<<g2, obmp::W_WARPS * 32, 0, st>>>(A);
     uint32_t launches = 8;
     if (d_out && out_cap) {
         k_exact_fill<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, lctl + 1, toff, d_out, out_cap);
         launches += 1;
     }
     /* work-record overflow -> status[3]: the caller must redo the scan with the exact kernels (mode 1) */
-    OBM_CUDA(h, cudaMemcpyAsync(status + ST_RESERVED, A.ctl + obmg::CT_OVF, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    OBM_CUDA(h, cudaMemcpyAsync(status + ST_RESERVED, A.ctl + obmq::CT_OVF, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     h->launches = launches;
     OBM_CUDA(h, cudaGetLastError());
     return OBM_OK;
@@ -542,7 +448,6 @@ extern "C" uint64_t obm_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
     b += align_up((uint64_t)scan_tiles(ndocs) * 8 + 8, 256);
     b += align_up(obm_fast_scratch_bytes(ndocs, total_bytes), 256);
     b += pipe_scratch_bytes(ndocs, total_bytes);
-    b += group_scratch_bytes(ndocs, total_bytes);
     return b;
 }
 
@@ -563,8 +468,7 @@ static int lex_device_impl(obm_handle *h, const void *d_bytes, const void *d_doc
     uint32_t *counts = (uint32_t *)sc; sc += align_up((uint64_t)ndocs * 4 + 4, 256);
     uint64_t *tile_sums = (uint64_t *)sc; sc += align_up((uint64_t)scan_tiles(ndocs) * 8 + 8, 256);
     void *fast_ws = sc; sc += align_up(obm_fast_scratch_bytes(ndocs, total_bytes), 256);
-    void *pipe_ws = sc; sc += pipe_scratch_bytes(ndocs, total_bytes);
-    void *group_ws = sc;
+    void *pipe_ws = sc;
     uint32_t *status = (uint32_t *)(d_status ? d_status : (void *)h->d_status);
     unsigned long long *totals = (unsigned long long *)(d_counts ? d_counts : (void *)h->d_counts);
     uint64_t *toff = (uint64_t *)d_doc_tuple_off;
@@ -573,11 +477,8 @@ static int lex_device_impl(obm_handle *h, const void *d_bytes, const void *d_doc
     if (ndocs == 0) { OBM_CUDA(h, cudaMemsetAsync(toff, 0, sizeof(uint64_t), st)); return OBM_OK; }
 
     if (h->mode == 0)
-        return obm_group_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
-                                (obm_tuple *)d_out, out_cap, toff, status, totals, counts, fast_ws, group_ws, st);
-    if (h->mode == 3)
         return obm_pipe_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
-                               (obm_tuple *)d_out, out_cap, toff, status, totals, counts, tile_sums, fast_ws, pipe_ws, st);
+                                (obm_tuple *)d_out, out_cap, toff, status, totals, counts, fast_ws, pipe_ws, st);
     if (h->mode == 2)
         return obm_fast_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
                                (obm_tuple *)d_out, out_cap, toff, status, totals, counts, fast_ws, st);

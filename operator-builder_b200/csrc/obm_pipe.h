@@ -1,22 +1,16 @@
 /*
- * obm_pipe.h -- host/device logic of the three-stage pipeline (mode 0), on top of obm_tile.h:
+ * obm_pipe.h -- host/device logic of the two-stage pipeline (mode 0), on top of obm_tile.h:
  *
- *   K1 scan      per 16 KiB tile, shared-memory resident: TMA stage, classify, bit-parallel line scan,
- *                owner classification.  Emits compact work records to HBM instead of lexing:
- *                  item  (8 B)  one per line that owns tuples, in position order
- *                  mline (16 B) one per MARKER line (a line containing '+'), dense list for K2
- *   K2 markers   one thread per marker line, any order, thousands of lines in flight per SM: the ASCII
- *                instantiation of obm::Lexer runs straight off HBM/L2 (the line was streamed by K1 moments
- *                ago).  Pass 1 counts the line's tuples; pass 2 (after K3) writes them at their final place
- *   K3 assemble  per tile again, no input bytes needed: tuple counts -> decoupled look-back -> final
- *                ordered positions; plain comment lines are materialised from their item, every marker line
- *                gets its output offset, documents that K1/K2 flagged (non-ASCII, interacting lines) are
- *                re-lexed sequentially by the exact (Unicode) instantiation
+ *   K1 scan   per 16 KiB tile, shared-memory resident: TMA stage, classify, bit-parallel line scan, owner
+ *             classification.  Emits compact work records to HBM instead of lexing: one 8-byte ITEM per line
+ *             that owns tuples (position order inside a unit), an EOF item per document, a 16-byte unit record
+ *   K2 units  one WARP per unit: marker items are lexed once (a lane per line) by the ASCII instantiation of
+ *             obm::Lexer from a shared-memory copy of the line, tuples staged in shared memory; item counts ->
+ *             unit total -> two-level decoupled look-back over units -> final positions -> write
  *
- * Why three kernels: in the fused tile kernel (obm_fast.cuh, mode 2) the marker phase is a long dependent
- * chain on a few warps while shared memory caps residency at 3 CTAs/SM (profiles/r01_*): latency-bound at
- * 19 % issue utilisation.  Splitting lets every stage run dense at full occupancy; the price is ~0.25 B/B
- * of extra HBM traffic (items, and marker lines re-read twice from L2/HBM) and lexing marker lines twice.
+ * Why two kernels: in the fused tile kernel (obm_fast.cuh, mode 2) the marker phase is a long dependent chain
+ * on a few warps while shared memory caps residency at 3 CTAs/SM and block barriers make every warp wait for
+ * the slowest line (profiles/r01_*).  Here K1 has no lexing and K2 has no block barrier.
  */
 #ifndef OBM_PIPE_H
 #define OBM_PIPE_H
@@ -36,7 +30,7 @@ using obmt::SmemScan;
  *  bit  43      plain line whose comment is "//"
  *  bit  44      dead (the line has specials but produces no tuple)
  *  bits 45..50  doc   document index inside the sub-batch (< DMAX = 64)
- *  marker lines: bits 51..63 unused; their slot number lives in item_slot[] */
+ *  (marker / EOF / LARGE items use the upper bits differently: see below) */
 typedef uint64_t item_t;
 OBM_HD item_t make_item(uint32_t ls, uint32_t pos, uint32_t line, bool marker, bool slash2, bool dead, uint32_t d) {
     return (item_t)ls | ((item_t)pos << 14) | ((item_t)line << 28) | ((item_t)marker << 42) | ((item_t)slash2 << 43) |
@@ -50,10 +44,6 @@ OBM_HD bool it_slash2(item_t i) { return (i >> 43) & 1; }
 OBM_HD bool it_dead(item_t i) { return (i >> 44) & 1; }
 OBM_HD uint32_t it_doc(item_t i) { return (uint32_t)((i >> 45) & 0x3F); }
 
-/* ---- mline: what K2 needs to lex one marker line (16 bytes) ---------------------------------------- */
-struct MLine { uint32_t doc; uint32_t ls_first; uint32_t line; uint32_t line_end; };
-/* ls_first = ls | first << 16 (document-relative, 14 bits each); line_end = offset of the line's '\n' (or doc length) */
-
 /* K2 result per marker line */
 OBM_HD uint32_t make_mres(uint32_t tuples, bool irregular) { return tuples | (irregular ? 0x80000000u : 0u); }
 OBM_HD uint32_t mres_tuples(uint32_t r) { return r & 0x7FFFFFFFu; }
@@ -61,33 +51,6 @@ OBM_HD bool mres_irregular(uint32_t r) { return r >> 31; }
 
 /* document flags (u32 per document) */
 enum : uint32_t { GF_NONASCII = 1, GF_INTERACT = 2, GF_QOVERFLOW = 4, GF_LARGE = 8 };
-
-/* ---- K1: owner o of the sub-batch -> item (+ mline for marker lines) -----------------------------
- * S.owner[o] holds the position of the line's first special byte (line scan output). */
-struct K1Out { item_t item; bool is_marker; MLine ml; };
-OBM_FN K1Out k1_owner(const SmemScan &S, uint32_t o, uint32_t doc_global_base) {
-    uint32_t first = S.owner[o];
-    uint32_t ls = obmt::line_start_of(S, first);
-    uint32_t d = obmt::doc_of(S, ls);
-    uint32_t dpos = S.dstart[d], dend = S.dstart[d + 1];
-    K1Out r; r.is_marker = false;
-    uint32_t rec = S.dflag[d] ? obmt::OW_NONE : obmt::classify_line(S, first, ls);
-    if (rec == obmt::OW_NONE) { r.item = make_item(ls - dpos, first - dpos, 0, false, false, true, d); return r; }
-    uint32_t line = 1 + obmt::nl_before(S, ls) - obmt::nl_before(S, dpos);
-    bool marker = (rec & obmt::OW_MARKER) != 0;
-    r.item = make_item(ls - dpos, obmt::ow_pos(rec) - dpos, line, marker, (rec & obmt::OW_SLASH2) != 0, false, d);
-    if (marker) {
-        /* end of the line: next newline bit at or after `first` (virtual newlines end the document's last line) */
-        uint32_t e = first;
-        for (;;) { if (e >= dend) { e = dend; break; } if (obmt::is_nl(S, e) && S.data[e] == '\n') break; uint32_t nx = obmt::next_event(S, e + 1); e = nx; }
-        r.is_marker = true;
-        r.ml.doc = doc_global_base + d;
-        r.ml.ls_first = (ls - dpos) | ((first - dpos) << 16);
-        r.ml.line = line;
-        r.ml.line_end = e - dpos;
-    }
-    return r;
-}
 
 /* ---- K2: one marker line straight from global memory -------------------------------------------- */
 /* lex / lexComment skipping without bitmaps: the next byte in [p, line_end] that is '\n' or one of # ' + /
@@ -113,24 +76,6 @@ struct LineAccel {
     }
 };
 typedef obm::Lexer<obm::SmallSink, LineAccel, true> GLineLexer;
-
-/* Lexes one marker line of the document doc[0..n) held in global memory (aligned 4-byte words around the
- * line are readable: see the buffer contract in obmarkers.h).  out/cap: nullptr/0 to count only.
- * Returns make_mres(count, irregular); adds the line's MarkerStart / lexeme counts when asked. */
-OBM_HD_NOINLINE uint32_t k2_marker_line(const obm::Tables &T, const uint8_t *doc, uint32_t n, const MLine &ml, obm_tuple *out,
-                                        uint32_t cap, uint32_t *markers = nullptr, uint32_t *lexemes = nullptr) {
-    uint32_t ls = ml.ls_first & 0xFFFFu, first = ml.ls_first >> 16;
-    LineAccel acc{doc, ml.line_end};
-    obm::SmallSink sink(out, cap);
-    GLineLexer lx(T, doc, n, sink, first, ml.line, ls, !(ml.line == 1 && ls == 0), acc);
-    lx.fill_windows(lx.p);
-    int st = lx.run<true>();
-    uint32_t end_line = lx.line_p - (st == obm::RUN_LINE_END ? 1u : 0u);
-    bool irregular = (st == obm::RUN_FATAL) || (end_line != ml.line);
-    if (markers) *markers += sink.n_markers;
-    if (lexemes) *lexemes += sink.n_lexemes;
-    return make_mres(sink.n_tuples, irregular);
-}
 
 OBM_HD uint32_t plain_count_fwd(item_t it) { return it_line(it) == 1 ? 1u : 2u; }
 
@@ -163,7 +108,7 @@ OBM_HD uint32_t unit_nd(const Unit &u) { return u.n >> 16; }
 constexpr uint32_t W_WARPS = 4;         /* warps per K2 CTA (each works alone) */
 constexpr uint32_t W_MLCAP = 32;        /* marker lines staged per block = one per lane */
 constexpr uint32_t W_LTS = 23;          /* staged tuples per marker line (odd stride: no bank clash) */
-constexpr uint32_t W_POOL = 192;        /* 16-byte chunks of line text staged per warp (3 KiB) */
+constexpr uint32_t W_POOL = 256;        /* 16-byte chunks of line text staged per warp (4 KiB) */
 constexpr uint32_t W_LOOK = 24;         /* bytes staged past a line's newline: whitespace run + longest peeked token */
 constexpr uint32_t W_TOKEN = 8;         /* >= the longest token a whitespace-skipping peek compares ("false") */
 constexpr uint32_t W_ICAP = 256;        /* items of a unit handled as one block (larger units: 32-item blocks) */
@@ -187,15 +132,14 @@ OBM_FN item_t k1_owner_item(const SmemScan &S, uint32_t o) {
 /* K2: lex the line of a marker item of document doc[0..n) (global memory) */
 OBM_HD_NOINLINE uint32_t k2_marker_item(const obm::Tables &T, const uint8_t *doc, uint32_t n, item_t it, obm_tuple *out, uint32_t cap,
                                         uint32_t *markers = nullptr, uint32_t *lexemes = nullptr) {
-    MLine ml; ml.doc = 0; ml.ls_first = it_ls(it) | (it_pos(it) << 16); ml.line = it_line(it); ml.line_end = it_line_end(it);
-    uint32_t ls = it_ls(it), first = it_pos(it);
-    LineAccel acc{doc, ml.line_end};
+    const uint32_t ls = it_ls(it), first = it_pos(it), line = it_line(it);
+    LineAccel acc{doc, it_line_end(it)};
     obm::SmallSink sink(out, cap);
-    GLineLexer lx(T, doc, n, sink, first, ml.line, ls, !(ml.line == 1 && ls == 0), acc);
+    GLineLexer lx(T, doc, n, sink, first, line, ls, !(line == 1 && ls == 0), acc);
     lx.fill_windows(lx.p);
     int st = lx.run<true>();
     uint32_t end_line = lx.line_p - (st == obm::RUN_LINE_END ? 1u : 0u);
-    bool irregular = (st == obm::RUN_FATAL) || (end_line != ml.line);
+    bool irregular = (st == obm::RUN_FATAL) || (end_line != line);
     if (markers) *markers += sink.n_markers;
     if (lexemes) *lexemes += sink.n_lexemes;
     return make_mres(sink.n_tuples, irregular);

@@ -39,8 +39,6 @@ def lib():
                                     ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
         L.hs_pipe_batch.restype = ctypes.c_uint64
         L.hs_pipe_batch.argtypes = L.hs_tile_batch.argtypes
-        L.hs_group_batch.restype = ctypes.c_uint64
-        L.hs_group_batch.argtypes = L.hs_tile_batch.argtypes
         L.hs_parse_float_err.argtypes = [ctypes.c_char_p, ctypes.c_uint32]
         L.hs_atoi_err.argtypes = [ctypes.c_char_p, ctypes.c_uint32]
         L.obm_decode_doc.restype = ctypes.c_int64
@@ -86,8 +84,7 @@ def fmt_tuples(tuples):
 
 
 def tile_batch(docs, skew=0, pipeline=False):
-    """CTA emulation of the tile fast path (pipeline=0 fused kernel, 1 three-stage pipeline, 2 ordered two-stage
-    pipeline) over a list of documents
+    """CTA emulation of the tile fast path (pipeline=0 fused kernel, 1 two-stage pipeline) over a list of documents
     -> (tuples, doc_tuple_off, stats)."""
     L = lib()
     data = np.frombuffer(b"".join(docs) + b"+" * 32, dtype=np.uint8).copy()  # readable (poisoned) past the end, like the device buffer contract
@@ -98,7 +95,7 @@ def tile_batch(docs, skew=0, pipeline=False):
     out = np.zeros(cap, dtype=np.uint64)
     toff = np.zeros(len(docs) + 1, dtype=np.uint64)
     stats = np.zeros(4, dtype=np.uint64)
-    fn = L.hs_group_batch if pipeline == 2 else L.hs_pipe_batch if pipeline else L.hs_tile_batch
+    fn = L.hs_pipe_batch if pipeline else L.hs_tile_batch
     n = fn(data.ctypes.data, off.ctypes.data, len(docs), out.ctypes.data, cap, toff.ctypes.data, skew, stats.ctypes.data)
     assert n <= cap
     return out[:n].copy(), toff, stats

@@ -198,129 +198,12 @@ extern "C" uint64_t hs_tile_batch(const uint8_t *bytes, const uint64_t *doc_off,
 
 
 /* ---------------------------------------------------------------------------------------------
- * Emulation of the three-stage pipeline (obm_pipe.cuh): k1_scan -> k2_markers<count> -> k3_assemble ->
- * k2_markers<write>, with the same obm_pipe.h functions.
- * ------------------------------------------------------------------------------------------- */
-extern "C" uint64_t hs_pipe_batch(const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs, obm_tuple *out, uint64_t cap,
-                                  uint64_t *tuple_off, uint32_t fake_skew, uint64_t *stats) {
-    static Emu emu;
-    using namespace obmp;
-    const uint64_t total = doc_off[ndocs];
-    const uint64_t ntiles = total / obmt::TILE + 1;
-    std::vector<item_t> items; std::vector<uint32_t> item_slot; std::vector<MLine> mlines;
-    std::vector<uint64_t> doc_item_off(ndocs + 1, 0); std::vector<uint32_t> doc_item_n(ndocs, 0), doc_flag(ndocs, 0);
-    struct Sub { uint32_t da, db; };
-    std::vector<std::vector<Sub>> tile_subs(ntiles);
-    std::vector<int64_t> tile_large(ntiles, -1);
-    /* K1 */
-    uint32_t d = 0;
-    for (uint64_t t = 0; t < ntiles; t++) {
-        uint32_t d_first = d;
-        while (d < ndocs && doc_off[d] < (t + 1) * (uint64_t)obmt::TILE) d++;
-        uint32_t d_last = d, d_small_end = d_last;
-        if (d_last > d_first && doc_off[d_last] - doc_off[d_last - 1] > obmt::MAXDOC) { d_small_end = d_last - 1; tile_large[t] = d_last - 1; doc_flag[d_last - 1] = GF_LARGE; }
-        for (uint32_t da = d_first; da < d_small_end; da += obmt::DMAX) {
-            uint32_t db = da + obmt::DMAX < d_small_end ? da + obmt::DMAX : d_small_end, nd = db - da;
-            tile_subs[t].push_back({da, db});
-            uint32_t n_owners = emu.scan(bytes, doc_off, da, db, fake_skew);
-            n_owners = emu.S.n_owners;
-            uint64_t ibase = items.size();
-            std::vector<item_t> sit(n_owners);
-            for (uint32_t o = 0; o < n_owners; o++) {
-                K1Out r = k1_owner(emu.S, o, da);
-                uint32_t slot = 0xFFFFFFFFu;
-                if (r.is_marker) { slot = (uint32_t)mlines.size(); mlines.push_back(r.ml); }
-                sit[o] = r.item; items.push_back(r.item); item_slot.push_back(slot);
-            }
-            for (uint32_t k = 0; k < nd; k++) {
-                uint32_t first = 0; while (first < n_owners && it_doc(sit[first]) < k) first++;
-                uint32_t last = first; while (last < n_owners && it_doc(sit[last]) <= k) last++;
-                doc_item_off[da + k] = ibase + first; doc_item_n[da + k] = last - first;
-                uint32_t f = emu.S.dflag[k];
-                doc_flag[da + k] = ((f & obmt::DF_NONASCII) ? GF_NONASCII : 0u) | ((f & obmt::DF_QOVERFLOW) ? GF_QOVERFLOW : 0u);
-            }
-        }
-    }
-    /* K2 count */
-    std::vector<uint32_t> mres(mlines.size());
-    for (size_t m = 0; m < mlines.size(); m++) {
-        const MLine &ml = mlines[m];
-        uint32_t r = k2_marker_line(TBL, bytes + doc_off[ml.doc], (uint32_t)(doc_off[ml.doc + 1] - doc_off[ml.doc]), ml, nullptr, 0);
-        mres[m] = r;
-        if (mres_irregular(r)) doc_flag[ml.doc] |= GF_INTERACT;
-    }
-    /* K3 */
-    std::vector<uint64_t> moff(mlines.size(), 0);
-    uint64_t base = 0; uint64_t st_m = 0, st_l = 0, st_e = 0, st_f = 0;
-    for (uint64_t t = 0; t < ntiles; t++) {
-        for (const Sub &sb : tile_subs[t]) {
-            uint32_t nd = sb.db - sb.da;
-            uint64_t ib = nd ? doc_item_off[sb.da] : 0;
-            uint32_t n_items = 0; std::vector<uint32_t> dfirst(nd + 1);
-            for (uint32_t k = 0; k < nd; k++) { dfirst[k] = n_items; n_items += doc_item_n[sb.da + k]; }
-            dfirst[nd] = n_items;
-            std::vector<uint32_t> E(n_items + 1, 0);
-            for (uint32_t i = 0; i < n_items; i++) {
-                item_t it = items[ib + i]; uint32_t v = 0;
-                if (!it_dead(it) && !doc_flag[sb.da + it_doc(it)]) v = it_marker(it) ? mres_tuples(mres[item_slot[ib + i]]) : plain_count(it);
-                E[i + 1] = E[i] + v;
-            }
-            std::vector<uint32_t> dcnt(nd + 1, 0);
-            for (uint32_t k = 0; k < nd; k++) {
-                uint32_t c;
-                if (doc_flag[sb.da + k]) { obm::SmallSink s(nullptr, 0); k3_doc_exact(TBL, bytes + doc_off[sb.da + k], (uint32_t)(doc_off[sb.da + k + 1] - doc_off[sb.da + k]), s); c = s.n_tuples; }
-                else c = E[dfirst[k + 1]] - E[dfirst[k]] + 1;
-                dcnt[k + 1] = dcnt[k] + c;
-            }
-            for (uint32_t i = 0; i < n_items; i++) {
-                item_t it = items[ib + i]; uint32_t k = it_doc(it);
-                if (it_dead(it) || doc_flag[sb.da + k]) continue;
-                uint64_t at = base + dcnt[k] + (E[i] - E[dfirst[k]]);
-                if (it_marker(it)) moff[item_slot[ib + i]] = at; else { plain_write(it, out, at, cap); st_l++; }
-            }
-            for (uint32_t k = 0; k < nd; k++) {
-                uint64_t at = base + dcnt[k];
-                tuple_off[sb.da + k] = at;
-                uint32_t len = (uint32_t)(doc_off[sb.da + k + 1] - doc_off[sb.da + k]);
-                if (doc_flag[sb.da + k]) {
-                    obm::SmallSink s(out + at, at < cap ? (uint32_t)(cap - at) : 0u);
-                    int st = k3_doc_exact(TBL, bytes + doc_off[sb.da + k], len, s);
-                    st_m += s.n_markers; st_l += s.n_lexemes; st_e++; st_f += st == obm::RUN_FATAL;
-                } else { uint64_t e = base + dcnt[k + 1] - 1; if (e < cap) out[e] = OBM_TUPLE(OBM_K_EOF, len, 0); st_l++; }
-            }
-            base += dcnt[nd];
-        }
-        if (tile_large[t] >= 0) {
-            uint32_t dl = (uint32_t)tile_large[t];
-            tuple_off[dl] = base;
-            obm::WriteSink sink(out + base, base < cap ? cap - base : 0);
-            obm::Lexer<obm::WriteSink> lx(TBL, bytes + doc_off[dl], (uint32_t)(doc_off[dl + 1] - doc_off[dl]), sink);
-            int st = lx.run<false>();
-            st_m += sink.n_markers; st_l += sink.n_lexemes; st_e++; st_f += st == obm::RUN_FATAL;
-            base += sink.n_tuples;
-        }
-    }
-    tuple_off[ndocs] = base;
-    /* K2 write */
-    for (size_t m = 0; m < mlines.size(); m++) {
-        const MLine &ml = mlines[m];
-        if (doc_flag[ml.doc]) continue;
-        uint64_t at = moff[m];
-        uint32_t mk = 0, lx = 0;
-        k2_marker_line(TBL, bytes + doc_off[ml.doc], (uint32_t)(doc_off[ml.doc + 1] - doc_off[ml.doc]), ml, out + at, at < cap ? (uint32_t)(cap - at) : 0u, &mk, &lx);
-        st_m += mk; st_l += lx;
-    }
-    if (stats) { stats[0] = st_m; stats[1] = st_l; stats[2] = st_e; stats[3] = st_f; }
-    return base;
-}
-
-/* ---------------------------------------------------------------------------------------------
- * Emulation of the two-stage pipeline (obm_group.cuh): k1_scan builds per-unit item runs with EOF
+ * Emulation of the two-stage pipeline (obm_pipe.cuh): k1_scan builds per-unit item runs with EOF
  * items and unit records; k2_units is replayed unit by unit (one warp each on the device) with the
  * same block structure, staging capacity, look-up sentinel and flag handling as the kernel.
  * ------------------------------------------------------------------------------------------- */
 namespace {
-struct GroupEmu {
+struct PipeEmu {
     const uint8_t *bytes; const uint64_t *doc_off; obm_tuple *out; uint64_t cap; uint64_t *tuple_off;
     std::vector<obmp::item_t> items; std::vector<obmp::Unit> units; std::vector<uint32_t> doc_flag, counts;
     uint64_t st_m = 0, st_l = 0, st_e = 0, st_f = 0;
@@ -431,11 +314,11 @@ struct GroupEmu {
 };
 } // namespace
 
-extern "C" uint64_t hs_group_batch(const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs, obm_tuple *out, uint64_t cap,
+extern "C" uint64_t hs_pipe_batch(const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs, obm_tuple *out, uint64_t cap,
                                    uint64_t *tuple_off, uint32_t fake_skew, uint64_t *stats) {
     static Emu emu;
     using namespace obmp;
-    GroupEmu G; G.bytes = bytes; G.doc_off = doc_off; G.out = out; G.cap = cap; G.tuple_off = tuple_off;
+    PipeEmu G; G.bytes = bytes; G.doc_off = doc_off; G.out = out; G.cap = cap; G.tuple_off = tuple_off;
     G.doc_flag.assign(ndocs, 0); G.counts.assign(ndocs, 0);
     const uint64_t total = doc_off[ndocs];
     G.total_bytes = total;

@@ -31,7 +31,7 @@ def pack(docs):
     return data, off
 
 
-def run_and_compare(scanner, oracle, docs, modes=(0, 1, 2, 3)):
+def run_and_compare(scanner, oracle, docs, modes=(0, 1, 2)):
     import operator_builder_b200 as ob
     data, off = pack(docs)
     want_stream, want_off, want_n = oracle.lex_batch_raw(data if len(data) else np.zeros(1, np.uint8), off)
@@ -127,7 +127,7 @@ def test_c2_10k_docs_bit_exact(scanner, oracle):
         doc = raw[i * 4096:(i + 1) * 4096]
         got = ob.decode_doc_raw(doc, res.tuples[int(res.doc_tuple_off[i]):int(res.doc_tuple_off[i + 1])])
         assert got == want_stream[int(want_off[i]):int(want_off[i + 1])], i
-    for mode in (1, 2, 3):
+    for mode in (1, 2):
         scanner.set_mode(mode)
         res1 = scanner.lex_batch(data, off)
         assert np.array_equal(res.tuples, res1.tuples) and np.array_equal(res.doc_tuple_off, res1.doc_tuple_off), mode
@@ -257,7 +257,7 @@ def test_full_size_properties_on_device(scanner):
     scanner.generate_corpus_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, doc_bytes, 0, 1, st)
     cap = ndocs * doc_bytes // 8
     outs = []
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 2):
         scanner.set_mode(mode)
         d_out = torch.zeros(cap, dtype=torch.int64, device=dev)
         d_toff = torch.zeros(ndocs + 1, dtype=torch.int64, device=dev)
@@ -270,7 +270,7 @@ def test_full_size_properties_on_device(scanner):
         assert int(d_counts[0].item()) == 8 * ndocs
         outs.append((d_out, d_toff, int(d_toff[-1].item()), int(d_counts[1].item())))
     scanner.set_mode(0)
-    for k in (1, 2, 3):
+    for k in (1, 2):
         assert outs[0][2] == outs[k][2] and outs[0][3] == outs[k][3]
         assert torch.equal(outs[0][1], outs[k][1]) and torch.equal(outs[0][0], outs[k][0])
     # shard property: documents [100000, 100000+4096) regenerated alone give the same tuples

@@ -130,7 +130,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
 
-    config = {"workload": f"configs[3]: {args.docs} synthetic manifests x {DOC_BYTES} B = {args.docs * DOC_BYTES / 2**30:.2f} GiB, "
+    cfg_name = "configs[3]" if args.flavour == 0 else "configs[2] (workload-collection spelling: +operator-builder:collection:field)"
+    config = {"workload": f"{cfg_name}: {args.docs} synthetic manifests x {DOC_BYTES} B = {args.docs * DOC_BYTES / 2**30:.2f} GiB, "
                           f"8 markers/file, sharded by file over {world} rank(s), HBM-resident",
               "docs": args.docs, "doc_bytes": DOC_BYTES, "flavour": args.flavour, "parallelism": f"file-shard x{world}",
               "l2": "inputs (>= 1.25 GiB per rank) exceed the 126 MB L2; no flush needed"}

@@ -157,7 +157,7 @@ int obm_generate_corpus_device(obm_handle *h, void *d_bytes, void *d_doc_off, ui
 int obm_generate_corpus_host(uint8_t *bytes, uint64_t *doc_off, uint32_t ndocs, uint32_t doc_bytes,
                              uint64_t first_doc, int flavour);
 
-/* Scanning strategy: 0 = three-stage pipeline (default), 1 = exact path for every document, 2 = fused tile
+/* Scanning strategy: 0 = two-stage pipeline (default), 1 = exact path for every document, 2 = fused tile
  * kernel.  All produce the identical tuple stream.  Returns the old mode. */
 int obm_set_mode(obm_handle *h, int mode);
 

@@ -303,7 +303,7 @@ __device__ __forceinline__ void k2_count_flagged_docs(K2Ctx &X) {
         if (f && !(f & obmp::GF_LARGE)) {
             const uint64_t o0 = X.A.doc_off[d];
             obm::SmallSink sink(nullptr, 0);
-            obmp::k3_doc_exact(X.T, X.A.bytes + o0, (uint32_t)(X.A.doc_off[d + 1] - o0), sink);
+            obmp::doc_exact(X.T, X.A.bytes + o0, (uint32_t)(X.A.doc_off[d + 1] - o0), sink);
             X.A.counts[d] = sink.n_tuples;
         }
     }
@@ -374,7 +374,7 @@ __device__ __forceinline__ uint64_t k2_write_block(K2Ctx &X, uint32_t b0, uint32
                     const uint64_t o0 = A.doc_off[d];
                     const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
                     obm::SmallSink sink(A.out + at, roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv);
-                    const int st = obmp::k3_doc_exact(X.T, A.bytes + o0, (uint32_t)(A.doc_off[d + 1] - o0), sink);
+                    const int st = obmp::doc_exact(X.T, A.bytes + o0, (uint32_t)(A.doc_off[d + 1] - o0), sink);
                     X.markers += sink.n_markers; X.lexemes += sink.n_lexemes; X.fatal += (st == obm::RUN_FATAL) ? 1u : 0u;
                 }
             }

@@ -192,7 +192,7 @@ OBM_HD void plain_write(item_t it, obm_tuple *out, uint64_t at, uint64_t cap) {
 
 /* whole document through the exact (Unicode) lexer, from global memory */
 typedef obm::Lexer<obm::SmallSink, obm::NoAccel, false> GDocLexer;
-OBM_HD_NOINLINE int k3_doc_exact(const obm::Tables &T, const uint8_t *doc, uint32_t n, obm::SmallSink &sink) {
+OBM_HD_NOINLINE int doc_exact(const obm::Tables &T, const uint8_t *doc, uint32_t n, obm::SmallSink &sink) {
     GDocLexer lx(T, doc, n, sink);
     return lx.run<false>();
 }

@@ -257,7 +257,7 @@ struct PipeEmu {
     void count_flagged_docs() {
         for (uint32_t q = 0; q < nd; q++) {
             const uint32_t d = d0 + q, f = doc_flag[d];
-            if (f && !(f & obmp::GF_LARGE)) { obm::SmallSink s(nullptr, 0); obmp::k3_doc_exact(TBL, bytes + doc_off[d], dlen(d), s); counts[d] = s.n_tuples; }
+            if (f && !(f & obmp::GF_LARGE)) { obm::SmallSink s(nullptr, 0); obmp::doc_exact(TBL, bytes + doc_off[d], dlen(d), s); counts[d] = s.n_tuples; }
         }
     }
     void apply_flags(uint32_t b0, uint32_t b1) {
@@ -293,7 +293,7 @@ struct PipeEmu {
                     lx.run<false>();
                 } else {
                     obm::SmallSink s(out + at, at < cap ? (uint32_t)(cap - at) : 0u);
-                    int st = k3_doc_exact(TBL, bytes + doc_off[d], dlen(d), s);
+                    int st = doc_exact(TBL, bytes + doc_off[d], dlen(d), s);
                     st_m += s.n_markers; st_l += s.n_lexemes; st_e++; st_f += st == obm::RUN_FATAL;
                 }
             } else if (c) { plain_write(it, out, at, cap); st_l++; }

@@ -295,10 +295,27 @@ OBM_HD_NOINLINE bool peeked_whitespaced_at(const uint8_t *d, uint32_t n, uint32_
     return true;
 }
 
-template <class Sink, class Accel = NoAccel, bool ASCII = false>
+/* ---- byte source of a lexer -------------------------------------------------------------------------
+ * Default: a plain pointer.  On the device K2 also uses ShBytes: the document bytes it may touch sit in a
+ * shared-memory copy, addressed through the 32-bit shared window so that loads are LDS (short scoreboard)
+ * instead of generic-address loads; `g` is the equivalent generic pointer for the cold helpers. */
+OBM_HD uint32_t src_mis(const uint8_t *d, uint32_t q) { return (uint32_t)((uintptr_t)(d + q) & 3u); }
+OBM_HD uint32_t src_ldw(const uint8_t *d, int32_t off) { return *reinterpret_cast<const uint32_t *>(d + off); }
+OBM_HD const uint8_t *src_raw(const uint8_t *d) { return d; }
+#if defined(__CUDACC__)
+struct ShBytes {
+    uint32_t sh; const uint8_t *g;
+    __device__ __forceinline__ uint32_t operator[](uint32_t i) const { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sh + i)); return v; }
+};
+__device__ __forceinline__ uint32_t src_mis(const ShBytes &d, uint32_t q) { return (d.sh + q) & 3u; }
+__device__ __forceinline__ uint32_t src_ldw(const ShBytes &d, int32_t off) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(d.sh + (uint32_t)off)); return v; }
+__device__ __forceinline__ const uint8_t *src_raw(const ShBytes &d) { return d.g; }
+#endif
+
+template <class Sink, class Accel = NoAccel, bool ASCII = false, class Src = const uint8_t *>
 struct Lexer {
     const Tables &T;
-    const uint8_t *d; uint32_t n;
+    Src d; uint32_t n;
     uint32_t p, s;                      /* read offset; `start` offset */
     uint32_t line_p, base_p, drift_p;   /* l.pos   == {line_p, p - base_p + 1 - drift_p} */
     uint32_t line_s, base_s;            /* l.start == {line_s, s - base_s + 1 - (drift of that line)} */
@@ -313,7 +330,7 @@ struct Lexer {
     /* A lexer instance begins at byte `start_off` of line `first_line`, whose first byte is at
      * `line_base` (document start: 0, 1, 0).  `announce_first`: the first located tuple must be
      * preceded by a LINE tuple (true for every line-mode instance except the document's first line). */
-    OBM_HD Lexer(const Tables &t, const uint8_t *doc, uint32_t len, Sink &sink, uint32_t start_off = 0,
+    OBM_HD Lexer(const Tables &t, Src doc, uint32_t len, Sink &sink, uint32_t start_off = 0,
                  uint32_t first_line = 1, uint32_t line_base = 0, bool announce_first = false, Accel acc = Accel())
         : T(t), d(doc), n(len), p(start_off), s(start_off), line_p(first_line), base_p(line_base), drift_p(0),
           line_s(first_line), base_s(line_base), line_e(announce_first ? 0u : 1u), base_e(0),
@@ -359,7 +376,7 @@ struct Lexer {
     /* ---- reader primitives ---- */
     OBM_HD int peek(uint32_t &w) const {
         if (ASCII) { if (p < n) { w = 1; return (int)d[p]; } w = 0; return RUNE_EOF; }
-        return decode_rune(d, p, n, w);
+        return decode_rune(src_raw(d), p, n, w);
     }
     OBM_HD int peek() const { uint32_t w; return peek(w); }
     OBM_HD uint32_t peek_byte() const { return p < n ? d[p] : 0x100u; } /* 0x100 = EOF sentinel */
@@ -413,16 +430,15 @@ struct Lexer {
      * loads and ~10 ALU ops per word.  The window is read as aligned 32-bit words and may extend a few
      * bytes around the document inside the staged buffer; words past the document end are not loaded. */
     OBM_HD void fill_windows(uint32_t q) {
-        const uint8_t *a = d + q;
-        const uint32_t mis = (uint32_t)((uintptr_t)a & 3u);
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(a - mis);
+        const uint32_t mis = src_mis(d, q);
+        const int32_t w0 = (int32_t)q - (int32_t)mis; /* byte offset of the aligned word that holds byte q */
         const uint32_t wlim = n - q + mis; /* bytes from the window start to the end of the document */
         uint32_t m[4];
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             uint32_t mk = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) { const uint32_t wi = (uint32_t)(g * 8 + k); mk |= nonletter4(wi * 4u < wlim ? w[wi] : 0u) << (4 * k); }
+            for (int k = 0; k < 8; k++) { const uint32_t wi = (uint32_t)(g * 8 + k); mk |= nonletter4(wi * 4u < wlim ? src_ldw(d, w0 + (int32_t)(wi * 4u)) : 0u) << (4 * k); }
             m[g] = mk;
         }
         wbase = (int32_t)q - (int32_t)mis; wm0 = m[0]; wm1 = m[1]; wm2 = m[2]; wm3 = m[3];
@@ -479,7 +495,7 @@ struct Lexer {
         }
     }
     OBM_HD bool peeked_whitespaced(const char *tok, uint32_t t, uint32_t &width) const {
-        return peeked_whitespaced_at<ASCII>(d, n, p, tok, t, width);
+        return peeked_whitespaced_at<ASCII>(src_raw(d), n, p, tok, t, width);
     }
     OBM_HD bool peeked_whitespaced_comment(uint32_t &width) const {
         return peeked_whitespaced("//", 2, width) || peeked_whitespaced("#", 1, width);
@@ -694,7 +710,7 @@ struct Lexer {
                     if (b == '.' || b == 'e' || b == 'E' || b == '-') { isfloat = true; continue; }
                     if (!(ASCII ? is_digit_ascii(peek()) : is_number(T, peek()))) break;
                 }
-                int code = isfloat ? parse_float_err(T, d + s, p - s) : atoi_err(d + s, p - s);
+                int code = isfloat ? parse_float_err(T, src_raw(d) + s, p - s) : atoi_err(src_raw(d) + s, p - s);
                 if (code) { numeric_error(isfloat ? OBM_K_ERR_FLOAT : OBM_K_ERR_INT); return TOP_FATAL; }
                 emit(isfloat ? OBM_K_FLOAT_LITERAL : OBM_K_INTEGER_LITERAL);
                 return -1;

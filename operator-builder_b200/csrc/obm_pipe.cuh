@@ -261,7 +261,7 @@ __device__ __forceinline__ bool k2_lex_block(K2Ctx &X, uint32_t b0, uint32_t b1,
             len = (uint32_t)(A.doc_off[d + 1] - o0); gdoc = A.bytes + o0;
             if (staged) v = obmp::line_view(gdoc, len, it, A.bytes, A.total_bytes);
         }
-        const uint8_t *doc = gdoc; uint32_t n_view = len;
+        const uint8_t *doc = gdoc; uint32_t n_view = len; bool in_smem = false;
         if (staged) {
             /* pack the lines' chunk runs into the pool (exclusive scan of chunk counts), cp.async them all, wait once */
             uint32_t want = (on && v.nch <= 32u) ? v.nch : 0u, incl = want;
@@ -282,11 +282,14 @@ __device__ __forceinline__ bool k2_lex_block(K2Ctx &X, uint32_t b0, uint32_t b1,
             if (fits) {
                 const uint8_t *sm = C.pool + (size_t)off * 16u;
                 const uint32_t nv = obmp::line_view_safe(sm, v, gdoc, len, it);
-                if (nv) { doc = sm + (intptr_t)((uintptr_t)gdoc - v.g0); n_view = nv; }
+                if (nv) { doc = sm + (intptr_t)((uintptr_t)gdoc - v.g0); n_view = nv; in_smem = true; }
             }
         }
         if (on) {
-            const uint32_t r = obmp::k2_marker_item(X.T, doc, n_view, it, staged ? C.stage + k * obmp::W_LTS : nullptr, staged ? obmp::W_LTS : 0u);
+            obm_tuple *so = staged ? C.stage + k * obmp::W_LTS : nullptr; const uint32_t sc = staged ? obmp::W_LTS : 0u;
+            uint32_t r;
+            if (in_smem) r = obmp::k2_marker_item(X.T, obm::ShBytes{(uint32_t)__cvta_generic_to_shared(C.pool) + (uint32_t)(doc - C.pool), doc}, n_view, it, so, sc);
+            else r = obmp::k2_marker_item(X.T, doc, n_view, it, so, sc); /* line not staged (too long / lookahead runs past the copy) */
             C.icnt[ib] = (uint16_t)obmp::mres_tuples(r);
             if (obmp::mres_irregular(r)) { atomicOr(&A.doc_flag[d], obmp::GF_INTERACT); any = true; }
         }

@@ -55,12 +55,13 @@ enum : uint32_t { GF_NONASCII = 1, GF_INTERACT = 2, GF_QOVERFLOW = 4, GF_LARGE =
 /* ---- K2: one marker line straight from global memory -------------------------------------------- */
 /* lex / lexComment skipping without bitmaps: the next byte in [p, line_end] that is '\n' or one of # ' + /
  * (same contract as obm::NoAccel but 4 bytes per step on the aligned words of the line) */
-struct LineAccel {
-    const uint8_t *d; uint32_t line_end;
+template <class Src>
+struct LineAccelT {
+    Src d; uint32_t line_end;
     OBM_HD uint32_t next_interesting(uint32_t p) const {
         while (p < line_end) {
-            uint32_t mis = (uint32_t)((uintptr_t)(d + p) & 3u);
-            uint32_t w = *reinterpret_cast<const uint32_t *>(d + p - mis);
+            uint32_t mis = obm::src_mis(d, p);
+            uint32_t w = obm::src_ldw(d, (int32_t)p - (int32_t)mis);
             uint32_t sp = obmt::zero_bytes4((w & 0xF3F3F3F3u) ^ 0x23232323u) >> mis;
             if (sp) {
 #if defined(__CUDA_ARCH__)
@@ -75,7 +76,9 @@ struct LineAccel {
         return line_end;
     }
 };
-typedef obm::Lexer<obm::SmallSink, LineAccel, true> GLineLexer;
+typedef LineAccelT<const uint8_t *> LineAccel;
+template <class Src> using GLineLexerT = obm::Lexer<obm::SmallSink, LineAccelT<Src>, true, Src>;
+typedef GLineLexerT<const uint8_t *> GLineLexer;
 
 OBM_HD uint32_t plain_count_fwd(item_t it) { return it_line(it) == 1 ? 1u : 2u; }
 
@@ -130,14 +133,15 @@ OBM_FN item_t k1_owner_item(const SmemScan &S, uint32_t o) {
 }
 
 /* K2: lex the line of a marker item of document doc[0..n) (global memory) */
-OBM_HD_NOINLINE uint32_t k2_marker_item(const obm::Tables &T, const uint8_t *doc, uint32_t n, item_t it, obm_tuple *out, uint32_t cap,
+template <class Src>
+OBM_HD_NOINLINE uint32_t k2_marker_item(const obm::Tables &T, Src doc, uint32_t n, item_t it, obm_tuple *out, uint32_t cap,
                                         uint32_t *markers = nullptr, uint32_t *lexemes = nullptr) {
     const uint32_t ls = it_ls(it), first = it_pos(it), line = it_line(it);
-    LineAccel acc{doc, it_line_end(it)};
+    LineAccelT<Src> acc{doc, it_line_end(it)};
     obm::SmallSink sink(out, cap);
-    GLineLexer lx(T, doc, n, sink, first, line, ls, !(line == 1 && ls == 0), acc);
+    GLineLexerT<Src> lx(T, doc, n, sink, first, line, ls, !(line == 1 && ls == 0), acc);
     lx.fill_windows(lx.p);
-    int st = lx.run<true>();
+    int st = lx.template run<true>();
     uint32_t end_line = lx.line_p - (st == obm::RUN_LINE_END ? 1u : 0u);
     bool irregular = (st == obm::RUN_FATAL) || (end_line != line);
     if (markers) *markers += sink.n_markers;

@@ -363,7 +363,13 @@ static uint32_t scan_tiles(uint32_t ndocs) { return (ndocs + SCAN_TILE - 1) / SC
 
 
 /* ---- two-stage pipeline (mode 0) --------------------------------------------------------------------- */
-static uint64_t pipe_items_cap(uint32_t ndocs, uint64_t total_bytes) { return total_bytes / 24 + 2ull * ndocs + obm_fast_ntiles(total_bytes) + 1024; }
+/* Structural bound, not an estimate: a unit holds at most QMAX owning lines (more -> its documents take the exact
+ * lexer and contribute no line items) and an owning line is at least 2 bytes, plus one EOF item per document and
+ * one item per large document.  ~0.53 B of scratch per input byte for 16 KiB tiles. */
+static uint64_t pipe_items_cap(uint32_t ndocs, uint64_t total_bytes) {
+    const uint64_t by_units = (obm_fast_ntiles(total_bytes) + ndocs / obmt::DMAX + 2) * (uint64_t)obmt::QMAX, by_bytes = total_bytes / 2 + 1;
+    return (by_units < by_bytes ? by_units : by_bytes) + 2ull * ndocs + obm_fast_ntiles(total_bytes) + 1024;
+}
 static uint64_t pipe_units_max(uint32_t ndocs, uint64_t total_bytes) { return obm_fast_ntiles(total_bytes) + ndocs / obmt::DMAX + 2; }
 static uint64_t pipe_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
     const uint64_t nt = obm_fast_ntiles(total_bytes), um = pipe_units_max(ndocs, total_bytes);

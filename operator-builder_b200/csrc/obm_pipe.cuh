@@ -229,6 +229,50 @@ struct K2Ctx {
     __device__ __forceinline__ uint32_t doc_of(item_t it) const { return obmp::it_large(it) ? d0 + nd : d0 + obmp::it_doc(it); }
 };
 
+/* Lanes with on == true lex the marker line of item `it` (document d) into out[0..cap) (cap 0: count only).
+ * The lines' text is packed into the warp's pool (exclusive scan of 16-byte chunk counts, cp.async for all of
+ * them, one wait) and lexed through the shared window; a line that does not fit, or whose lookahead could
+ * run past its copy (obm_pipe.h: line_view_safe), is lexed from global memory.  Whole warp must call. */
+__device__ __forceinline__ uint32_t k2_lex_lines(K2Ctx &X, bool on, item_t it, uint32_t d, obm_tuple *out, uint32_t cap, uint32_t *mk, uint32_t *lx) {
+    K2Warp &C = X.C; const PipeArgs &A = X.A; const uint32_t lane = X.lane;
+    uint32_t len = 0; const uint8_t *gdoc = nullptr;
+    obmp::LineView v{0, 0, 0};
+    if (on) {
+        const uint64_t o0 = A.doc_off[d];
+        len = (uint32_t)(A.doc_off[d + 1] - o0); gdoc = A.bytes + o0;
+        v = obmp::line_view(gdoc, len, it, A.bytes, A.total_bytes);
+    }
+    const uint32_t want = (on && v.nch <= 32u) ? v.nch : 0u;
+    uint32_t incl = want;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+    const bool fits = want != 0 && incl <= obmp::W_POOL;
+    const uint32_t off = incl - want;
+    uint32_t todo = __ballot_sync(0xffffffffu, fits);
+    while (todo) {
+        const uint32_t q = (uint32_t)__ffs((int)todo) - 1u; todo &= todo - 1u;
+        const uint32_t nq = __shfl_sync(0xffffffffu, want, q), oq = __shfl_sync(0xffffffffu, off, q);
+        const unsigned long long gq = __shfl_sync(0xffffffffu, (unsigned long long)v.g0, q);
+        if (lane < nq) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(C.pool + (size_t)(oq + lane) * 16u);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gq + (unsigned long long)lane * 16ull) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    uint32_t r = 0;
+    if (on) {
+        uint32_t nv = 0; const uint8_t *sm = C.pool + (size_t)off * 16u;
+        if (fits) nv = obmp::line_view_safe(sm, v, gdoc, len, it);
+        if (nv) {
+            const uint8_t *doc = sm + (intptr_t)((uintptr_t)gdoc - v.g0);
+            r = obmp::k2_marker_item(X.T, obm::ShBytes{(uint32_t)__cvta_generic_to_shared(C.pool) + (uint32_t)(doc - C.pool), doc}, nv, it, out, cap, mk, lx);
+        } else r = obmp::k2_marker_item(X.T, gdoc, len, it, out, cap, mk, lx);
+    }
+    __syncwarp(); /* the pool is reused by the next round */
+    return r;
+}
+
 /* Block [b0, b1) of the unit's items: compact the marker items, lex each line once (lane per line, the first
  * W_MLCAP lines stage their tuples), counts of everything else.  stable: document flags are final (large
  * units, second sweep) -- lines of flagged documents are skipped.  Returns lane-local "needs the flag pass". */
@@ -252,44 +296,11 @@ __device__ __forceinline__ bool k2_lex_block(K2Ctx &X, uint32_t b0, uint32_t b1,
     __syncwarp();
     for (uint32_t k0 = 0; k0 < n_ml; k0 += 32) {
         const uint32_t k = k0 + lane; const bool on = k < n_ml;
-        const bool staged = k0 == 0; /* the first W_MLCAP lines: text and tuples staged in shared memory */
-        uint32_t ib = 0, d = 0, len = 0; item_t it = 0; const uint8_t *gdoc = nullptr;
-        obmp::LineView v{0, 0, 0};
+        const bool staged = k0 == 0; /* the first W_MLCAP lines also stage their tuples */
+        uint32_t ib = 0, d = 0; item_t it = 0;
+        if (on) { ib = C.mlist[k]; it = A.items[X.i0 + b0 + ib]; d = X.doc_of(it); }
+        const uint32_t r = k2_lex_lines(X, on, it, d, staged ? C.stage + k * obmp::W_LTS : nullptr, staged ? obmp::W_LTS : 0u, nullptr, nullptr);
         if (on) {
-            ib = C.mlist[k]; it = A.items[X.i0 + b0 + ib]; d = X.doc_of(it);
-            const uint64_t o0 = A.doc_off[d];
-            len = (uint32_t)(A.doc_off[d + 1] - o0); gdoc = A.bytes + o0;
-            if (staged) v = obmp::line_view(gdoc, len, it, A.bytes, A.total_bytes);
-        }
-        const uint8_t *doc = gdoc; uint32_t n_view = len; bool in_smem = false;
-        if (staged) {
-            /* pack the lines' chunk runs into the pool (exclusive scan of chunk counts), cp.async them all, wait once */
-            uint32_t want = (on && v.nch <= 32u) ? v.nch : 0u, incl = want;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
-            const bool fits = want != 0 && incl <= obmp::W_POOL;
-            const uint32_t off = incl - want;
-            for (uint32_t q = 0; q < 32 && q < n_ml; q++) {
-                const uint32_t nq = __shfl_sync(0xffffffffu, fits ? want : 0u, q), oq = __shfl_sync(0xffffffffu, off, q);
-                const unsigned long long gq = __shfl_sync(0xffffffffu, (unsigned long long)v.g0, q);
-                if (lane < nq) {
-                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(C.pool + (size_t)(oq + lane) * 16u);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gq + (unsigned long long)lane * 16ull) : "memory");
-                }
-            }
-            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            if (fits) {
-                const uint8_t *sm = C.pool + (size_t)off * 16u;
-                const uint32_t nv = obmp::line_view_safe(sm, v, gdoc, len, it);
-                if (nv) { doc = sm + (intptr_t)((uintptr_t)gdoc - v.g0); n_view = nv; in_smem = true; }
-            }
-        }
-        if (on) {
-            obm_tuple *so = staged ? C.stage + k * obmp::W_LTS : nullptr; const uint32_t sc = staged ? obmp::W_LTS : 0u;
-            uint32_t r;
-            if (in_smem) r = obmp::k2_marker_item(X.T, obm::ShBytes{(uint32_t)__cvta_generic_to_shared(C.pool) + (uint32_t)(doc - C.pool), doc}, n_view, it, so, sc);
-            else r = obmp::k2_marker_item(X.T, doc, n_view, it, so, sc); /* line not staged (too long / lookahead runs past the copy) */
             C.icnt[ib] = (uint16_t)obmp::mres_tuples(r);
             if (obmp::mres_irregular(r)) { atomicOr(&A.doc_flag[d], obmp::GF_INTERACT); any = true; }
         }
@@ -353,18 +364,12 @@ __device__ __forceinline__ uint64_t k2_write_block(K2Ctx &X, uint32_t b0, uint32
         for (int o = 1; o < 32; o <<= 1) { const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
         const uint64_t at = at0 + run + incl - c;
         const uint32_t bal = __ballot_sync(0xffffffffu, m);
+        bool relex = false;
         if (m) {
             const uint32_t k = mrun + (uint32_t)__popc(bal & ((1u << lane) - 1u));
             if (c) {
                 if (k < obmp::W_MLCAP && c <= obmp::W_LTS) C.moff[k] = at;
-                else if (X.writing) {
-                    const uint64_t o0 = A.doc_off[d];
-                    const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
-                    uint32_t mk = 0, lx = 0; /* locals: taking the context's address would push it to the stack */
-                    obmp::k2_marker_item(X.T, A.bytes + o0, (uint32_t)(A.doc_off[d + 1] - o0), it, A.out + at,
-                                         roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv, &mk, &lx);
-                    X.markers += mk; X.lexemes += lx;
-                }
+                else relex = X.writing; /* not staged, or more tuples than a staging slot: lexed again, straight to its place */
             }
         } else if (eof) {
             A.tuple_off[d + 1] = at + c;
@@ -384,6 +389,12 @@ __device__ __forceinline__ uint64_t k2_write_block(K2Ctx &X, uint32_t b0, uint32
         } else if (valid && c) {
             if (X.writing) obmp::plain_write(it, A.out, at, A.out_cap);
             X.lexemes++;
+        }
+        if (__any_sync(0xffffffffu, relex)) {
+            const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
+            uint32_t mk = 0, lx = 0; /* locals: taking the context's address would push it to the stack */
+            k2_lex_lines(X, relex, it, d, A.out + at, roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv, &mk, &lx);
+            X.markers += mk; X.lexemes += lx;
         }
         run += __shfl_sync(0xffffffffu, incl, 31);
         mrun += (uint32_t)__popc(bal);

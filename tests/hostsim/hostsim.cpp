@@ -212,6 +212,29 @@ struct PipeEmu {
     uint64_t i0; uint32_t d0, nd; uint64_t total_bytes = 0; uint64_t views = 0, unsafe_views = 0;
     uint32_t doc_of(obmp::item_t it) const { return obmp::it_large(it) ? d0 + nd : d0 + obmp::it_doc(it); }
     uint32_t dlen(uint32_t d) const { return (uint32_t)(doc_off[d + 1] - doc_off[d]); }
+    /* k2_lex_lines: up to 32 lines (one per lane) with their text packed into the pool; everything outside the copied
+     * chunks is poison, so any dependence on bytes past a view shows up */
+    void lex_lines(uint32_t kn, const obmp::item_t *its, const uint32_t *ds, obm_tuple *const *outs, const uint32_t *caps, uint32_t *rs,
+                   uint32_t *mk, uint32_t *lx) {
+        using namespace obmp;
+        alignas(16) static uint8_t pool[W_POOL * 16];
+        memset(pool, 0x2B, sizeof pool);
+        uint32_t pool_used = 0;
+        for (uint32_t q = 0; q < kn; q++) {
+            const uint32_t d = ds[q]; item_t it = its[q];
+            const uint8_t *doc = bytes + doc_off[d]; uint32_t n_view = dlen(d);
+            LineView v = line_view(bytes + doc_off[d], dlen(d), it, bytes, total_bytes);
+            const uint32_t want = v.nch <= 32u ? v.nch : 0u;
+            pool_used += want; /* the scan is over all lines, fitting or not, exactly like the warp scan */
+            if (want && pool_used <= W_POOL) {
+                uint8_t *sm = pool + (size_t)(pool_used - want) * 16u;
+                memcpy(sm, (const void *)v.g0, (size_t)want * 16u);
+                const uint32_t nv = line_view_safe(sm, v, bytes + doc_off[d], dlen(d), it);
+                if (nv) { doc = sm + (intptr_t)((uintptr_t)(bytes + doc_off[d]) - v.g0); n_view = nv; views++; } else unsafe_views++;
+            }
+            rs[q] = k2_marker_item(TBL, doc, n_view, it, outs[q], caps[q], mk, lx);
+        }
+    }
     bool lex_block(uint32_t b0, uint32_t b1, bool stable, uint32_t &n_ml_out) {
         using namespace obmp;
         uint32_t n_ml = 0; bool any = false;
@@ -226,30 +249,20 @@ struct PipeEmu {
             }
             if (m) mlist[n_ml++] = (uint8_t)(i - b0);
         }
-        /* staged line text: same packing rule as the kernel (exclusive scan of chunk counts over the first 32 lines);
-         * everything outside the copied chunks is poison, so any dependence on bytes past a view shows up */
-        alignas(16) static uint8_t pool[W_POOL * 16];
-        memset(pool, 0x2B, sizeof pool);
-        uint32_t pool_used = 0;
-        for (uint32_t k = 0; k < n_ml; k++) {
-            const uint32_t ib = mlist[k]; item_t it = items[i0 + b0 + ib];
-            const uint32_t d = doc_of(it);
-            const bool staged = k < W_MLCAP;
-            const uint8_t *doc = bytes + doc_off[d]; uint32_t n_view = dlen(d);
-            if (staged) {
-                LineView v = line_view(bytes + doc_off[d], dlen(d), it, bytes, total_bytes);
-                const uint32_t want = v.nch <= 32u ? v.nch : 0u;
-                pool_used += want; /* the scan is over all lines, fitting or not, exactly like the warp scan */
-                if (want && pool_used <= W_POOL) {
-                    uint8_t *sm = pool + (size_t)(pool_used - want) * 16u;
-                    memcpy(sm, (const void *)v.g0, (size_t)want * 16u);
-                    const uint32_t nv = line_view_safe(sm, v, bytes + doc_off[d], dlen(d), it);
-                    if (nv) { doc = sm + (intptr_t)((uintptr_t)(bytes + doc_off[d]) - v.g0); n_view = nv; views++; } else unsafe_views++;
-                }
+        /* lines are lexed in rounds of 32 (one per lane); every round packs its text into the pool */
+        for (uint32_t k0 = 0; k0 < n_ml; k0 += 32) {
+            const uint32_t kn = n_ml - k0 < 32 ? n_ml - k0 : 32;
+            item_t its[32]; uint32_t ds[32], rs[32]; obm_tuple *outs[32]; uint32_t caps[32];
+            for (uint32_t q = 0; q < kn; q++) {
+                its[q] = items[i0 + b0 + mlist[k0 + q]]; ds[q] = doc_of(its[q]);
+                outs[q] = k0 == 0 ? stage + q * W_LTS : nullptr; caps[q] = k0 == 0 ? W_LTS : 0u;
             }
-            uint32_t r = k2_marker_item(TBL, doc, n_view, it, staged ? stage + k * W_LTS : nullptr, staged ? W_LTS : 0u);
-            icnt[ib] = (uint16_t)mres_tuples(r);
-            if (mres_irregular(r)) { doc_flag[d] |= GF_INTERACT; any = true; }
+            lex_lines(kn, its, ds, outs, caps, rs, nullptr, nullptr);
+            for (uint32_t q = 0; q < kn; q++) {
+                const uint32_t ib = mlist[k0 + q], d = ds[q], r = rs[q];
+                icnt[ib] = (uint16_t)mres_tuples(r);
+                if (mres_irregular(r)) { doc_flag[d] |= GF_INTERACT; any = true; }
+            }
         }
         n_ml_out = n_ml;
         return any;
@@ -268,10 +281,20 @@ struct PipeEmu {
         for (uint32_t i = b0; i < b1; i++) { uint32_t c = icnt[i - b0]; if (c == obmp::G_CNT_LOOKUP) c = counts[doc_of(items[i0 + i])]; sum += c; }
         return sum;
     }
+    void flush_relex(std::vector<obmp::item_t> &its, std::vector<uint32_t> &ds, std::vector<uint64_t> &ats) {
+        if (its.empty()) return;
+        obm_tuple *outs[32]; uint32_t caps[32], rs[32], mk = 0, lx = 0;
+        for (size_t q = 0; q < its.size(); q++) { outs[q] = out + ats[q]; caps[q] = ats[q] < cap ? (uint32_t)(cap - ats[q]) : 0u; }
+        lex_lines((uint32_t)its.size(), its.data(), ds.data(), outs, caps, rs, &mk, &lx);
+        st_m += mk; st_l += lx;
+        its.clear(); ds.clear(); ats.clear();
+    }
     uint64_t write_block(uint32_t b0, uint32_t b1, uint32_t n_ml, uint64_t at0, bool stable) {
         using namespace obmp;
         uint64_t at = at0; uint32_t k = 0;
+        std::vector<item_t> relex_it; std::vector<uint32_t> relex_d; std::vector<uint64_t> relex_at;
         for (uint32_t i = b0; i < b1; i++) {
+            if (((i - b0) & 31u) == 0) flush_relex(relex_it, relex_d, relex_at); /* the kernel re-lexes per 32-item chunk */
             item_t it = items[i0 + i];
             uint32_t c = icnt[i - b0]; const bool lookup = c == G_CNT_LOOKUP;
             const uint32_t d = doc_of(it);
@@ -279,7 +302,7 @@ struct PipeEmu {
             if (it_marker(it) && !(stable && doc_flag[d])) { /* same membership rule as lex_block's mlist */
                 if (c) {
                     if (k < W_MLCAP && c <= W_LTS) moff[k] = at;
-                    else { uint32_t mk = 0, lx = 0; k2_marker_item(TBL, bytes + doc_off[d], dlen(d), it, out + at, at < cap ? (uint32_t)(cap - at) : 0u, &mk, &lx); st_m += mk; st_l += lx; }
+                    else { relex_it.push_back(it); relex_d.push_back(d); relex_at.push_back(at); }
                 }
                 k++;
             } else if (it_marker(it)) {
@@ -299,6 +322,7 @@ struct PipeEmu {
             } else if (c) { plain_write(it, out, at, cap); st_l++; }
             at += c;
         }
+        flush_relex(relex_it, relex_d, relex_at);
         for (uint32_t q = 0; q < (n_ml < W_MLCAP ? n_ml : W_MLCAP); q++) {
             if (moff[q] == ~0ull) continue;
             const uint32_t c = icnt[mlist[q]];

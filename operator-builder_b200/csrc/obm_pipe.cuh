@@ -442,21 +442,24 @@ k2_units(PipeArgs A) {
             if (any) { k2_count_flagged_docs(X); k2_apply_flags(X, 0, n_items); }
             total = k2_block_total(X, 0, n_items);
         } else {
-            /* large unit: count sweep in 32-item blocks (repeated once if it discovered interacting lines),
-             * then the write sweep lexes block by block again */
-            bool stable = false;
-            for (;;) {
-                total = 0; bool any = false;
+            /* large unit: count sweep in 32-item blocks; only if it met flagged documents (K1 flags or interacting
+             * lines found on the way) the flags are settled and the sweep is repeated; the write sweep lexes again */
+            total = 0; bool any = false;
+            for (uint32_t b0 = 0; b0 < n_items; b0 += 32) {
+                const uint32_t b1 = min(b0 + 32u, n_items);
+                uint32_t nm;
+                any |= k2_lex_block(X, b0, b1, false, nm);
+                total += k2_block_total(X, b0, b1);
+            }
+            if (__any_sync(0xffffffffu, any)) {
+                k2_count_flagged_docs(X); /* flags are final now: no line of an unflagged document is irregular */
+                total = 0;
                 for (uint32_t b0 = 0; b0 < n_items; b0 += 32) {
                     const uint32_t b1 = min(b0 + 32u, n_items);
                     uint32_t nm;
-                    any |= k2_lex_block(X, b0, b1, stable, nm);
-                    if (stable) total += k2_block_total(X, b0, b1);
+                    k2_lex_block(X, b0, b1, true, nm);
+                    total += k2_block_total(X, b0, b1);
                 }
-                if (stable) break;
-                (void)__any_sync(0xffffffffu, any);
-                k2_count_flagged_docs(X); /* flags are final now: no line of an unflagged document is irregular */
-                stable = true;
             }
         }
         const uint64_t base = obmf::lookback2_warp(A.st_tuples, A.st_blocks, u, nunits, total);

@@ -402,10 +402,13 @@ extern "C" uint64_t hs_pipe_batch(const uint8_t *bytes, const uint64_t *doc_off,
             if (G.lex_block(0, n_items, false, n_ml)) { G.count_flagged_docs(); G.apply_flags(0, n_items); }
             base += G.write_block(0, n_items, n_ml, base, false);
         } else {
-            for (uint32_t b0 = 0; b0 < n_items; b0 += 32) { uint32_t nm; G.lex_block(b0, b0 + 32 < n_items ? b0 + 32 : n_items, false, nm); }
-            G.count_flagged_docs();
-            uint64_t total_u = 0;
-            for (uint32_t b0 = 0; b0 < n_items; b0 += 32) { uint32_t nm, b1 = b0 + 32 < n_items ? b0 + 32 : n_items; G.lex_block(b0, b1, true, nm); total_u += G.block_total(b0, b1); }
+            uint64_t total_u = 0; bool any = false;
+            for (uint32_t b0 = 0; b0 < n_items; b0 += 32) { uint32_t nm, b1 = b0 + 32 < n_items ? b0 + 32 : n_items; any |= G.lex_block(b0, b1, false, nm); total_u += G.block_total(b0, b1); }
+            if (any) {
+                G.count_flagged_docs();
+                total_u = 0;
+                for (uint32_t b0 = 0; b0 < n_items; b0 += 32) { uint32_t nm, b1 = b0 + 32 < n_items ? b0 + 32 : n_items; G.lex_block(b0, b1, true, nm); total_u += G.block_total(b0, b1); }
+            }
             uint64_t at = base;
             for (uint32_t b0 = 0; b0 < n_items; b0 += 32) { uint32_t nm, b1 = b0 + 32 < n_items ? b0 + 32 : n_items; G.lex_block(b0, b1, true, nm); at += G.write_block(b0, b1, nm, at, true); }
             if (at - base != total_u) { fprintf(stderr, "hostsim: large-unit sweeps disagree (%llu vs %llu)\n", (unsigned long long)(at - base), (unsigned long long)total_u); abort(); }

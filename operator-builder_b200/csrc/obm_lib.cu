@@ -51,6 +51,7 @@ enum { ST_OVERFLOW = 0, ST_DOCS_EXACT = 1, ST_DOCS_FATAL = 2, ST_RESERVED = 3 };
 
 #include "obm_fast.cuh"
 #include "obm_pipe.cuh"
+#include "obm_large.h"
 
 /* ------------------------------------------------------------------------------------------- */
 /* exact path: one thread per document                                                          */
@@ -172,6 +173,171 @@ k_scan_add(uint64_t *__restrict__ off, uint32_t n, const uint64_t *__restrict__ 
     for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) off[base + k] += add;
     /* off[n] was written by k_scan_sums (grand_total points at it) */
     if (blockIdx.x == 0 && threadIdx.x == 0 && status && off[n] > out_cap) status[ST_OVERFLOW] = 1;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* large documents (> obmt::MAXDOC bytes): chunk-parallel exact lexing, see obm_large.h          */
+/* plan (chunks per document, scan) -> prep (chunk starts, newline counts) -> lines -> count ->  */
+/* resolve (chain check, offsets, or sequential fallback) ... main scan ... -> fill              */
+/* ------------------------------------------------------------------------------------------- */
+struct LargeWs {
+    const uint32_t *large_list; const uint32_t *n_large; uint32_t max_large;
+    uint32_t *lch; uint64_t *lbase; uint64_t *lsums; uint32_t *lvalid;
+    uint32_t *cs, *cnl, *cline, *ccnt, *cend, *cflag, *cmk, *clx; uint64_t *choff;
+};
+static uint64_t large_chunks_max(uint64_t total_bytes) { return total_bytes / obml::LCHUNK + obm_fast_max_large(total_bytes) + 2; }
+static uint32_t scan_tiles(uint32_t ndocs);
+static uint64_t align_up(uint64_t v, uint64_t a);
+static uint64_t large_scratch_bytes(uint64_t total_bytes) {
+    const uint64_t ml = obm_fast_max_large(total_bytes), nc = large_chunks_max(total_bytes);
+    return align_up((ml + 1) * 4, 256) + align_up((ml + 2) * 8, 256) + align_up(((uint64_t)scan_tiles((uint32_t)ml + 1) + 1) * 8, 256) +
+           align_up((ml + 1) * 4, 256) + 8 * align_up((nc + 1) * 4, 256) + align_up((nc + 1) * 8, 256);
+}
+static LargeWs large_carve(void *ws, uint64_t total_bytes, const uint32_t *large_list, const uint32_t *n_large) {
+    const uint64_t ml = obm_fast_max_large(total_bytes), nc = large_chunks_max(total_bytes);
+    uint8_t *q = (uint8_t *)ws; LargeWs W;
+    W.large_list = large_list; W.n_large = n_large; W.max_large = (uint32_t)ml;
+    W.lch = (uint32_t *)q; q += align_up((ml + 1) * 4, 256);
+    W.lbase = (uint64_t *)q; q += align_up((ml + 2) * 8, 256);
+    W.lsums = (uint64_t *)q; q += align_up(((uint64_t)scan_tiles((uint32_t)ml + 1) + 1) * 8, 256);
+    W.lvalid = (uint32_t *)q; q += align_up((ml + 1) * 4, 256);
+    uint32_t **arr[8] = {&W.cs, &W.cnl, &W.cline, &W.ccnt, &W.cend, &W.cflag, &W.cmk, &W.clx};
+    for (auto a : arr) { *a = (uint32_t *)q; q += align_up((nc + 1) * 4, 256); }
+    W.choff = (uint64_t *)q;
+    return W;
+}
+/* the large document that owns global chunk g: last i with lbase[i] <= g */
+__device__ __forceinline__ uint32_t large_of_chunk(const LargeWs &W, uint32_t n_large, uint64_t g) {
+    uint32_t lo = 0, hi = n_large;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (W.lbase[mid] <= g) lo = mid; else hi = mid; }
+    return lo;
+}
+__global__ void __launch_bounds__(256)
+k_large_nchunks(const uint64_t *__restrict__ doc_off, LargeWs W) {
+    const uint32_t n_large = *W.n_large;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= W.max_large; i += gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+        if (i < n_large) { const uint32_t d = W.large_list[i]; v = obml::n_chunks((uint32_t)(doc_off[d + 1] - doc_off[d])); }
+        W.lch[i] = v;
+    }
+}
+__global__ void __launch_bounds__(128)
+k_large_prep(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, LargeWs W) {
+    const uint32_t n_large = *W.n_large;
+    if (n_large == 0) return;
+    const uint64_t total = W.lbase[W.max_large + 1];
+    for (uint64_t g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t i = large_of_chunk(W, n_large, g), d = W.large_list[i], c = (uint32_t)(g - W.lbase[i]);
+        const uint8_t *doc = bytes + doc_off[d]; const uint32_t n = (uint32_t)(doc_off[d + 1] - doc_off[d]);
+        uint32_t sk;
+        W.cs[g] = obml::chunk_start(doc, n, c, &sk);
+        W.cline[g] = sk;
+        W.cnl[g] = obml::chunk_newlines(doc, n, c);
+    }
+}
+__global__ void __launch_bounds__(128)
+k_large_lines(LargeWs W) {
+    const uint32_t n_large = *W.n_large;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_large; i += gridDim.x * blockDim.x) {
+        const uint64_t g0 = W.lbase[i]; const uint32_t nc = (uint32_t)(W.lbase[i + 1] - g0);
+        uint32_t acc = 0;
+        for (uint32_t c = 0; c < nc; c++) { const uint32_t sk = W.cline[g0 + c]; W.cline[g0 + c] = 1u + acc + sk; acc += W.cnl[g0 + c]; }
+    }
+}
+__global__ void __launch_bounds__(128)
+k_large_count(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, LargeWs W) {
+    const uint32_t n_large = *W.n_large;
+    if (n_large == 0) return;
+    const uint64_t total = W.lbase[W.max_large + 1];
+    const obm::Tables T = device_tables();
+    for (uint64_t g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t i = large_of_chunk(W, n_large, g), d = W.large_list[i], c = (uint32_t)(g - W.lbase[i]);
+        const uint32_t nc = (uint32_t)(W.lbase[i + 1] - W.lbase[i]);
+        const uint8_t *doc = bytes + doc_off[d]; const uint32_t n = (uint32_t)(doc_off[d + 1] - doc_off[d]);
+        const uint32_t stop = c + 1 < nc ? W.cs[g + 1] : n;
+        obm::SmallSink sink(nullptr, 0);
+        uint32_t end;
+        W.cflag[g] = obml::lex_chunk(T, doc, n, W.cs[g], W.cline[g], stop, sink, &end);
+        W.cend[g] = end; W.ccnt[g] = sink.n_tuples; W.cmk[g] = sink.n_markers; W.clx[g] = sink.n_lexemes;
+    }
+}
+__global__ void __launch_bounds__(128)
+k_large_resolve(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, LargeWs W, uint32_t *__restrict__ counts,
+                unsigned long long *__restrict__ totals, uint32_t *__restrict__ status) {
+    const uint32_t n_large = *W.n_large;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_large; i += gridDim.x * blockDim.x) {
+        const uint32_t d = W.large_list[i];
+        const uint64_t g0 = W.lbase[i]; const uint32_t nc = (uint32_t)(W.lbase[i + 1] - g0);
+        const uint32_t n = (uint32_t)(doc_off[d + 1] - doc_off[d]);
+        bool valid = true;
+        for (uint32_t c = 0; c < nc; c++) {
+            const uint32_t stop = c + 1 < nc ? W.cs[g0 + c + 1] : n;
+            if (W.cflag[g0 + c] || W.cend[g0 + c] != stop) { valid = false; break; }
+        }
+        uint64_t mk = 0, lx = 0; uint32_t fatal = 0;
+        if (valid) {
+            uint64_t off = 0;
+            for (uint32_t c = 0; c < nc; c++) { W.choff[g0 + c] = off; off += W.ccnt[g0 + c]; mk += W.cmk[g0 + c]; lx += W.clx[g0 + c]; }
+            counts[d] = (uint32_t)(off + 1); lx += 1; /* EOF */
+        } else {
+            /* a construct crosses a chunk boundary, or the document ends in a fatal error: lex it sequentially */
+            const obm::Tables T = device_tables();
+            obm::CountSink sink;
+            obm::Lexer<obm::CountSink> lex(T, bytes + doc_off[d], n, sink);
+            const int st = lex.run<false>();
+            counts[d] = (uint32_t)sink.n_tuples; mk = sink.n_markers; lx = sink.n_lexemes; fatal = st == obm::RUN_FATAL;
+        }
+        W.lvalid[i] = valid ? 1u : 0u;
+        if (totals) { atomicAdd(&totals[0], (unsigned long long)mk); atomicAdd(&totals[1], (unsigned long long)lx); }
+        if (status) { atomicAdd(&status[ST_DOCS_EXACT], 1u); if (fatal) atomicAdd(&status[ST_DOCS_FATAL], 1u); }
+    }
+}
+__global__ void __launch_bounds__(128)
+k_large_fill(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, LargeWs W, const uint64_t *__restrict__ tuple_off,
+             obm_tuple *__restrict__ out, uint64_t out_cap) {
+    const uint32_t n_large = *W.n_large;
+    if (n_large == 0) return;
+    const uint64_t total = W.lbase[W.max_large + 1];
+    const obm::Tables T = device_tables();
+    for (uint64_t g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t i = large_of_chunk(W, n_large, g), d = W.large_list[i], c = (uint32_t)(g - W.lbase[i]);
+        const uint32_t nc = (uint32_t)(W.lbase[i + 1] - W.lbase[i]);
+        const uint8_t *doc = bytes + doc_off[d]; const uint32_t n = (uint32_t)(doc_off[d + 1] - doc_off[d]);
+        if (!W.lvalid[i]) {
+            if (c == 0) {
+                const uint64_t t0 = tuple_off[d];
+                obm::WriteSink sink(out + t0, t0 < out_cap ? out_cap - t0 : 0);
+                obm::Lexer<obm::WriteSink> lex(T, doc, n, sink);
+                lex.run<false>();
+            }
+            continue;
+        }
+        const uint64_t t0 = tuple_off[d] + W.choff[g];
+        const uint32_t stop = c + 1 < nc ? W.cs[g + 1] : n;
+        obm::WriteSink sink(out + t0, t0 < out_cap ? out_cap - t0 : 0);
+        uint32_t end;
+        obml::lex_chunk(T, doc, n, W.cs[g], W.cline[g], stop, sink, &end);
+        if (c == nc - 1) { const uint64_t e = t0 + W.ccnt[g]; if (e < out_cap) out[e] = OBM_TUPLE(OBM_K_EOF, n, 0); }
+    }
+}
+
+static void large_count_launch(cudaStream_t st, int sms, const uint8_t *d_bytes, const uint64_t *d_doc_off, const LargeWs &W,
+                               uint32_t *counts, unsigned long long *totals, uint32_t *status) {
+    const uint32_t n = W.max_large + 1, nt = scan_tiles(n);
+    const uint32_t g = (uint32_t)sms * 8u, gl = (n + 255) / 256 < g ? (n + 255) / 256 : g;
+    k_large_nchunks<<<gl, 256, 0, st>>>(d_doc_off, W);
+    k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(W.lch, n, W.lbase, W.lsums);
+    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(W.lsums, nt, W.lbase + n);
+    k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(W.lbase, n, W.lsums, ~0ull, nullptr);
+    k_large_prep<<<g, 128, 0, st>>>(d_bytes, d_doc_off, W);
+    k_large_lines<<<gl, 128, 0, st>>>(W);
+    k_large_count<<<g, 128, 0, st>>>(d_bytes, d_doc_off, W);
+    k_large_resolve<<<gl, 128, 0, st>>>(d_bytes, d_doc_off, W, counts, totals, status);
+}
+constexpr uint32_t LARGE_COUNT_LAUNCHES = 8;
+static void large_fill_launch(cudaStream_t st, int sms, const uint8_t *d_bytes, const uint64_t *d_doc_off, const LargeWs &W,
+                              const uint64_t *toff, obm_tuple *d_out, uint64_t out_cap) {
+    k_large_fill<<<(uint32_t)sms * 8u, 128, 0, st>>>(d_bytes, d_doc_off, W, toff, d_out, out_cap);
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -307,7 +473,7 @@ static int ensure(obm_handle *h, T **p, uint64_t *cap, uint64_t need) {
 }
 
 /* Fast path: index kernel -> exact count of large documents -> tile kernel -> exact fill of large documents. */
-static int obm_fast_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t *d_doc_off, uint32_t ndocs, uint64_t total_bytes,
+static int obm_fast_launch(obm_handle *h, void *large_ws, const uint8_t *d_bytes, const uint64_t *d_doc_off, uint32_t ndocs, uint64_t total_bytes,
                            obm_tuple *d_out, uint64_t out_cap, uint64_t *toff, uint32_t *status, unsigned long long *totals,
                            uint32_t *counts, void *ws, cudaStream_t st) {
     static bool attr_set = false;
@@ -329,8 +495,10 @@ static int obm_fast_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     OBM_CUDA(h, cudaMemsetAsync(tile_state, 0, ((uint64_t)ntiles + 1) * 8, st));
     OBM_CUDA(h, cudaMemsetAsync(ctl, 0, 16, st));
     obmf::k_tile_index<<<(ndocs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, ndocs, ntiles, tile_first, large_list, ctl + 1);
-    const uint32_t nb_large = (uint32_t)((max_large + 127) / 128);
-    k_exact_count<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, ctl + 1, counts, totals, status);
+    int dev_sms = 0, per_sm = 0;
+    OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
+    const LargeWs LW = large_carve(large_ws, total_bytes, large_list, ctl + 1);
+    large_count_launch(st, dev_sms, d_bytes, d_doc_off, LW, counts, totals, status);
     obmf::TileArgs A;
     A.bytes = d_bytes; A.doc_off = d_doc_off; A.ndocs = ndocs; A.total_bytes = total_bytes;
     A.tile_first = tile_first; A.ntiles = ntiles; A.counts = counts;
@@ -341,15 +509,13 @@ static int obm_fast_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
         if (msplit < 0) { const char *e = getenv("OBM_MSPLIT"); msplit = e ? atoi(e) : 8; if (msplit < 1) msplit = 1; if (msplit > (int)(obmt::NT / 32)) msplit = obmt::NT / 32; }
         A.msplit = (uint32_t)msplit;
     }
-    int dev_sms = 0, per_sm = 0;
-    OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
     OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, obmf::k_tile_scan, (int)obmt::NT, smem));
     if (per_sm < 1) per_sm = 1;
     uint32_t grid = (uint32_t)dev_sms * (uint32_t)per_sm; /* persistent CTAs: a multiple of the SM count */
     if (grid > ntiles) grid = ntiles;
     obmf::k_tile_scan<<<grid, obmt::NT, smem, st>>>(A);
-    if (d_out && out_cap) k_exact_fill<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, ctl + 1, toff, d_out, out_cap);
-    h->launches = 3 + ((d_out && out_cap) ? 1 : 0);
+    if (d_out && out_cap) large_fill_launch(st, dev_sms, d_bytes, d_doc_off, LW, toff, d_out, out_cap);
+    h->launches = 2 + LARGE_COUNT_LAUNCHES + ((d_out && out_cap) ? 1 : 0);
     OBM_CUDA(h, cudaGetLastError());
     return OBM_OK;
 }
@@ -382,7 +548,7 @@ static uint64_t pipe_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
  * large documents. */
 static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t *d_doc_off, uint32_t ndocs, uint64_t total_bytes,
                             obm_tuple *d_out, uint64_t out_cap, uint64_t *toff, uint32_t *status, unsigned long long *totals,
-                            uint32_t *counts, void *fast_ws, void *pipe_ws, cudaStream_t st) {
+                            uint32_t *counts, void *fast_ws, void *pipe_ws, void *large_ws, cudaStream_t st) {
     static bool attr_set = false;
     const size_t smem1 = sizeof(obmq::K1Shared);
     if (!attr_set) {
@@ -418,14 +584,14 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     OBM_CUDA(h, cudaMemsetAsync(A.st_tuples, 0, up((um + 1) * 8) + up((um / 32 + 2) * 8) + 64, st)); /* look-back chains + control words */
     OBM_CUDA(h, cudaMemsetAsync(lctl, 0, 16, st));
     obmf::k_tile_index<<<(ndocs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, ndocs, ntiles, tile_first, large_list, lctl + 1);
-    const uint32_t nb_large = (uint32_t)((max_large + 127) / 128);
-    k_exact_count<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, lctl + 1, counts, totals, status);
+    int dev_sms = 0, per_sm1 = 0, per_sm2 = 0;
+    OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
+    const LargeWs LW = large_carve(large_ws, total_bytes, large_list, lctl + 1);
+    large_count_launch(st, dev_sms, d_bytes, d_doc_off, LW, counts, totals, status);
     obmq::k_tile_units<<<(ntiles + 255) / 256, 256, 0, st>>>(d_doc_off, tile_first, ntiles, nsub);
     k_scan_tiles<<<nt_u, SCAN_THREADS, 0, st>>>(nsub, ntiles, ubase, usums);
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(usums, nt_u, ubase + ntiles);
     k_scan_add<<<nt_u, SCAN_THREADS, 0, st>>>(ubase, ntiles, usums, ~0ull, nullptr);
-    int dev_sms = 0, per_sm1 = 0, per_sm2 = 0;
-    OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
     OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, obmq::k1_scan, (int)obmt::NT, smem1));
     OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, obmq::k2_units, (int)(obmp::W_WARPS * 32), 0));
     if (per_sm1 < 1) per_sm1 = 1;
@@ -437,9 +603,9 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     if (g2 > g2max) g2 = (uint32_t)g2max;
     obmq::k1_scan<<<g1, obmt::NT, smem1, st>>>(A);
     obmq::k2_units<<<g2, obmp::W_WARPS * 32, 0, st>>>(A);
-    uint32_t launches = 8;
+    uint32_t launches = 7 + LARGE_COUNT_LAUNCHES;
     if (d_out && out_cap) {
-        k_exact_fill<<<nb_large, 128, 0, st>>>(d_bytes, d_doc_off, large_list, 0, lctl + 1, toff, d_out, out_cap);
+        large_fill_launch(st, dev_sms, d_bytes, d_doc_off, LW, toff, d_out, out_cap);
         launches += 1;
     }
     /* work-record overflow -> status[3]: the caller must redo the scan with the exact kernels (mode 1) */
@@ -454,6 +620,7 @@ extern "C" uint64_t obm_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
     b += align_up((uint64_t)scan_tiles(ndocs) * 8 + 8, 256);
     b += align_up(obm_fast_scratch_bytes(ndocs, total_bytes), 256);
     b += pipe_scratch_bytes(ndocs, total_bytes);
+    b += large_scratch_bytes(total_bytes);
     return b;
 }
 
@@ -474,7 +641,8 @@ static int lex_device_impl(obm_handle *h, const void *d_bytes, const void *d_doc
     uint32_t *counts = (uint32_t *)sc; sc += align_up((uint64_t)ndocs * 4 + 4, 256);
     uint64_t *tile_sums = (uint64_t *)sc; sc += align_up((uint64_t)scan_tiles(ndocs) * 8 + 8, 256);
     void *fast_ws = sc; sc += align_up(obm_fast_scratch_bytes(ndocs, total_bytes), 256);
-    void *pipe_ws = sc;
+    void *pipe_ws = sc; sc += pipe_scratch_bytes(ndocs, total_bytes);
+    void *large_ws = sc;
     uint32_t *status = (uint32_t *)(d_status ? d_status : (void *)h->d_status);
     unsigned long long *totals = (unsigned long long *)(d_counts ? d_counts : (void *)h->d_counts);
     uint64_t *toff = (uint64_t *)d_doc_tuple_off;
@@ -484,9 +652,9 @@ static int lex_device_impl(obm_handle *h, const void *d_bytes, const void *d_doc
 
     if (h->mode == 0)
         return obm_pipe_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
-                                (obm_tuple *)d_out, out_cap, toff, status, totals, counts, fast_ws, pipe_ws, st);
+                                (obm_tuple *)d_out, out_cap, toff, status, totals, counts, fast_ws, pipe_ws, large_ws, st);
     if (h->mode == 2)
-        return obm_fast_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
+        return obm_fast_launch(h, large_ws, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
                                (obm_tuple *)d_out, out_cap, toff, status, totals, counts, fast_ws, st);
     uint32_t nb = (ndocs + 127) / 128;
     h->launches = 4 + ((d_out && out_cap) ? 1 : 0);

@@ -18,6 +18,7 @@ def build(force=False):
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_core.h"),
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_tile.h"),
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_pipe.h"),
+            os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_large.h"),
             os.path.join(_ROOT, "include", "obmarkers.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-shared", "-o", so,
@@ -39,6 +40,8 @@ def lib():
                                     ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
         L.hs_pipe_batch.restype = ctypes.c_uint64
         L.hs_pipe_batch.argtypes = L.hs_tile_batch.argtypes
+        L.hs_large_doc.restype = ctypes.c_uint64
+        L.hs_large_doc.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)]
         L.hs_parse_float_err.argtypes = [ctypes.c_char_p, ctypes.c_uint32]
         L.hs_atoi_err.argtypes = [ctypes.c_char_p, ctypes.c_uint32]
         L.obm_decode_doc.restype = ctypes.c_int64
@@ -60,6 +63,17 @@ def lex_doc(doc: bytes, by_lines=False):
         n = L.hs_lex_doc(doc, len(doc), out.ctypes.data, cap, None, None)
     assert n <= cap
     return out[:n].copy()
+
+
+def large_doc(doc: bytes):
+    """chunk-parallel exact path (obm_large.h) -> (tuples, chain_validated)"""
+    L = lib()
+    cap = 2 * len(doc) + 16
+    out = np.zeros(cap, dtype=np.uint64)
+    used = ctypes.c_uint32(0)
+    n = L.hs_large_doc(doc, len(doc), out.ctypes.data, cap, ctypes.byref(used))
+    assert n <= cap
+    return out[:n].copy(), bool(used.value)
 
 
 def decode(doc: bytes, tuples, L=None) -> bytes:

@@ -420,3 +420,37 @@ extern "C" uint64_t hs_pipe_batch(const uint8_t *bytes, const uint64_t *doc_off,
     if (getenv("HS_VIEW_STATS")) fprintf(stderr, "hostsim: %llu staged line views, %llu rejected\n", (unsigned long long)G.views, (unsigned long long)G.unsafe_views);
     return base;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Large documents: the chunk-parallel exact path (obm_large.h), replayed sequentially with the same
+ * chain check and the same fallback as k_large_count / k_large_resolve / k_large_fill.
+ * returns the tuple count; *used_chunks = 1 when the chain validated (no sequential fallback)
+ * ------------------------------------------------------------------------------------------- */
+#include "../../operator-builder_b200/csrc/obm_large.h"
+extern "C" uint64_t hs_large_doc(const uint8_t *doc, uint32_t n, obm_tuple *out, uint64_t cap, uint32_t *used_chunks) {
+    using namespace obml;
+    const uint32_t nc = n_chunks(n);
+    std::vector<uint32_t> cs(nc + 1), line(nc), cnt(nc), cend(nc), flag(nc);
+    uint32_t acc = 0;
+    for (uint32_t c = 0; c < nc; c++) { uint32_t sk; cs[c] = chunk_start(doc, n, c, &sk); line[c] = 1 + acc + sk; acc += chunk_newlines(doc, n, c); }
+    cs[nc] = n;
+    bool valid = true;
+    for (uint32_t c = 0; c < nc; c++) {
+        obm::SmallSink s(nullptr, 0);
+        flag[c] = lex_chunk(TBL, doc, n, cs[c], line[c], cs[c + 1], s, &cend[c]);
+        cnt[c] = s.n_tuples;
+        if (flag[c] || cend[c] != cs[c + 1]) valid = false;
+    }
+    if (used_chunks) *used_chunks = valid;
+    if (!valid) return hs_lex_doc(doc, n, out, cap, nullptr, nullptr);
+    uint64_t at = 0;
+    for (uint32_t c = 0; c < nc; c++) {
+        obm::WriteSink s(out + at, at < cap ? cap - at : 0);
+        uint32_t e;
+        lex_chunk(TBL, doc, n, cs[c], line[c], cs[c + 1], s, &e);
+        if (s.n_tuples != cnt[c]) { fprintf(stderr, "hostsim: chunk count changed between passes\n"); abort(); }
+        at += cnt[c];
+    }
+    if (at < cap) out[at] = OBM_TUPLE(OBM_K_EOF, n, 0);
+    return at + 1;
+}

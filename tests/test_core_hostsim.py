@@ -107,3 +107,35 @@ def test_fuzz_valid(oracle, seed):
     rng = random.Random(8800 + seed)
     for _ in range(400):
         check(oracle, cu.fuzz_doc_valid(rng))
+
+
+def test_large_documents_chunk_parallel_path():
+    """obm_large.h: chunks of 4 KiB starting at line boundaries, lexed independently, chain-checked; the result must
+    equal the sequential stream whether the chain validates or the document falls back"""
+    import random
+    from tests import corpus_util as cu
+    rng = random.Random(99)
+    pool = [b"key: value\n", b"  - item  # +operator-builder:field:name=a.b,type=int,default=3\n", b"\n", b"path: /a/b+c\n",
+            b"x" * 300 + b"\n", b"# plain comment\n", b"a: 'q'  # +x:y=\"s t\",z\n", b"1+1\n", b"++x:y\n", b"# +noscope\n"]
+    validated = 0
+    for trial in range(12):
+        parts, n = [], 0
+        target = rng.choice([5000, 17000, 40000, 120000])
+        multi = trial % 3 == 2  # sprinkle constructs that cross lines (and sometimes chunk boundaries)
+        while n < target:
+            ln = rng.choice(pool + ([b"# +x:y=`multi\n  # line`\n", b"# +a:b=\n   true\n"] if multi else []))
+            parts.append(ln); n += len(ln)
+        doc = b"".join(parts)
+        if trial % 4 == 1:
+            doc = doc[:-1]  # no trailing newline
+        got, ok = hostsim.large_doc(doc)
+        assert np.array_equal(got, hostsim.lex_doc(doc)), trial
+        validated += ok
+    assert validated >= 6
+    # adversarial: a back-tick literal swallowing a chunk boundary, a fatal error early, a single line longer than many chunks
+    for doc in (b"k: v\n" * 700 + b"# +x:y=`" + b"z\n" * 3000 + b"`\n" + b"k: v\n" * 100,
+                b"# +a:b=\"unterminated\n" + b"k: v # +c:d=1\n" * 2000,
+                b"# +a:b=" + b"v" * 30000 + b"\nk: v # +c:d=1\n" * 10,
+                b"", b"\n", b"x" * 4096, b"x" * 4095 + b"\n" + b"# +a:b\n", "# é +a:b=ü\n".encode() * 900):
+        got, ok = hostsim.large_doc(doc)
+        assert np.array_equal(got, hostsim.lex_doc(doc))

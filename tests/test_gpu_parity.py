@@ -196,6 +196,29 @@ def test_large_documents(scanner, oracle):
     run_and_compare(scanner, oracle, big + [b"+a:b"] + big[:1])
 
 
+def test_large_documents_chunk_parallel(scanner, oracle):
+    """documents above the tile size take the chunk-parallel exact path (csrc/obm_large.h): regular documents validate
+    their chunk chain, a back-tick literal across a chunk boundary / a fatal error force the sequential fallback, single
+    lines longer than several chunks leave empty chunks; non-ASCII text; small documents in between"""
+    rng = random.Random(23)
+    pool = [b"key: value\n", b"  - item  # +operator-builder:field:name=a.b,type=int,default=3\n", b"\n", b"path: /a/b+c\n",
+            b"x" * 300 + b"\n", b"# plain comment\n", b"a: 'q'  # +x:y=\"s t\",z\n", b"1+1\n", b"++x:y\n", b"# +noscope\n"]
+    docs = []
+    for target in (17000, 40000, 300000, 2 << 20):
+        parts, n = [], 0
+        while n < target:
+            ln = rng.choice(pool); parts.append(ln); n += len(ln)
+        docs.append(b"".join(parts))
+        docs.append(b"k: v # +s:a=1\n")
+    docs.append(docs[2][:-1])                                                   # no trailing newline
+    docs.append(b"k: v\n" * 700 + b"# +x:y=`" + b"z\n" * 3000 + b"`\n" + b"k: v\n" * 100)   # crosses chunk boundaries -> fallback
+    docs.append(b"# +a:b=\"unterminated\n" + b"k: v # +c:d=1\n" * 2000)                      # fatal early -> fallback
+    docs.append(b"# +a:b=" + b"v" * 30000 + b"\n" + b"k: v # +c:d=1\n" * 10)                   # one line over 7 chunks
+    docs.append("# é +a:b=ü\n".encode() * 2500)
+    docs.append(b"x" * 16369)
+    res = run_and_compare(scanner, oracle, docs)
+
+
 def test_device_entry_point_and_capacity(scanner, oracle):
     import torch
     import operator_builder_b200 as ob

@@ -19,7 +19,7 @@
 
 namespace obml {
 
-constexpr uint32_t LCHUNK = 4096;
+constexpr uint32_t LCHUNK = 1024;
 enum : uint32_t { CF_FATAL = 1, CF_OVERSHOOT = 2 };
 
 OBM_HD uint32_t n_chunks(uint32_t len) { return len == 0 ? 1u : (uint32_t)(((uint64_t)len + LCHUNK - 1) / LCHUNK); }

@@ -915,52 +915,64 @@ extern "C" int obm_generate_corpus_device(obm_handle *h, void *d_bytes, void *d_
  * exchange over NVLink (hard part 1). */
 struct DevRegistry { uint32_t n; uint32_t off[9]; uint8_t text[512]; }; /* names back to back, off[n] = end */
 
+/* One WARP per document, a lane per tuple (coalesced 8-byte loads); the few MarkerStart candidates do the
+ * look-back for a stale buffer and the name match themselves.  Records keep tuple order (ballot ranks). */
 template <bool WRITE>
 __global__ void __launch_bounds__(256)
 k_marker_index(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs,
                const obm_tuple *__restrict__ tuples, const uint64_t *__restrict__ tuple_off, DevRegistry reg,
                uint32_t *__restrict__ counts, const uint64_t *__restrict__ rec_off, uint4 *__restrict__ records, uint64_t cap) {
-    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= ndocs) return;
-    const uint8_t *doc = bytes + doc_off[d];
-    const obm_tuple *t = tuples + tuple_off[d];
-    const uint32_t n = (uint32_t)(tuple_off[d + 1] - tuple_off[d]);
-    uint32_t found = 0;
-    uint64_t at = WRITE ? rec_off[d] : 0;
-    bool pending = false; /* the lexer's buffer holds stale text: the next Value is not a plain input slice */
-    for (uint32_t i = 0; i < n; i++) {
-        const obm_tuple tu = t[i];
-        const uint32_t k = OBM_TUPLE_KIND(tu);
-        if (k == OBM_K_PART) { pending = true; continue; }
-        if (k == OBM_K_FLUSH) { pending = false; continue; }
-        if (k < OBM_K_COMMENT || k > OBM_K_QUOTE) continue; /* synthetic, positional and in-band message tuples carry no buffer text */
-        const bool clean = !pending;
-        pending = false;
-        if (k != OBM_K_MARKER_START || !clean || OBM_TUPLE_LEN(tu) != 1) continue;
-        /* candidate registry entries are narrowed while the name "+scope:scope" is matched byte by byte */
-        uint32_t alive = (1u << reg.n) - 1u, pos = 1, scopes = 0, j = i + 1;
-        for (uint32_t r = 0; r < reg.n; r++) if (reg.text[reg.off[r]] != '+') alive &= ~(1u << r);
-        for (;;) {
-            if (j + 1 >= n || OBM_TUPLE_KIND(t[j]) != OBM_K_SCOPE || OBM_TUPLE_KIND(t[j + 1]) != OBM_K_SEPARATOR) break;
-            const uint32_t so = OBM_TUPLE_OFF(t[j]), sl = OBM_TUPLE_LEN(t[j]);
-            if (scopes) { /* the ':' between scopes */
-                for (uint32_t r = 0; r < reg.n; r++) if ((alive >> r & 1u) && (reg.off[r] + pos >= reg.off[r + 1] || reg.text[reg.off[r] + pos] != ':')) alive &= ~(1u << r);
-                pos++;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t d = warp; d < ndocs; d += nwarps) {
+        const uint8_t *doc = bytes + doc_off[d];
+        const obm_tuple *t = tuples + tuple_off[d];
+        const uint32_t n = (uint32_t)(tuple_off[d + 1] - tuple_off[d]);
+        uint32_t found = 0;
+        uint64_t at = WRITE ? rec_off[d] : 0;
+        for (uint32_t c0 = 0; c0 < n; c0 += 32) {
+            const uint32_t i = c0 + lane;
+            const obm_tuple tu = i < n ? t[i] : 0;
+            int hit = -1; uint32_t scopes = 0;
+            if (i < n && OBM_TUPLE_KIND(tu) == OBM_K_MARKER_START && OBM_TUPLE_LEN(tu) == 1) {
+                /* the lexer's buffer must not hold stale text: walking back over tuples that carry no buffer text, the
+                 * first PART / FLUSH / slice tuple decides */
+                bool clean = true;
+                for (uint32_t j = i; j-- > 0;) {
+                    const uint32_t kj = OBM_TUPLE_KIND(t[j]);
+                    if (kj == OBM_K_PART) { clean = false; break; }
+                    if (kj == OBM_K_FLUSH || (kj >= OBM_K_COMMENT && kj <= OBM_K_QUOTE)) break;
+                }
+                if (clean) {
+                    /* candidate registry entries are narrowed while the name "+scope:scope" is matched byte by byte */
+                    uint32_t alive = (1u << reg.n) - 1u, pos = 1, j = i + 1;
+                    for (uint32_t r = 0; r < reg.n; r++) if (reg.text[reg.off[r]] != '+') alive &= ~(1u << r);
+                    for (;;) {
+                        if (j + 1 >= n || OBM_TUPLE_KIND(t[j]) != OBM_K_SCOPE || OBM_TUPLE_KIND(t[j + 1]) != OBM_K_SEPARATOR) break;
+                        const uint32_t so = OBM_TUPLE_OFF(t[j]), sl = OBM_TUPLE_LEN(t[j]);
+                        if (scopes) { /* the ':' between scopes */
+                            for (uint32_t r = 0; r < reg.n; r++) if ((alive >> r & 1u) && (reg.off[r] + pos >= reg.off[r + 1] || reg.text[reg.off[r] + pos] != ':')) alive &= ~(1u << r);
+                            pos++;
+                        }
+                        for (uint32_t b = 0; b < sl && alive; b++) {
+                            const uint8_t c = doc[so + b];
+                            for (uint32_t r = 0; r < reg.n; r++) if ((alive >> r & 1u) && (reg.off[r] + pos + b >= reg.off[r + 1] || reg.text[reg.off[r] + pos + b] != c)) alive &= ~(1u << r);
+                        }
+                        pos += sl; scopes++; j += 2;
+                    }
+                    if (scopes && j < n && OBM_TUPLE_KIND(t[j]) == OBM_K_ARG)
+                        for (uint32_t r = 0; r < reg.n; r++) if ((alive >> r & 1u) && reg.off[r] + pos == reg.off[r + 1]) hit = (int)r;
+                }
             }
-            for (uint32_t b = 0; b < sl && alive; b++) {
-                const uint8_t c = doc[so + b];
-                for (uint32_t r = 0; r < reg.n; r++) if ((alive >> r & 1u) && (reg.off[r] + pos + b >= reg.off[r + 1] || reg.text[reg.off[r] + pos + b] != c)) alive &= ~(1u << r);
+            const uint32_t bal = __ballot_sync(0xffffffffu, hit >= 0);
+            if (WRITE && hit >= 0) {
+                const uint64_t w = at + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                if (w < cap) records[w] = make_uint4(d, i, OBM_TUPLE_OFF(tu), (uint32_t)hit | (scopes << 16));
             }
-            pos += sl; scopes++; j += 2;
+            at += (uint32_t)__popc(bal); found += (uint32_t)__popc(bal);
         }
-        if (!scopes || j >= n || OBM_TUPLE_KIND(t[j]) != OBM_K_ARG) continue;
-        int hit = -1;
-        for (uint32_t r = 0; r < reg.n; r++) if ((alive >> r & 1u) && reg.off[r] + pos == reg.off[r + 1]) hit = (int)r;
-        if (hit < 0) continue;
-        if (WRITE) { if (at < cap) records[at] = make_uint4(d, i, OBM_TUPLE_OFF(tu), (uint32_t)hit | (scopes << 16)); at++; }
-        found++;
+        if (!WRITE && lane == 0) counts[d] = found;
     }
-    if (!WRITE) counts[d] = found;
 }
 
 extern "C" int obm_marker_index_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
@@ -987,7 +999,11 @@ extern "C" int obm_marker_index_device(obm_handle *h, const obm_registry *reg, c
     uint32_t *counts = (uint32_t *)h->scratch;
     uint64_t *tile_sums = (uint64_t *)((uint8_t *)h->scratch + align_up((uint64_t)ndocs * 4 + 4, 256));
     uint64_t *roff = (uint64_t *)d_doc_rec_off;
-    const uint32_t nb = (ndocs + 255) / 256, nt = scan_tiles(ndocs);
+    int sms_i = 0;
+    OBM_CUDA(h, cudaDeviceGetAttribute(&sms_i, cudaDevAttrMultiProcessorCount, h->device));
+    const uint32_t nt = scan_tiles(ndocs);
+    uint32_t nb = (uint32_t)sms_i * 8u; /* persistent warps, a document each per step */
+    if (nb > (ndocs + 7) / 8) nb = (ndocs + 7) / 8;
     k_marker_index<false><<<nb, 256, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, (const obm_tuple *)d_tuples,
                                                (const uint64_t *)d_doc_tuple_off, R, counts, nullptr, nullptr, 0);
     k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(counts, ndocs, roff, tile_sums);
@@ -1036,38 +1052,83 @@ k_rewrite_collection(const uint8_t *__restrict__ bytes, const uint64_t *__restri
 
 /* Each record: { u32 doc, u32 a, u32 b, u32 0 }: extracted manifest = "\n" + content[a:b) (ExtractManifests
  * rebuilds it as "\n" + line for every line between separators; a separator is a line that equals "---" after
- * trimming trailing spaces; empty groups are dropped). */
+ * trimming trailing spaces).  Lines between two separators form one record; so do the lines before the first
+ * and after the last one (the final, possibly empty, line included).
+ *
+ * One WARP per document, 512 bytes per step: every lane loads 16 bytes (aligned uint4), builds a newline mask
+ * and a dash mask with exact SIMD-within-register byte tests, and only the rare "dash at a line start" positions
+ * are verified byte by byte.  Separators are then folded into records in order through warp-uniform state. */
+__device__ __forceinline__ uint32_t eq_bytes4(uint32_t v, uint32_t pat) { /* 4-bit mask of bytes of v equal to pat's byte (exact for any byte value) */
+    const uint32_t t = v ^ pat;
+    const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
+    return ((z >> 7) * 0x00204081u >> 21) & 0xFu;
+}
 template <bool WRITE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_split_docs(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs, uint32_t *__restrict__ counts,
              const uint64_t *__restrict__ rec_off, uint4 *__restrict__ records, uint64_t cap) {
-    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= ndocs) return;
-    const uint8_t *src = bytes + doc_off[d];
-    const uint32_t n = (uint32_t)(doc_off[d + 1] - doc_off[d]);
-    uint32_t found = 0;
-    uint64_t at = WRITE ? rec_off[d] : 0;
-    /* strings.Split(content, "\n") yields lines [ls, le) for every '\n' plus a final (possibly empty) line */
-    bool open = false; uint32_t a = 0, last_end = 0;
-    uint32_t ls = 0;
-    for (;;) {
-        uint32_t le = ls;
-        while (le < n && src[le] != '\n') le++;
-        /* separator? */
-        uint32_t te = le;
-        while (te > ls && src[te - 1] == ' ') te--;
-        const bool sep = (te - ls == 3) && src[ls] == '-' && src[ls + 1] == '-' && src[ls + 2] == '-';
-        if (sep) {
-            if (open) { if (WRITE) { if (at < cap) records[at] = make_uint4(d, a, last_end, 0); at++; } found++; open = false; }
-        } else {
-            if (!open) { open = true; a = ls; }
-            last_end = le;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t d = warp; d < ndocs; d += nwarps) {
+        const uint8_t *src = bytes + doc_off[d];
+        const uint32_t n = (uint32_t)(doc_off[d + 1] - doc_off[d]);
+        const uint32_t skew = (uint32_t)((uintptr_t)src & 15u);
+        const uint4 *base = reinterpret_cast<const uint4 *>(src - skew);
+        uint32_t found = 0;
+        uint64_t at = WRITE ? rec_off[d] : 0;
+        uint32_t rs = 0; bool closed = false; /* start of the open group; closed: the document ended with a separator */
+        uint32_t prev_nl = 1;                   /* the byte before the document counts as a line end */
+        for (uint32_t c0 = 0; c0 < n + skew; c0 += 512) {
+            const uint32_t q0 = c0 + lane * 16u;            /* buffer-relative position of this lane's first byte */
+            uint32_t nl = 0, da = 0;
+            if (q0 < n + skew) {
+                const uint4 v = base[q0 >> 4];
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) { nl |= eq_bytes4(w[k], 0x0A0A0A0Au) << (4 * k); da |= eq_bytes4(w[k], 0x2D2D2D2Du) << (4 * k); }
+            }
+            /* keep document bytes only */
+            uint32_t keep = 0xFFFFu;
+            if (q0 < skew) keep &= (skew - q0 >= 16) ? 0u : (0xFFFFu << (skew - q0));
+            if (q0 + 16 > n + skew) keep &= (q0 >= n + skew) ? 0u : (0xFFFFu >> (q0 + 16 - n - skew));
+            nl &= keep; da &= keep;
+            /* line starts: the byte after a newline, and the first byte of the document */
+            uint32_t before = __shfl_up_sync(0xffffffffu, nl >> 15, 1);
+            if (lane == 0) before = c0 == 0 ? 0u : prev_nl;
+            uint32_t ls_mask = ((nl << 1) | (before & 1u)) & 0xFFFFu;
+            if (q0 <= skew && skew < q0 + 16) ls_mask |= 1u << (skew - q0);
+            prev_nl = __shfl_sync(0xffffffffu, nl >> 15, 31);
+            uint32_t cand = da & ls_mask & keep;
+            /* verify: "---" + spaces* + ('\n' | end) */
+            uint32_t seps = 0;
+            for (uint32_t m = cand; m; m &= m - 1) {
+                const uint32_t b = (uint32_t)__ffs((int)m) - 1u, p = q0 + b - skew;
+                if (p + 2 < n && src[p + 1] == '-' && src[p + 2] == '-') {
+                    uint32_t e = p + 3;
+                    while (e < n && src[e] == ' ') e++;
+                    if (e == n || src[e] == '\n') seps |= 1u << b;
+                }
+            }
+            /* fold the step's separators into records, in order */
+            uint32_t todo = __ballot_sync(0xffffffffu, seps != 0);
+            while (todo) {
+                const uint32_t owner = (uint32_t)__ffs((int)todo) - 1u;
+                uint32_t mine = __shfl_sync(0xffffffffu, seps, owner);
+                const uint32_t oq0 = c0 + owner * 16u;
+                while (mine) {
+                    const uint32_t b = (uint32_t)__ffs((int)mine) - 1u; mine &= mine - 1;
+                    const uint32_t ls = oq0 + b - skew;
+                    uint32_t e = ls + 3;
+                    while (e < n && src[e] == ' ') e++; /* every lane recomputes the (short) tail: warp-uniform */
+                    if (rs < ls) { if (WRITE && lane == 0 && at < cap) records[at] = make_uint4(d, rs, ls - 1, 0); at++; found++; }
+                    if (e < n) rs = e + 1; else closed = true;
+                }
+                todo &= todo - 1;
+            }
         }
-        if (le >= n) break;
-        ls = le + 1;
+        if (!closed) { if (WRITE && lane == 0 && at < cap) records[at] = make_uint4(d, rs, n, 0); at++; found++; }
+        if (!WRITE && lane == 0) counts[d] = found;
     }
-    if (open) { if (WRITE) { if (at < cap) records[at] = make_uint4(d, a, last_end, 0); at++; } found++; }
-    if (!WRITE) counts[d] = found;
 }
 
 static int two_pass_scratch(obm_handle *h, uint32_t ndocs, cudaStream_t st, uint32_t **counts, uint64_t **tile_sums) {
@@ -1111,13 +1172,17 @@ extern "C" int obm_split_docs_device(obm_handle *h, const void *d_bytes, const v
     uint32_t *counts; uint64_t *tile_sums; int rc;
     if ((rc = two_pass_scratch(h, ndocs, st, &counts, &tile_sums)) != OBM_OK) return rc;
     uint64_t *roff = (uint64_t *)d_doc_rec_off;
-    const uint32_t nb = (ndocs + 127) / 128, nt = scan_tiles(ndocs);
-    k_split_docs<false><<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, counts, nullptr, nullptr, 0);
+    int sms_i = 0;
+    OBM_CUDA(h, cudaDeviceGetAttribute(&sms_i, cudaDevAttrMultiProcessorCount, h->device));
+    const uint32_t nt = scan_tiles(ndocs);
+    uint32_t nb = (uint32_t)sms_i * 8u; /* persistent warps, a document each per step */
+    if (nb > (ndocs + 7) / 8) nb = (ndocs + 7) / 8;
+    k_split_docs<false><<<nb, 256, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, counts, nullptr, nullptr, 0);
     k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(counts, ndocs, roff, tile_sums);
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, roff + ndocs);
     k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(roff, ndocs, tile_sums, ~0ull, nullptr);
     if (d_records && cap)
-        k_split_docs<true><<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, nullptr, roff, (uint4 *)d_records, cap);
+        k_split_docs<true><<<nb, 256, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, nullptr, roff, (uint4 *)d_records, cap);
     OBM_CUDA(h, cudaGetLastError());
     return OBM_OK;
 }

@@ -110,7 +110,7 @@ def test_fuzz_valid(oracle, seed):
 
 
 def test_large_documents_chunk_parallel_path():
-    """obm_large.h: chunks of 4 KiB starting at line boundaries, lexed independently, chain-checked; the result must
+    """obm_large.h: chunks of LCHUNK bytes starting at line boundaries, lexed independently, chain-checked; the result must
     equal the sequential stream whether the chain validates or the document falls back"""
     import random
     from tests import corpus_util as cu

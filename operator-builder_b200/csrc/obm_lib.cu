@@ -915,13 +915,19 @@ extern "C" int obm_generate_corpus_device(obm_handle *h, void *d_bytes, void *d_
  * exchange over NVLink (hard part 1). */
 struct DevRegistry { uint32_t n; uint32_t off[9]; uint8_t text[512]; }; /* names back to back, off[n] = end */
 
-/* One WARP per document, a lane per tuple (coalesced 8-byte loads); the few MarkerStart candidates do the
- * look-back for a stale buffer and the name match themselves.  Records keep tuple order (ballot ranks). */
+/* One WARP per document, a lane per tuple.  The document's tuples are staged in shared memory 256 at a time
+ * (coalesced 8-byte loads) so the few MarkerStart candidates can look back for a stale buffer and forward along
+ * the Scope/Separator chain without dependent global loads; the marker name is then compared with the registry
+ * entries of the same length in one pass over the (contiguous) "+scope:scope" text, no early exit, so the byte
+ * loads are independent.  Records keep tuple order (ballot ranks). */
+constexpr uint32_t MI_STAGE = 256, MI_STEP = 192; /* tuples staged / tuples whose candidates are handled per round */
 template <bool WRITE>
 __global__ void __launch_bounds__(256)
 k_marker_index(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs,
                const obm_tuple *__restrict__ tuples, const uint64_t *__restrict__ tuple_off, DevRegistry reg,
                uint32_t *__restrict__ counts, const uint64_t *__restrict__ rec_off, uint4 *__restrict__ records, uint64_t cap) {
+    __shared__ obm_tuple stage[8][MI_STAGE];
+    obm_tuple *sm = stage[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t d = warp; d < ndocs; d += nwarps) {
@@ -930,46 +936,66 @@ k_marker_index(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ d
         const uint32_t n = (uint32_t)(tuple_off[d + 1] - tuple_off[d]);
         uint32_t found = 0;
         uint64_t at = WRITE ? rec_off[d] : 0;
-        for (uint32_t c0 = 0; c0 < n; c0 += 32) {
-            const uint32_t i = c0 + lane;
-            const obm_tuple tu = i < n ? t[i] : 0;
-            int hit = -1; uint32_t scopes = 0;
-            if (i < n && OBM_TUPLE_KIND(tu) == OBM_K_MARKER_START && OBM_TUPLE_LEN(tu) == 1) {
-                /* the lexer's buffer must not hold stale text: walking back over tuples that carry no buffer text, the
-                 * first PART / FLUSH / slice tuple decides */
-                bool clean = true;
-                for (uint32_t j = i; j-- > 0;) {
-                    const uint32_t kj = OBM_TUPLE_KIND(t[j]);
-                    if (kj == OBM_K_PART) { clean = false; break; }
-                    if (kj == OBM_K_FLUSH || (kj >= OBM_K_COMMENT && kj <= OBM_K_QUOTE)) break;
-                }
-                if (clean) {
-                    /* candidate registry entries are narrowed while the name "+scope:scope" is matched byte by byte */
-                    uint32_t alive = (1u << reg.n) - 1u, pos = 1, j = i + 1;
-                    for (uint32_t r = 0; r < reg.n; r++) if (reg.text[reg.off[r]] != '+') alive &= ~(1u << r);
-                    for (;;) {
-                        if (j + 1 >= n || OBM_TUPLE_KIND(t[j]) != OBM_K_SCOPE || OBM_TUPLE_KIND(t[j + 1]) != OBM_K_SEPARATOR) break;
-                        const uint32_t so = OBM_TUPLE_OFF(t[j]), sl = OBM_TUPLE_LEN(t[j]);
-                        if (scopes) { /* the ':' between scopes */
-                            for (uint32_t r = 0; r < reg.n; r++) if ((alive >> r & 1u) && (reg.off[r] + pos >= reg.off[r + 1] || reg.text[reg.off[r] + pos] != ':')) alive &= ~(1u << r);
-                            pos++;
-                        }
-                        for (uint32_t b = 0; b < sl && alive; b++) {
-                            const uint8_t c = doc[so + b];
-                            for (uint32_t r = 0; r < reg.n; r++) if ((alive >> r & 1u) && (reg.off[r] + pos + b >= reg.off[r + 1] || reg.text[reg.off[r] + pos + b] != c)) alive &= ~(1u << r);
-                        }
-                        pos += sl; scopes++; j += 2;
+        for (uint32_t base = 0; base < n; base += MI_STEP) {
+            /* stage [lo, lo + cnt): 32 tuples of look-back, the round's tuples, 32 of look-ahead */
+            const uint32_t lo = base >= 32 ? base - 32 : 0, cnt = (n - lo < MI_STAGE) ? n - lo : MI_STAGE;
+            __syncwarp();
+            for (uint32_t k = lane; k < cnt; k += 32) sm[k] = t[lo + k];
+            __syncwarp();
+            auto T = [&](uint32_t j) -> obm_tuple { return (j >= lo && j - lo < cnt) ? sm[j - lo] : t[j]; };
+            const uint32_t hi = (n - base < MI_STEP) ? n : base + MI_STEP;
+            for (uint32_t c0 = base; c0 < hi; c0 += 32) {
+                const uint32_t i = c0 + lane;
+                const obm_tuple tu = i < hi ? T(i) : 0;
+                int hit = -1; uint32_t scopes = 0;
+                if (i < hi && OBM_TUPLE_KIND(tu) == OBM_K_MARKER_START && OBM_TUPLE_LEN(tu) == 1) {
+                    /* the lexer's buffer must not hold stale text: walking back over tuples that carry no buffer text,
+                     * the first PART / FLUSH / slice tuple decides */
+                    bool clean = true;
+                    for (uint32_t j = i; j-- > 0;) {
+                        const uint32_t kj = OBM_TUPLE_KIND(T(j));
+                        if (kj == OBM_K_PART) { clean = false; break; }
+                        if (kj == OBM_K_FLUSH || (kj >= OBM_K_COMMENT && kj <= OBM_K_QUOTE)) break;
                     }
-                    if (scopes && j < n && OBM_TUPLE_KIND(t[j]) == OBM_K_ARG)
-                        for (uint32_t r = 0; r < reg.n; r++) if ((alive >> r & 1u) && reg.off[r] + pos == reg.off[r + 1]) hit = (int)r;
+                    if (clean) {
+                        /* "+scope:scope:...": Scope/Separator pairs tile the text after the '+', so the name is the
+                         * contiguous slice doc[off, off + pos) */
+                        uint32_t pos = 1, j = i + 1; bool contiguous = true;
+                        const uint32_t off = OBM_TUPLE_OFF(tu);
+                        for (;;) {
+                            if (j + 1 >= n) break;
+                            const obm_tuple a = T(j), b = T(j + 1);
+                            if (OBM_TUPLE_KIND(a) != OBM_K_SCOPE || OBM_TUPLE_KIND(b) != OBM_K_SEPARATOR) break;
+                            contiguous &= OBM_TUPLE_OFF(a) == off + pos + (scopes ? 1u : 0u);
+                            pos += OBM_TUPLE_LEN(a) + (scopes ? 1u : 0u); scopes++; j += 2;
+                        }
+                        if (scopes && j < n && OBM_TUPLE_KIND(T(j)) == OBM_K_ARG) {
+                            for (uint32_t r = 0; r < reg.n; r++) {
+                                if (reg.off[r + 1] - reg.off[r] != pos) continue;
+                                uint32_t diff = 0;
+                                if (contiguous) {
+                                    for (uint32_t b = 0; b < pos; b++) diff |= (uint32_t)doc[off + b] ^ (uint32_t)(uint8_t)reg.text[reg.off[r] + b];
+                                } else { /* scope slices apart from each other: compare piece by piece */
+                                    uint32_t q = 1; diff = (uint32_t)(uint8_t)reg.text[reg.off[r]] ^ (uint32_t)'+';
+                                    for (uint32_t jj = i + 1, sc = 0; sc < scopes; jj += 2, sc++) {
+                                        const obm_tuple a = T(jj);
+                                        if (sc) { diff |= (uint32_t)(uint8_t)reg.text[reg.off[r] + q] ^ (uint32_t)':'; q++; }
+                                        for (uint32_t b = 0; b < OBM_TUPLE_LEN(a); b++) diff |= (uint32_t)doc[OBM_TUPLE_OFF(a) + b] ^ (uint32_t)(uint8_t)reg.text[reg.off[r] + q + b];
+                                        q += OBM_TUPLE_LEN(a);
+                                    }
+                                }
+                                if (diff == 0) hit = (int)r;
+                            }
+                        }
+                    }
                 }
+                const uint32_t bal = __ballot_sync(0xffffffffu, hit >= 0);
+                if (WRITE && hit >= 0) {
+                    const uint64_t w = at + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                    if (w < cap) records[w] = make_uint4(d, i, OBM_TUPLE_OFF(tu), (uint32_t)hit | (scopes << 16));
+                }
+                at += (uint32_t)__popc(bal); found += (uint32_t)__popc(bal);
             }
-            const uint32_t bal = __ballot_sync(0xffffffffu, hit >= 0);
-            if (WRITE && hit >= 0) {
-                const uint64_t w = at + (uint32_t)__popc(bal & ((1u << lane) - 1u));
-                if (w < cap) records[w] = make_uint4(d, i, OBM_TUPLE_OFF(tu), (uint32_t)hit | (scopes << 16));
-            }
-            at += (uint32_t)__popc(bal); found += (uint32_t)__popc(bal);
         }
         if (!WRITE && lane == 0) counts[d] = found;
     }
@@ -1022,6 +1048,11 @@ extern "C" int obm_marker_index_device(obm_handle *h, const obm_registry *reg, c
 /* First versions: one thread per document, two passes (count, exclusive scan, write).  Correct and */
 /* measured; not yet bandwidth-shaped (DESIGN.md lists the chunked, coalesced form as next).        */
 /* ------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t eq_bytes4(uint32_t v, uint32_t pat) { /* 4-bit mask of bytes of v equal to pat's byte (exact for any byte value) */
+    const uint32_t t = v ^ pat;
+    const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
+    return ((z >> 7) * 0x00204081u >> 21) & 0xFu;
+}
 __device__ __forceinline__ bool dev_match(const uint8_t *p, uint32_t avail, const char *pat, uint32_t len) {
     if (avail < len) return false;
     for (uint32_t k = 0; k < len; k++) if (p[k] != (uint8_t)pat[k]) return false;
@@ -1029,25 +1060,87 @@ __device__ __forceinline__ bool dev_match(const uint8_t *p, uint32_t avail, cons
 }
 /* strings.ReplaceAll(ReplaceAll(content, "+operator-builder:collection:field", "+operator-builder:field"),
  *                    "collectionField", "field"): the two patterns cannot overlap each other or themselves and the
- * first replacement cannot create an occurrence of the second, so one left-to-right pass is equivalent. */
+ * first replacement cannot create an occurrence of the second, so one left-to-right pass is equivalent.  Both
+ * replacements are deletions: "+operator-builder:" [collection:] "field" drops 11 bytes at +18, and
+ * [collection] "Field" -> "field" drops 10 bytes and lowers one letter.
+ *
+ * One WARP per document.  Detection: 16 bytes per lane and step (aligned uint4), exact SIMD byte tests for '+'
+ * and 'c', the rare candidates verified byte by byte.  Copy: the runs between deletions are moved with
+ * byte-interleaved lanes (lane k moves bytes k, k+32, ...), so every load/store instruction touches one or two
+ * sectors whatever the shift between input and output is. */
+/* dst[0..len) = src[0..len) by one warp: up to 3 head bytes, then 4 destination-aligned bytes per lane and step
+ * (two aligned source words funnel-shifted together when the source is not 4-aligned relative to the
+ * destination; reads at most 2 bytes past the run -- inside the buffer slack obmarkers.h asks for), then the tail */
+__device__ __forceinline__ void warp_copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t len, uint32_t lane) {
+    uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
+    if (head > len) head = len;
+    if (lane < head) dst[lane] = src[lane];
+    dst += head; src += head; len -= head;
+    const uint32_t nw = len >> 2, ms = (uint32_t)((uintptr_t)src & 3u);
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - ms);
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
+    for (uint32_t j = lane; j < nw; j += 32) {
+        const uint32_t a = sw[j], b = ms ? sw[j + 1] : 0u;
+        dw[j] = __funnelshift_r(a, b, ms * 8u);
+    }
+    const uint32_t tail = len & 3u;
+    if (lane < tail) dst[nw * 4 + lane] = src[nw * 4 + lane];
+}
 template <bool WRITE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_rewrite_collection(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs,
                      uint32_t *__restrict__ new_len, const uint64_t *__restrict__ new_off, uint8_t *__restrict__ out) {
-    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= ndocs) return;
-    const uint8_t *src = bytes + doc_off[d];
-    const uint32_t n = (uint32_t)(doc_off[d + 1] - doc_off[d]);
-    uint8_t *dst = WRITE ? out + new_off[d] : nullptr;
-    const char P1[] = "+operator-builder:collection:field", R1[] = "+operator-builder:field", P2[] = "collectionField", R2[] = "field";
-    uint32_t o = 0;
-    for (uint32_t i = 0; i < n;) {
-        const uint8_t c = src[i];
-        if (c == '+' && dev_match(src + i, n - i, P1, 34)) { if (WRITE) for (uint32_t k = 0; k < 23; k++) dst[o + k] = (uint8_t)R1[k]; o += 23; i += 34; }
-        else if (c == 'c' && dev_match(src + i, n - i, P2, 15)) { if (WRITE) for (uint32_t k = 0; k < 5; k++) dst[o + k] = (uint8_t)R2[k]; o += 5; i += 15; }
-        else { if (WRITE) dst[o] = c; o++; i++; }
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const char P1[] = "+operator-builder:collection:field", P2[] = "collectionField";
+    for (uint32_t d = warp; d < ndocs; d += nwarps) {
+        const uint8_t *src = bytes + doc_off[d];
+        const uint32_t n = (uint32_t)(doc_off[d + 1] - doc_off[d]);
+        uint8_t *dst = WRITE ? out + new_off[d] : nullptr;
+        const uint32_t skew = (uint32_t)((uintptr_t)src & 15u);
+        const uint4 *base = reinterpret_cast<const uint4 *>(src - skew);
+        uint32_t cur = 0, o = 0; /* next input byte to copy, bytes written so far (warp-uniform) */
+        for (uint32_t c0 = 0; c0 < n + skew; c0 += 512) {
+            const uint32_t q0 = c0 + lane * 16u;
+            uint32_t plus = 0, cee = 0;
+            if (q0 < n + skew) {
+                const uint4 v = base[q0 >> 4];
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) { plus |= eq_bytes4(w[k], 0x2B2B2B2Bu) << (4 * k); cee |= eq_bytes4(w[k], 0x63636363u) << (4 * k); }
+            }
+            uint32_t keep = 0xFFFFu;
+            if (q0 < skew) keep &= (skew - q0 >= 16) ? 0u : (0xFFFFu << (skew - q0));
+            if (q0 + 16 > n + skew) keep &= (q0 >= n + skew) ? 0u : (0xFFFFu >> (q0 + 16 - n - skew));
+            uint32_t m1 = 0, m2 = 0;
+            for (uint32_t m = plus & keep; m; m &= m - 1) { const uint32_t b = (uint32_t)__ffs((int)m) - 1u, p = q0 + b - skew; if (dev_match(src + p, n - p, P1, 34)) m1 |= 1u << b; }
+            for (uint32_t m = cee & keep; m; m &= m - 1) { const uint32_t b = (uint32_t)__ffs((int)m) - 1u, p = q0 + b - skew; if (dev_match(src + p, n - p, P2, 15)) m2 |= 1u << b; }
+            /* matches of the step in position order; a "collectionField" inside an already deleted range cannot occur
+             * (the deleted text is "collection:" / "collection") */
+            uint32_t todo = __ballot_sync(0xffffffffu, (m1 | m2) != 0);
+            while (todo) {
+                const uint32_t owner = (uint32_t)__ffs((int)todo) - 1u;
+                const uint32_t a1 = __shfl_sync(0xffffffffu, m1, owner), a2 = __shfl_sync(0xffffffffu, m2, owner);
+                const uint32_t oq0 = c0 + owner * 16u;
+                for (uint32_t m = a1 | a2; m; m &= m - 1) {
+                    const uint32_t b = (uint32_t)__ffs((int)m) - 1u, p = oq0 + b - skew;
+                    const bool first = (a1 >> b) & 1u;
+                    const uint32_t del0 = first ? p + 18 : p, del1 = first ? p + 29 : p + 10;
+                    if (del0 < cur) continue; /* defensive: never true for these two patterns */
+                    if (WRITE) {
+                        warp_copy_bytes(dst + o, src + cur, del0 - cur, lane);
+                        if (!first && lane == 0) dst[o + (del0 - cur)] = 'f'; /* "Field" -> "field": written after the run, before the next copy starts there */
+                    }
+                    o += del0 - cur; cur = del1;
+                    if (!first) { o += 1; cur += 1; } /* the lowered 'F' */
+                }
+                todo &= todo - 1;
+            }
+        }
+        if (WRITE) warp_copy_bytes(dst + o, src + cur, n - cur, lane);
+        o += n - cur;
+        if (!WRITE && lane == 0) new_len[d] = o;
     }
-    if (!WRITE) new_len[d] = o;
 }
 
 /* Each record: { u32 doc, u32 a, u32 b, u32 0 }: extracted manifest = "\n" + content[a:b) (ExtractManifests
@@ -1058,11 +1151,6 @@ k_rewrite_collection(const uint8_t *__restrict__ bytes, const uint64_t *__restri
  * One WARP per document, 512 bytes per step: every lane loads 16 bytes (aligned uint4), builds a newline mask
  * and a dash mask with exact SIMD-within-register byte tests, and only the rare "dash at a line start" positions
  * are verified byte by byte.  Separators are then folded into records in order through warp-uniform state. */
-__device__ __forceinline__ uint32_t eq_bytes4(uint32_t v, uint32_t pat) { /* 4-bit mask of bytes of v equal to pat's byte (exact for any byte value) */
-    const uint32_t t = v ^ pat;
-    const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
-    return ((z >> 7) * 0x00204081u >> 21) & 0xFu;
-}
 template <bool WRITE>
 __global__ void __launch_bounds__(256)
 k_split_docs(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs, uint32_t *__restrict__ counts,
@@ -1151,14 +1239,18 @@ extern "C" int obm_rewrite_collection_markers_device(obm_handle *h, const void *
     uint32_t *counts; uint64_t *tile_sums; int rc;
     if ((rc = two_pass_scratch(h, ndocs, st, &counts, &tile_sums)) != OBM_OK) return rc;
     uint64_t *noff = (uint64_t *)d_out_doc_off;
-    const uint32_t nb = (ndocs + 127) / 128, nt = scan_tiles(ndocs);
-    k_rewrite_collection<false><<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, counts, nullptr, nullptr);
+    int sms_i = 0;
+    OBM_CUDA(h, cudaDeviceGetAttribute(&sms_i, cudaDevAttrMultiProcessorCount, h->device));
+    const uint32_t nt = scan_tiles(ndocs);
+    uint32_t nb = (uint32_t)sms_i * 8u; /* persistent warps, a document each per step */
+    if (nb > (ndocs + 7) / 8) nb = (ndocs + 7) / 8;
+    k_rewrite_collection<false><<<nb, 256, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, counts, nullptr, nullptr);
     k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(counts, ndocs, noff, tile_sums);
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, noff + ndocs);
     k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(noff, ndocs, tile_sums, ~0ull, nullptr);
     (void)out_cap; /* the rewrite only shrinks: a buffer of the input size always suffices */
     if (d_out_bytes)
-        k_rewrite_collection<true><<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, nullptr, noff, (uint8_t *)d_out_bytes);
+        k_rewrite_collection<true><<<nb, 256, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, nullptr, noff, (uint8_t *)d_out_bytes);
     OBM_CUDA(h, cudaGetLastError());
     return OBM_OK;
 }

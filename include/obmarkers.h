@@ -135,7 +135,8 @@ int obm_lex_batch(obm_handle *h, const uint8_t *bytes, const uint64_t *doc_off, 
  * d_status[0] = 1 (d_status is a device uint32[4]: {overflow, n_docs_exact, n_docs_fatal, scratch_overflow}).
  * scratch_overflow != 0 means the pipeline's internal work-record buffers were too small for this input
  * (far denser in markers than manifests are): the output is invalid, rerun with obm_set_mode(h, 1).
- * d_bytes must be readable up to the next 16-byte boundary past total_bytes (any cudaMalloc'd buffer is).
+ * d_bytes must be readable from the 16-byte boundary at or before it up to the next 16-byte boundary past
+ * d_bytes + total_bytes (any cudaMalloc'd buffer is): TMA, cp.async and aligned vector loads round to 16 bytes.
  * d_counts (device uint64[2], may be NULL) receives {n_markers, n_lexemes}.
  */
 int obm_lex_batch_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,

@@ -1045,8 +1045,7 @@ extern "C" int obm_marker_index_device(obm_handle *h, const obm_registry *reg, c
 /* ------------------------------------------------------------------------------------------- */
 /* collection prefix rewrite (manifests/manifest.go:89-95) on the device  */
 /* manifest splitting on "---" lines (manifests/manifest.go:57-80)         */
-/* First versions: one thread per document, two passes (count, exclusive scan, write).  Correct and */
-/* measured; not yet bandwidth-shaped (DESIGN.md lists the chunked, coalesced form as next).        */
+/* One warp per document, two passes (count, exclusive scan, write); numbers in profiles/r01_next_rows.json */
 /* ------------------------------------------------------------------------------------------- */
 __device__ __forceinline__ uint32_t eq_bytes4(uint32_t v, uint32_t pat) { /* 4-bit mask of bytes of v equal to pat's byte (exact for any byte value) */
     const uint32_t t = v ^ pat;

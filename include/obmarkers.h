@@ -133,8 +133,9 @@ int obm_lex_batch(obm_handle *h, const uint8_t *bytes, const uint64_t *doc_off, 
  * given (NULL = CUDA's default stream).  Asynchronous: returns after enqueueing.  d_doc_tuple_off[ndocs] holds the
  * total tuple count; if it exceeds out_cap the kernels write nothing past out_cap and set
  * d_status[0] = 1 (d_status is a device uint32[4]: {overflow, n_docs_exact, n_docs_fatal, scratch_overflow}).
- * scratch_overflow != 0 means the pipeline's internal work-record buffers were too small for this input
- * (far denser in markers than manifests are): the output is invalid, rerun with obm_set_mode(h, 1).
+ * scratch_overflow != 0 means the pipeline's internal work-record buffers were too small: the output is invalid,
+ * rerun with obm_set_mode(h, 1).  The capacities behind obm_scratch_bytes are structural bounds, so this is a
+ * defensive check, not an expected outcome (obm_lex_batch reruns by itself).
  * d_bytes must be readable from the 16-byte boundary at or before it up to the next 16-byte boundary past
  * d_bytes + total_bytes (any cudaMalloc'd buffer is): TMA, cp.async and aligned vector loads round to 16 bytes.
  * d_counts (device uint64[2], may be NULL) receives {n_markers, n_lexemes}.

@@ -7,7 +7,7 @@
  * One CTA owns the documents that START inside a TILE-byte range of the packed batch.  Documents of
  * at most MAXDOC bytes are staged whole in shared memory and lexed line-parallel:
  *
- *   P2 classify     every 32-byte word -> newline bitmap, special bitmap ({# ' + /}: everything that
+ *   P2 classify     every 32-byte word -> newline bitmap, special bitmap ('#', '+', "//": everything that
  *                   can start a comment or a marker), non-ASCII flag
  *   P3 doc prep     a virtual newline in front of every document start; per-document non-ASCII flag
  *   P4 line scan    newline prefix counts (line numbers) + "owners": looking forward from every
@@ -64,7 +64,7 @@ OBM_HD uint32_t ow_ls(uint32_t r) { return (r >> 16) & 0x7FFFu; }
 struct SmemScan {
     alignas(16) uint8_t data[NW * 32];
     alignas(16) uint32_t nlw[NW];   /* bit i of word w: byte 32w+i is '\n' (or precedes a document start) */
-    alignas(16) uint32_t spw[NW];   /* bit i of word w: byte 32w+i is one of # ' + / */
+    alignas(16) uint32_t spw[NW];   /* bit i of word w: byte 32w+i is '#', '+', or a '/' that may start "//" */
     uint16_t nlpre[NW];             /* number of nlw bits in words [0, w) */
     uint32_t naw[NW / 32];          /* bit w%32 of naw[w/32]: word w holds a byte >= 0x80 */
     uint32_t owner[QMAX];           /* owner records in position order */
@@ -96,7 +96,7 @@ OBM_HD uint32_t zero_bytes4(uint32_t t) {
 
 OBM_HD void classify_word(SmemScan &S, uint32_t wi) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(S.data) + wi * 8;
-    uint32_t nl = 0, sp = 0, hi = 0;
+    uint32_t nl = 0, hp = 0, sl = 0, hi = 0;
 #if defined(__CUDA_ARCH__)
     const uint4 a = reinterpret_cast<const uint4 *>(src)[0], b = reinterpret_cast<const uint4 *>(src)[1];
     const uint32_t x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -108,8 +108,12 @@ OBM_HD void classify_word(SmemScan &S, uint32_t wi) {
         uint32_t v = x[k];
         hi |= v;
         nl |= zero_bytes4(v ^ 0x0A0A0A0Au) << (4 * k);
-        sp |= zero_bytes4((v & 0xF3F3F3F3u) ^ 0x23232323u) << (4 * k);
+        hp |= zero_bytes4((v & 0xF7F7F7F7u) ^ 0x23232323u) << (4 * k); /* '#' (0x23) or '+' (0x2B) */
+        sl |= zero_bytes4(v ^ 0x2F2F2F2Fu) << (4 * k);                  /* '/' */
     }
+    /* specials: the bytes that can start a comment or a marker in state lex / lexComment (state.go:20-33,48):
+     * '#', '+', and a '/' followed by another '/' (the word's last byte cannot see its successor: kept) */
+    const uint32_t sp = hp | (sl & ((sl >> 1) | 0x80000000u));
     /* keep only bytes inside [lo_pos, hi_pos) */
     uint32_t w0 = wi * 32;
     uint32_t keep = 0xFFFFFFFFu;

@@ -540,7 +540,7 @@ static uint64_t pipe_units_max(uint32_t ndocs, uint64_t total_bytes) { return ob
 static uint64_t pipe_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
     const uint64_t nt = obm_fast_ntiles(total_bytes), um = pipe_units_max(ndocs, total_bytes);
     return align_up(pipe_items_cap(ndocs, total_bytes) * 8, 256) + align_up(nt * 4 + 4, 256) + align_up((nt + 1) * 8, 256) +
-           align_up(((uint64_t)scan_tiles((uint32_t)nt) + 1) * 8, 256) + align_up((um + 1) * 16, 256) +
+           align_up(((uint64_t)scan_tiles((uint32_t)nt) + 1) * 8, 256) + align_up((nt + 1) * sizeof(obmp::TileRec), 256) + align_up((um + 1) * 16, 256) +
            align_up((uint64_t)ndocs * 4 + 4, 256) + align_up((um + 1) * 8, 256) + align_up((um / 32 + 2) * 8, 256) + 256;
 }
 
@@ -574,6 +574,7 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     uint32_t *nsub = (uint32_t *)q; q += up((uint64_t)ntiles * 4 + 4);
     uint64_t *ubase = (uint64_t *)q; q += up(((uint64_t)ntiles + 1) * 8); A.ubase = ubase;
     uint64_t *usums = (uint64_t *)q; q += up(((uint64_t)nt_u + 1) * 8);
+    obmp::TileRec *trec = (obmp::TileRec *)q; q += up(((uint64_t)ntiles + 1) * sizeof(obmp::TileRec)); A.trec = trec;
     A.units = (obmp::Unit *)q; q += up((um + 1) * 16);
     A.doc_flag = (uint32_t *)q; q += up((uint64_t)ndocs * 4 + 4);
     A.st_tuples = (uint64_t *)q; q += up((um + 1) * 8);
@@ -588,7 +589,7 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
     const LargeWs LW = large_carve(large_ws, total_bytes, large_list, lctl + 1);
     large_count_launch(st, dev_sms, d_bytes, d_doc_off, LW, counts, totals, status);
-    obmq::k_tile_units<<<(ntiles + 255) / 256, 256, 0, st>>>(d_doc_off, tile_first, ntiles, nsub);
+    obmq::k_tile_units<<<(ntiles + 255) / 256, 256, 0, st>>>(d_doc_off, tile_first, ntiles, nsub, trec);
     k_scan_tiles<<<nt_u, SCAN_THREADS, 0, st>>>(nsub, ntiles, ubase, usums);
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(usums, nt_u, ubase + ntiles);
     k_scan_add<<<nt_u, SCAN_THREADS, 0, st>>>(ubase, ntiles, usums, ~0ull, nullptr);

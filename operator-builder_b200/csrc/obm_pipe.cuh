@@ -27,6 +27,7 @@ struct PipeArgs {
     const uint8_t *bytes; const uint64_t *doc_off; uint32_t ndocs; uint64_t total_bytes;
     const uint32_t *tile_first; uint32_t ntiles;
     const uint64_t *ubase;      /* [ntiles+1] exclusive scan of units per tile; [ntiles] = number of units */
+    const obmp::TileRec *trec;  /* [ntiles] */
     /* K1 -> K2 */
     item_t *items; uint64_t items_cap;
     obmp::Unit *units;          /* [nunits] */
@@ -48,18 +49,23 @@ __device__ __forceinline__ obm::Tables dev_tables() {
 }
 
 __global__ void __launch_bounds__(256)
-k_tile_units(const uint64_t *__restrict__ doc_off, const uint32_t *__restrict__ tile_first, uint32_t ntiles, uint32_t *__restrict__ nsub) {
+k_tile_units(const uint64_t *__restrict__ doc_off, const uint32_t *__restrict__ tile_first, uint32_t ntiles, uint32_t *__restrict__ nsub,
+             obmp::TileRec *__restrict__ trec) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
     const uint32_t d0 = tile_first[t], d1 = tile_first[t + 1];
     uint32_t n = 0;
+    obmp::TileRec r{d0, d1, 0, 0, 0, 0};
     if (d1 > d0) {
         const uint32_t large = (doc_off[d1] - doc_off[d1 - 1] > obmt::MAXDOC) ? 1u : 0u;
         const uint32_t ns = d1 - d0 - large;
         n = (ns + obmt::DMAX - 1) / obmt::DMAX;
         if (n == 0) n = 1;
+        r.d_last = d1 | (large << 31);
+        r.b0 = doc_off[d0]; r.b1 = doc_off[d0 + (ns < obmt::DMAX ? ns : obmt::DMAX)];
     }
     nsub[t] = n;
+    trec[t] = r;
 }
 
 /* ---------------------------------------------------------------------------------------------- K1 -- */
@@ -69,7 +75,9 @@ struct K1Shared {
     uint16_t dlast[obmt::DMAX + 1];       /* index after the last owner of document k */
     alignas(8) uint64_t mbar;
     uint64_t item_base;
-    uint32_t tile;
+    obmp::TileRec rec;                    /* the NEXT tile's record (prefetched while this one is processed) */
+    uint64_t u0;
+    uint32_t tile, pre_issued;
 };
 
 __global__ void __launch_bounds__(obmt::NT, 4)
@@ -82,18 +90,35 @@ k1_scan(PipeArgs A) {
     __syncthreads();
     uint32_t mbar_phase = 0;
     item_t *sitems = C.sitems;
+    /* software pipeline over tiles: the ticket of the next tile is taken when this one starts, its record is
+     * fetched in the middle, and its first TMA load is issued as soon as this tile is done with S.data */
+    if (tid == 0) C.tile = atomicAdd(&A.ctl[CT_T1], 1u);
+    __syncthreads();
+    uint32_t t = C.tile;
+    obmp::TileRec rec{0, 0, 0, 0, 0, 0}; uint64_t u0 = 0; bool pre_issued = false;
+    if (t < A.ntiles) { rec = A.trec[t]; u0 = A.ubase[t]; }
+    __syncthreads();
     for (;;) {
-        if (tid == 0) C.tile = atomicAdd(&A.ctl[CT_T1], 1u);
-        __syncthreads();
-        const uint32_t t = C.tile;
         if (t >= A.ntiles) break;
-        const uint32_t d_first = A.tile_first[t], d_last = A.tile_first[t + 1];
-        if (d_last == d_first) { __syncthreads(); continue; }
-        const bool has_large = A.doc_off[d_last] - A.doc_off[d_last - 1] > obmt::MAXDOC;
+        uint32_t nt = 0; obmp::TileRec nrec{0, 0, 0, 0, 0, 0}; uint64_t nu0 = 0; bool fetched = false, issued_next = false;
+        if (tid == 0) nt = atomicAdd(&A.ctl[CT_T1], 1u);
+        auto fetch_next = [&]() { if (!fetched) { fetched = true; if (nt < A.ntiles) { nrec = A.trec[nt]; nu0 = A.ubase[nt]; } } };
+        auto publish_next = [&]() { /* thread 0, before the barrier that ends the tile */
+            fetch_next();
+            C.tile = nt; C.rec = nrec; C.u0 = nu0; C.pre_issued = issued_next ? 1u : 0u;
+        };
+        const uint32_t d_first = rec.d_first, d_last = rec.d_last & 0x7FFFFFFFu;
+        const bool has_large = (rec.d_last >> 31) != 0;
+        if (d_last == d_first) {
+            if (tid == 0) publish_next();
+            __syncthreads();
+            t = C.tile; rec = C.rec; u0 = C.u0; pre_issued = false;
+            __syncthreads();
+            continue;
+        }
         const uint32_t d_small_end = d_last - (has_large ? 1u : 0u);
         uint32_t nsub = (d_small_end - d_first + obmt::DMAX - 1) / obmt::DMAX;
         if (nsub == 0) nsub = 1;
-        const uint64_t u0 = A.ubase[t];
         if (has_large && tid == 0) A.doc_flag[d_last - 1] = obmp::GF_LARGE;
         for (uint32_t k = 0; k < nsub; k++) {
             const uint32_t da = d_first + k * obmt::DMAX, db = min(da + obmt::DMAX, d_small_end), nd = db - da;
@@ -101,12 +126,12 @@ k1_scan(PipeArgs A) {
             const uint64_t u = u0 + k;
             uint32_t n_owners = 0, n_live = 0;
             if (nd) {
-                const uint64_t b0 = A.doc_off[da], b1 = A.doc_off[db];
+                const uint64_t b0 = k == 0 ? rec.b0 : A.doc_off[da], b1 = k == 0 ? rec.b1 : A.doc_off[db];
                 const uint64_t abs0 = (uint64_t)(uintptr_t)A.bytes + b0, base_abs = abs0 & ~15ull;
                 const uint32_t skew = (uint32_t)(abs0 - base_abs), span = (uint32_t)(b1 - b0) + skew, load = (span + 15u) & ~15u;
                 if (tid == 0) {
                     S.nd = nd; S.lo_pos = skew; S.hi_pos = span; S.n_owners = 0;
-                    if (load) { obmf::fence_proxy_async(); obmf::mbar_expect_tx(&C.mbar, load); obmf::tma_bulk_g2s(S.data, (const void *)(uintptr_t)base_abs, load, &C.mbar); }
+                    if (load && !(k == 0 && pre_issued)) { obmf::fence_proxy_async(); obmf::mbar_expect_tx(&C.mbar, load); obmf::tma_bulk_g2s(S.data, (const void *)(uintptr_t)base_abs, load, &C.mbar); }
                 }
                 if (tid <= nd) S.dstart[tid] = (uint32_t)(A.doc_off[da + tid] - b0) + skew;
                 __syncthreads();
@@ -118,6 +143,7 @@ k1_scan(PipeArgs A) {
                 __syncthreads();
                 /* P3 doc prep */
                 if (tid < nd) obmt::doc_prep(S, tid);
+                if (tid == 0) fetch_next(); /* the ticket taken at the top has long arrived; the record is used at the end of the tile */
                 __syncthreads();
                 /* P4 bit-parallel line scan */
                 uint32_t nl[obmt::WPT], sp[obmt::WPT], lm[obmt::WPT];
@@ -183,6 +209,16 @@ k1_scan(PipeArgs A) {
                     __syncthreads();
                 }
                 n_live = live_run;
+                /* S.data is dead from here on: issue the next tile's first load now, under the rest of this tile */
+                if (tid == 0 && k == nsub - 1) {
+                    fetch_next();
+                    if (nt < A.ntiles && (nrec.d_last & 0x7FFFFFFFu) > nrec.d_first && nrec.b1 > nrec.b0) {
+                        const uint64_t nabs0 = (uint64_t)(uintptr_t)A.bytes + nrec.b0, nbase = nabs0 & ~15ull;
+                        const uint32_t nload = ((uint32_t)(nrec.b1 - nrec.b0) + (uint32_t)(nabs0 - nbase) + 15u) & ~15u;
+                        obmf::fence_proxy_async(); obmf::mbar_expect_tx(&C.mbar, nload); obmf::tma_bulk_g2s(S.data, (const void *)(uintptr_t)nbase, nload, &C.mbar);
+                        issued_next = true;
+                    }
+                }
                 /* per document: index after its last owner (owners are in position order, hence grouped by document) */
                 if (tid < nd) {
                     uint32_t lo = 0, hi = n_owners;
@@ -207,9 +243,12 @@ k1_scan(PipeArgs A) {
             if (tid == 0) {
                 if (!room) A.ctl[CT_OVF] = 1;
                 A.units[u] = obmp::Unit{ibase, da, n_items | (nd << 16)};
+                if (k == nsub - 1) publish_next();
             }
             __syncthreads();
         }
+        t = C.tile; rec = C.rec; u0 = C.u0; pre_issued = C.pre_issued != 0;
+        __syncthreads();
     }
 }
 

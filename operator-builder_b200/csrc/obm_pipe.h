@@ -108,6 +108,10 @@ struct Unit { uint64_t item_base; uint32_t doc_base; uint32_t n; /* n_items | nd
 OBM_HD uint32_t unit_items(const Unit &u) { return u.n & 0xFFFFu; }
 OBM_HD uint32_t unit_nd(const Unit &u) { return u.n >> 16; }
 
+/* per-tile record for K1 (written by k_tile_units): everything the tile loop needs before it can issue its first
+ * TMA load, so that one 32-byte load replaces a chain of dependent ones and the next tile's load can be issued early */
+struct TileRec { uint32_t d_first; uint32_t d_last; /* bit 31: the last document is large */ uint32_t pad0, pad1; uint64_t b0, b1; /* byte range of the first sub-batch */ };
+
 constexpr uint32_t W_WARPS = 4;         /* warps per K2 CTA (each works alone) */
 constexpr uint32_t W_MLCAP = 32;        /* marker lines staged per block = one per lane */
 constexpr uint32_t W_LTS = 23;          /* staged tuples per marker line (odd stride: no bank clash) */

@@ -269,11 +269,6 @@ struct NoAccel {
 
 /* ASCII = true: the caller guarantees every byte of the document is < 0x80 (tile path); rune decoding,
  * the Unicode tables and the U+FFFD over-discard drop out at compile time. */
-/* cold path: a slice longer than OBM_MAX_LEN is sent as PART pieces; returns the remaining (off, len) */
-template <class Sink>
-OBM_HD_NOINLINE void put_long_prefix(Sink &out, uint32_t &off, uint32_t &len) {
-    while (len > OBM_MAX_LEN) { out.put(OBM_K_PART, off, OBM_MAX_LEN); off += OBM_MAX_LEN; len -= OBM_MAX_LEN; }
-}
 
 /* peek.go:65-89 for one ASCII token `tok[0..t)` at offset p of doc d[0..n): on success returns true and
  * sets `width` (= l.width after the final peekN: whitespace BYTES + token bytes). */
@@ -346,12 +341,18 @@ struct Lexer {
         }
     }
     OBM_HD void sync_start() { s = p; line_s = line_p; base_s = base_p; }
+    /* a slice longer than OBM_MAX_LEN is sent as PART pieces.  Inline on purpose: an out-of-line helper taking the
+     * sink by reference would force the sink (and its counters) out of registers into local memory for EVERY put.
+     * The ASCII instantiation only sees tile-path documents (<= 16 KiB): the loop vanishes at compile time. */
+    OBM_HD void put_long_prefix(uint32_t &off, uint32_t &len) {
+        if (!ASCII) while (len > OBM_MAX_LEN) { out.put(OBM_K_PART, off, OBM_MAX_LEN); off += OBM_MAX_LEN; len -= OBM_MAX_LEN; }
+    }
     /* un-emitted text doc[s,p) becomes a PART (kept in the decoder's pending buffer) */
     OBM_HD void part_tail() {
         if (p > s) {
             ensure_line(line_s, base_s);
             uint32_t off = s, len = p - s;
-            if (len > OBM_MAX_LEN) put_long_prefix(out, off, len);
+            put_long_prefix(off, len);
             out.put(OBM_K_PART, off, len);
             sync_start();
         }
@@ -360,7 +361,7 @@ struct Lexer {
     OBM_HD void emit(uint32_t kind) {
         ensure_line(line_s, base_s);
         uint32_t off = s, len = p - s;
-        if (len > OBM_MAX_LEN) put_long_prefix(out, off, len);
+        put_long_prefix(off, len);
         out.put(kind, off, len);
         last_type = kind;
         sync_start();

@@ -232,7 +232,7 @@ k_large_prep(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc
         uint32_t sk;
         W.cs[g] = obml::chunk_start(doc, n, c, &sk);
         W.cline[g] = sk;
-        W.cnl[g] = obml::chunk_newlines(doc, n, c);
+        W.cnl[g] = obml::chunk_newlines(doc, n, c) | (obml::chunk_non_ascii(doc, n, c) ? 0x80000000u : 0u);
     }
 }
 __global__ void __launch_bounds__(128)
@@ -240,8 +240,12 @@ k_large_lines(LargeWs W) {
     const uint32_t n_large = *W.n_large;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_large; i += gridDim.x * blockDim.x) {
         const uint64_t g0 = W.lbase[i]; const uint32_t nc = (uint32_t)(W.lbase[i + 1] - g0);
-        uint32_t acc = 0;
-        for (uint32_t c = 0; c < nc; c++) { const uint32_t sk = W.cline[g0 + c]; W.cline[g0 + c] = 1u + acc + sk; acc += W.cnl[g0 + c]; }
+        uint32_t acc = 0, na = 0;
+        for (uint32_t c = 0; c < nc; c++) {
+            const uint32_t sk = W.cline[g0 + c], v = W.cnl[g0 + c];
+            W.cline[g0 + c] = 1u + acc + sk; acc += v & 0x7FFFFFFFu; na |= v >> 31;
+        }
+        W.lch[i] = na ? 0u : 1u; /* reused after the scan: 1 = the document is all ASCII (fast lexer instantiation) */
     }
 }
 __global__ void __launch_bounds__(128)
@@ -257,7 +261,8 @@ k_large_count(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ do
         const uint32_t stop = c + 1 < nc ? W.cs[g + 1] : n;
         obm::SmallSink sink(nullptr, 0);
         uint32_t end;
-        W.cflag[g] = obml::lex_chunk(T, doc, n, W.cs[g], W.cline[g], stop, sink, &end);
+        W.cflag[g] = W.lch[i] ? obml::lex_chunk<obm::SmallSink, true>(T, doc, n, W.cs[g], W.cline[g], stop, sink, &end)
+                              : obml::lex_chunk<obm::SmallSink, false>(T, doc, n, W.cs[g], W.cline[g], stop, sink, &end);
         W.cend[g] = end; W.ccnt[g] = sink.n_tuples; W.cmk[g] = sink.n_markers; W.clx[g] = sink.n_lexemes;
     }
 }
@@ -316,7 +321,8 @@ k_large_fill(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc
         const uint32_t stop = c + 1 < nc ? W.cs[g + 1] : n;
         obm::WriteSink sink(out + t0, t0 < out_cap ? out_cap - t0 : 0);
         uint32_t end;
-        obml::lex_chunk(T, doc, n, W.cs[g], W.cline[g], stop, sink, &end);
+        if (W.lch[i]) obml::lex_chunk<obm::WriteSink, true>(T, doc, n, W.cs[g], W.cline[g], stop, sink, &end);
+        else obml::lex_chunk<obm::WriteSink, false>(T, doc, n, W.cs[g], W.cline[g], stop, sink, &end);
         if (c == nc - 1) { const uint64_t e = t0 + W.ccnt[g]; if (e < out_cap) out[e] = OBM_TUPLE(OBM_K_EOF, n, 0); }
     }
 }

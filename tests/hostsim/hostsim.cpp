@@ -434,10 +434,12 @@ extern "C" uint64_t hs_large_doc(const uint8_t *doc, uint32_t n, obm_tuple *out,
     uint32_t acc = 0;
     for (uint32_t c = 0; c < nc; c++) { uint32_t sk; cs[c] = chunk_start(doc, n, c, &sk); line[c] = 1 + acc + sk; acc += chunk_newlines(doc, n, c); }
     cs[nc] = n;
-    bool valid = true;
+    bool valid = true, ascii = true;
+    for (uint32_t c = 0; c < nc; c++) ascii = ascii && !chunk_non_ascii(doc, n, c);
     for (uint32_t c = 0; c < nc; c++) {
         obm::SmallSink s(nullptr, 0);
-        flag[c] = lex_chunk(TBL, doc, n, cs[c], line[c], cs[c + 1], s, &cend[c]);
+        flag[c] = ascii ? lex_chunk<obm::SmallSink, true>(TBL, doc, n, cs[c], line[c], cs[c + 1], s, &cend[c])
+                        : lex_chunk<obm::SmallSink, false>(TBL, doc, n, cs[c], line[c], cs[c + 1], s, &cend[c]);
         cnt[c] = s.n_tuples;
         if (flag[c] || cend[c] != cs[c + 1]) valid = false;
     }
@@ -447,7 +449,8 @@ extern "C" uint64_t hs_large_doc(const uint8_t *doc, uint32_t n, obm_tuple *out,
     for (uint32_t c = 0; c < nc; c++) {
         obm::WriteSink s(out + at, at < cap ? cap - at : 0);
         uint32_t e;
-        lex_chunk(TBL, doc, n, cs[c], line[c], cs[c + 1], s, &e);
+        if (ascii) lex_chunk<obm::WriteSink, true>(TBL, doc, n, cs[c], line[c], cs[c + 1], s, &e);
+        else lex_chunk<obm::WriteSink, false>(TBL, doc, n, cs[c], line[c], cs[c + 1], s, &e);
         if (s.n_tuples != cnt[c]) { fprintf(stderr, "hostsim: chunk count changed between passes\n"); abort(); }
         at += cnt[c];
     }

@@ -139,3 +139,18 @@ def test_large_documents_chunk_parallel_path():
                 b"", b"\n", b"x" * 4096, b"x" * 4095 + b"\n" + b"# +a:b\n", "# é +a:b=ü\n".encode() * 900):
         got, ok = hostsim.large_doc(doc)
         assert np.array_equal(got, hostsim.lex_doc(doc))
+
+
+def test_chunk_path_ascii_fast_lexer_on_fuzz():
+    """the chunk threads run the ASCII instantiation (word-wise skipping, token loop) line by line from the line START,
+    not from the first special byte as the tile path does: any document, any size, must still equal the sequential stream"""
+    import random
+    from tests import corpus_util as cu
+    rng = random.Random(1234)
+    docs = list(cu.TARGETED) + [d for _p, d in cu.fixtures()]
+    docs += [cu.fuzz_doc(rng, max_len=rng.choice([5, 60, 400, 3000, 9000])) for _ in range(500)]
+    docs += [cu.fuzz_doc_valid(rng) for _ in range(200)]
+    docs += [b"".join(cu.fuzz_doc(rng, max_len=700) for _ in range(30)) for _ in range(20)]
+    for doc in docs:
+        got, _ok = hostsim.large_doc(doc)
+        assert np.array_equal(got, hostsim.lex_doc(doc)), doc[:300]

@@ -366,6 +366,7 @@ struct obm_handle {
     int device;
     cudaStream_t stream;
     cudaEvent_t ev[4];
+    cudaStream_t side; cudaEvent_t ev_fork, ev_join; /* large-document bookkeeping runs beside k1_scan */
     char err[512];
     /* scratch kept across calls */
     void *scratch; uint64_t scratch_bytes;
@@ -431,6 +432,8 @@ extern "C" int obm_create(int device_ordinal, obm_handle **out) {
         delete h; return OBM_E_CUDA;
     }
     for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
+    cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (cudaMalloc(&h->d_status, 4 * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&h->d_counts, 2 * sizeof(unsigned long long)) != cudaSuccess) {
         set_err(nullptr, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete h; return OBM_E_CUDA;
@@ -455,6 +458,7 @@ extern "C" void obm_destroy(obm_handle *h) {
         cudaEventDestroy(sl.ev_scan); cudaStreamDestroy(sl.st);
     }
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
+    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaStreamDestroy(h->side);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -594,7 +598,12 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     int dev_sms = 0, per_sm1 = 0, per_sm2 = 0;
     OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
     const LargeWs LW = large_carve(large_ws, total_bytes, large_list, lctl + 1);
-    large_count_launch(st, dev_sms, d_bytes, d_doc_off, LW, counts, totals, status);
+    /* the eight small kernels that plan and count the large documents depend only on k_tile_index and are needed
+     * by k2_units: they run on a side stream under k1_scan instead of in front of it */
+    OBM_CUDA(h, cudaEventRecord(h->ev_fork, st));
+    OBM_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    large_count_launch(h->side, dev_sms, d_bytes, d_doc_off, LW, counts, totals, status);
+    OBM_CUDA(h, cudaEventRecord(h->ev_join, h->side));
     obmq::k_tile_units<<<(ntiles + 255) / 256, 256, 0, st>>>(d_doc_off, tile_first, ntiles, nsub, trec);
     k_scan_tiles<<<nt_u, SCAN_THREADS, 0, st>>>(nsub, ntiles, ubase, usums);
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(usums, nt_u, ubase + ntiles);
@@ -609,6 +618,7 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     const uint64_t g2max = (um + obmp::W_WARPS - 1) / obmp::W_WARPS;
     if (g2 > g2max) g2 = (uint32_t)g2max;
     obmq::k1_scan<<<g1, obmt::NT, smem1, st>>>(A);
+    OBM_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
     obmq::k2_units<<<g2, obmp::W_WARPS * 32, 0, st>>>(A);
     uint32_t launches = 7 + LARGE_COUNT_LAUNCHES;
     if (d_out && out_cap) {

@@ -237,7 +237,7 @@ def main():
         return 3
 
     # full-tuple all-gather, timed separately (SURVEY.md section 7 hard part 1: it, not the scan, bounds N=8)
-    gather = None
+    gather = compact = None
     if world > 1:
         mx = torch.tensor([n_tuples], dtype=torch.int64, device=dev)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -255,6 +255,47 @@ def main():
         gms = g0.elapsed_time(g1) / 3
         gather = {"ms": gms, "bytes_received_per_rank": pad * 8 * (world - 1), "gb_s_per_rank": pad * 8 * (world - 1) / gms / 1e6}
         del g_out
+        # the compact alternative: one 16-byte record per REGISTERED marker instead of every tuple;
+        # index kernel over the resident tuples, then an all-gather of the records (padded to the largest rank)
+        from operator_builder_b200 import _native
+        L = _native.lib()
+        reg = ob.Registry()
+        rec_cap = ndocs * 16
+        d_rec = torch.empty(rec_cap * 4, dtype=torch.int32, device=dev)
+        d_roff = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
+
+        def index():
+            rc = L.obm_marker_index_device(sc.handle, reg.handle, d_bytes.data_ptr(), d_off.data_ptr(), ndocs, d_out.data_ptr(), d_toff.data_ptr(),
+                                           d_rec.data_ptr(), rec_cap, d_roff.data_ptr(), sp)
+            assert rc == 0
+        index()
+        barrier()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record(stream)
+        for _ in range(3):
+            index()
+        i1.record(stream)
+        barrier()
+        ims = i0.elapsed_time(i1) / 3
+        nrec = int(d_roff[-1].item())
+        mxr = torch.tensor([nrec], dtype=torch.int64, device=dev)
+        dist.all_reduce(mxr, op=dist.ReduceOp.MAX)
+        rpad = int(mxr.item()) * 4
+        r_out = torch.empty(rpad * world, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(r_out, d_rec[:rpad])
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        for _ in range(3):
+            dist.all_gather_into_tensor(r_out, d_rec[:rpad])
+        r1.record(stream)
+        barrier()
+        rms = r0.elapsed_time(r1) / 3
+        tm = torch.tensor([ims, rms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        compact = {"index_ms": float(tm[0]), "allgather_ms": float(tm[1]), "records_this_rank": nrec,
+                   "bytes_received_per_rank": rpad * 4 * (world - 1)}
+        del r_out
 
     # max over ranks
     t = torch.tensor([ms, ms_scan], dtype=torch.float64, device=dev)
@@ -329,7 +370,8 @@ def main():
                          "algorithmic_bytes_per_launch": total_bytes // world,
                          "note": "1 B read per input byte (SURVEY 8d); time = all kernels of one scan, per GPU"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "exchange": ({"index_allgather": "4 B/doc counts inside the timed step", "full_tuple_allgather": gather} if world > 1 else None)}
+            "exchange": ({"index_allgather": "4 B/doc counts inside the timed step", "full_tuple_allgather": gather,
+                          "marker_index_allgather": compact} if world > 1 else None)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -268,19 +268,6 @@ struct K2Ctx {
     __device__ __forceinline__ uint32_t doc_of(item_t it) const { return obmp::it_large(it) ? d0 + nd : d0 + obmp::it_doc(it); }
 };
 
-/* lanes with uni == true: a line with bytes >= 0x80 of a valid-UTF-8 document, lexed from its start by the Unicode
- * lexer straight from global memory.  Kept apart from k2_lex_lines so that this rare call does not weigh on the
- * register allocation of the hot path.  Whole warp must call. */
-__device__ __forceinline__ uint32_t k2_lex_uni_lines(K2Ctx &X, bool uni, item_t it, uint32_t d, obm_tuple *out, uint32_t cap, uint32_t *mk, uint32_t *lx) {
-    uint32_t r = 0;
-    if (uni) {
-        const uint64_t o0 = X.A.doc_off[d];
-        r = obmp::k2_unicode_item(X.T, X.A.bytes + o0, (uint32_t)(X.A.doc_off[d + 1] - o0), it, out, cap, mk, lx);
-    }
-    __syncwarp();
-    return r;
-}
-
 /* Lanes with on == true lex the marker line of item `it` (document d) into out[0..cap) (cap 0: count only).
  * The lines' text is packed into the warp's pool (exclusive scan of 16-byte chunk counts, cp.async for all of
  * them, one wait) and lexed through the shared window; a line that does not fit, or whose lookahead could
@@ -294,7 +281,8 @@ __device__ __forceinline__ uint32_t k2_lex_lines(K2Ctx &X, bool on, item_t it, u
         len = (uint32_t)(A.doc_off[d + 1] - o0); gdoc = A.bytes + o0;
         v = obmp::line_view(gdoc, len, it, A.bytes, A.total_bytes);
     }
-    const uint32_t want = (on && v.nch <= 32u) ? v.nch : 0u;
+    const bool uni = on && obmp::it_unicode(it); /* Unicode lexer from the line start, from global memory: nothing to stage */
+    const uint32_t want = (on && !uni && v.nch <= 32u) ? v.nch : 0u;
     uint32_t incl = want;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
@@ -313,7 +301,8 @@ __device__ __forceinline__ uint32_t k2_lex_lines(K2Ctx &X, bool on, item_t it, u
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     uint32_t r = 0;
-    if (on) {
+    if (uni) r = obmp::k2_unicode_item(X.T, gdoc, len, it, out, cap, mk, lx);
+    else if (on) {
         uint32_t nv = 0; const uint8_t *sm = C.pool + (size_t)off * 16u;
         if (fits) nv = obmp::line_view_safe(sm, v, gdoc, len, it);
         if (nv) {
@@ -351,10 +340,7 @@ __device__ __forceinline__ bool k2_lex_block(K2Ctx &X, uint32_t b0, uint32_t b1,
         const bool staged = k0 == 0; /* the first W_MLCAP lines also stage their tuples */
         uint32_t ib = 0, d = 0; item_t it = 0;
         if (on) { ib = C.mlist[k]; it = A.items[X.i0 + b0 + ib]; d = X.doc_of(it); }
-        const bool uni = on && obmp::it_unicode(it);
-        obm_tuple *so = staged ? C.stage + k * obmp::W_LTS : nullptr; const uint32_t sc = staged ? obmp::W_LTS : 0u;
-        uint32_t r = k2_lex_lines(X, on && !uni, it, d, so, sc, nullptr, nullptr);
-        if (__any_sync(0xffffffffu, uni)) r |= k2_lex_uni_lines(X, uni, it, d, so, sc, nullptr, nullptr);
+        const uint32_t r = k2_lex_lines(X, on, it, d, staged ? C.stage + k * obmp::W_LTS : nullptr, staged ? obmp::W_LTS : 0u, nullptr, nullptr);
         if (on) {
             C.icnt[ib] = (uint16_t)obmp::mres_tuples(r);
             if (obmp::mres_irregular(r)) { atomicOr(&A.doc_flag[d], obmp::GF_INTERACT); any = true; }
@@ -448,10 +434,7 @@ __device__ __forceinline__ uint64_t k2_write_block(K2Ctx &X, uint32_t b0, uint32
         if (__any_sync(0xffffffffu, relex)) {
             const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
             uint32_t mk = 0, lx = 0; /* locals: taking the context's address would push it to the stack */
-            const bool uni = relex && obmp::it_unicode(it);
-            const uint32_t rc = roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv;
-            k2_lex_lines(X, relex && !uni, it, d, A.out + at, rc, &mk, &lx);
-            if (__any_sync(0xffffffffu, uni)) k2_lex_uni_lines(X, uni, it, d, A.out + at, rc, &mk, &lx);
+            k2_lex_lines(X, relex, it, d, A.out + at, roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv, &mk, &lx);
             X.markers += mk; X.lexemes += lx;
         }
         run += __shfl_sync(0xffffffffu, incl, 31);

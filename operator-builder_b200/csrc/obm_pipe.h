@@ -231,21 +231,11 @@ OBM_HD void plain_write(item_t it, obm_tuple *out, uint64_t at, uint64_t cap) {
     if (at + k < cap) out[at + k] = OBM_TUPLE(OBM_K_COMMENT, it_pos(it), it_slash2(it) ? 2 : 1);
 }
 
-/* whole document through the exact (Unicode) lexer, from global memory: line after line in LINE mode plus the EOF
- * tuple -- the composition tests/hostsim checks against the whole-document run (hs_lex_doc_by_lines).  Written this
- * way so that K2 carries ONE instantiation of the Unicode lexer's run loop (run<true>, shared with k2_unicode_item):
- * a second one costs ~280 KB of code and showed up as instruction-cache misses in the hot ASCII path. */
+/* whole document through the exact (Unicode) lexer, from global memory */
+typedef obm::Lexer<obm::SmallSink, obm::NoAccel, false> GDocLexer;
 OBM_HD_NOINLINE int doc_exact(const obm::Tables &T, const uint8_t *doc, uint32_t n, obm::SmallSink &sink) {
-    uint32_t pos = 0, line = 1;
-    while (pos < n) {
-        GUniLexer lx(T, doc, n, sink, pos, line, pos, !(line == 1 && pos == 0));
-        const int st = lx.run<true>();
-        if (st == obm::RUN_FATAL) return obm::RUN_FATAL;
-        if (st == obm::RUN_EOF) break;
-        pos = lx.p; line = lx.line_p;
-    }
-    sink.put(OBM_K_EOF, n, 0);
-    return obm::RUN_EOF;
+    GDocLexer lx(T, doc, n, sink);
+    return lx.run<false>();
 }
 
 } /* namespace obmp */

@@ -142,7 +142,7 @@ k1_scan(PipeArgs A) {
                 for (uint32_t wi = nwr + tid; wi < obmt::NW; wi += obmt::NT) { S.nlw[wi] = 0; S.spw[wi] = 0; }
                 __syncthreads();
                 /* P3 doc prep */
-                if (tid < nd) obmt::doc_prep(S, tid, true);
+                if (tid < nd) obmt::doc_prep(S, tid);
                 if (tid == 0) fetch_next(); /* the ticket taken at the top has long arrived; the record is used at the end of the tile */
                 __syncthreads();
                 /* P4 bit-parallel line scan */
@@ -237,7 +237,7 @@ k1_scan(PipeArgs A) {
             const bool room = ibase + n_items <= A.items_cap;
             if (room) {
                 for (uint32_t o = tid; o < n_owners; o += obmt::NT) { const item_t it = sitems[o]; if (!obmp::it_dead(it)) A.items[ibase + S.owner[o] + obmp::it_doc(it)] = it; }
-                if (tid < nd) A.items[ibase + C.dlast[tid] + tid] = obmp::make_eof_item(S.dstart[tid + 1] - S.dstart[tid], tid, (S.dflag[tid] & obmt::DF_EXACT_MASK) != 0);
+                if (tid < nd) A.items[ibase + C.dlast[tid] + tid] = obmp::make_eof_item(S.dstart[tid + 1] - S.dstart[tid], tid, S.dflag[tid] != 0);
                 if (extra && tid == 0) A.items[ibase + n_items - 1] = obmp::make_large_item();
             }
             if (tid == 0) {
@@ -281,8 +281,7 @@ __device__ __forceinline__ uint32_t k2_lex_lines(K2Ctx &X, bool on, item_t it, u
         len = (uint32_t)(A.doc_off[d + 1] - o0); gdoc = A.bytes + o0;
         v = obmp::line_view(gdoc, len, it, A.bytes, A.total_bytes);
     }
-    const bool uni = on && obmp::it_unicode(it); /* Unicode lexer from the line start, from global memory: nothing to stage */
-    const uint32_t want = (on && !uni && v.nch <= 32u) ? v.nch : 0u;
+    const uint32_t want = (on && v.nch <= 32u) ? v.nch : 0u;
     uint32_t incl = want;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
@@ -301,8 +300,7 @@ __device__ __forceinline__ uint32_t k2_lex_lines(K2Ctx &X, bool on, item_t it, u
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     uint32_t r = 0;
-    if (uni) r = obmp::k2_unicode_item(X.T, gdoc, len, it, out, cap, mk, lx);
-    else if (on) {
+    if (on) {
         uint32_t nv = 0; const uint8_t *sm = C.pool + (size_t)off * 16u;
         if (fits) nv = obmp::line_view_safe(sm, v, gdoc, len, it);
         if (nv) {

@@ -609,7 +609,7 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(usums, nt_u, ubase + ntiles);
     k_scan_add<<<nt_u, SCAN_THREADS, 0, st>>>(ubase, ntiles, usums, ~0ull, nullptr);
     OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, obmq::k1_scan, (int)obmt::NT, smem1));
-    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, obmq::k2_units, (int)(obmp::W_WARPS * 32), 0));
+    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, obmq::k2_units<false>, (int)(obmp::W_WARPS * 32), 0));
     if (per_sm1 < 1) per_sm1 = 1;
     if (per_sm2 < 1) per_sm2 = 1;
     uint32_t g1 = (uint32_t)dev_sms * (uint32_t)per_sm1; /* persistent CTAs: multiples of the SM count */
@@ -619,8 +619,9 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     if (g2 > g2max) g2 = (uint32_t)g2max;
     obmq::k1_scan<<<g1, obmt::NT, smem1, st>>>(A);
     OBM_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
-    obmq::k2_units<<<g2, obmp::W_WARPS * 32, 0, st>>>(A);
-    uint32_t launches = 7 + LARGE_COUNT_LAUNCHES;
+    obmq::k2_units<false><<<g2, obmp::W_WARPS * 32, 0, st>>>(A); /* batches without non-ASCII text */
+    obmq::k2_units<true><<<g2, obmp::W_WARPS * 32, 0, st>>>(A);  /* batches with valid UTF-8 beyond ASCII: per-line Unicode lexing */
+    uint32_t launches = 8 + LARGE_COUNT_LAUNCHES;
     if (d_out && out_cap) {
         large_fill_launch(st, dev_sms, d_bytes, d_doc_off, LW, toff, d_out, out_cap);
         launches += 1;

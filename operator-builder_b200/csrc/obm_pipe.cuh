@@ -38,7 +38,7 @@ struct PipeArgs {
     uint32_t *status; unsigned long long *totals;
     uint32_t *ctl;
 };
-enum { CT_T1 = 0, CT_T2 = 1, CT_ITOP = 4 /* u64 at ctl[4..5] */, CT_OVF = 6 };
+enum { CT_T1 = 0, CT_T2 = 1, CT_UNI = 2 /* some document needs per-line Unicode lexing */, CT_ITOP = 4 /* u64 at ctl[4..5] */, CT_OVF = 6 };
 
 __device__ __forceinline__ obm::Tables dev_tables() {
     obm::Tables T;
@@ -142,7 +142,7 @@ k1_scan(PipeArgs A) {
                 for (uint32_t wi = nwr + tid; wi < obmt::NW; wi += obmt::NT) { S.nlw[wi] = 0; S.spw[wi] = 0; }
                 __syncthreads();
                 /* P3 doc prep */
-                if (tid < nd) obmt::doc_prep(S, tid);
+                if (tid < nd) obmt::doc_prep(S, tid, true);
                 if (tid == 0) fetch_next(); /* the ticket taken at the top has long arrived; the record is used at the end of the tile */
                 __syncthreads();
                 /* P4 bit-parallel line scan */
@@ -226,6 +226,7 @@ k1_scan(PipeArgs A) {
                     C.dlast[tid] = (uint16_t)(lo < n_owners ? S.owner[lo] : n_live); /* live items before the next document */
                     const uint32_t f = S.dflag[tid];
                     A.doc_flag[da + tid] = ((f & obmt::DF_NONASCII) ? obmp::GF_NONASCII : 0u) | ((f & obmt::DF_QOVERFLOW) ? obmp::GF_QOVERFLOW : 0u);
+                    if (f & obmt::DF_UNI) A.ctl[CT_UNI] = 1;
                 }
             }
             __syncthreads();
@@ -237,7 +238,7 @@ k1_scan(PipeArgs A) {
             const bool room = ibase + n_items <= A.items_cap;
             if (room) {
                 for (uint32_t o = tid; o < n_owners; o += obmt::NT) { const item_t it = sitems[o]; if (!obmp::it_dead(it)) A.items[ibase + S.owner[o] + obmp::it_doc(it)] = it; }
-                if (tid < nd) A.items[ibase + C.dlast[tid] + tid] = obmp::make_eof_item(S.dstart[tid + 1] - S.dstart[tid], tid, S.dflag[tid] != 0);
+                if (tid < nd) A.items[ibase + C.dlast[tid] + tid] = obmp::make_eof_item(S.dstart[tid + 1] - S.dstart[tid], tid, (S.dflag[tid] & obmt::DF_EXACT_MASK) != 0);
                 if (extra && tid == 0) A.items[ibase + n_items - 1] = obmp::make_large_item();
             }
             if (tid == 0) {
@@ -267,6 +268,19 @@ struct K2Ctx {
     uint32_t markers, lexemes, exact, fatal;
     __device__ __forceinline__ uint32_t doc_of(item_t it) const { return obmp::it_large(it) ? d0 + nd : d0 + obmp::it_doc(it); }
 };
+
+/* lanes with uni == true: a line with bytes >= 0x80 of a valid-UTF-8 document, lexed from its start by the Unicode
+ * lexer straight from global memory.  Kept apart from k2_lex_lines so that this rare call does not weigh on the
+ * register allocation of the hot path.  Whole warp must call. */
+__device__ __forceinline__ uint32_t k2_lex_uni_lines(K2Ctx &X, bool uni, item_t it, uint32_t d, obm_tuple *out, uint32_t cap, uint32_t *mk, uint32_t *lx) {
+    uint32_t r = 0;
+    if (uni) {
+        const uint64_t o0 = X.A.doc_off[d];
+        r = obmp::k2_unicode_item(X.T, X.A.bytes + o0, (uint32_t)(X.A.doc_off[d + 1] - o0), it, out, cap, mk, lx);
+    }
+    __syncwarp();
+    return r;
+}
 
 /* Lanes with on == true lex the marker line of item `it` (document d) into out[0..cap) (cap 0: count only).
  * The lines' text is packed into the warp's pool (exclusive scan of 16-byte chunk counts, cp.async for all of
@@ -315,6 +329,7 @@ __device__ __forceinline__ uint32_t k2_lex_lines(K2Ctx &X, bool on, item_t it, u
 /* Block [b0, b1) of the unit's items: compact the marker items, lex each line once (lane per line, the first
  * W_MLCAP lines stage their tuples), counts of everything else.  stable: document flags are final (large
  * units, second sweep) -- lines of flagged documents are skipped.  Returns lane-local "needs the flag pass". */
+template <bool UNI>
 __device__ __forceinline__ bool k2_lex_block(K2Ctx &X, uint32_t b0, uint32_t b1, bool stable, uint32_t &n_ml_out) {
     K2Warp &C = X.C; const PipeArgs &A = X.A; const uint32_t lane = X.lane;
     uint32_t n_ml = 0; bool any = false;
@@ -338,7 +353,13 @@ __device__ __forceinline__ bool k2_lex_block(K2Ctx &X, uint32_t b0, uint32_t b1,
         const bool staged = k0 == 0; /* the first W_MLCAP lines also stage their tuples */
         uint32_t ib = 0, d = 0; item_t it = 0;
         if (on) { ib = C.mlist[k]; it = A.items[X.i0 + b0 + ib]; d = X.doc_of(it); }
-        const uint32_t r = k2_lex_lines(X, on, it, d, staged ? C.stage + k * obmp::W_LTS : nullptr, staged ? obmp::W_LTS : 0u, nullptr, nullptr);
+        obm_tuple *so = staged ? C.stage + k * obmp::W_LTS : nullptr; const uint32_t sc = staged ? obmp::W_LTS : 0u;
+        uint32_t r;
+        if constexpr (UNI) {
+            const bool uni = on && obmp::it_unicode(it);
+            r = k2_lex_lines(X, on && !uni, it, d, so, sc, nullptr, nullptr);
+            if (__any_sync(0xffffffffu, uni)) r |= k2_lex_uni_lines(X, uni, it, d, so, sc, nullptr, nullptr);
+        } else r = k2_lex_lines(X, on, it, d, so, sc, nullptr, nullptr);
         if (on) {
             C.icnt[ib] = (uint16_t)obmp::mres_tuples(r);
             if (obmp::mres_irregular(r)) { atomicOr(&A.doc_flag[d], obmp::GF_INTERACT); any = true; }
@@ -386,6 +407,7 @@ __device__ __forceinline__ uint64_t k2_block_total(K2Ctx &X, uint32_t b0, uint32
 
 /* final positions of the block starting at `at0`: comment / EOF tuples in place, exact documents, unstaged
  * lines; then the staged marker tuples, a lane per tuple.  Returns the block's tuple count. */
+template <bool UNI>
 __device__ __forceinline__ uint64_t k2_write_block(K2Ctx &X, uint32_t b0, uint32_t b1, uint32_t n_ml, uint64_t at0, bool stable) {
     K2Warp &C = X.C; const PipeArgs &A = X.A; const uint32_t lane = X.lane;
     uint64_t run = 0; uint32_t mrun = 0;
@@ -432,7 +454,12 @@ __device__ __forceinline__ uint64_t k2_write_block(K2Ctx &X, uint32_t b0, uint32
         if (__any_sync(0xffffffffu, relex)) {
             const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
             uint32_t mk = 0, lx = 0; /* locals: taking the context's address would push it to the stack */
-            k2_lex_lines(X, relex, it, d, A.out + at, roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv, &mk, &lx);
+            const uint32_t rc = roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv;
+            if constexpr (UNI) {
+                const bool uni = relex && obmp::it_unicode(it);
+                k2_lex_lines(X, relex && !uni, it, d, A.out + at, rc, &mk, &lx);
+                if (__any_sync(0xffffffffu, uni)) k2_lex_uni_lines(X, uni, it, d, A.out + at, rc, &mk, &lx);
+            } else k2_lex_lines(X, relex, it, d, A.out + at, rc, &mk, &lx);
             X.markers += mk; X.lexemes += lx;
         }
         run += __shfl_sync(0xffffffffu, incl, 31);
@@ -458,9 +485,13 @@ __device__ __forceinline__ uint64_t k2_write_block(K2Ctx &X, uint32_t b0, uint32
     return run;
 }
 
+/* UNI = false: no document of the batch needs per-line Unicode lexing (the common case; this instantiation carries no
+ * Unicode line lexer, which keeps its register allocation and code footprint); UNI = true: the other batches.  Both are
+ * launched, the one that does not apply returns at once. */
+template <bool UNI>
 __global__ void __launch_bounds__(obmp::W_WARPS * 32, 5)
 k2_units(PipeArgs A) {
-    if (A.ctl[CT_OVF]) return; /* work records overflowed in k1: the host redoes the batch with the exact kernels */
+    if (A.ctl[CT_OVF] || (A.ctl[CT_UNI] != 0) != UNI) return; /* work records overflowed in k1: the host redoes the batch with the exact kernels */
     __shared__ K2Warp WS[obmp::W_WARPS];
     const obm::Tables T = dev_tables();
     const uint32_t lane = threadIdx.x & 31;
@@ -477,7 +508,7 @@ k2_units(PipeArgs A) {
         uint64_t total; uint32_t n_ml = 0;
         const bool one_block = n_items <= obmp::W_ICAP;
         if (one_block) {
-            const bool any = __any_sync(0xffffffffu, k2_lex_block(X, 0, n_items, false, n_ml));
+            const bool any = __any_sync(0xffffffffu, k2_lex_block<UNI>(X, 0, n_items, false, n_ml));
             if (any) { k2_count_flagged_docs(X); k2_apply_flags(X, 0, n_items); }
             total = k2_block_total(X, 0, n_items);
         } else {
@@ -487,7 +518,7 @@ k2_units(PipeArgs A) {
             for (uint32_t b0 = 0; b0 < n_items; b0 += 32) {
                 const uint32_t b1 = min(b0 + 32u, n_items);
                 uint32_t nm;
-                any |= k2_lex_block(X, b0, b1, false, nm);
+                any |= k2_lex_block<UNI>(X, b0, b1, false, nm);
                 total += k2_block_total(X, b0, b1);
             }
             if (__any_sync(0xffffffffu, any)) {
@@ -496,7 +527,7 @@ k2_units(PipeArgs A) {
                 for (uint32_t b0 = 0; b0 < n_items; b0 += 32) {
                     const uint32_t b1 = min(b0 + 32u, n_items);
                     uint32_t nm;
-                    k2_lex_block(X, b0, b1, true, nm);
+                    k2_lex_block<UNI>(X, b0, b1, true, nm);
                     total += k2_block_total(X, b0, b1);
                 }
             }
@@ -506,14 +537,14 @@ k2_units(PipeArgs A) {
             if (u == 0) A.tuple_off[0] = 0;
             if (u == nunits - 1 && A.out && base + total > A.out_cap) A.status[0] = 1;
         }
-        if (one_block) k2_write_block(X, 0, n_items, n_ml, base, false);
+        if (one_block) k2_write_block<UNI>(X, 0, n_items, n_ml, base, false);
         else {
             uint64_t at = base;
             for (uint32_t b0 = 0; b0 < n_items; b0 += 32) {
                 const uint32_t b1 = min(b0 + 32u, n_items);
                 uint32_t nm;
-                k2_lex_block(X, b0, b1, true, nm);
-                at += k2_write_block(X, b0, b1, nm, at, true);
+                k2_lex_block<UNI>(X, b0, b1, true, nm);
+                at += k2_write_block<UNI>(X, b0, b1, nm, at, true);
             }
         }
     }

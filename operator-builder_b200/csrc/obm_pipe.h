@@ -41,7 +41,7 @@ OBM_HD uint32_t it_pos(item_t i) { return (uint32_t)((i >> 14) & 0x3FFF); }
 OBM_HD uint32_t it_line(item_t i) { return (uint32_t)((i >> 28) & 0x3FFF); }
 OBM_HD bool it_marker(item_t i) { return (i >> 42) & 1; }
 OBM_HD bool it_slash2(item_t i) { return (i >> 43) & 1; }
-OBM_HD bool it_dead(item_t i) { return (i >> 44) & 1; }
+OBM_HD bool it_dead(item_t i) { return !it_marker(i) && ((i >> 44) & 1); } /* marker items reuse bit 44 (it_unicode) */
 OBM_HD uint32_t it_doc(item_t i) { return (uint32_t)((i >> 45) & 0x3F); }
 
 /* K2 result per marker line */
@@ -96,6 +96,7 @@ OBM_HD item_t make_marker_item(uint32_t ls, uint32_t first, uint32_t line, uint3
     return (item_t)ls | ((item_t)first << 14) | ((item_t)line << 28) | ((item_t)1 << 42) | ((item_t)((line_end >> 13) & 1u) << 43) |
            ((item_t)d << 45) | ((item_t)(line_end & 0x1FFFu) << 51);
 }
+OBM_HD bool it_unicode(item_t i) { return it_marker(i) && ((i >> 44) & 1); } /* lexed from the line start by the Unicode lexer */
 OBM_HD uint32_t it_line_end(item_t i) { return (uint32_t)((i >> 51) & 0x1FFF) | ((uint32_t)((i >> 43) & 1) << 13); }
 OBM_HD item_t make_eof_item(uint32_t len, uint32_t d, bool exact) { return (item_t)len | ((item_t)d << 45) | ((item_t)1 << 51) | ((item_t)exact << 52); }
 OBM_HD item_t make_large_item() { return ((item_t)1 << 51) | ((item_t)1 << 53); }
@@ -127,13 +128,45 @@ OBM_FN item_t k1_owner_item(const SmemScan &S, uint32_t o) {
     uint32_t ls = obmt::line_start_of(S, first);
     uint32_t d = obmt::doc_of(S, ls);
     uint32_t dpos = S.dstart[d], dend = S.dstart[d + 1];
-    uint32_t rec = S.dflag[d] ? obmt::OW_NONE : obmt::classify_line(S, first, ls);
+    const uint32_t df = S.dflag[d];
+    if (df & obmt::DF_EXACT_MASK) return make_item(ls - dpos, first - dpos, 0, false, false, true, d);
+    if (df & obmt::DF_UNI) {
+        /* valid UTF-8 document: a line with bytes >= 0x80 (judged per 32-byte word: conservative) is lexed as a whole
+         * by the Unicode lexer, from its start; all-ASCII lines take the usual path */
+        uint32_t e = first;
+        for (;;) { if (e >= dend) { e = dend; break; } if (obmt::is_nl(S, e) && S.data[e] == '\n') break; e = obmt::next_event(S, e + 1); }
+        const uint32_t last = e < S.hi_pos ? e : S.hi_pos - 1;
+        bool na = false;
+        for (uint32_t w = ls >> 5; w <= (last >> 5); w++) na |= ((S.naw[w >> 5] >> (w & 31)) & 1u) != 0;
+        if (na) {
+            const uint32_t line = 1 + obmt::nl_before(S, ls) - obmt::nl_before(S, dpos);
+            return make_marker_item(ls - dpos, ls - dpos, line, d, e - dpos) | ((item_t)1 << 44);
+        }
+    }
+    uint32_t rec = obmt::classify_line(S, first, ls);
     if (rec == obmt::OW_NONE) return make_item(ls - dpos, first - dpos, 0, false, false, true, d);
     uint32_t line = 1 + obmt::nl_before(S, ls) - obmt::nl_before(S, dpos);
     if (!(rec & obmt::OW_MARKER)) return make_item(ls - dpos, obmt::ow_pos(rec) - dpos, line, false, (rec & obmt::OW_SLASH2) != 0, false, d);
     uint32_t e = first;
     for (;;) { if (e >= dend) { e = dend; break; } if (obmt::is_nl(S, e) && S.data[e] == '\n') break; e = obmt::next_event(S, e + 1); }
     return make_marker_item(ls - dpos, first - dpos, line, d, e - dpos);
+}
+
+/* K2: a line of a valid-UTF-8 document that contains bytes >= 0x80: the Unicode lexer in LINE mode from the line
+ * start, straight from global memory.  Regular iff it stopped exactly behind this line's newline. */
+typedef obm::Lexer<obm::SmallSink, obm::NoAccel, false> GUniLexer;
+OBM_HD_NOINLINE uint32_t k2_unicode_item(const obm::Tables &T, const uint8_t *doc, uint32_t n, item_t it, obm_tuple *out, uint32_t cap,
+                                         uint32_t *markers = nullptr, uint32_t *lexemes = nullptr) {
+    const uint32_t ls = it_ls(it), line = it_line(it), le = it_line_end(it);
+    obm::SmallSink sink(out, cap);
+    GUniLexer lx(T, doc, n, sink, ls, line, ls, !(line == 1 && ls == 0));
+    const int st = lx.run<true>();
+    const uint32_t end_line = lx.line_p - (st == obm::RUN_LINE_END ? 1u : 0u);
+    const bool regular = st != obm::RUN_FATAL && end_line == line &&
+                         (st == obm::RUN_LINE_END ? lx.p == le + 1u : (le == n && lx.p == n));
+    if (markers) *markers += sink.n_markers;
+    if (lexemes) *lexemes += sink.n_lexemes;
+    return make_mres(sink.n_tuples, !regular);
 }
 
 /* K2: lex the line of a marker item of document doc[0..n) (global memory) */
@@ -198,11 +231,21 @@ OBM_HD void plain_write(item_t it, obm_tuple *out, uint64_t at, uint64_t cap) {
     if (at + k < cap) out[at + k] = OBM_TUPLE(OBM_K_COMMENT, it_pos(it), it_slash2(it) ? 2 : 1);
 }
 
-/* whole document through the exact (Unicode) lexer, from global memory */
-typedef obm::Lexer<obm::SmallSink, obm::NoAccel, false> GDocLexer;
+/* whole document through the exact (Unicode) lexer, from global memory: line after line in LINE mode plus the EOF
+ * tuple -- the composition tests/hostsim checks against the whole-document run (hs_lex_doc_by_lines).  Written this
+ * way so that K2 carries ONE instantiation of the Unicode lexer's run loop (run<true>, shared with k2_unicode_item):
+ * a second one costs ~280 KB of code and showed up as instruction-cache misses in the hot ASCII path. */
 OBM_HD_NOINLINE int doc_exact(const obm::Tables &T, const uint8_t *doc, uint32_t n, obm::SmallSink &sink) {
-    GDocLexer lx(T, doc, n, sink);
-    return lx.run<false>();
+    uint32_t pos = 0, line = 1;
+    while (pos < n) {
+        GUniLexer lx(T, doc, n, sink, pos, line, pos, !(line == 1 && pos == 0));
+        const int st = lx.run<true>();
+        if (st == obm::RUN_FATAL) return obm::RUN_FATAL;
+        if (st == obm::RUN_EOF) break;
+        pos = lx.p; line = lx.line_p;
+    }
+    sink.put(OBM_K_EOF, n, 0);
+    return obm::RUN_EOF;
 }
 
 } /* namespace obmp */

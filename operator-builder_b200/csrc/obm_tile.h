@@ -52,7 +52,10 @@ constexpr uint32_t QMAX = 1024;     /* owners per sub-batch */
 constexpr uint32_t NSTAGE = 48;     /* marker owners whose tuples are staged in shared memory */
 constexpr uint32_t STRIDE = 40;     /* staged tuples per marker owner */
 
-enum : uint32_t { DF_NONASCII = 1, DF_INTERACT = 2, DF_QOVERFLOW = 4 };
+/* DF_NONASCII: the document must be lexed sequentially by the Unicode lexer (invalid UTF-8 or Unicode white space,
+ * or any non-ASCII byte when the caller does not do per-line Unicode lexing); DF_UNI: valid UTF-8 beyond ASCII, no
+ * Unicode white space -- only the lines that contain such bytes need the Unicode lexer (two-stage pipeline) */
+enum : uint32_t { DF_NONASCII = 1, DF_INTERACT = 2, DF_QOVERFLOW = 4, DF_UNI = 8, DF_EXACT_MASK = 7 };
 
 /* owner record: bits 0..14 position of the first special ('+' lines) or of the comment start (plain
  * lines), bit 15 = marker line, bits 16..30 line start, bit 31 = plain line whose comment is "//" */
@@ -94,6 +97,11 @@ OBM_HD uint32_t zero_bytes4(uint32_t t) {
     return (eq * 0x00204081u >> 21) & 0xFu;
 }
 
+/* the same for any byte values */
+OBM_HD uint32_t zero_bytes4_exact(uint32_t t) {
+    const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
+    return ((z >> 7) * 0x00204081u >> 21) & 0xFu;
+}
 OBM_HD void classify_word(SmemScan &S, uint32_t wi) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(S.data) + wi * 8;
     uint32_t nl = 0, hp = 0, sl = 0, hi = 0;
@@ -110,6 +118,18 @@ OBM_HD void classify_word(SmemScan &S, uint32_t wi) {
         nl |= zero_bytes4(v ^ 0x0A0A0A0Au) << (4 * k);
         hp |= zero_bytes4((v & 0xF7F7F7F7u) ^ 0x23232323u) << (4 * k); /* '#' (0x23) or '+' (0x2B) */
         sl |= zero_bytes4(v ^ 0x2F2F2F2Fu) << (4 * k);                  /* '/' */
+    }
+    if (hi & 0x80808080u) {
+        /* bytes >= 0x80 in this word: the carry-free byte test above is only exact for 7-bit input -- redo the word with
+         * the exact form (the bitmaps of such words now matter: valid UTF-8 documents stay on the line-parallel path) */
+        nl = hp = sl = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t v = x[k];
+            nl |= zero_bytes4_exact(v ^ 0x0A0A0A0Au) << (4 * k);
+            hp |= zero_bytes4_exact((v & 0xF7F7F7F7u) ^ 0x23232323u) << (4 * k);
+            sl |= zero_bytes4_exact(v ^ 0x2F2F2F2Fu) << (4 * k);
+        }
     }
     /* specials: the bytes that can start a comment or a marker in state lex / lexComment (state.go:20-33,48):
      * '#', '+', and a '/' followed by another '/' (the word's last byte cannot see its successor: kept) */
@@ -147,7 +167,46 @@ OBM_HD uint32_t atomic_inc_u32(uint32_t *p) {
 }
 
 /* ---- P3: per-document preparation (thread d < nd) ---------------------------------------------- */
-OBM_FN void doc_prep(SmemScan &S, uint32_t d) {
+/* Go's utf8.DecodeRune validity (no overlongs, no surrogates, <= U+10FFFF) over bytes [q, e) of S.data, plus: no
+ * code point of unicode.IsSpace beyond ASCII (U+0085, U+00A0, U+1680, U+2000-200A, U+2028, U+2029, U+202F, U+205F,
+ * U+3000).  Why both: an invalid byte makes the reference discard 3 bytes for 1 (discard.go:27-30) and Unicode white
+ * space is skipped by peekedWhitespaced / consumed as `width` RUNES (peek.go:65-89, consume.go:39-41) -- either can
+ * reach across a newline from a line that owns no tuple, so such documents are lexed sequentially.  Valid text
+ * without them keeps every line independent: only ASCII white space separates tokens. */
+OBM_FN bool utf8_plain(const SmemScan &S, uint32_t q, uint32_t e) {
+    uint32_t p = q;
+    while (p < e) {
+        const uint32_t w = p >> 5;
+        if (!((S.naw[w >> 5] >> (w & 31)) & 1u)) { p = (w + 1) << 5; continue; } /* all-ASCII word */
+        const uint32_t wend = ((w + 1) << 5) < e ? ((w + 1) << 5) : e;
+        while (p < wend) {
+            const uint32_t b0 = S.data[p];
+            if (b0 < 0x80) { p++; continue; }
+            uint32_t need, lo = 0x80, hi = 0xBF;
+            if (b0 >= 0xC2 && b0 <= 0xDF) need = 1;
+            else if (b0 >= 0xE0 && b0 <= 0xEF) { need = 2; if (b0 == 0xE0) lo = 0xA0; if (b0 == 0xED) hi = 0x9F; }
+            else if (b0 >= 0xF0 && b0 <= 0xF4) { need = 3; if (b0 == 0xF0) lo = 0x90; if (b0 == 0xF4) hi = 0x8F; }
+            else return false;
+            if (p + need >= e) return false; /* truncated at the end of the document */
+            const uint32_t b1 = S.data[p + 1];
+            if (b1 < lo || b1 > hi) return false;
+            uint32_t b2 = 0, b3 = 0;
+            if (need >= 2) { b2 = S.data[p + 2]; if (b2 < 0x80 || b2 > 0xBF) return false; }
+            if (need == 3) { b3 = S.data[p + 3]; if (b3 < 0x80 || b3 > 0xBF) return false; }
+            /* Unicode white space */
+            if (b0 == 0xC2 && (b1 == 0x85 || b1 == 0xA0)) return false;
+            if (b0 == 0xE1 && b1 == 0x9A && b2 == 0x80) return false;
+            if (b0 == 0xE2 && b1 == 0x80 && (b2 <= 0x8A || b2 == 0xA8 || b2 == 0xA9 || b2 == 0xAF)) return false;
+            if (b0 == 0xE2 && b1 == 0x81 && b2 == 0x9F) return false;
+            if (b0 == 0xE3 && b1 == 0x80 && b2 == 0x80) return false;
+            p += need + 1;
+        }
+    }
+    return true;
+}
+/* uni_lines: the caller lexes lines with non-ASCII bytes one by one with the Unicode lexer (two-stage pipeline);
+ * otherwise any byte >= 0x80 sends the whole document to the sequential path (fused kernel) */
+OBM_FN void doc_prep(SmemScan &S, uint32_t d, bool uni_lines = false) {
     uint32_t q = S.dstart[d], e = S.dstart[d + 1];
     if (q > S.lo_pos) atomic_or_u32(&S.nlw[(q - 1) >> 5], 1u << ((q - 1) & 31)); /* virtual newline before the document */
     uint32_t flag = 0;
@@ -160,6 +219,7 @@ OBM_FN void doc_prep(SmemScan &S, uint32_t d) {
             if (w1 < hiw) m &= 0xFFFFFFFFu >> (hiw - w1);
             if (m) { flag = DF_NONASCII; break; }
         }
+        if (flag && uni_lines && utf8_plain(S, q, e)) flag = DF_UNI;
     }
     S.dflag[d] = flag;
 }

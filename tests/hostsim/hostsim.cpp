@@ -59,6 +59,7 @@ using obmt::Smem;
 struct Emu {
     Smem S;
     uint32_t sub_total = 0;
+    bool uni_lines = false; /* the two-stage pipeline lexes lines with non-ASCII bytes one by one (doc_prep) */
     /* P1..P4: stage, classify, doc prep, bit-parallel line scan -> S.owner[] = first special of each owning line */
     uint32_t scan(const uint8_t *bytes, const uint64_t *doc_off, uint32_t da, uint32_t db, uint32_t fake_skew) {
         const uint32_t nd = db - da;
@@ -73,7 +74,7 @@ struct Emu {
         for (uint32_t wi = 0; wi < obmt::NW; wi++) {
             if (wi < ((nwords + 31u) & ~31u)) obmt::classify_word(S, wi); else { S.nlw[wi] = 0; S.spw[wi] = 0; }
         }
-        for (uint32_t t = 0; t < nd; t++) obmt::doc_prep(S, t);
+        for (uint32_t t = 0; t < nd; t++) obmt::doc_prep(S, t, uni_lines);
         /* P4: per-thread generate/propagate, warp look-ahead from emulated ballots, cross-warp resolve */
         std::vector<uint32_t> my_nl(obmt::NT), my_own(obmt::NT), g(obmt::NT), pr(obmt::NT), cin_t(obmt::NT);
         std::vector<obmt::LineBits> lbs(obmt::NT);
@@ -223,6 +224,7 @@ struct PipeEmu {
         for (uint32_t q = 0; q < kn; q++) {
             const uint32_t d = ds[q]; item_t it = its[q];
             const uint8_t *doc = bytes + doc_off[d]; uint32_t n_view = dlen(d);
+            if (it_unicode(it)) { rs[q] = k2_unicode_item(TBL, doc, n_view, it, outs[q], caps[q], mk, lx); continue; }
             LineView v = line_view(bytes + doc_off[d], dlen(d), it, bytes, total_bytes);
             const uint32_t want = v.nch <= 32u ? v.nch : 0u;
             pool_used += want; /* the scan is over all lines, fitting or not, exactly like the warp scan */
@@ -340,7 +342,7 @@ struct PipeEmu {
 
 extern "C" uint64_t hs_pipe_batch(const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs, obm_tuple *out, uint64_t cap,
                                    uint64_t *tuple_off, uint32_t fake_skew, uint64_t *stats) {
-    static Emu emu;
+    static Emu emu; emu.uni_lines = true;
     using namespace obmp;
     PipeEmu G; G.bytes = bytes; G.doc_off = doc_off; G.out = out; G.cap = cap; G.tuple_off = tuple_off;
     G.doc_flag.assign(ndocs, 0); G.counts.assign(ndocs, 0);
@@ -384,7 +386,7 @@ extern "C" uint64_t hs_pipe_batch(const uint8_t *bytes, const uint64_t *doc_off,
                 lo = lp[lo];
                 const uint32_t f = emu.S.dflag[q];
                 G.doc_flag[da + q] = ((f & obmt::DF_NONASCII) ? GF_NONASCII : 0u) | ((f & obmt::DF_QOVERFLOW) ? GF_QOVERFLOW : 0u);
-                G.items[ibase + lo + q] = make_eof_item(emu.S.dstart[q + 1] - emu.S.dstart[q], q, f != 0);
+                G.items[ibase + lo + q] = make_eof_item(emu.S.dstart[q + 1] - emu.S.dstart[q], q, (f & obmt::DF_EXACT_MASK) != 0);
             }
             if (extra) G.items[ibase + n_items - 1] = make_large_item();
             for (uint64_t i = ibase; i < ibase + n_items; i++) if (G.items[i] == ~0ull) { fprintf(stderr, "hostsim: item hole\n"); abort(); }

@@ -54,9 +54,37 @@ def test_targeted_as_one_batch():
         check_batch(docs, skew)
 
 
-def test_non_ascii_goes_exact():
-    stats = check_batch(list(cu.NON_ASCII) + [b"# +a:b\n"] * 5)
-    assert stats[2] >= len(cu.NON_ASCII) - 2
+GO_UNICODE_SPACE = set([0x85, 0xA0, 0x1680, 0x2028, 0x2029, 0x202F, 0x205F, 0x3000]) | set(range(0x2000, 0x200B))
+
+
+def needs_sequential_lexer(doc: bytes) -> bool:
+    """invalid UTF-8 (utf8.DecodeRune) or unicode.IsSpace beyond ASCII: the two things that let a line without tuples
+    reach across a newline (csrc/obm_tile.h utf8_plain)"""
+    try:
+        text = doc.decode("utf-8")
+    except UnicodeDecodeError:
+        return True
+    return any(ord(ch) in GO_UNICODE_SPACE for ch in text)
+
+
+def test_non_ascii_documents():
+    """invalid UTF-8 / Unicode white space -> sequential Unicode lexer for the document; other non-ASCII text stays on the
+    line-parallel path of the pipeline (only its non-ASCII lines take the Unicode lexer), the fused kernel sends both away"""
+    docs = list(cu.NON_ASCII) + [b"# +a:b\n"] * 5
+    stats = check_batch(docs)  # stats of the pipeline emulation
+    must = sum(needs_sequential_lexer(d) for d in docs)
+    assert must >= 8 and must <= int(stats[2]) < len(cu.NON_ASCII)
+    # valid text beyond ASCII inside otherwise regular documents, at every alignment of the 32-byte classification words
+    base = b"k: v  # +operator-builder:field:name=a,type=string\n" * 3
+    uni = ["é", "中文", "😀", "ß=ü", "# +ключ:значение=да", "x: 'naïve'  # +s:a=\"ö\",b"]
+    many = []
+    for u in uni:
+        for pad in range(0, 40, 3):
+            many.append(base + b" " * pad + u.encode() + b"\n" + base)
+            if "=" not in u:  # appended to a naked string value / inside a comment in front of a marker
+                many.append(base[:-1] + u.encode() + b"\n" + b"# " + u.encode() + b" +s:t=1\n")
+    stats = check_batch(many, skew=5)
+    assert int(stats[2]) == 0
 
 
 def test_fixtures_and_golden():

@@ -42,6 +42,7 @@ def lib():
         L.hs_pipe_batch.argtypes = L.hs_tile_batch.argtypes
         L.hs_large_doc.restype = ctypes.c_uint64
         L.hs_large_doc.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)]
+        L.hs_utf8_plain.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32]
         L.hs_parse_float_err.argtypes = [ctypes.c_char_p, ctypes.c_uint32]
         L.hs_atoi_err.argtypes = [ctypes.c_char_p, ctypes.c_uint32]
         L.obm_decode_doc.restype = ctypes.c_int64

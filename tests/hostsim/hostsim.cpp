@@ -459,3 +459,13 @@ extern "C" uint64_t hs_large_doc(const uint8_t *doc, uint32_t n, obm_tuple *out,
     if (at < cap) out[at] = OBM_TUPLE(OBM_K_EOF, n, 0);
     return at + 1;
 }
+
+/* utf8_plain (obm_tile.h) on one document staged the way k1_scan stages it: 1 = valid UTF-8 without Unicode white space */
+extern "C" int hs_utf8_plain(const uint8_t *doc, uint32_t n, uint32_t fake_skew) {
+    static Emu emu;
+    if (n > obmt::MAXDOC) return -1;
+    const uint64_t off[2] = {0, n};
+    emu.uni_lines = true;
+    emu.scan(doc, off, 0, 1, fake_skew);
+    return (emu.S.dflag[0] & obmt::DF_NONASCII) ? 0 : 1; /* ASCII documents are trivially plain */
+}

@@ -152,3 +152,27 @@ def test_staged_line_views_lookahead_across_the_newline():
         check_batch(docs[lo:lo + 400], skew=lo % 16)
     # the same at the very end of a document / of the batch (the copy is cut at the document end)
     check_batch([t + b"\n" + b" " * w for t in tails for w in (0, 1, 5, 30)] + [tails[0]])
+
+
+def test_utf8_check_matches_go_semantics():
+    """K1's per-document check (valid per utf8.DecodeRune, no unicode.IsSpace beyond ASCII) against Python's strict decoder
+    plus the white-space set: random byte soup biased towards lead / continuation bytes, every alignment"""
+    L = hostsim.lib()
+    rng = random.Random(31337)
+    pieces = [bytes([b]) for b in (0x80, 0xBF, 0xC0, 0xC1, 0xC2, 0xDF, 0xE0, 0xE1, 0xEC, 0xED, 0xEE, 0xEF, 0xF0, 0xF1, 0xF3, 0xF4, 0xF5, 0xFF,
+                                   0x85, 0xA0, 0x9A, 0x9F, 0x90, 0x8F, 0xA8, 0xAF, 0x81, 0x8A, 0x8B)]
+    pieces += ["é".encode(), "€".encode(), "😀".encode(), "\u00a0".encode(), "\u0085".encode(), "\u1680".encode(), "\u2003".encode(),
+               "\u200a".encode(), "\u200b".encode(), "\u2028".encode(), "\u202f".encode(), "\u205f".encode(), "\u3000".encode(), "\u3001".encode(),
+               "\ud7ff".encode(), "\ue000".encode(), "\U0010ffff".encode(), b"\xed\xa0\x80", b"\xf4\x90\x80\x80", b"\xe0\x9f\xbf", b"\xf0\x8f\xbf\xbf",
+               b"a", b"\n", b" ", b"#", b"+x:y=1"]
+    valid = [p for p in pieces if not needs_sequential_lexer(p)]
+    n_plain = 0
+    for it in range(20000):
+        doc = b"".join(rng.choice(valid if it % 2 and rng.random() < 0.9 else pieces) for _ in range(rng.randint(1, 12)))
+        if rng.random() < 0.3:
+            doc = b"k: v\n" * rng.randint(0, 20) + doc + b"\nz" * rng.randint(0, 40)
+        got = L.hs_utf8_plain(doc, len(doc), rng.randint(0, 15))
+        want = 0 if needs_sequential_lexer(doc) else 1
+        assert got == want, (doc, got, want)
+        n_plain += want
+    assert 2000 < n_plain < 18000

@@ -219,6 +219,31 @@ def test_large_documents_chunk_parallel(scanner, oracle):
     res = run_and_compare(scanner, oracle, docs)
 
 
+def test_valid_utf8_documents_stay_line_parallel(scanner, oracle):
+    """valid UTF-8 beyond ASCII without Unicode white space: only the lines with such bytes take the Unicode lexer
+    (k2_units<true>); invalid UTF-8 / Unicode white space send the document to the sequential lexer; same stream either way"""
+    base = b"k: v  # +operator-builder:field:name=a,type=string\n" * 3
+    uni = ["é", "中文", "😀", "ß=ü", "# +ключ:значение=да", "x: 'naïve'  # +s:a=\"ö\",b"]
+    docs = []
+    for u in uni:
+        for pad in range(0, 40, 3):
+            docs.append(base + b" " * pad + u.encode() + b"\n" + base)
+            if "=" not in u:
+                docs.append(base[:-1] + u.encode() + b"\n" + b"# " + u.encode() + b" +s:t=1\n")
+    import operator_builder_b200 as ob
+    data0, _ = ob.generate_corpus_host(64, 4096, 0, 0)
+    raw = data0.tobytes()
+    for i in range(64):
+        d = raw[i * 4096:(i + 1) * 4096]
+        docs.append(d.replace(b"plain", "plén".encode(), 1) if i % 3 else d)
+    docs += list(cu.NON_ASCII) + ["# caf\u00e9\u00a0+a:b\n".encode(), b"k: v\n\xff\n# +a:b\n"]
+    run_and_compare(scanner, oracle, docs)
+    scanner.set_mode(0)
+    data, off = pack(docs[:len(docs) - len(cu.NON_ASCII) - 2])
+    res = scanner.lex_batch(data, off)
+    assert res.stats["n_docs_exact"] == 0
+
+
 def test_device_entry_point_and_capacity(scanner, oracle):
     import torch
     import operator_builder_b200 as ob

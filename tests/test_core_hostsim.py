@@ -154,3 +154,16 @@ def test_chunk_path_ascii_fast_lexer_on_fuzz():
     for doc in docs:
         got, _ok = hostsim.large_doc(doc)
         assert np.array_equal(got, hostsim.lex_doc(doc)), doc[:300]
+
+
+def test_decoder_survives_arbitrary_tuple_streams():
+    """obm_decode_doc is handed device output by callers of the C ABI: whatever the 64-bit words are (kinds, offsets and
+    lengths far outside the document), it must clamp and return, never read outside the document"""
+    import random
+    rng = random.Random(5)
+    L = hostsim.lib()
+    for _ in range(5000):
+        doc = bytes(rng.randrange(256) for _ in range(rng.randint(0, 60)))
+        tup = np.array([(rng.randrange(32) << 59) | ((rng.randrange(1 << 27) if rng.random() < 0.2 else rng.randint(0, 70)) << 32)
+                        | (rng.randrange(1 << 32) if rng.random() < 0.2 else rng.randint(0, 70)) for _ in range(rng.randint(0, 12))], dtype=np.uint64)
+        assert isinstance(hostsim.decode(doc, tup, L), bytes)

@@ -102,7 +102,12 @@ def tile_batch(docs, skew=0, pipeline=False):
     """CTA emulation of the tile fast path (pipeline=0 fused kernel, 1 two-stage pipeline) over a list of documents
     -> (tuples, doc_tuple_off, stats)."""
     L = lib()
-    data = np.frombuffer(b"".join(docs) + b"+" * 32, dtype=np.uint8).copy()  # readable (poisoned) past the end, like the device buffer contract
+    # the batch sits at address = 16k + skew inside a poisoned buffer (readable around it, like the device buffer contract)
+    payload = b"".join(docs)
+    buf = np.full(len(payload) + 96, 0x2B, dtype=np.uint8)
+    start = (-buf.ctypes.data) % 16 + 16 + (skew & 15)
+    buf[start:start + len(payload)] = np.frombuffer(payload, dtype=np.uint8)
+    data = buf[start:]
     off = np.zeros(len(docs) + 1, dtype=np.uint64)
     if docs:
         off[1:] = np.cumsum([len(d) for d in docs])

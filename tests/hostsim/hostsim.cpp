@@ -60,15 +60,28 @@ struct Emu {
     Smem S;
     uint32_t sub_total = 0;
     bool uni_lines = false; /* the two-stage pipeline lexes lines with non-ASCII bytes one by one (doc_prep) */
+    uint64_t total_bytes = 0; /* size of the packed batch (bytes after a sub-batch that the bulk copy also brings in) */
     /* P1..P4: stage, classify, doc prep, bit-parallel line scan -> S.owner[] = first special of each owning line */
     uint32_t scan(const uint8_t *bytes, const uint64_t *doc_off, uint32_t da, uint32_t db, uint32_t fake_skew) {
         const uint32_t nd = db - da;
         const uint64_t b0 = doc_off[da], b1 = doc_off[db];
-        const uint32_t skew = fake_skew & 15u; /* the device derives it from the absolute address */
+        (void)fake_skew; /* callers place the batch at the alignment they want to test (tests/hostsim/__init__.py) */
+        const uint32_t skew = (uint32_t)((uintptr_t)(bytes + b0) & 15u); /* as on the device: from the absolute address, so that
+                                                                          * K1's 32-byte words and K2's aligned 4-byte loads line up */
         const uint32_t span = (uint32_t)(b1 - b0) + skew;
         S.nd = nd; S.lo_pos = skew; S.hi_pos = span; S.n_owners = 0;
-        memset(S.data, 0x2B, sizeof S.data); /* '+' garbage outside the range must never matter */
+        memset(S.data, 0x2B, sizeof S.data); /* '+' garbage outside the loaded range must never matter */
         memcpy(S.data + skew, bytes + b0, (size_t)(b1 - b0));
+        /* the device's bulk copy starts at the 16-byte boundary below the first document and ends at the one above the
+         * last: the neighbouring documents' real bytes are in the buffer too (they decide, e.g., whether the 32-byte
+         * word around a document boundary counts as non-ASCII).  `total` bounds what exists after the batch. */
+        if (b0 >= skew) memcpy(S.data, bytes + b0 - skew, skew);
+        {
+            const uint32_t load = (span + 15u) & ~15u;
+            const uint64_t avail = total_bytes > b1 ? total_bytes - b1 : 0;
+            const uint32_t extra = load - span < avail ? load - span : (uint32_t)avail;
+            if (extra) memcpy(S.data + span, bytes + b1, extra);
+        }
         for (uint32_t t = 0; t <= nd; t++) S.dstart[t] = (uint32_t)(doc_off[da + t] - b0) + skew;
         const uint32_t nwords = (span + 31) >> 5;
         for (uint32_t wi = 0; wi < obmt::NW; wi++) {
@@ -166,6 +179,7 @@ extern "C" uint64_t hs_tile_batch(const uint8_t *bytes, const uint64_t *doc_off,
                                   uint64_t *tuple_off, uint32_t fake_skew, uint64_t *stats /* markers, lexemes, exact, fatal */) {
     static Emu emu;
     const uint64_t total = doc_off[ndocs];
+    emu.total_bytes = total;
     const uint64_t ntiles = total / obmt::TILE + 1;
     uint64_t base = 0;
     obmt::FillStats fs = {0, 0, 0, 0};
@@ -342,7 +356,7 @@ struct PipeEmu {
 
 extern "C" uint64_t hs_pipe_batch(const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs, obm_tuple *out, uint64_t cap,
                                    uint64_t *tuple_off, uint32_t fake_skew, uint64_t *stats) {
-    static Emu emu; emu.uni_lines = true;
+    static Emu emu; emu.uni_lines = true; emu.total_bytes = doc_off[ndocs];
     using namespace obmp;
     PipeEmu G; G.bytes = bytes; G.doc_off = doc_off; G.out = out; G.cap = cap; G.tuple_off = tuple_off;
     G.doc_flag.assign(ndocs, 0); G.counts.assign(ndocs, 0);
@@ -390,6 +404,7 @@ extern "C" uint64_t hs_pipe_batch(const uint8_t *bytes, const uint64_t *doc_off,
             }
             if (extra) G.items[ibase + n_items - 1] = make_large_item();
             for (uint64_t i = ibase; i < ibase + n_items; i++) if (G.items[i] == ~0ull) { fprintf(stderr, "hostsim: item hole\n"); abort(); }
+            if (getenv("HS_DUMP_ITEMS")) for (uint64_t i = ibase; i < ibase + n_items; i++) fprintf(stderr, "item %llu: marker=%d uni=%d eof=%d dead=%d doc=%u ls=%u pos=%u line=%u le=%u dflag=%u\n", (unsigned long long)i, (int)it_marker(G.items[i]), (int)it_unicode(G.items[i]), (int)it_eof(G.items[i]), (int)it_dead(G.items[i]), it_doc(G.items[i]), it_ls(G.items[i]), it_pos(G.items[i]), it_line(G.items[i]), it_marker(G.items[i]) ? it_line_end(G.items[i]) : 0u, emu.S.dflag[it_doc(G.items[i]) < nd ? it_doc(G.items[i]) : 0]);
             G.units.push_back(Unit{ibase, da, n_items | (nd << 16)});
         }
     }
@@ -465,7 +480,7 @@ extern "C" int hs_utf8_plain(const uint8_t *doc, uint32_t n, uint32_t fake_skew)
     static Emu emu;
     if (n > obmt::MAXDOC) return -1;
     const uint64_t off[2] = {0, n};
-    emu.uni_lines = true;
+    emu.uni_lines = true; emu.total_bytes = n;
     emu.scan(doc, off, 0, 1, fake_skew);
     return (emu.S.dflag[0] & obmt::DF_NONASCII) ? 0 : 1; /* ASCII documents are trivially plain */
 }

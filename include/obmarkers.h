@@ -159,8 +159,9 @@ int obm_generate_corpus_device(obm_handle *h, void *d_bytes, void *d_doc_off, ui
 int obm_generate_corpus_host(uint8_t *bytes, uint64_t *doc_off, uint32_t ndocs, uint32_t doc_bytes,
                              uint64_t first_doc, int flavour);
 
-/* Scanning strategy: 0 = two-stage pipeline (default), 1 = exact path for every document, 2 = fused tile
- * kernel.  All produce the identical tuple stream.  Returns the old mode. */
+/* Scanning strategy: 0 = fused warp kernel (default; csrc/obm_warp.h), 1 = exact path for every document,
+ * 2 = round 1's fused tile kernel, 3 = round 1's two-stage pipeline (keeps valid UTF-8 documents line-parallel).
+ * All produce the identical tuple stream.  Returns the old mode. */
 int obm_set_mode(obm_handle *h, int mode);
 
 /* obm_lex_batch pipelines host batches of at least two chunks: H2D of chunk k+1, the scan of chunk k and D2H of

@@ -2,7 +2,7 @@
  * obm_core.h -- the exact marker lexer as straight-line code over an in-memory document, emitting
  * the canonical tuple stream defined in include/obmarkers.h.
  *
- * Compiled for the device by nvcc (used by every kernel in obm_kernels.cu) and, for logic tests
+ * Compiled for the device by nvcc (used by every kernel in obm_lib.cu) and, for logic tests
  * only, for the host by g++ (tests/hostsim).  It is NOT a CPU fallback: libobmarkers.so exports no
  * host lexing entry point.
  *
@@ -297,6 +297,7 @@ OBM_HD_NOINLINE bool peeked_whitespaced_at(const uint8_t *d, uint32_t n, uint32_
 OBM_HD uint32_t src_mis(const uint8_t *d, uint32_t q) { return (uint32_t)((uintptr_t)(d + q) & 3u); }
 OBM_HD uint32_t src_ldw(const uint8_t *d, int32_t off) { return *reinterpret_cast<const uint32_t *>(d + off); }
 OBM_HD const uint8_t *src_raw(const uint8_t *d) { return d; }
+OBM_HD const uint8_t *src_add(const uint8_t *d, uint32_t off) { return d + off; }
 #if defined(__CUDACC__)
 struct ShBytes {
     uint32_t sh; const uint8_t *g;
@@ -305,6 +306,7 @@ struct ShBytes {
 __device__ __forceinline__ uint32_t src_mis(const ShBytes &d, uint32_t q) { return (d.sh + q) & 3u; }
 __device__ __forceinline__ uint32_t src_ldw(const ShBytes &d, int32_t off) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(d.sh + (uint32_t)off)); return v; }
 __device__ __forceinline__ const uint8_t *src_raw(const ShBytes &d) { return d.g; }
+__device__ __forceinline__ ShBytes src_add(const ShBytes &d, uint32_t off) { return ShBytes{d.sh + off, d.g + off}; }
 #endif
 
 template <class Sink, class Accel = NoAccel, bool ASCII = false, class Src = const uint8_t *>

@@ -395,7 +395,8 @@ k_tile_scan(TileArgs A) {
 
 /* scratch: tile_first u32[ntiles+2] | tile_state u64[ntiles+1] | large_list u32[max_large+1] | ctl u32[4] */
 static inline uint64_t obm_fast_ntiles(uint64_t total_bytes) { return total_bytes / obmt::TILE + 1; }
-static inline uint64_t obm_fast_max_large(uint64_t total_bytes) { return total_bytes / obmt::MAXDOC + 1; }
+/* table size for the list of large documents: a bound for every path's threshold (obmt::MAXDOC, obmw::MAXDOC > 8192) */
+static inline uint64_t obm_fast_max_large(uint64_t total_bytes) { return total_bytes / 8192 + 1; }
 static inline uint64_t obm_fast_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
     (void)ndocs;
     uint64_t nt = obm_fast_ntiles(total_bytes);

@@ -51,7 +51,9 @@ enum { ST_OVERFLOW = 0, ST_DOCS_EXACT = 1, ST_DOCS_FATAL = 2, ST_RESERVED = 3 };
 
 #include "obm_fast.cuh"
 #include "obm_pipe.cuh"
+#include "obm_warp.cuh"
 #include "obm_large.h"
+static_assert(obmw::MAXDOC > 8192 && obmt::MAXDOC > 8192, "obm_fast_max_large");
 
 /* ------------------------------------------------------------------------------------------- */
 /* exact path: one thread per document                                                          */
@@ -633,12 +635,74 @@ static int obm_pipe_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     return OBM_OK;
 }
 
+/* ---- fused warp kernel (mode 0) ----------------------------------------------------------------------- */
+static uint64_t warp_ntiles(uint64_t total_bytes) { return total_bytes / obmw::TILE + 1; }
+static uint64_t warp_units_max(uint32_t ndocs, uint64_t total_bytes) { return 2 * warp_ntiles(total_bytes) + ndocs / obmw::DMAX + 2; }
+static uint64_t warp_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
+    const uint64_t nt = warp_ntiles(total_bytes), um = warp_units_max(ndocs, total_bytes);
+    return align_up((nt + 2) * 4, 256) + align_up((obm_fast_max_large(total_bytes) + 1) * 4, 256) + align_up(nt * 4 + 4, 256) + align_up((nt + 1) * 8, 256) +
+           align_up(((uint64_t)scan_tiles((uint32_t)nt) + 1) * 8, 256) + align_up((nt + 1) * sizeof(obmw::WRec), 256) + align_up((um + 1) * 8, 256) +
+           align_up((um / 32 + 2) * 8, 256) + 512;
+}
+/* tile index -> (large documents planned and counted on a side stream) units per tile + scan -> k_warp_scan -> fill of
+ * the large documents */
+static int obm_warp_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t *d_doc_off, uint32_t ndocs, uint64_t total_bytes,
+                           obm_tuple *d_out, uint64_t out_cap, uint64_t *toff, uint32_t *status, unsigned long long *totals,
+                           uint32_t *counts, void *warp_ws, void *large_ws, cudaStream_t st) {
+    const size_t smem = sizeof(obmw::WarpSmem) * obmw::WPC;
+    OBM_CUDA(h, cudaFuncSetAttribute(obmw::k_warp_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); /* per device: set on every call (cheap) */
+    const uint64_t nt64 = warp_ntiles(total_bytes), um = warp_units_max(ndocs, total_bytes);
+    if (nt64 > 0xFFFFFFF0ull || um > 0xFFFFFFF0ull) { set_err(h, "batch too large for the tile index"); return OBM_E_ARG; }
+    const uint32_t ntiles = (uint32_t)nt64, nt_u = scan_tiles(ntiles);
+    auto up = [](uint64_t v) { return (v + 255) / 256 * 256; };
+    uint8_t *q = (uint8_t *)warp_ws;
+    uint32_t *tile_first = (uint32_t *)q; q += up(((uint64_t)ntiles + 2) * 4);
+    uint32_t *large_list = (uint32_t *)q; q += up((obm_fast_max_large(total_bytes) + 1) * 4);
+    uint32_t *nun = (uint32_t *)q; q += up((uint64_t)ntiles * 4 + 4);
+    uint64_t *ubase = (uint64_t *)q; q += up(((uint64_t)ntiles + 1) * 8);
+    uint64_t *usums = (uint64_t *)q; q += up(((uint64_t)nt_u + 1) * 8);
+    obmw::WRec *wrec = (obmw::WRec *)q; q += up(((uint64_t)ntiles + 1) * sizeof(obmw::WRec));
+    obmw::WArgs A;
+    A.bytes = d_bytes; A.doc_off = d_doc_off; A.ndocs = ndocs; A.total_bytes = total_bytes; A.tile_first = tile_first; A.ntiles = ntiles;
+    A.wrec = wrec; A.ubase = ubase;
+    A.st_tuples = (uint64_t *)q; q += up((um + 1) * 8);
+    A.st_blocks = (uint64_t *)q; q += up((um / 32 + 2) * 8);
+    A.ctl = (uint32_t *)q; /* [0] ticket, [1] n_large */
+    A.counts = counts; A.out = d_out; A.out_cap = d_out ? out_cap : 0; A.tuple_off = toff; A.status = status; A.totals = totals;
+    OBM_CUDA(h, cudaMemsetAsync(A.st_tuples, 0, up((um + 1) * 8) + up((um / 32 + 2) * 8) + 64, st)); /* look-back chains + control words */
+    obmw::k_wtile_index<<<(ndocs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, ndocs, ntiles, tile_first, large_list, A.ctl + 1);
+    int dev_sms = 0, per_sm = 0;
+    OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
+    const LargeWs LW = large_carve(large_ws, total_bytes, large_list, A.ctl + 1);
+    OBM_CUDA(h, cudaEventRecord(h->ev_fork, st));
+    OBM_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    large_count_launch(h->side, dev_sms, d_bytes, d_doc_off, LW, counts, totals, status);
+    OBM_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+    obmw::k_wunits<<<(ntiles + 255) / 256, 256, 0, st>>>(d_doc_off, tile_first, ntiles, nun, wrec);
+    k_scan_tiles<<<nt_u, SCAN_THREADS, 0, st>>>(nun, ntiles, ubase, usums);
+    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(usums, nt_u, ubase + ntiles);
+    k_scan_add<<<nt_u, SCAN_THREADS, 0, st>>>(ubase, ntiles, usums, ~0ull, nullptr);
+    OBM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, obmw::k_warp_scan, (int)(obmw::WPC * 32), smem));
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = (uint32_t)dev_sms * (uint32_t)per_sm; /* persistent warps: a multiple of the SM count */
+    const uint32_t gmax = (ntiles + obmw::WPC - 1) / obmw::WPC;
+    if (grid > gmax) grid = gmax;
+    OBM_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+    obmw::k_warp_scan<<<grid, obmw::WPC * 32, smem, st>>>(A);
+    uint32_t launches = 6 + LARGE_COUNT_LAUNCHES;
+    if (d_out && out_cap) { large_fill_launch(st, dev_sms, d_bytes, d_doc_off, LW, toff, d_out, out_cap); launches += 1; }
+    h->launches = launches;
+    OBM_CUDA(h, cudaGetLastError());
+    return OBM_OK;
+}
+
 extern "C" uint64_t obm_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
     uint64_t b = align_up((uint64_t)ndocs * 4 + 4, 256);
     b += align_up((uint64_t)scan_tiles(ndocs) * 8 + 8, 256);
     b += align_up(obm_fast_scratch_bytes(ndocs, total_bytes), 256);
     b += pipe_scratch_bytes(ndocs, total_bytes);
     b += large_scratch_bytes(total_bytes);
+    b += warp_scratch_bytes(ndocs, total_bytes);
     return b;
 }
 
@@ -660,7 +724,8 @@ static int lex_device_impl(obm_handle *h, const void *d_bytes, const void *d_doc
     uint64_t *tile_sums = (uint64_t *)sc; sc += align_up((uint64_t)scan_tiles(ndocs) * 8 + 8, 256);
     void *fast_ws = sc; sc += align_up(obm_fast_scratch_bytes(ndocs, total_bytes), 256);
     void *pipe_ws = sc; sc += pipe_scratch_bytes(ndocs, total_bytes);
-    void *large_ws = sc;
+    void *large_ws = sc; sc += large_scratch_bytes(total_bytes);
+    void *warp_ws = sc;
     uint32_t *status = (uint32_t *)(d_status ? d_status : (void *)h->d_status);
     unsigned long long *totals = (unsigned long long *)(d_counts ? d_counts : (void *)h->d_counts);
     uint64_t *toff = (uint64_t *)d_doc_tuple_off;
@@ -669,6 +734,9 @@ static int lex_device_impl(obm_handle *h, const void *d_bytes, const void *d_doc
     if (ndocs == 0) { OBM_CUDA(h, cudaMemsetAsync(toff, 0, sizeof(uint64_t), st)); return OBM_OK; }
 
     if (h->mode == 0)
+        return obm_warp_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes, (obm_tuple *)d_out, out_cap, toff, status,
+                               totals, counts, warp_ws, large_ws, st);
+    if (h->mode == 3)
         return obm_pipe_launch(h, (const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total_bytes,
                                 (obm_tuple *)d_out, out_cap, toff, status, totals, counts, fast_ws, pipe_ws, large_ws, st);
     if (h->mode == 2)

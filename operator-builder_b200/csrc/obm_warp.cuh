@@ -1,0 +1,106 @@
+/*
+ * obm_warp.cuh -- device side of the fused warp kernel (logic: obm_warp.h / obm_warp_core.h).
+ *
+ *   k_wtile_index   tile -> first document starting in it; list of large documents (> obmw::MAXDOC)
+ *   k_wunits        per tile: unit count + record; an exclusive scan gives every unit a static id in document order
+ *   k_warp_scan     persistent warps (no block barrier anywhere): a warp takes a tile by ticket, stages the text of
+ *                   each of its units with one TMA bulk copy (cp.async.bulk + mbarrier) into its own slice of shared
+ *                   memory and runs obmw::process_unit on it
+ */
+#pragma once
+#include "obm_fast.cuh"
+#include "obm_pipe.cuh"
+
+#define WLANE() (threadIdx.x & 31u)
+#define WBALLOT(p) __ballot_sync(0xffffffffu, (p))
+#define WSHFL(v, s) __shfl_sync(0xffffffffu, (v), (s))
+#define WSHFL_UP(v, d) __shfl_up_sync(0xffffffffu, (v), (d))
+#define WSYNC() __syncwarp()
+#define WTEXT(S) obm::ShBytes{obmf::smem_u32((S).text), (S).text}
+#define WATOMIC_OR(p, v) atomicOr((p), (v))
+#include "obm_warp_core.h"
+
+namespace obmw {
+
+constexpr uint32_t WPC = 4; /* warps per CTA; each works alone on its own shared-memory slice */
+enum { WC_TICKET = 0 };
+
+__global__ void __launch_bounds__(256)
+k_wtile_index(const uint64_t *__restrict__ doc_off, uint32_t ndocs, uint32_t ntiles, uint32_t *__restrict__ tile_first,
+              uint32_t *__restrict__ large_list, uint32_t *__restrict__ n_large) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d > ndocs) return;
+    /* tiles t with  off[d-1] < t*TILE <= off[d]  have tile_first[t] = d; d == ndocs closes the table */
+    const uint64_t tprev_plus1 = d == 0 ? 0 : doc_off[d - 1] / TILE + 1;
+    const uint64_t tcur = d == ndocs ? (uint64_t)ntiles : doc_off[d] / TILE;
+    if (d == ndocs && ndocs > 0 && tprev_plus1 > tcur) return;
+    for (uint64_t t = tprev_plus1; t <= tcur && t <= ntiles; t++) tile_first[t] = d;
+    if (d < ndocs && doc_off[d + 1] - doc_off[d] > MAXDOC) large_list[atomicAdd(n_large, 1u)] = d;
+}
+
+__global__ void __launch_bounds__(256)
+k_wunits(const uint64_t *__restrict__ doc_off, const uint32_t *__restrict__ tile_first, uint32_t ntiles, uint32_t *__restrict__ nunits, WRec *__restrict__ wrec) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const WRec r = make_wrec(doc_off, tile_first[t], tile_first[t + 1]);
+    nunits[t] = r.n_units;
+    wrec[t] = r;
+}
+
+struct DevHooks {
+    const WArgs &A; uint32_t phase;
+    __device__ __forceinline__ void stage(WarpSmem &S, const void *gsrc, uint32_t nbytes) {
+        if (WLANE() == 0 && nbytes) {
+            obmf::fence_proxy_async(); /* the warp's earlier generic-proxy accesses to S.text precede the async write */
+            obmf::mbar_expect_tx(&S.mbar, nbytes);
+            obmf::tma_bulk_g2s(S.text, gsrc, nbytes, &S.mbar);
+        }
+    }
+    __device__ __forceinline__ void stage_wait(WarpSmem &S, uint32_t nbytes) {
+        if (nbytes) { obmf::mbar_wait(&S.mbar, phase); phase ^= 1u; }
+    }
+    __device__ __forceinline__ uint64_t lookback(uint32_t u, uint32_t n, uint64_t total) { return obmf::lookback2_warp(A.st_tuples, A.st_blocks, u, n, total); }
+};
+
+__global__ void __launch_bounds__(WPC * 32)
+k_warp_scan(WArgs A) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    WarpSmem &S = reinterpret_cast<WarpSmem *>(smem_raw)[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u;
+    if (lane == 0) { obmf::mbar_init(&S.mbar, 1); obmf::fence_mbar_init(); }
+    __syncwarp();
+    const obm::Tables T = obmq::dev_tables();
+    const uint32_t nunits = (uint32_t)A.ubase[A.ntiles];
+    DevHooks H{A, 0};
+    WAcc acc{0, 0, 0, 0};
+    /* the next tile's ticket is taken while this one is processed (the atomic's round trip is off the critical path) */
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(&A.ctl[WC_TICKET], 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    while (t < A.ntiles) {
+        uint32_t tn = 0;
+        if (lane == 0) tn = atomicAdd(&A.ctl[WC_TICKET], 1u);
+        const WRec rec = A.wrec[t];
+        const uint32_t u0 = (uint32_t)A.ubase[t];
+        for (uint32_t k = 0; k < rec.n_units; k++) {
+            uint32_t da, db, extra;
+            wrec_unit(rec, k, da, db, extra);
+            process_unit(S, A, T, H, u0 + k, nunits, da, db, extra, acc);
+        }
+        t = __shfl_sync(0xffffffffu, tn, 0);
+    }
+    uint32_t markers = acc.markers, lexemes = acc.lexemes, exact = acc.exact, fatal = acc.fatal;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        markers += __shfl_down_sync(0xffffffffu, markers, o); lexemes += __shfl_down_sync(0xffffffffu, lexemes, o);
+        exact += __shfl_down_sync(0xffffffffu, exact, o); fatal += __shfl_down_sync(0xffffffffu, fatal, o);
+    }
+    if (lane == 0) {
+        if (markers) atomicAdd(&A.totals[0], (unsigned long long)markers);
+        if (lexemes) atomicAdd(&A.totals[1], (unsigned long long)lexemes);
+        if (exact) atomicAdd(&A.status[1], exact);
+        if (fatal) atomicAdd(&A.status[2], fatal);
+    }
+}
+
+} /* namespace obmw */

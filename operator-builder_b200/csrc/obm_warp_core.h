@@ -1,0 +1,420 @@
+/*
+ * obm_warp_core.h -- the body of the fused warp kernel (see obm_warp.h), written against a small set of warp
+ * collectives so that the very same source runs on the device (obm_warp.cuh: CUDA intrinsics) and, for logic
+ * tests, on the host (tests/hostsim/warp_emu.h: 32 fibers in lock step).  The includer defines, before
+ * including this file:
+ *     WLANE()                lane id 0..31
+ *     WBALLOT(pred)          __ballot_sync
+ *     WSHFL(v, src)          __shfl_sync (u32), WSHFL_UP(v, delta)
+ *     WSYNC()                __syncwarp (also orders the warp's shared-memory accesses)
+ *     WTEXT(S)               the byte source of the staged text (ShBytes on the device, pointer on the host)
+ *     WATOMIC_OR(p, v)       atomicOr on shared memory
+ * and supplies a Hooks type with
+ *     stage(S, gsrc, nbytes) bring nbytes (multiple of 16) from the 16-byte aligned global address gsrc into S.text
+ *     lookback(u, n, total)  exclusive prefix of unit u's tuple count over the units (all lanes; returns in all)
+ */
+#ifndef OBM_WARP_CORE_H
+#define OBM_WARP_CORE_H
+
+#include "obm_warp.h"
+
+#ifndef OBMW_STAT
+#define OBMW_STAT(name) ((void)0) /* the host replay counts how lines were lexed */
+#endif
+#if defined(__CUDACC__)
+#define OBMW_DEV __device__ __forceinline__
+#else
+#define OBMW_DEV inline
+#endif
+
+namespace obmw {
+
+struct WarpSmem {
+    alignas(16) uint8_t text[BUFB + 64];
+    union {
+        struct { uint32_t nlw[NWORDS]; uint32_t spw[NWORDS]; } bm; /* phases A, B */
+        uint32_t stage[MLCAP * LTS];                               /* phases C, D (the bitmaps are dead by then) */
+    } u;
+    uint16_t nlpre[NWORDS];     /* newline bits in words [0, w) */
+    orec_t orec[OWN_CAP];       /* phase A: position of the line's first special; phase B: owner record */
+    uint16_t ocnt[OWN_CAP];     /* tuples of the owner; after the scan: exclusive prefix over owners */
+    uint16_t mlist[OWN_CAP];    /* marker rank -> owner */
+    uint32_t dstart[DMAX + 2];  /* document starts, buffer-relative; [nd] = end */
+    uint32_t dflag[DMAX + 1];
+    uint32_t dcnt[DMAX + 1];    /* tuples of the document; after the scan: exclusive offsets inside the unit */
+    uint16_t dfo[DMAX + 2];     /* first owner of the document */
+    uint32_t mstat[MLCAP];      /* staged line: markers | lexemes << 8 | tuples << 16; MS_NONE: not staged */
+    alignas(8) uint64_t mbar;
+};
+static_assert(sizeof(uint32_t) * MLCAP * LTS <= sizeof(uint32_t) * 2 * NWORDS, "the staging area overlays the bitmaps");
+
+struct WArgs {
+    const uint8_t *bytes; const uint64_t *doc_off; uint32_t ndocs; uint64_t total_bytes;
+    const uint32_t *tile_first; uint32_t ntiles;
+    const WRec *wrec; const uint64_t *ubase; /* [ntiles + 1] exclusive scan of units per tile */
+    uint64_t *st_tuples, *st_blocks;         /* two-level look-back chain over units */
+    const uint32_t *counts;                  /* tuple counts of large documents (k_large_resolve) */
+    obm_tuple *out; uint64_t out_cap; uint64_t *tuple_off;
+    uint32_t *status; unsigned long long *totals; uint32_t *ctl;
+};
+struct WAcc { uint32_t markers, lexemes, exact, fatal; };
+constexpr uint32_t MS_NONE = 0xFFFFFFFFu;
+
+/* ---- bitmap helpers (phase B) ------------------------------------------------------------------------- */
+OBM_HD bool w_is_nl(const WarpSmem &S, uint32_t pos) { return (S.u.bm.nlw[pos >> 5] >> (pos & 31)) & 1u; }
+OBM_HD bool w_is_sp(const WarpSmem &S, uint32_t pos) { return (S.u.bm.spw[pos >> 5] >> (pos & 31)) & 1u; }
+/* first position >= from whose special or newline bit is set, or hi */
+OBM_FN uint32_t w_next_event(const WarpSmem &S, uint32_t from, uint32_t hi) {
+    if (from >= hi) return hi;
+    uint32_t w = from >> 5;
+    uint32_t m = (S.u.bm.spw[w] | S.u.bm.nlw[w]) & (0xFFFFFFFFu << (from & 31));
+    const uint32_t wend = (hi + 31) >> 5;
+    while (m == 0) {
+        if (++w >= wend) return hi;
+        m = S.u.bm.spw[w] | S.u.bm.nlw[w];
+    }
+    const uint32_t pos = w * 32 + OBMT_CTZ(m);
+    return pos < hi ? pos : hi;
+}
+/* position after the last newline bit below pos (or lo) */
+OBM_FN uint32_t w_line_start(const WarpSmem &S, uint32_t pos, uint32_t lo) {
+    uint32_t w = pos >> 5;
+    uint32_t m = S.u.bm.nlw[w] & ((1u << (pos & 31)) - 1u);
+    const uint32_t wlo = lo >> 5;
+    while (m == 0) {
+        if (w == wlo) return lo;
+        m = S.u.bm.nlw[--w];
+    }
+#if defined(__CUDA_ARCH__)
+    const uint32_t top = 31u - (uint32_t)__clz((int)m);
+#else
+    const uint32_t top = 31u - (uint32_t)__builtin_clz(m);
+#endif
+    const uint32_t ls = w * 32 + top + 1;
+    return ls > lo ? ls : lo;
+}
+OBM_HD uint32_t w_nl_before(const WarpSmem &S, uint32_t q) {
+    const uint32_t w = q >> 5;
+    if (w >= NWORDS) return (uint32_t)S.nlpre[NWORDS - 1] + OBMT_POPC(S.u.bm.nlw[NWORDS - 1]);
+    return (uint32_t)S.nlpre[w] + OBMT_POPC(S.u.bm.nlw[w] & ((1u << (q & 31)) - 1u));
+}
+
+/* inclusive warp scan of a u32 */
+#define OBMW_SCAN_INCL(v)                                                                                \
+    do {                                                                                                 \
+        _Pragma("unroll") for (uint32_t o_ = 1; o_ < 32; o_ <<= 1) { const uint32_t t_ = WSHFL_UP(v, o_); if (lane >= o_) v += t_; } \
+    } while (0)
+
+/* the line of owner record r, lexed by the generic ASCII lexer (hand-over target of the stepper): tuples into out[0..cap) */
+template <class Src>
+OBM_HD uint32_t generic_line(const obm::Tables &T, const Src &text, orec_t r, uint32_t dpos, uint32_t dend, obm_tuple *out, uint32_t cap,
+                             uint32_t *mk, uint32_t *lx) {
+    const uint32_t n = dend - dpos;
+    uint32_t e = or_first(r); /* end of the line: the generic lexer's skipping is bounded by it (obmp::LineAccel) */
+    while (e < n && text[dpos + e] != '\n') e++;
+    const obmp::item_t it = obmp::make_marker_item(or_ls(r), or_first(r), or_line(r), 0, e);
+    return obmp::k2_marker_item(T, obm::src_add(text, dpos), n, it, out, cap, mk, lx);
+}
+
+template <class Hooks>
+OBMW_DEV void process_unit(WarpSmem &S, const WArgs &A, const obm::Tables &T, Hooks &H, uint32_t u, uint32_t nunits, uint32_t da, uint32_t db,
+                         uint32_t extra, WAcc &acc) {
+    const uint32_t lane = WLANE();
+    const uint32_t nd = db - da;
+    const bool writing = A.out != nullptr && A.out_cap != 0;
+    uint32_t n_owners = 0, n_ml = 0;
+    uint32_t lo_pos = 0, hi_pos = 0;
+    uint64_t b0 = 0;
+    if (nd) {
+        b0 = A.doc_off[da];
+        const uint64_t b1 = A.doc_off[db];
+        const uint64_t abs0 = (uint64_t)(uintptr_t)A.bytes + b0, base_abs = abs0 & ~15ull;
+        const uint32_t skew = (uint32_t)(abs0 - base_abs), span = (uint32_t)(b1 - b0) + skew, load = (span + 15u) & ~15u;
+        lo_pos = skew; hi_pos = span;
+        H.stage(S, (const void *)(uintptr_t)base_abs, load);
+        if (lane <= nd) S.dstart[lane] = (uint32_t)(A.doc_off[da + lane] - b0) + skew;
+        if (lane < nd) S.dflag[lane] = 0;
+        WSYNC();
+        H.stage_wait(S, load);
+        const auto text = WTEXT(S);
+
+        /* ---- A: rows ---- */
+        const uint32_t nrows = (span + ROW - 1) / ROW;
+        uint32_t nl_run = 0, own_run = 0, cin_row = 0, prev_top = 0, nextd = 1;
+        for (uint32_t r = 0; r < nrows; r++) {
+            const uint32_t row0 = r * ROW, pos0 = row0 + lane * 32u;
+            uint32_t x[8];
+            {
+                const uint4 a = reinterpret_cast<const uint4 *>(S.text + pos0)[0], b = reinterpret_cast<const uint4 *>(S.text + pos0)[1];
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+            }
+            const Masks m = classify32(x);
+            const uint32_t keep = range_mask(pos0, lo_pos, hi_pos);
+            uint32_t nl = m.nl & keep;
+            const uint32_t hp = m.hp & keep, sl = m.sl & keep;
+            /* bytes >= 0x80 inside the range: the documents that touch this lane's 32 bytes take the exact lexer */
+            bool na = false;
+            if (m.hi && keep) {
+                if (keep == 0xFFFFFFFFu) na = true;
+                else for (uint32_t k = 0; k < 32; k++) if (((keep >> k) & 1u) && S.text[pos0 + k] >= 0x80) na = true;
+            }
+            const uint32_t nab = WBALLOT(na);
+            if (nab && lane < nd) { /* rare: exact attribution, byte by byte */
+                const uint32_t q = S.dstart[lane], e = S.dstart[lane + 1];
+                for (uint32_t mm = nab; mm; mm &= mm - 1) {
+                    const uint32_t l0 = row0 + (OBMW_FFS(mm) - 1u) * 32u;
+                    const uint32_t a = q > l0 ? q : l0, b = e < l0 + 32u ? e : l0 + 32u;
+                    for (uint32_t p = a; p < b; p++) if (S.text[p] >= 0x80) S.dflag[lane] |= DF_NONASCII;
+                }
+            }
+            /* "//": a '/' whose successor is a '/' (the successor of the lane's last byte sits in the next lane's chunk) */
+            const uint32_t nxt = (pos0 + 32u < hi_pos && S.text[pos0 + 32u] == '/') ? 0x80000000u : 0u;
+            uint32_t ss = sl & ((sl >> 1) | nxt);
+            /* virtual newline on the byte before every document start (a line starts there, whatever the byte is) */
+            while (nextd < nd) {
+                const uint32_t q = S.dstart[nextd];
+                if (q > lo_pos) {
+                    if (q - 1u >= row0 + ROW) break;
+                    if (((q - 1u - row0) >> 5) == lane) { const uint32_t bit = 1u << ((q - 1u) & 31u); nl |= bit; ss &= ~bit; }
+                }
+                nextd++;
+            }
+            const uint32_t sp = hp | ss;
+            const uint32_t ev = nl | sp;
+            /* line starts: after every newline, and at the first byte of the range */
+            const uint32_t top = nl >> 31;
+            uint32_t up = WSHFL_UP(top, 1);
+            if (lane == 0) up = prev_top;
+            uint32_t M = (nl << 1) | up;
+            if (r == 0 && lo_pos < hi_pos && (lo_pos >> 5) == lane) M |= 1u << (lo_pos & 31u);
+            /* first event of every line: (~ev + M) & ev, the carry resolved across lanes by generate / propagate */
+            const uint32_t G = (uint32_t)((((uint64_t)(~ev)) + M) >> 32);
+            const uint32_t Gb = WBALLOT(G != 0), Pb = WBALLOT(ev == 0 && G == 0);
+            uint32_t cout;
+            const uint32_t Cm = obmt::carry_lookahead32(Gb, Pb, cin_row, &cout);
+            const uint32_t cin = (Cm >> lane) & 1u;
+            uint32_t own = (uint32_t)(((uint64_t)(~ev)) + M + cin) & ev & sp;
+            cin_row = cout;
+            prev_top = WSHFL(top, 31);
+            S.u.bm.nlw[r * 32u + lane] = nl;
+            S.u.bm.spw[r * 32u + lane] = sp;
+            uint32_t cnt = OBMT_POPC(nl) | (OBMT_POPC(own) << 16);
+            const uint32_t mine = cnt;
+            OBMW_SCAN_INCL(cnt);
+            const uint32_t excl = cnt - mine;
+            S.nlpre[r * 32u + lane] = (uint16_t)(nl_run + (excl & 0xFFFFu));
+            uint32_t o = own_run + (excl >> 16);
+            while (own) {
+                if (o < OWN_CAP) S.orec[o] = pos0 + (OBMW_FFS(own) - 1u);
+                o++; own &= own - 1u;
+            }
+            const uint32_t tot = WSHFL(cnt, 31);
+            nl_run += tot & 0xFFFFu; own_run += tot >> 16;
+        }
+        WSYNC();
+        n_owners = own_run;
+        if (n_owners > OWN_CAP) { n_owners = 0; if (lane < nd) S.dflag[lane] |= DF_QOVERFLOW; }
+        WSYNC();
+
+        /* ---- B: owners ---- */
+        for (uint32_t o0 = 0; o0 < n_owners; o0 += 32) {
+            const uint32_t o = o0 + lane; const bool valid = o < n_owners;
+            bool marker = false;
+            if (valid) {
+                const uint32_t first = (uint32_t)S.orec[o];
+                const uint32_t ls = w_line_start(S, first, lo_pos);
+                uint32_t dlo = 0, dhi = nd; /* last d with dstart[d] <= ls */
+                while (dhi - dlo > 1) { const uint32_t mid = (dlo + dhi) >> 1; if (S.dstart[mid] <= ls) dlo = mid; else dhi = mid; }
+                const uint32_t d = dlo, dpos = S.dstart[d];
+                if (S.dflag[d]) S.orec[o] = make_orec(ls - dpos, first - dpos, 0, false, false, true, d, 0);
+                else {
+                    const uint32_t line = 1 + w_nl_before(S, ls) - w_nl_before(S, dpos);
+                    const uint32_t c = text[first];
+                    uint32_t plus = first;
+                    marker = c == '+';
+                    if (!marker) { /* is there a '+' further on this line?  (state.go:46-57: lexComment looks for nothing else) */
+                        uint32_t e = first;
+                        for (;;) {
+                            if (w_is_nl(S, e)) break; /* a special on the document's last byte */
+                            e = w_next_event(S, e + 1, hi_pos);
+                            if (e >= hi_pos || !w_is_sp(S, e)) break;
+                            if (text[e] == '+') { marker = true; plus = e; break; }
+                        }
+                    }
+                    const uint32_t pd = plus - first < 255u ? plus - first : 255u;
+                    S.orec[o] = make_orec(ls - dpos, first - dpos, line, marker, c == '/', false, d, pd);
+                    if (!marker) S.ocnt[o] = (uint16_t)(line == 1 ? 1u : 2u);
+                }
+                if (or_dead(S.orec[o])) S.ocnt[o] = 0;
+            }
+            const uint32_t bal = WBALLOT(marker);
+            if (marker) S.mlist[n_ml + OBMT_POPC(bal & ((1u << lane) - 1u))] = (uint16_t)o;
+            n_ml += OBMT_POPC(bal);
+        }
+        WSYNC(); /* the bitmaps are dead from here on: their space becomes the staging area */
+
+        /* ---- C: marker lines, a lane per line; the first MLCAP lines stage their tuples ---- */
+        for (uint32_t k0 = 0; k0 < n_ml; k0 += 32) {
+            const uint32_t k = k0 + lane; const bool on = k < n_ml;
+            if (on) {
+                const uint32_t o = S.mlist[k];
+                const orec_t r = S.orec[o];
+                const uint32_t d = or_doc(r), dpos = S.dstart[d], dend = S.dstart[d + 1];
+                const bool staged = k0 == 0;
+                PackSink sink(S.u.stage + lane * LTS, staged ? LTS : 0u);
+                uint32_t res = FL_FALLBACK;
+                if (or_plusd(r) != 255u)
+                    res = fast_line(text, dpos + or_first(r), dpos + or_first(r) + or_plusd(r), dpos + or_ls(r), or_line(r), dpos, dend, sink);
+                uint32_t cntv; bool stg = staged;
+                if (res == FL_OK) { cntv = sink.n; if (sink.ovf) stg = false; OBMW_STAT(fast); }
+                else { /* outside the well-formed grammar: the generic lexer decides (count only; written in place later) */
+                    OBMW_STAT(generic);
+                    const uint32_t gr = generic_line(T, text, r, dpos, dend, nullptr, 0, nullptr, nullptr);
+                    cntv = obmp::mres_tuples(gr); stg = false;
+                    S.orec[o] = r | ((orec_t)255u << 50); /* remember: this line is the generic lexer's */
+                    if (obmp::mres_irregular(gr)) WATOMIC_OR(&S.dflag[d], DF_INTERACT);
+                }
+                if (cntv >= 0xFFFFu) { WATOMIC_OR(&S.dflag[d], DF_INTERACT); cntv = 0; }
+                S.ocnt[o] = (uint16_t)cntv;
+                if (staged) S.mstat[lane] = (stg && cntv) ? (sink.mk | (sink.lx << 8) | (cntv << 16)) : MS_NONE; /* cntv <= LTS: the counters fit */
+            }
+        }
+        WSYNC();
+    }
+
+    /* ---- D: counts -> positions ---- */
+    /* documents that need the exact lexer (K2 of r01: k2_count_flagged_docs) */
+    uint32_t dflag = 0, dtot = 0;
+    if (lane < nd) {
+        dflag = S.dflag[lane];
+        if (dflag) {
+            const uint32_t dpos = S.dstart[lane], dend = S.dstart[lane + 1];
+            obm::SmallSink sink(nullptr, 0);
+            obmp::doc_exact(T, S.text + dpos, dend - dpos, sink);
+            dtot = sink.n_tuples;
+        }
+        /* first owner of the document: owners are in position order, hence grouped by document */
+        uint32_t lo = 0, hi = n_owners;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (or_doc(S.orec[mid]) < lane) lo = mid + 1; else hi = mid; }
+        S.dfo[lane] = (uint16_t)lo;
+    }
+    if (lane == nd) S.dfo[nd] = (uint16_t)n_owners;
+    WSYNC();
+    /* exclusive prefix over the owners' tuple counts (owners of flagged documents count 0) */
+    {
+        uint32_t run = 0;
+        for (uint32_t o0 = 0; o0 < n_owners; o0 += 32) {
+            const uint32_t o = o0 + lane;
+            uint32_t c = 0;
+            if (o < n_owners) { c = S.ocnt[o]; if (S.dflag[or_doc(S.orec[o])]) c = 0; }
+            uint32_t v = c;
+            OBMW_SCAN_INCL(v);
+            if (o < n_owners) S.ocnt[o] = (uint16_t)(run + v - c);
+            run += WSHFL(v, 31);
+        }
+        WSYNC();
+        if (lane < nd && !dflag) {
+            const uint32_t f0 = S.dfo[lane], f1 = S.dfo[lane + 1];
+            const uint32_t p0 = f0 < n_owners ? S.ocnt[f0] : run, p1 = f1 < n_owners ? S.ocnt[f1] : run;
+            dtot = p1 - p0 + 1u; /* + EOF */
+        }
+    }
+    uint32_t dincl = lane < nd ? dtot : 0u;
+    OBMW_SCAN_INCL(dincl);
+    const uint32_t dexcl = dincl - (lane < nd ? dtot : 0u);
+    uint64_t total = WSHFL(dincl, 31);
+    uint32_t large_cnt = 0;
+    if (extra) { large_cnt = A.counts[da + nd]; total += large_cnt; }
+    const uint64_t base = H.lookback(u, nunits, total);
+    if (lane == 0) {
+        if (u == 0) A.tuple_off[0] = 0;
+        if (u == nunits - 1 && A.out && base + total > A.out_cap) A.status[0] = 1;
+        if (extra) A.tuple_off[da + nd + 1] = base + total;
+    }
+    if (lane < nd) {
+        S.dcnt[lane] = dexcl;
+        A.tuple_off[da + lane + 1] = base + dexcl + dtot;
+    }
+    WSYNC();
+
+    /* ---- D: write ---- */
+    if (nd == 0) return;
+    const auto text = WTEXT(S);
+    if (lane < nd) {
+        const uint32_t dpos = S.dstart[lane], dend = S.dstart[lane + 1];
+        const uint64_t at = base + dexcl;
+        if (dflag) {
+            acc.exact++;
+            if (writing) {
+                const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
+                obm::SmallSink sink(A.out + at, roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv);
+                const int st = obmp::doc_exact(T, S.text + dpos, dend - dpos, sink);
+                acc.markers += sink.n_markers; acc.lexemes += sink.n_lexemes; acc.fatal += (st == obm::RUN_FATAL) ? 1u : 0u;
+            }
+        } else {
+            const uint64_t eof_at = at + dtot - 1u;
+            if (writing && eof_at < A.out_cap) A.out[eof_at] = OBM_TUPLE(OBM_K_EOF, dend - dpos, 0);
+            acc.lexemes++;
+        }
+    }
+    /* plain lines in place; marker lines that are not staged are lexed again, straight to their place */
+    for (uint32_t o0 = 0; o0 < n_owners; o0 += 32) {
+        const uint32_t o = o0 + lane;
+        if (o >= n_owners) continue;
+        const orec_t r = S.orec[o];
+        const uint32_t d = or_doc(r);
+        if (or_dead(r) || S.dflag[d]) continue;
+        const uint64_t at = base + S.dcnt[d] + (uint32_t)(S.ocnt[o] - S.ocnt[S.dfo[d]]);
+        if (!or_marker(r)) {
+            if (writing) {
+                uint32_t k = 0;
+                if (or_line(r) != 1) { if (at < A.out_cap) A.out[at] = OBM_TUPLE(OBM_K_LINE, or_ls(r), or_line(r)); k = 1; }
+                if (at + k < A.out_cap) A.out[at + k] = OBM_TUPLE(OBM_K_COMMENT, or_first(r), or_slash2(r) ? 2 : 1);
+            }
+            acc.lexemes++;
+        }
+    }
+    for (uint32_t k0 = 0; k0 < n_ml; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        if (k >= n_ml) continue;
+        if (k0 == 0 && S.mstat[lane] != MS_NONE) continue; /* staged */
+        const uint32_t o = S.mlist[k];
+        const orec_t r = S.orec[o];
+        const uint32_t d = or_doc(r), dpos = S.dstart[d], dend = S.dstart[d + 1];
+        if (S.dflag[d]) continue;
+        const uint64_t at = base + S.dcnt[d] + (uint32_t)(S.ocnt[o] - S.ocnt[S.dfo[d]]);
+        if (!writing) continue;
+        const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
+        const uint32_t rc = roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv;
+        if (or_plusd(r) != 255u) {
+            DirectSink sink(A.out + at, rc);
+            fast_line(text, dpos + or_first(r), dpos + or_first(r) + or_plusd(r), dpos + or_ls(r), or_line(r), dpos, dend, sink);
+            acc.markers += sink.mk; acc.lexemes += sink.lx;
+        } else {
+            uint32_t mk = 0, lx = 0;
+            generic_line(T, text, r, dpos, dend, A.out + at, rc, &mk, &lx);
+            acc.markers += mk; acc.lexemes += lx;
+        }
+    }
+    WSYNC();
+    /* staged marker tuples: a lane per tuple */
+    {
+        const uint32_t ns = n_ml < MLCAP ? n_ml : MLCAP;
+        for (uint32_t k = 0; k < ns; k++) {
+            const uint32_t ms = S.mstat[k];
+            if (ms == MS_NONE) continue;
+            const uint32_t o = S.mlist[k];
+            const orec_t r = S.orec[o];
+            const uint32_t d = or_doc(r);
+            if (S.dflag[d]) continue;
+            const uint64_t at = base + S.dcnt[d] + (uint32_t)(S.ocnt[o] - S.ocnt[S.dfo[d]]);
+            const uint32_t c = ms >> 16;
+            if (writing && lane < c && at + lane < A.out_cap) A.out[at + lane] = st_unpack(S.u.stage[k * LTS + lane]);
+            if (lane == 0) { acc.markers += ms & 0xFFu; acc.lexemes += (ms >> 8) & 0xFFu; }
+        }
+    }
+    WSYNC(); /* the next unit reuses the shared memory */
+}
+
+} /* namespace obmw */
+#endif

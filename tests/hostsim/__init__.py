@@ -19,9 +19,12 @@ def build(force=False):
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_tile.h"),
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_pipe.h"),
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_large.h"),
+            os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_warp.h"),
+            os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_warp_core.h"),
+            os.path.join(_HERE, "warp_emu.h"),
             os.path.join(_ROOT, "include", "obmarkers.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-shared", "-o", so,
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-Wno-unknown-pragmas", "-shared", "-o", so,
                                srcs[0], srcs[1], srcs[2]])
     return so
 
@@ -40,6 +43,8 @@ def lib():
                                     ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
         L.hs_pipe_batch.restype = ctypes.c_uint64
         L.hs_pipe_batch.argtypes = L.hs_tile_batch.argtypes
+        L.hs_warp_batch.restype = ctypes.c_uint64
+        L.hs_warp_batch.argtypes = L.hs_tile_batch.argtypes
         L.hs_large_doc.restype = ctypes.c_uint64
         L.hs_large_doc.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)]
         L.hs_utf8_plain.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32]
@@ -99,7 +104,8 @@ def fmt_tuples(tuples):
 
 
 def tile_batch(docs, skew=0, pipeline=False):
-    """CTA emulation of the tile fast path (pipeline=0 fused kernel, 1 two-stage pipeline) over a list of documents
+    """Emulation of the device fast paths (pipeline=0 r01 fused tile kernel, 1 r01 two-stage pipeline, 2 the fused warp
+    kernel of mode 0, run by 32 fibers per warp) over a list of documents
     -> (tuples, doc_tuple_off, stats)."""
     L = lib()
     # the batch sits at address = 16k + skew inside a poisoned buffer (readable around it, like the device buffer contract)
@@ -115,7 +121,7 @@ def tile_batch(docs, skew=0, pipeline=False):
     out = np.zeros(cap, dtype=np.uint64)
     toff = np.zeros(len(docs) + 1, dtype=np.uint64)
     stats = np.zeros(4, dtype=np.uint64)
-    fn = L.hs_pipe_batch if pipeline else L.hs_tile_batch
+    fn = {0: L.hs_tile_batch, 1: L.hs_pipe_batch, 2: L.hs_warp_batch}[int(pipeline)]
     n = fn(data.ctypes.data, off.ctypes.data, len(docs), out.ctypes.data, cap, toff.ctypes.data, skew, stats.ctypes.data)
     assert n <= cap
     return out[:n].copy(), toff, stats

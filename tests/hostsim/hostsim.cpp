@@ -484,3 +484,88 @@ extern "C" int hs_utf8_plain(const uint8_t *doc, uint32_t n, uint32_t fake_skew)
     emu.scan(doc, off, 0, 1, fake_skew);
     return (emu.S.dflag[0] & obmt::DF_NONASCII) ? 0 : 1; /* ASCII documents are trivially plain */
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * The fused warp kernel (csrc/obm_warp_core.h, mode 0): the device source itself, compiled for the host and run by
+ * 32 fibers per warp (warp_emu.h).  Units are processed in id order, which is what the look-back chain enforces.
+ * ------------------------------------------------------------------------------------------- */
+#include "warp_emu.h"
+struct uint4 { uint32_t x, y, z, w; };
+#define WLANE() wemu::lane()
+#define WBALLOT(p) wemu::ballot((p))
+#define WSHFL(v, s) wemu::shfl((uint32_t)(v), (uint32_t)(s))
+#define WSHFL_UP(v, d) wemu::shfl_up((uint32_t)(v), (uint32_t)(d))
+#define WSYNC() wemu::sync()
+#define WTEXT(S) ((const uint8_t *)(S).text)
+#define WATOMIC_OR(p, v) (*(p) |= (v))
+static uint64_t g_wstat_fast = 0, g_wstat_generic = 0;
+#define OBMW_STAT(name) (g_wstat_##name++)
+#include "../../operator-builder_b200/csrc/obm_warp_core.h"
+extern "C" void hs_warp_line_stats(uint64_t *fast, uint64_t *generic) { *fast = g_wstat_fast; *generic = g_wstat_generic; }
+
+namespace {
+struct HostHooks {
+    uint64_t base = 0; uint64_t got = 0;
+    void stage(obmw::WarpSmem &S, const void *gsrc, uint32_t nbytes) {
+        if (wemu::lane() == 0) {
+            /* whatever the previous unit left behind stays in the buffer, like on the device; poison only once */
+            memcpy(S.text, gsrc, nbytes);
+        }
+    }
+    void stage_wait(obmw::WarpSmem &, uint32_t) {}
+    uint64_t lookback(uint32_t, uint32_t, uint64_t total) { if (wemu::lane() == 0) got = total; return base; }
+};
+}
+
+extern "C" uint64_t hs_warp_batch(const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs, obm_tuple *out, uint64_t cap,
+                                  uint64_t *tuple_off, uint32_t fake_skew, uint64_t *stats) {
+    (void)fake_skew;
+    using namespace obmw;
+    static WarpSmem S; static wemu::Warp W; static bool poisoned = false;
+    if (!poisoned) { memset(&S, 0x2B, sizeof S); poisoned = true; }
+    const uint64_t total = doc_off[ndocs];
+    const uint64_t ntiles = total / TILE + 1;
+    std::vector<uint32_t> counts(ndocs + 1, 0);
+    uint32_t status[4] = {0, 0, 0, 0}; unsigned long long totals[2] = {0, 0};
+    WArgs A; memset(&A, 0, sizeof A);
+    A.bytes = bytes; A.doc_off = doc_off; A.ndocs = ndocs; A.total_bytes = total; A.ntiles = (uint32_t)ntiles;
+    A.counts = counts.data(); A.out = out; A.out_cap = cap; A.tuple_off = tuple_off; A.status = status; A.totals = totals;
+    /* pass 1: units per tile */
+    std::vector<WRec> recs(ntiles); std::vector<uint64_t> ubase(ntiles + 1, 0);
+    uint32_t d = 0;
+    for (uint64_t t = 0; t < ntiles; t++) {
+        const uint32_t d0 = d;
+        while (d < ndocs && doc_off[d] < (t + 1) * (uint64_t)TILE) d++;
+        recs[t] = make_wrec(doc_off, d0, d);
+        ubase[t + 1] = ubase[t] + recs[t].n_units;
+    }
+    const uint32_t nunits = (uint32_t)ubase[ntiles];
+    HostHooks H; WAcc acc_sum{0, 0, 0, 0};
+    uint64_t st_m = 0, st_l = 0, st_e = 0, st_f = 0;
+    for (uint64_t t = 0; t < ntiles; t++) {
+        for (uint32_t k = 0; k < recs[t].n_units; k++) {
+            uint32_t da, db, extra;
+            wrec_unit(recs[t], k, da, db, extra);
+            if (extra) { /* the large path (k_large_*): counted before, filled after */
+                const uint32_t dl = db;
+                obm::SmallSink s(nullptr, 0); obm::Lexer<obm::SmallSink> lx(TBL, bytes + doc_off[dl], (uint32_t)(doc_off[dl + 1] - doc_off[dl]), s);
+                int st = lx.run<false>(); counts[dl] = s.n_tuples; st_m += s.n_markers; st_l += s.n_lexemes; st_e++; st_f += st == obm::RUN_FATAL;
+            }
+            WAcc lane_acc[32]; memset(lane_acc, 0, sizeof lane_acc);
+            const uint32_t u = (uint32_t)ubase[t] + k;
+            wemu::run(W, [&]() { process_unit(S, A, TBL, H, u, nunits, da, db, extra, lane_acc[wemu::lane()]); });
+            for (int l = 0; l < 32; l++) { st_m += lane_acc[l].markers; st_l += lane_acc[l].lexemes; st_e += lane_acc[l].exact; st_f += lane_acc[l].fatal; }
+            if (extra) {
+                const uint32_t dl = db; const uint64_t at = tuple_off[dl];
+                obm::WriteSink sink(out + at, at < cap ? cap - at : 0);
+                obm::Lexer<obm::WriteSink> lx(TBL, bytes + doc_off[dl], (uint32_t)(doc_off[dl + 1] - doc_off[dl]), sink);
+                lx.run<false>();
+            }
+            H.base += H.got;
+        }
+    }
+    (void)acc_sum;
+    if (ndocs == 0) tuple_off[0] = 0;
+    if (stats) { stats[0] = st_m; stats[1] = st_l; stats[2] = st_e; stats[3] = st_f; }
+    return H.base;
+}

@@ -31,7 +31,7 @@ def pack(docs):
     return data, off
 
 
-def run_and_compare(scanner, oracle, docs, modes=(0, 1, 2)):
+def run_and_compare(scanner, oracle, docs, modes=(0, 1, 2, 3)):
     import operator_builder_b200 as ob
     data, off = pack(docs)
     want_stream, want_off, want_n = oracle.lex_batch_raw(data if len(data) else np.zeros(1, np.uint8), off)
@@ -127,7 +127,7 @@ def test_c2_10k_docs_bit_exact(scanner, oracle):
         doc = raw[i * 4096:(i + 1) * 4096]
         got = ob.decode_doc_raw(doc, res.tuples[int(res.doc_tuple_off[i]):int(res.doc_tuple_off[i + 1])])
         assert got == want_stream[int(want_off[i]):int(want_off[i + 1])], i
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         scanner.set_mode(mode)
         res1 = scanner.lex_batch(data, off)
         assert np.array_equal(res.tuples, res1.tuples) and np.array_equal(res.doc_tuple_off, res1.doc_tuple_off), mode
@@ -145,7 +145,7 @@ def test_chunked_overlapped_host_path(scanner, oracle):
     one = scanner.lex_batch(pdata, poff)
     old = scanner.set_chunk_bytes(1 << 20)
     try:
-        for mode in (0, 1):
+        for mode in (0, 1, 3):
             scanner.set_mode(mode)
             res = scanner.lex_batch(pdata, poff)
             assert np.array_equal(res.tuples, one.tuples) and np.array_equal(res.doc_tuple_off, one.doc_tuple_off), mode
@@ -238,10 +238,14 @@ def test_valid_utf8_documents_stay_line_parallel(scanner, oracle):
         docs.append(d.replace(b"plain", "plén".encode(), 1) if i % 3 else d)
     docs += list(cu.NON_ASCII) + ["# caf\u00e9\u00a0+a:b\n".encode(), b"k: v\n\xff\n# +a:b\n"]
     run_and_compare(scanner, oracle, docs)
+    # valid UTF-8 without Unicode white space: r01's pipeline (mode 3) keeps such documents line-parallel (only the lines
+    # with bytes >= 0x80 take the Unicode lexer); the fused warp kernel (mode 0) lexes exactly those documents sequentially
+    plain = docs[:len(docs) - len(cu.NON_ASCII) - 2]
+    data, off = pack(plain)
+    scanner.set_mode(3)
+    assert scanner.lex_batch(data, off).stats["n_docs_exact"] == 0
     scanner.set_mode(0)
-    data, off = pack(docs[:len(docs) - len(cu.NON_ASCII) - 2])
-    res = scanner.lex_batch(data, off)
-    assert res.stats["n_docs_exact"] == 0
+    assert scanner.lex_batch(data, off).stats["n_docs_exact"] == sum(any(b >= 0x80 for b in d) for d in plain)
 
 
 def test_device_entry_point_and_capacity(scanner, oracle):
@@ -305,7 +309,7 @@ def test_full_size_properties_on_device(scanner):
     scanner.generate_corpus_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, doc_bytes, 0, 1, st)
     cap = ndocs * doc_bytes // 8
     outs = []
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         scanner.set_mode(mode)
         d_out = torch.zeros(cap, dtype=torch.int64, device=dev)
         d_toff = torch.zeros(ndocs + 1, dtype=torch.int64, device=dev)
@@ -318,7 +322,7 @@ def test_full_size_properties_on_device(scanner):
         assert int(d_counts[0].item()) == 8 * ndocs
         outs.append((d_out, d_toff, int(d_toff[-1].item()), int(d_counts[1].item())))
     scanner.set_mode(0)
-    for k in (1, 2):
+    for k in (1, 2, 3):
         assert outs[0][2] == outs[k][2] and outs[0][3] == outs[k][3]
         assert torch.equal(outs[0][1], outs[k][1]) and torch.equal(outs[0][0], outs[k][0])
     # shard property: documents [100000, 100000+4096) regenerated alone give the same tuples

@@ -12,9 +12,12 @@ from tests import corpus_util as cu
 from tests import hostsim
 
 
-def check_batch(docs, skew=0):
-    """both device organisations -- the fused tile kernel and the two-stage pipeline -- against the exact path"""
-    for pipeline in (0, 1):
+def check_batch(docs, skew=0, which=1):
+    """every device organisation -- r01's fused tile kernel (0) and two-stage pipeline (1), and the fused warp kernel of
+    mode 0 (2; the device source itself, run by 32 fibers per warp) -- against the exact path.  Returns the stats of
+    organisation `which`."""
+    keep = None
+    for pipeline in (0, 1, 2):
         tup, toff, stats = hostsim.tile_batch(docs, skew, pipeline=pipeline)
         for i, doc in enumerate(docs):
             want = hostsim.lex_doc(doc)
@@ -26,7 +29,9 @@ def check_batch(docs, skew=0):
         kinds = (tup >> np.uint64(59)).astype(np.int64)
         assert int(stats[0]) == int((kinds == 2).sum()), (pipeline, stats)
         assert int(stats[1]) == int(((kinds < 21) | (kinds > 25)).sum()), (pipeline, stats)
-    return stats
+        if pipeline == which:
+            keep = stats
+    return keep
 
 
 def test_dense_marker_lines_long_lines_and_large_documents():
@@ -85,6 +90,9 @@ def test_non_ascii_documents():
                 many.append(base[:-1] + u.encode() + b"\n" + b"# " + u.encode() + b" +s:t=1\n")
     stats = check_batch(many, skew=5)
     assert int(stats[2]) == 0
+    # the fused warp kernel sends every document with a byte >= 0x80 to the exact lexer, and no other
+    stats = check_batch(docs + many, skew=3, which=2)
+    assert int(stats[2]) == sum(any(b >= 0x80 for b in d) for d in docs + many)
 
 
 def test_fixtures_and_golden():

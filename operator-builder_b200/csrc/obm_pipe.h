@@ -62,7 +62,8 @@ struct LineAccelT {
         while (p < line_end) {
             uint32_t mis = obm::src_mis(d, p);
             uint32_t w = obm::src_ldw(d, (int32_t)p - (int32_t)mis);
-            uint32_t sp = obmt::zero_bytes4((w & 0xF3F3F3F3u) ^ 0x23232323u) >> mis;
+            /* exact form: the aligned word may hold bytes >= 0x80 of a NEIGHBOURING document below p, whose carries would hide a match */
+            uint32_t sp = obmt::zero_bytes4_exact((w & 0xF3F3F3F3u) ^ 0x23232323u) >> mis;
             if (sp) {
 #if defined(__CUDA_ARCH__)
                 uint32_t q = p + (uint32_t)(__ffs((int)sp) - 1);

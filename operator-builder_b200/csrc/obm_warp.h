@@ -177,8 +177,9 @@ template <class Src>
 OBM_HD uint32_t scan_byte_or_nl(const Src &t, uint32_t p, uint32_t lim, uint32_t c) {
     const uint32_t rep = c * 0x01010101u;
     uint32_t a = p & ~3u;
-    uint32_t w = tw_ldw(t, a);
-    uint32_t z = (zflag7(w ^ rep) | zflag7(w ^ 0x0A0A0A0Au)) & (0xFFFFFFFFu << ((p & 3u) * 8u));
+    const uint32_t from = 0xFFFFFFFFu << ((p & 3u) * 8u);
+    uint32_t w = tw_ldw(t, a) & from; /* bytes below p may belong to a neighbouring document (>= 0x80: their carries would hide a match) */
+    uint32_t z = (zflag7(w ^ rep) | zflag7(w ^ 0x0A0A0A0Au)) & from;
     for (;;) {
         if (z) { const uint32_t q = a + ((OBMW_FFS(z) - 1u) >> 3); return q < lim ? q : lim; }
         a += 4u;

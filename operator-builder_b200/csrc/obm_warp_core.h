@@ -113,6 +113,9 @@ OBM_HD uint32_t generic_line(const obm::Tables &T, const Src &text, orec_t r, ui
     uint32_t e = or_first(r); /* end of the line: the generic lexer's skipping is bounded by it (obmp::LineAccel) */
     while (e < n && text[dpos + e] != '\n') e++;
     const obmp::item_t it = obmp::make_marker_item(or_ls(r), or_first(r), or_line(r), 0, e);
+#ifdef OBMW_DEBUG
+    { uint32_t rr = obmp::k2_marker_item(T, obm::src_add(text, dpos), n, it, out, cap, mk, lx); fprintf(stderr, "   generic: n %u e %u item ls %u first %u line %u le %u -> %08x\n", n, e, obmp::it_ls(it), obmp::it_pos(it), obmp::it_line(it), obmp::it_line_end(it), rr); return rr; }
+#endif
     return obmp::k2_marker_item(T, obm::src_add(text, dpos), n, it, out, cap, mk, lx);
 }
 
@@ -212,6 +215,9 @@ OBMW_DEV void process_unit(WarpSmem &S, const WArgs &A, const obm::Tables &T, Ho
             nl_run += tot & 0xFFFFu; own_run += tot >> 16;
         }
         WSYNC();
+#ifdef OBMW_DEBUG
+        if (lane == 0) fprintf(stderr, "unit %u da %u nd %u lo %u hi %u owners %u nl_run %u first_own %u\n", u, da, nd, lo_pos, hi_pos, own_run, nl_run, own_run ? (uint32_t)S.orec[0] : 0u);
+#endif
         n_owners = own_run;
         if (n_owners > OWN_CAP) { n_owners = 0; if (lane < nd) S.dflag[lane] |= DF_QOVERFLOW; }
         WSYNC();
@@ -276,6 +282,9 @@ OBMW_DEV void process_unit(WarpSmem &S, const WArgs &A, const obm::Tables &T, Ho
                 }
                 if (cntv >= 0xFFFFu) { WATOMIC_OR(&S.dflag[d], DF_INTERACT); cntv = 0; }
                 S.ocnt[o] = (uint16_t)cntv;
+#ifdef OBMW_DEBUG
+                fprintf(stderr, "  C: unit %u o %u res %u cnt %u staged %d dflag %u plusd %u first %u ls %u line %u\n", u, o, res, cntv, (int)stg, S.dflag[d], or_plusd(r), or_first(r), or_ls(r), or_line(r));
+#endif
                 if (staged) S.mstat[lane] = (stg && cntv) ? (sink.mk | (sink.lx << 8) | (cntv << 16)) : MS_NONE; /* cntv <= LTS: the counters fit */
             }
         }
@@ -319,6 +328,9 @@ OBMW_DEV void process_unit(WarpSmem &S, const WArgs &A, const obm::Tables &T, Ho
             dtot = p1 - p0 + 1u; /* + EOF */
         }
     }
+#ifdef OBMW_DEBUG
+    if (lane < nd) fprintf(stderr, "  D: unit %u doc %u dflag %u dtot %u dfo %u..%u n_owners %u\n", u, lane, dflag, dtot, S.dfo[lane], S.dfo[lane + 1], n_owners);
+#endif
     uint32_t dincl = lane < nd ? dtot : 0u;
     OBMW_SCAN_INCL(dincl);
     const uint32_t dexcl = dincl - (lane < nd ? dtot : 0u);

@@ -24,7 +24,7 @@ def build(force=False):
             os.path.join(_HERE, "warp_emu.h"),
             os.path.join(_ROOT, "include", "obmarkers.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-Wno-unknown-pragmas", "-shared", "-o", so,
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-Wno-unknown-pragmas", *(["-DOBMW_DEBUG"] if os.environ.get("OBMW_DEBUG") else []), "-shared", "-o", so,
                                srcs[0], srcs[1], srcs[2]])
     return so
 

@@ -53,6 +53,16 @@ def test_dense_marker_lines_long_lines_and_large_documents():
     check_batch([b""] * 200 + [big] + [b""] * 3)
 
 
+def test_non_ascii_neighbour_in_the_same_aligned_word():
+    """a document whose last bytes are >= 0x80 followed, inside the same aligned 4-byte word, by an ASCII document that
+    starts with a marker: the word-wise skipping of the line lexers must not let the neighbour's bytes hide the '+'"""
+    for tail in (b"\xff", b"\xc3\xa9", b"\xf0\x9f\x98\x80", b"\x80\xff\xfe"):
+        for pad in range(0, 9):
+            docs = [b"x" * pad + b"k: v\n" + tail, b"+lerhacA\n9='", b"k" * pad + tail, b"+a:b=\"q\",c\n", b"y" * pad + tail, b"# +a:b:c='x',d=1\n"]
+            for skew in (0, 1, 2, 3, 6):
+                check_batch(docs, skew)
+
+
 def test_targeted_as_one_batch():
     docs = list(cu.TARGETED)
     for skew in (0, 1, 7, 15):

@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libobmarkers.so")
+SO_PATH = os.environ.get("OBM_LIB") or os.path.join(_HERE, "libobmarkers.so")  # OBM_LIB: a build variant (tuning experiments)
 
 OBM_OK, OBM_E_NO_DEVICE, OBM_E_CUDA, OBM_E_CAPACITY, OBM_E_ARG, OBM_E_NOMEM = 0, -1, -2, -3, -4, -5
 

@@ -127,11 +127,14 @@ __device__ __forceinline__ uint64_t lookback_read_warp(volatile uint64_t *state,
  * earlier elements of its own block and for a 32-wide walk over blocks, so one round trip advances the
  * resolved frontier by up to 1024 elements instead of 32.  Executed by all 32 lanes; returns the exclusive
  * prefix of element t (n = number of elements). */
-__device__ __forceinline__ uint64_t lookback2_warp(volatile uint64_t *st0, volatile uint64_t *st1, uint32_t t, uint32_t n, uint64_t my_total) {
+__device__ __forceinline__ void lookback2_publish(volatile uint64_t *st0, uint32_t t, uint64_t my_total) {
+    if ((threadIdx.x & 31) == 0) { st0[t] = LB_AGG | my_total; __threadfence(); }
+}
+/* the waiting half; may run long after lookback2_publish (the fused warp kernel scans its next unit in between) */
+__device__ __forceinline__ uint64_t lookback2_resolve(volatile uint64_t *st0, volatile uint64_t *st1, uint32_t t, uint32_t n, uint64_t my_total) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t b = t >> 5, r = t & 31;
     const uint32_t bs = min(32u, n - (b << 5));
-    if (lane == 0) { st0[t] = LB_AGG | my_total; __threadfence(); }
     uint64_t s;
     for (;;) {
         s = lane < r ? st0[(b << 5) + lane] : LB_AGG;
@@ -143,6 +146,10 @@ __device__ __forceinline__ uint64_t lookback2_warp(volatile uint64_t *st0, volat
     for (int o = 16; o > 0; o >>= 1) partial += __shfl_xor_sync(0xffffffffu, partial, o);
     const uint64_t P = (r == bs - 1) ? lookback_warp(st1, b, partial + my_total) : lookback_read_warp(st1, b);
     return P + partial;
+}
+__device__ __forceinline__ uint64_t lookback2_warp(volatile uint64_t *st0, volatile uint64_t *st1, uint32_t t, uint32_t n, uint64_t my_total) {
+    lookback2_publish(st0, t, my_total);
+    return lookback2_resolve(st0, st1, t, n, my_total);
 }
 
 /* ---- pre-kernel: tile -> first document map, list of large documents ----------------------------- */

@@ -642,7 +642,7 @@ static uint64_t warp_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
     const uint64_t nt = warp_ntiles(total_bytes), um = warp_units_max(ndocs, total_bytes);
     return align_up((nt + 2) * 4, 256) + align_up((obm_fast_max_large(total_bytes) + 1) * 4, 256) + align_up(nt * 4 + 4, 256) + align_up((nt + 1) * 8, 256) +
            align_up(((uint64_t)scan_tiles((uint32_t)nt) + 1) * 8, 256) + align_up((nt + 1) * sizeof(obmw::WRec), 256) + align_up((um + 1) * 8, 256) +
-           align_up((um / 32 + 2) * 8, 256) + 512;
+           align_up(2 * (um / 32 + 2) * 8, 256) + 512;
 }
 /* tile index -> (large documents planned and counted on a side stream) units per tile + scan -> k_warp_scan -> fill of
  * the large documents */
@@ -666,10 +666,10 @@ static int obm_warp_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t
     A.bytes = d_bytes; A.doc_off = d_doc_off; A.ndocs = ndocs; A.total_bytes = total_bytes; A.tile_first = tile_first; A.ntiles = ntiles;
     A.wrec = wrec; A.ubase = ubase;
     A.st_tuples = (uint64_t *)q; q += up((um + 1) * 8);
-    A.st_blocks = (uint64_t *)q; q += up((um / 32 + 2) * 8);
+    A.st_blocks = (uint64_t *)q; q += up(2 * (um / 32 + 2) * 8); A.units_max = um;
     A.ctl = (uint32_t *)q; /* [0] ticket, [1] n_large */
     A.counts = counts; A.out = d_out; A.out_cap = d_out ? out_cap : 0; A.tuple_off = toff; A.status = status; A.totals = totals;
-    OBM_CUDA(h, cudaMemsetAsync(A.st_tuples, 0, up((um + 1) * 8) + up((um / 32 + 2) * 8) + 64, st)); /* look-back chains + control words */
+    OBM_CUDA(h, cudaMemsetAsync(A.st_tuples, 0, up((um + 1) * 8) + up(2 * (um / 32 + 2) * 8) + 64, st)); /* chain arrays + control words */
     obmw::k_wtile_index<<<(ndocs + 1 + 255) / 256, 256, 0, st>>>(d_doc_off, ndocs, ntiles, tile_first, large_list, A.ctl + 1);
     int dev_sms = 0, per_sm = 0;
     OBM_CUDA(h, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));

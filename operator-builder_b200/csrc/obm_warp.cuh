@@ -22,7 +22,7 @@
 
 namespace obmw {
 
-constexpr uint32_t WPC = 4; /* warps per CTA; each works alone on its own shared-memory slice */
+constexpr uint32_t WPC = 1; /* warps per CTA; each works alone on its own shared-memory slice (1: the most warps a given amount of shared memory allows) */
 enum { WC_TICKET = 0 };
 
 __global__ void __launch_bounds__(256)
@@ -48,7 +48,7 @@ k_wunits(const uint64_t *__restrict__ doc_off, const uint32_t *__restrict__ tile
 }
 
 struct DevHooks {
-    const WArgs &A; uint32_t phase;
+    uint32_t phase;
     __device__ __forceinline__ void stage(WarpSmem &S, const void *gsrc, uint32_t nbytes) {
         if (WLANE() == 0 && nbytes) {
             obmf::fence_proxy_async(); /* the warp's earlier generic-proxy accesses to S.text precede the async write */
@@ -59,9 +59,66 @@ struct DevHooks {
     __device__ __forceinline__ void stage_wait(WarpSmem &S, uint32_t nbytes) {
         if (nbytes) { obmf::mbar_wait(&S.mbar, phase); phase ^= 1u; }
     }
-    __device__ __forceinline__ uint64_t lookback(uint32_t u, uint32_t n, uint64_t total) { return obmf::lookback2_warp(A.st_tuples, A.st_blocks, u, n, total); }
 };
 
+/* ---- the chain over the units' tuple counts ---------------------------------------------------------------
+ * Two levels, both fed at PUBLISH time so that nothing on it depends on another warp's (deferred) resolve:
+ *   st0[u]   LB_AGG | tuples of unit u                                  (plain store: flag and value are one word)
+ *   blk[b]   atomic accumulator of block b = units [32b, 32b+32): count << 56 | sum of tuples
+ *   bex[b]   BEX_FLAG | exclusive prefix of block b, stored by whichever unit of the block resolves it first
+ * resolve(u) = bex[b] (or a walk back over complete blocks, 32 per step, down to the nearest stored prefix) + the
+ * st0 entries of the earlier units of u's own block. */
+#define BEX_FLAG (1ull << 63)
+__device__ __forceinline__ void chain_publish(const WArgs &A, uint32_t u, uint64_t total) {
+    if ((threadIdx.x & 31) == 0) {
+        reinterpret_cast<volatile uint64_t *>(A.st_tuples)[u] = LB_AGG | total;
+        atomicAdd(reinterpret_cast<unsigned long long *>(A.st_blocks) + (u >> 5), (unsigned long long)((1ull << 56) | total));
+    }
+}
+__device__ __forceinline__ uint64_t chain_resolve(const WArgs &A, uint32_t u, uint32_t nblocks) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t b = u >> 5, r = u & 31;
+    volatile uint64_t *st0 = A.st_tuples, *blk = A.st_blocks, *bex = A.st_blocks + nblocks;
+    uint64_t s;
+    for (;;) {
+        s = lane < r ? st0[(b << 5) + lane] : LB_AGG;
+        if (__ballot_sync(0xffffffffu, (s >> 62) == 0) == 0) break;
+        __nanosleep(64);
+    }
+    uint64_t partial = s & LB_MASK;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) partial += __shfl_xor_sync(0xffffffffu, partial, o);
+    uint64_t P = 0;
+    const uint64_t mine = b ? bex[b] : BEX_FLAG;
+    if (mine & BEX_FLAG) P = mine & ~BEX_FLAG;
+    else {
+        int64_t hi = (int64_t)b - 1; /* nearest block not yet accounted for */
+        for (;;) {
+            const int64_t j = hi - (int64_t)lane;
+            const uint64_t e = j > 0 ? bex[j] : BEX_FLAG /* block 0 (and the virtual ones before it) start at 0 */;
+            const uint64_t a = j >= 0 ? blk[j] : (32ull << 56);
+            const uint32_t have = __ballot_sync(0xffffffffu, (e & BEX_FLAG) != 0);
+            const uint32_t part = __ballot_sync(0xffffffffu, (a >> 56) != 32u); /* every block before b is a full one */
+            const uint32_t upto = have ? (uint32_t)__ffs((int)have) - 1u : 31u;
+            const uint32_t need = upto == 31u ? 0xffffffffu : ((2u << upto) - 1u);
+            if (part & need) { __nanosleep(64); continue; }
+            uint64_t v = lane <= upto ? (a & ((1ull << 56) - 1)) : 0;
+            if (have && lane == upto) v += e & ~BEX_FLAG;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            P += v;
+            if (have) break;
+            hi -= 32;
+        }
+        if (lane == 0) bex[b] = BEX_FLAG | P;
+    }
+    return P + partial;
+}
+
+/* Software pipeline over the warp's units: scan unit i (compute_unit), publish its tuple count to the look-back
+ * chain, THEN write unit i-1 (whose exclusive prefix has had a whole unit's time to arrive: no waiting on the
+ * chain), then scan unit i+1 ...  A unit whose write needs the staged text (documents for the exact lexer,
+ * marker lines that are not staged) is written at once instead. */
 __global__ void __launch_bounds__(WPC * 32)
 k_warp_scan(WArgs A) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -71,8 +128,10 @@ k_warp_scan(WArgs A) {
     __syncwarp();
     const obm::Tables T = obmq::dev_tables();
     const uint32_t nunits = (uint32_t)A.ubase[A.ntiles];
-    DevHooks H{A, 0};
+    const uint32_t nblocks = (uint32_t)(A.units_max / 32 + 2); /* layout of st_blocks: blk[nblocks] | bex[nblocks] */
+    DevHooks H{0};
     WAcc acc{0, 0, 0, 0};
+    UnitRegs pend; bool have_pend = false; uint32_t cur = 0;
     /* the next tile's ticket is taken while this one is processed (the atomic's round trip is off the critical path) */
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(&A.ctl[WC_TICKET], 1u);
@@ -85,9 +144,24 @@ k_warp_scan(WArgs A) {
         for (uint32_t k = 0; k < rec.n_units; k++) {
             uint32_t da, db, extra;
             wrec_unit(rec, k, da, db, extra);
-            process_unit(S, A, T, H, u0 + k, nunits, da, db, extra, acc);
+            UnitRegs R;
+            compute_unit(S, S.set[cur], A, T, H, u0 + k, da, db, extra, R);
+            chain_publish(A, R.u, R.total);
+            if (have_pend) {
+                const uint64_t base = chain_resolve(A, pend.u, nblocks);
+                write_unit(S, S.set[cur ^ 1u], A, T, pend, nunits, base, acc);
+                have_pend = false;
+            }
+            if (R.needs_text) {
+                const uint64_t base = chain_resolve(A, R.u, nblocks);
+                write_unit(S, S.set[cur], A, T, R, nunits, base, acc);
+            } else { pend = R; have_pend = true; cur ^= 1u; }
         }
         t = __shfl_sync(0xffffffffu, tn, 0);
+    }
+    if (have_pend) {
+        const uint64_t base = chain_resolve(A, pend.u, nblocks);
+        write_unit(S, S.set[cur ^ 1u], A, T, pend, nunits, base, acc);
     }
     uint32_t markers = acc.markers, lexemes = acc.lexemes, exact = acc.exact, fatal = acc.fatal;
 #pragma unroll

@@ -10,8 +10,9 @@
  *     WTEXT(S)               the byte source of the staged text (ShBytes on the device, pointer on the host)
  *     WATOMIC_OR(p, v)       atomicOr on shared memory
  * and supplies a Hooks type with
- *     stage(S, gsrc, nbytes) bring nbytes (multiple of 16) from the 16-byte aligned global address gsrc into S.text
- *     lookback(u, n, total)  exclusive prefix of unit u's tuple count over the units (all lanes; returns in all)
+ *     stage(W, gsrc, nbytes) bring nbytes (multiple of 16) from the 16-byte aligned global address gsrc into W.text
+ *     stage_wait(W, nbytes)  ... and wait for them
+ * The look-back chain over the units' tuple counts is driven by the caller between compute_unit and write_unit.
  */
 #ifndef OBM_WARP_CORE_H
 #define OBM_WARP_CORE_H
@@ -29,30 +30,43 @@
 
 namespace obmw {
 
-struct WarpSmem {
-    alignas(16) uint8_t text[BUFB + 64];
+/* what the (deferred) write of a unit needs; double-buffered so that a warp can scan its next unit while the tuple
+ * counts of the previous one travel through the look-back chain */
+struct UnitSet {
     union {
         struct { uint32_t nlw[NWORDS]; uint32_t spw[NWORDS]; } bm; /* phases A, B */
-        uint32_t stage[MLCAP * LTS];                               /* phases C, D (the bitmaps are dead by then) */
+        uint32_t stage[MLCAP * LTS];                               /* phase C on (the bitmaps are dead by then) */
     } u;
-    uint16_t nlpre[NWORDS];     /* newline bits in words [0, w) */
     orec_t orec[OWN_CAP];       /* phase A: position of the line's first special; phase B: owner record */
-    uint16_t ocnt[OWN_CAP];     /* tuples of the owner; after the scan: exclusive prefix over owners */
-    uint16_t mlist[OWN_CAP];    /* marker rank -> owner */
+    uint16_t opos[OWN_CAP];     /* tuples of the owner; after the assembly: its tuple position inside the unit */
+    uint8_t mlist[OWN_CAP];     /* marker rank -> owner */
+    uint32_t mstat[MLCAP];      /* staged line: markers | lexemes << 8 | tuples << 16; MS_NONE: not staged */
+};
+struct WarpSmem {
+    alignas(16) uint8_t text[BUFB + 64];
+    UnitSet set[2];
+    uint16_t nlpre[NWORDS];     /* newline bits in words [0, w) */
     uint32_t dstart[DMAX + 2];  /* document starts, buffer-relative; [nd] = end */
     uint32_t dflag[DMAX + 1];
-    uint32_t dcnt[DMAX + 1];    /* tuples of the document; after the scan: exclusive offsets inside the unit */
+    uint32_t dcnt[DMAX + 1];    /* exclusive tuple offsets of the documents inside the unit */
     uint16_t dfo[DMAX + 2];     /* first owner of the document */
-    uint32_t mstat[MLCAP];      /* staged line: markers | lexemes << 8 | tuples << 16; MS_NONE: not staged */
     alignas(8) uint64_t mbar;
 };
 static_assert(sizeof(uint32_t) * MLCAP * LTS <= sizeof(uint32_t) * 2 * NWORDS, "the staging area overlays the bitmaps");
+static_assert(OWN_CAP <= 256, "mlist holds owner indices in a byte");
+
+/* a scanned unit between its two halves: warp-uniform values, and one document per lane */
+struct UnitRegs {
+    uint32_t u, da, nd, extra, n_owners, n_ml; uint64_t total; bool needs_text;
+    uint32_t dflag, dtot, dexcl, dlen; /* lane d < nd: document da + d */
+};
 
 struct WArgs {
     const uint8_t *bytes; const uint64_t *doc_off; uint32_t ndocs; uint64_t total_bytes;
     const uint32_t *tile_first; uint32_t ntiles;
     const WRec *wrec; const uint64_t *ubase; /* [ntiles + 1] exclusive scan of units per tile */
-    uint64_t *st_tuples, *st_blocks;         /* two-level look-back chain over units */
+    uint64_t *st_tuples, *st_blocks;         /* chain over the units' tuple counts (obm_warp.cuh: chain_publish / chain_resolve) */
+    uint64_t units_max;                      /* capacity the chain arrays were carved for */
     const uint32_t *counts;                  /* tuple counts of large documents (k_large_resolve) */
     obm_tuple *out; uint64_t out_cap; uint64_t *tuple_off;
     uint32_t *status; unsigned long long *totals; uint32_t *ctl;
@@ -61,10 +75,10 @@ struct WAcc { uint32_t markers, lexemes, exact, fatal; };
 constexpr uint32_t MS_NONE = 0xFFFFFFFFu;
 
 /* ---- bitmap helpers (phase B) ------------------------------------------------------------------------- */
-OBM_HD bool w_is_nl(const WarpSmem &S, uint32_t pos) { return (S.u.bm.nlw[pos >> 5] >> (pos & 31)) & 1u; }
-OBM_HD bool w_is_sp(const WarpSmem &S, uint32_t pos) { return (S.u.bm.spw[pos >> 5] >> (pos & 31)) & 1u; }
+OBM_HD bool w_is_nl(const UnitSet &S, uint32_t pos) { return (S.u.bm.nlw[pos >> 5] >> (pos & 31)) & 1u; }
+OBM_HD bool w_is_sp(const UnitSet &S, uint32_t pos) { return (S.u.bm.spw[pos >> 5] >> (pos & 31)) & 1u; }
 /* first position >= from whose special or newline bit is set, or hi */
-OBM_FN uint32_t w_next_event(const WarpSmem &S, uint32_t from, uint32_t hi) {
+OBM_FN uint32_t w_next_event(const UnitSet &S, uint32_t from, uint32_t hi) {
     if (from >= hi) return hi;
     uint32_t w = from >> 5;
     uint32_t m = (S.u.bm.spw[w] | S.u.bm.nlw[w]) & (0xFFFFFFFFu << (from & 31));
@@ -77,7 +91,7 @@ OBM_FN uint32_t w_next_event(const WarpSmem &S, uint32_t from, uint32_t hi) {
     return pos < hi ? pos : hi;
 }
 /* position after the last newline bit below pos (or lo) */
-OBM_FN uint32_t w_line_start(const WarpSmem &S, uint32_t pos, uint32_t lo) {
+OBM_FN uint32_t w_line_start(const UnitSet &S, uint32_t pos, uint32_t lo) {
     uint32_t w = pos >> 5;
     uint32_t m = S.u.bm.nlw[w] & ((1u << (pos & 31)) - 1u);
     const uint32_t wlo = lo >> 5;
@@ -93,10 +107,10 @@ OBM_FN uint32_t w_line_start(const WarpSmem &S, uint32_t pos, uint32_t lo) {
     const uint32_t ls = w * 32 + top + 1;
     return ls > lo ? ls : lo;
 }
-OBM_HD uint32_t w_nl_before(const WarpSmem &S, uint32_t q) {
+OBM_HD uint32_t w_nl_before(const WarpSmem &W, const UnitSet &S, uint32_t q) {
     const uint32_t w = q >> 5;
-    if (w >= NWORDS) return (uint32_t)S.nlpre[NWORDS - 1] + OBMT_POPC(S.u.bm.nlw[NWORDS - 1]);
-    return (uint32_t)S.nlpre[w] + OBMT_POPC(S.u.bm.nlw[w] & ((1u << (q & 31)) - 1u));
+    if (w >= NWORDS) return (uint32_t)W.nlpre[NWORDS - 1] + OBMT_POPC(S.u.bm.nlw[NWORDS - 1]);
+    return (uint32_t)W.nlpre[w] + OBMT_POPC(S.u.bm.nlw[w] & ((1u << (q & 31)) - 1u));
 }
 
 /* inclusive warp scan of a u32 */
@@ -113,33 +127,29 @@ OBM_HD uint32_t generic_line(const obm::Tables &T, const Src &text, orec_t r, ui
     uint32_t e = or_first(r); /* end of the line: the generic lexer's skipping is bounded by it (obmp::LineAccel) */
     while (e < n && text[dpos + e] != '\n') e++;
     const obmp::item_t it = obmp::make_marker_item(or_ls(r), or_first(r), or_line(r), 0, e);
-#ifdef OBMW_DEBUG
-    { uint32_t rr = obmp::k2_marker_item(T, obm::src_add(text, dpos), n, it, out, cap, mk, lx); fprintf(stderr, "   generic: n %u e %u item ls %u first %u line %u le %u -> %08x\n", n, e, obmp::it_ls(it), obmp::it_pos(it), obmp::it_line(it), obmp::it_line_end(it), rr); return rr; }
-#endif
     return obmp::k2_marker_item(T, obm::src_add(text, dpos), n, it, out, cap, mk, lx);
 }
 
+/* ---- first half: phases A, B, C and the assembly of the unit's tuple positions --------------------------- */
 template <class Hooks>
-OBMW_DEV void process_unit(WarpSmem &S, const WArgs &A, const obm::Tables &T, Hooks &H, uint32_t u, uint32_t nunits, uint32_t da, uint32_t db,
-                         uint32_t extra, WAcc &acc) {
+OBMW_DEV void compute_unit(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tables &T, Hooks &H, uint32_t u, uint32_t da, uint32_t db,
+                           uint32_t extra, UnitRegs &R) {
     const uint32_t lane = WLANE();
     const uint32_t nd = db - da;
-    const bool writing = A.out != nullptr && A.out_cap != 0;
     uint32_t n_owners = 0, n_ml = 0;
     uint32_t lo_pos = 0, hi_pos = 0;
-    uint64_t b0 = 0;
+    bool unstaged = false;
     if (nd) {
-        b0 = A.doc_off[da];
-        const uint64_t b1 = A.doc_off[db];
+        const uint64_t b0 = A.doc_off[da], b1 = A.doc_off[db];
         const uint64_t abs0 = (uint64_t)(uintptr_t)A.bytes + b0, base_abs = abs0 & ~15ull;
         const uint32_t skew = (uint32_t)(abs0 - base_abs), span = (uint32_t)(b1 - b0) + skew, load = (span + 15u) & ~15u;
         lo_pos = skew; hi_pos = span;
-        H.stage(S, (const void *)(uintptr_t)base_abs, load);
-        if (lane <= nd) S.dstart[lane] = (uint32_t)(A.doc_off[da + lane] - b0) + skew;
-        if (lane < nd) S.dflag[lane] = 0;
+        H.stage(W, (const void *)(uintptr_t)base_abs, load);
+        if (lane <= nd) W.dstart[lane] = (uint32_t)(A.doc_off[da + lane] - b0) + skew;
+        if (lane < nd) W.dflag[lane] = 0;
         WSYNC();
-        H.stage_wait(S, load);
-        const auto text = WTEXT(S);
+        H.stage_wait(W, load);
+        const auto text = WTEXT(W);
 
         /* ---- A: rows ---- */
         const uint32_t nrows = (span + ROW - 1) / ROW;
@@ -148,34 +158,34 @@ OBMW_DEV void process_unit(WarpSmem &S, const WArgs &A, const obm::Tables &T, Ho
             const uint32_t row0 = r * ROW, pos0 = row0 + lane * 32u;
             uint32_t x[8];
             {
-                const uint4 a = reinterpret_cast<const uint4 *>(S.text + pos0)[0], b = reinterpret_cast<const uint4 *>(S.text + pos0)[1];
+                const uint4 a = reinterpret_cast<const uint4 *>(W.text + pos0)[0], b = reinterpret_cast<const uint4 *>(W.text + pos0)[1];
                 x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
             }
             const Masks m = classify32(x);
             const uint32_t keep = range_mask(pos0, lo_pos, hi_pos);
             uint32_t nl = m.nl & keep;
             const uint32_t hp = m.hp & keep, sl = m.sl & keep;
-            /* bytes >= 0x80 inside the range: the documents that touch this lane's 32 bytes take the exact lexer */
+            /* bytes >= 0x80 inside the range: the documents that hold them take the exact lexer */
             bool na = false;
             if (m.hi && keep) {
                 if (keep == 0xFFFFFFFFu) na = true;
-                else for (uint32_t k = 0; k < 32; k++) if (((keep >> k) & 1u) && S.text[pos0 + k] >= 0x80) na = true;
+                else for (uint32_t k = 0; k < 32; k++) if (((keep >> k) & 1u) && W.text[pos0 + k] >= 0x80) na = true;
             }
             const uint32_t nab = WBALLOT(na);
             if (nab && lane < nd) { /* rare: exact attribution, byte by byte */
-                const uint32_t q = S.dstart[lane], e = S.dstart[lane + 1];
+                const uint32_t q = W.dstart[lane], e = W.dstart[lane + 1];
                 for (uint32_t mm = nab; mm; mm &= mm - 1) {
                     const uint32_t l0 = row0 + (OBMW_FFS(mm) - 1u) * 32u;
                     const uint32_t a = q > l0 ? q : l0, b = e < l0 + 32u ? e : l0 + 32u;
-                    for (uint32_t p = a; p < b; p++) if (S.text[p] >= 0x80) S.dflag[lane] |= DF_NONASCII;
+                    for (uint32_t p = a; p < b; p++) if (W.text[p] >= 0x80) W.dflag[lane] |= DF_NONASCII;
                 }
             }
             /* "//": a '/' whose successor is a '/' (the successor of the lane's last byte sits in the next lane's chunk) */
-            const uint32_t nxt = (pos0 + 32u < hi_pos && S.text[pos0 + 32u] == '/') ? 0x80000000u : 0u;
+            const uint32_t nxt = (pos0 + 32u < hi_pos && W.text[pos0 + 32u] == '/') ? 0x80000000u : 0u;
             uint32_t ss = sl & ((sl >> 1) | nxt);
             /* virtual newline on the byte before every document start (a line starts there, whatever the byte is) */
             while (nextd < nd) {
-                const uint32_t q = S.dstart[nextd];
+                const uint32_t q = W.dstart[nextd];
                 if (q > lo_pos) {
                     if (q - 1u >= row0 + ROW) break;
                     if (((q - 1u - row0) >> 5) == lane) { const uint32_t bit = 1u << ((q - 1u) & 31u); nl |= bit; ss &= ~bit; }
@@ -205,7 +215,7 @@ OBMW_DEV void process_unit(WarpSmem &S, const WArgs &A, const obm::Tables &T, Ho
             const uint32_t mine = cnt;
             OBMW_SCAN_INCL(cnt);
             const uint32_t excl = cnt - mine;
-            S.nlpre[r * 32u + lane] = (uint16_t)(nl_run + (excl & 0xFFFFu));
+            W.nlpre[r * 32u + lane] = (uint16_t)(nl_run + (excl & 0xFFFFu));
             uint32_t o = own_run + (excl >> 16);
             while (own) {
                 if (o < OWN_CAP) S.orec[o] = pos0 + (OBMW_FFS(own) - 1u);
@@ -215,11 +225,8 @@ OBMW_DEV void process_unit(WarpSmem &S, const WArgs &A, const obm::Tables &T, Ho
             nl_run += tot & 0xFFFFu; own_run += tot >> 16;
         }
         WSYNC();
-#ifdef OBMW_DEBUG
-        if (lane == 0) fprintf(stderr, "unit %u da %u nd %u lo %u hi %u owners %u nl_run %u first_own %u\n", u, da, nd, lo_pos, hi_pos, own_run, nl_run, own_run ? (uint32_t)S.orec[0] : 0u);
-#endif
         n_owners = own_run;
-        if (n_owners > OWN_CAP) { n_owners = 0; if (lane < nd) S.dflag[lane] |= DF_QOVERFLOW; }
+        if (n_owners > OWN_CAP) { n_owners = 0; if (lane < nd) W.dflag[lane] |= DF_QOVERFLOW; }
         WSYNC();
 
         /* ---- B: owners ---- */
@@ -230,11 +237,11 @@ OBMW_DEV void process_unit(WarpSmem &S, const WArgs &A, const obm::Tables &T, Ho
                 const uint32_t first = (uint32_t)S.orec[o];
                 const uint32_t ls = w_line_start(S, first, lo_pos);
                 uint32_t dlo = 0, dhi = nd; /* last d with dstart[d] <= ls */
-                while (dhi - dlo > 1) { const uint32_t mid = (dlo + dhi) >> 1; if (S.dstart[mid] <= ls) dlo = mid; else dhi = mid; }
-                const uint32_t d = dlo, dpos = S.dstart[d];
-                if (S.dflag[d]) S.orec[o] = make_orec(ls - dpos, first - dpos, 0, false, false, true, d, 0);
+                while (dhi - dlo > 1) { const uint32_t mid = (dlo + dhi) >> 1; if (W.dstart[mid] <= ls) dlo = mid; else dhi = mid; }
+                const uint32_t d = dlo, dpos = W.dstart[d];
+                if (W.dflag[d]) { S.orec[o] = make_orec(ls - dpos, first - dpos, 0, false, false, true, d, 0); S.opos[o] = 0; }
                 else {
-                    const uint32_t line = 1 + w_nl_before(S, ls) - w_nl_before(S, dpos);
+                    const uint32_t line = 1 + w_nl_before(W, S, ls) - w_nl_before(W, S, dpos);
                     const uint32_t c = text[first];
                     uint32_t plus = first;
                     marker = c == '+';
@@ -249,12 +256,11 @@ OBMW_DEV void process_unit(WarpSmem &S, const WArgs &A, const obm::Tables &T, Ho
                     }
                     const uint32_t pd = plus - first < 255u ? plus - first : 255u;
                     S.orec[o] = make_orec(ls - dpos, first - dpos, line, marker, c == '/', false, d, pd);
-                    if (!marker) S.ocnt[o] = (uint16_t)(line == 1 ? 1u : 2u);
+                    if (!marker) S.opos[o] = (uint16_t)(line == 1 ? 1u : 2u);
                 }
-                if (or_dead(S.orec[o])) S.ocnt[o] = 0;
             }
             const uint32_t bal = WBALLOT(marker);
-            if (marker) S.mlist[n_ml + OBMT_POPC(bal & ((1u << lane) - 1u))] = (uint16_t)o;
+            if (marker) S.mlist[n_ml + OBMT_POPC(bal & ((1u << lane) - 1u))] = (uint8_t)o;
             n_ml += OBMT_POPC(bal);
         }
         WSYNC(); /* the bitmaps are dead from here on: their space becomes the staging area */
@@ -265,7 +271,7 @@ OBMW_DEV void process_unit(WarpSmem &S, const WArgs &A, const obm::Tables &T, Ho
             if (on) {
                 const uint32_t o = S.mlist[k];
                 const orec_t r = S.orec[o];
-                const uint32_t d = or_doc(r), dpos = S.dstart[d], dend = S.dstart[d + 1];
+                const uint32_t d = or_doc(r), dpos = W.dstart[d], dend = W.dstart[d + 1];
                 const bool staged = k0 == 0;
                 PackSink sink(S.u.stage + lane * LTS, staged ? LTS : 0u);
                 uint32_t res = FL_FALLBACK;
@@ -278,154 +284,161 @@ OBMW_DEV void process_unit(WarpSmem &S, const WArgs &A, const obm::Tables &T, Ho
                     const uint32_t gr = generic_line(T, text, r, dpos, dend, nullptr, 0, nullptr, nullptr);
                     cntv = obmp::mres_tuples(gr); stg = false;
                     S.orec[o] = r | ((orec_t)255u << 50); /* remember: this line is the generic lexer's */
-                    if (obmp::mres_irregular(gr)) WATOMIC_OR(&S.dflag[d], DF_INTERACT);
+                    if (obmp::mres_irregular(gr)) WATOMIC_OR(&W.dflag[d], DF_INTERACT);
                 }
-                if (cntv >= 0xFFFFu) { WATOMIC_OR(&S.dflag[d], DF_INTERACT); cntv = 0; }
-                S.ocnt[o] = (uint16_t)cntv;
-#ifdef OBMW_DEBUG
-                fprintf(stderr, "  C: unit %u o %u res %u cnt %u staged %d dflag %u plusd %u first %u ls %u line %u\n", u, o, res, cntv, (int)stg, S.dflag[d], or_plusd(r), or_first(r), or_ls(r), or_line(r));
-#endif
+                if (cntv >= 0xFFFFu) { WATOMIC_OR(&W.dflag[d], DF_INTERACT); cntv = 0; }
+                S.opos[o] = (uint16_t)cntv;
                 if (staged) S.mstat[lane] = (stg && cntv) ? (sink.mk | (sink.lx << 8) | (cntv << 16)) : MS_NONE; /* cntv <= LTS: the counters fit */
+                if (cntv && !stg) unstaged = true;
             }
         }
         WSYNC();
     }
 
-    /* ---- D: counts -> positions ---- */
-    /* documents that need the exact lexer (K2 of r01: k2_count_flagged_docs) */
-    uint32_t dflag = 0, dtot = 0;
+    /* ---- assembly: counts -> positions inside the unit ---- */
+    uint32_t dflag = 0, dtot = 0, dlen = 0;
     if (lane < nd) {
-        dflag = S.dflag[lane];
-        if (dflag) {
-            const uint32_t dpos = S.dstart[lane], dend = S.dstart[lane + 1];
+        dflag = W.dflag[lane];
+        const uint32_t dpos = W.dstart[lane], dend = W.dstart[lane + 1];
+        dlen = dend - dpos;
+        if (dflag) { /* documents that need the exact lexer (as in r01's K2) */
             obm::SmallSink sink(nullptr, 0);
-            obmp::doc_exact(T, S.text + dpos, dend - dpos, sink);
+            obmp::doc_exact(T, W.text + dpos, dlen, sink);
             dtot = sink.n_tuples;
         }
         /* first owner of the document: owners are in position order, hence grouped by document */
         uint32_t lo = 0, hi = n_owners;
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (or_doc(S.orec[mid]) < lane) lo = mid + 1; else hi = mid; }
-        S.dfo[lane] = (uint16_t)lo;
+        W.dfo[lane] = (uint16_t)lo;
     }
-    if (lane == nd) S.dfo[nd] = (uint16_t)n_owners;
+    if (lane == nd) W.dfo[nd] = (uint16_t)n_owners;
     WSYNC();
     /* exclusive prefix over the owners' tuple counts (owners of flagged documents count 0) */
-    {
-        uint32_t run = 0;
-        for (uint32_t o0 = 0; o0 < n_owners; o0 += 32) {
-            const uint32_t o = o0 + lane;
-            uint32_t c = 0;
-            if (o < n_owners) { c = S.ocnt[o]; if (S.dflag[or_doc(S.orec[o])]) c = 0; }
-            uint32_t v = c;
-            OBMW_SCAN_INCL(v);
-            if (o < n_owners) S.ocnt[o] = (uint16_t)(run + v - c);
-            run += WSHFL(v, 31);
-        }
-        WSYNC();
-        if (lane < nd && !dflag) {
-            const uint32_t f0 = S.dfo[lane], f1 = S.dfo[lane + 1];
-            const uint32_t p0 = f0 < n_owners ? S.ocnt[f0] : run, p1 = f1 < n_owners ? S.ocnt[f1] : run;
-            dtot = p1 - p0 + 1u; /* + EOF */
-        }
+    uint32_t run = 0;
+    for (uint32_t o0 = 0; o0 < n_owners; o0 += 32) {
+        const uint32_t o = o0 + lane;
+        uint32_t c = 0;
+        if (o < n_owners) { c = S.opos[o]; if (W.dflag[or_doc(S.orec[o])]) c = 0; }
+        uint32_t v = c;
+        OBMW_SCAN_INCL(v);
+        if (o < n_owners) S.opos[o] = (uint16_t)(run + v - c);
+        run += WSHFL(v, 31);
     }
-#ifdef OBMW_DEBUG
-    if (lane < nd) fprintf(stderr, "  D: unit %u doc %u dflag %u dtot %u dfo %u..%u n_owners %u\n", u, lane, dflag, dtot, S.dfo[lane], S.dfo[lane + 1], n_owners);
-#endif
+    WSYNC();
+    uint32_t p0 = 0; /* prefix of the document's first owner */
+    if (lane < nd) {
+        const uint32_t f0 = W.dfo[lane], f1 = W.dfo[lane + 1];
+        p0 = f0 < n_owners ? S.opos[f0] : run;
+        const uint32_t p1 = f1 < n_owners ? S.opos[f1] : run;
+        if (!dflag) dtot = p1 - p0 + 1u; /* + EOF */
+    }
     uint32_t dincl = lane < nd ? dtot : 0u;
     OBMW_SCAN_INCL(dincl);
     const uint32_t dexcl = dincl - (lane < nd ? dtot : 0u);
     uint64_t total = WSHFL(dincl, 31);
-    uint32_t large_cnt = 0;
-    if (extra) { large_cnt = A.counts[da + nd]; total += large_cnt; }
-    const uint64_t base = H.lookback(u, nunits, total);
-    if (lane == 0) {
-        if (u == 0) A.tuple_off[0] = 0;
-        if (u == nunits - 1 && A.out && base + total > A.out_cap) A.status[0] = 1;
-        if (extra) A.tuple_off[da + nd + 1] = base + total;
-    }
-    if (lane < nd) {
-        S.dcnt[lane] = dexcl;
-        A.tuple_off[da + lane + 1] = base + dexcl + dtot;
+    if (lane < nd) W.dcnt[lane] = dexcl - p0; /* owner prefix + this = tuple position inside the unit */
+    WSYNC();
+    for (uint32_t o0 = 0; o0 < n_owners; o0 += 32) {
+        const uint32_t o = o0 + lane;
+        if (o < n_owners) S.opos[o] = (uint16_t)(W.dcnt[or_doc(S.orec[o])] + S.opos[o]);
     }
     WSYNC();
+    if (extra) total += A.counts[da + nd];
+    R.u = u; R.da = da; R.nd = nd; R.extra = extra; R.n_owners = n_owners; R.n_ml = n_ml; R.total = total;
+    R.dflag = dflag; R.dtot = dtot; R.dexcl = dexcl; R.dlen = dlen;
+    R.needs_text = WBALLOT(unstaged || dflag != 0) != 0;
+}
 
-    /* ---- D: write ---- */
+/* ---- second half: the unit's tuples at their final positions (base = tuples of all earlier units) ----------
+ * Units with needs_text are written before the warp stages its next unit; all others only use the UnitSet. */
+OBMW_DEV void write_unit(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tables &T, const UnitRegs &R, uint32_t nunits, uint64_t base, WAcc &acc) {
+    const uint32_t lane = WLANE();
+    const uint32_t nd = R.nd, n_owners = R.n_owners, n_ml = R.n_ml;
+    const bool writing = A.out != nullptr && A.out_cap != 0;
+    if (lane == 0) {
+        if (R.u == 0) A.tuple_off[0] = 0;
+        if (R.u == nunits - 1 && A.out && base + R.total > A.out_cap) A.status[0] = 1;
+        if (R.extra) A.tuple_off[R.da + nd + 1] = base + R.total;
+    }
     if (nd == 0) return;
-    const auto text = WTEXT(S);
     if (lane < nd) {
-        const uint32_t dpos = S.dstart[lane], dend = S.dstart[lane + 1];
-        const uint64_t at = base + dexcl;
-        if (dflag) {
+        const uint64_t at = base + R.dexcl;
+        A.tuple_off[R.da + lane + 1] = at + R.dtot;
+        if (R.dflag) { /* only with needs_text: the text and the document table are still this unit's */
             acc.exact++;
             if (writing) {
                 const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
                 obm::SmallSink sink(A.out + at, roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv);
-                const int st = obmp::doc_exact(T, S.text + dpos, dend - dpos, sink);
+                const int st = obmp::doc_exact(T, W.text + W.dstart[lane], R.dlen, sink);
                 acc.markers += sink.n_markers; acc.lexemes += sink.n_lexemes; acc.fatal += (st == obm::RUN_FATAL) ? 1u : 0u;
             }
         } else {
-            const uint64_t eof_at = at + dtot - 1u;
-            if (writing && eof_at < A.out_cap) A.out[eof_at] = OBM_TUPLE(OBM_K_EOF, dend - dpos, 0);
+            const uint64_t eof_at = at + R.dtot - 1u;
+            if (writing && eof_at < A.out_cap) A.out[eof_at] = OBM_TUPLE(OBM_K_EOF, R.dlen, 0);
             acc.lexemes++;
         }
     }
-    /* plain lines in place; marker lines that are not staged are lexed again, straight to their place */
+    /* plain lines in place */
     for (uint32_t o0 = 0; o0 < n_owners; o0 += 32) {
         const uint32_t o = o0 + lane;
         if (o >= n_owners) continue;
         const orec_t r = S.orec[o];
-        const uint32_t d = or_doc(r);
-        if (or_dead(r) || S.dflag[d]) continue;
-        const uint64_t at = base + S.dcnt[d] + (uint32_t)(S.ocnt[o] - S.ocnt[S.dfo[d]]);
-        if (!or_marker(r)) {
-            if (writing) {
-                uint32_t k = 0;
-                if (or_line(r) != 1) { if (at < A.out_cap) A.out[at] = OBM_TUPLE(OBM_K_LINE, or_ls(r), or_line(r)); k = 1; }
-                if (at + k < A.out_cap) A.out[at + k] = OBM_TUPLE(OBM_K_COMMENT, or_first(r), or_slash2(r) ? 2 : 1);
+        if (or_dead(r) || or_marker(r)) continue;
+        if (R.needs_text && W.dflag[or_doc(r)]) continue; /* without needs_text no document is flagged */
+        const uint64_t at = base + S.opos[o];
+        if (writing) {
+            uint32_t k = 0;
+            if (or_line(r) != 1) { if (at < A.out_cap) A.out[at] = OBM_TUPLE(OBM_K_LINE, or_ls(r), or_line(r)); k = 1; }
+            if (at + k < A.out_cap) A.out[at + k] = OBM_TUPLE(OBM_K_COMMENT, or_first(r), or_slash2(r) ? 2 : 1);
+        }
+        acc.lexemes++;
+    }
+    /* marker lines that are not staged are lexed again, straight to their place (needs_text) */
+    if (R.needs_text) {
+        const auto text = WTEXT(W);
+        for (uint32_t k0 = 0; k0 < n_ml; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            if (k >= n_ml) continue;
+            if (k0 == 0 && S.mstat[lane] != MS_NONE) continue; /* staged */
+            const uint32_t o = S.mlist[k];
+            const orec_t r = S.orec[o];
+            const uint32_t d = or_doc(r), dpos = W.dstart[d], dend = W.dstart[d + 1];
+            if (W.dflag[d] || !writing) continue;
+            const uint64_t at = base + S.opos[o];
+            const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
+            const uint32_t rc = roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv;
+            if (or_plusd(r) != 255u) {
+                DirectSink sink(A.out + at, rc);
+                fast_line(text, dpos + or_first(r), dpos + or_first(r) + or_plusd(r), dpos + or_ls(r), or_line(r), dpos, dend, sink);
+                acc.markers += sink.mk; acc.lexemes += sink.lx;
+            } else {
+                uint32_t mk = 0, lx = 0;
+                generic_line(T, text, r, dpos, dend, A.out + at, rc, &mk, &lx);
+                acc.markers += mk; acc.lexemes += lx;
             }
-            acc.lexemes++;
         }
     }
-    for (uint32_t k0 = 0; k0 < n_ml; k0 += 32) {
-        const uint32_t k = k0 + lane;
-        if (k >= n_ml) continue;
-        if (k0 == 0 && S.mstat[lane] != MS_NONE) continue; /* staged */
-        const uint32_t o = S.mlist[k];
-        const orec_t r = S.orec[o];
-        const uint32_t d = or_doc(r), dpos = S.dstart[d], dend = S.dstart[d + 1];
-        if (S.dflag[d]) continue;
-        const uint64_t at = base + S.dcnt[d] + (uint32_t)(S.ocnt[o] - S.ocnt[S.dfo[d]]);
-        if (!writing) continue;
-        const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
-        const uint32_t rc = roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv;
-        if (or_plusd(r) != 255u) {
-            DirectSink sink(A.out + at, rc);
-            fast_line(text, dpos + or_first(r), dpos + or_first(r) + or_plusd(r), dpos + or_ls(r), or_line(r), dpos, dend, sink);
-            acc.markers += sink.mk; acc.lexemes += sink.lx;
-        } else {
-            uint32_t mk = 0, lx = 0;
-            generic_line(T, text, r, dpos, dend, A.out + at, rc, &mk, &lx);
-            acc.markers += mk; acc.lexemes += lx;
+    /* staged marker tuples: line after line, a lane per tuple (a line's tuples are contiguous on both sides) */
+    {
+        const uint32_t ns = n_ml < MLCAP ? n_ml : MLCAP;
+        uint32_t c = 0, rel = 0;
+        if (lane < ns) {
+            const uint32_t ms = S.mstat[lane];
+            const uint32_t o = S.mlist[lane];
+            if (ms != MS_NONE && !(R.needs_text && W.dflag[or_doc(S.orec[o])])) {
+                c = ms >> 16; rel = S.opos[o];
+                acc.markers += ms & 0xFFu; acc.lexemes += (ms >> 8) & 0xFFu;
+            }
+        }
+        if (writing) {
+            for (uint32_t k = 0; k < ns; k++) {
+                const uint32_t ck = WSHFL(c, k), rk = WSHFL(rel, k);
+                const uint64_t at = base + rk + lane;
+                if (lane < ck && at < A.out_cap) A.out[at] = st_unpack(S.u.stage[k * LTS + lane]);
+            }
         }
     }
     WSYNC();
-    /* staged marker tuples: a lane per tuple */
-    {
-        const uint32_t ns = n_ml < MLCAP ? n_ml : MLCAP;
-        for (uint32_t k = 0; k < ns; k++) {
-            const uint32_t ms = S.mstat[k];
-            if (ms == MS_NONE) continue;
-            const uint32_t o = S.mlist[k];
-            const orec_t r = S.orec[o];
-            const uint32_t d = or_doc(r);
-            if (S.dflag[d]) continue;
-            const uint64_t at = base + S.dcnt[d] + (uint32_t)(S.ocnt[o] - S.ocnt[S.dfo[d]]);
-            const uint32_t c = ms >> 16;
-            if (writing && lane < c && at + lane < A.out_cap) A.out[at + lane] = st_unpack(S.u.stage[k * LTS + lane]);
-            if (lane == 0) { acc.markers += ms & 0xFFu; acc.lexemes += (ms >> 8) & 0xFFu; }
-        }
-    }
-    WSYNC(); /* the next unit reuses the shared memory */
 }
 
 } /* namespace obmw */

@@ -505,18 +505,15 @@ extern "C" void hs_warp_line_stats(uint64_t *fast, uint64_t *generic) { *fast = 
 
 namespace {
 struct HostHooks {
-    uint64_t base = 0; uint64_t got = 0;
     void stage(obmw::WarpSmem &S, const void *gsrc, uint32_t nbytes) {
-        if (wemu::lane() == 0) {
-            /* whatever the previous unit left behind stays in the buffer, like on the device; poison only once */
-            memcpy(S.text, gsrc, nbytes);
-        }
+        if (wemu::lane() == 0) memcpy(S.text, gsrc, nbytes); /* whatever the previous unit left behind stays in the buffer, like on the device */
     }
     void stage_wait(obmw::WarpSmem &, uint32_t) {}
-    uint64_t lookback(uint32_t, uint32_t, uint64_t total) { if (wemu::lane() == 0) got = total; return base; }
 };
 }
 
+/* the same software pipeline as k_warp_scan (one warp processes every unit in order): scan unit i, "publish", write unit
+ * i - 1 from its UnitSet while the text buffer already holds unit i, ... */
 extern "C" uint64_t hs_warp_batch(const uint8_t *bytes, const uint64_t *doc_off, uint32_t ndocs, obm_tuple *out, uint64_t cap,
                                   uint64_t *tuple_off, uint32_t fake_skew, uint64_t *stats) {
     (void)fake_skew;
@@ -530,7 +527,6 @@ extern "C" uint64_t hs_warp_batch(const uint8_t *bytes, const uint64_t *doc_off,
     WArgs A; memset(&A, 0, sizeof A);
     A.bytes = bytes; A.doc_off = doc_off; A.ndocs = ndocs; A.total_bytes = total; A.ntiles = (uint32_t)ntiles;
     A.counts = counts.data(); A.out = out; A.out_cap = cap; A.tuple_off = tuple_off; A.status = status; A.totals = totals;
-    /* pass 1: units per tile */
     std::vector<WRec> recs(ntiles); std::vector<uint64_t> ubase(ntiles + 1, 0);
     uint32_t d = 0;
     for (uint64_t t = 0; t < ntiles; t++) {
@@ -540,32 +536,49 @@ extern "C" uint64_t hs_warp_batch(const uint8_t *bytes, const uint64_t *doc_off,
         ubase[t + 1] = ubase[t] + recs[t].n_units;
     }
     const uint32_t nunits = (uint32_t)ubase[ntiles];
-    HostHooks H; WAcc acc_sum{0, 0, 0, 0};
-    uint64_t st_m = 0, st_l = 0, st_e = 0, st_f = 0;
+    HostHooks H;
+    uint64_t st_m = 0, st_l = 0, st_e = 0, st_f = 0, chain = 0;
+    UnitRegs pend[32]; uint64_t pend_base = 0; bool have_pend = false; uint32_t cur = 0;
+    std::vector<uint32_t> large_docs;
+    auto add_acc = [&](WAcc *a) { for (int l = 0; l < 32; l++) { st_m += a[l].markers; st_l += a[l].lexemes; st_e += a[l].exact; st_f += a[l].fatal; } };
     for (uint64_t t = 0; t < ntiles; t++) {
         for (uint32_t k = 0; k < recs[t].n_units; k++) {
             uint32_t da, db, extra;
             wrec_unit(recs[t], k, da, db, extra);
-            if (extra) { /* the large path (k_large_*): counted before, filled after */
+            if (extra) { /* the large path (k_large_*): counted before the scan, filled after it */
                 const uint32_t dl = db;
                 obm::SmallSink s(nullptr, 0); obm::Lexer<obm::SmallSink> lx(TBL, bytes + doc_off[dl], (uint32_t)(doc_off[dl + 1] - doc_off[dl]), s);
                 int st = lx.run<false>(); counts[dl] = s.n_tuples; st_m += s.n_markers; st_l += s.n_lexemes; st_e++; st_f += st == obm::RUN_FATAL;
+                large_docs.push_back(dl);
             }
-            WAcc lane_acc[32]; memset(lane_acc, 0, sizeof lane_acc);
             const uint32_t u = (uint32_t)ubase[t] + k;
-            wemu::run(W, [&]() { process_unit(S, A, TBL, H, u, nunits, da, db, extra, lane_acc[wemu::lane()]); });
-            for (int l = 0; l < 32; l++) { st_m += lane_acc[l].markers; st_l += lane_acc[l].lexemes; st_e += lane_acc[l].exact; st_f += lane_acc[l].fatal; }
-            if (extra) {
-                const uint32_t dl = db; const uint64_t at = tuple_off[dl];
-                obm::WriteSink sink(out + at, at < cap ? cap - at : 0);
-                obm::Lexer<obm::WriteSink> lx(TBL, bytes + doc_off[dl], (uint32_t)(doc_off[dl + 1] - doc_off[dl]), sink);
-                lx.run<false>();
+            UnitRegs R[32];
+            wemu::run(W, [&]() { compute_unit(S, S.set[cur], A, TBL, H, u, da, db, extra, R[wemu::lane()]); });
+            const uint64_t my_base = chain; chain += R[0].total; /* publish */
+            if (have_pend) {
+                WAcc a[32]; memset(a, 0, sizeof a);
+                wemu::run(W, [&]() { write_unit(S, S.set[cur ^ 1u], A, TBL, pend[wemu::lane()], nunits, pend_base, a[wemu::lane()]); });
+                add_acc(a); have_pend = false;
             }
-            H.base += H.got;
+            if (R[0].needs_text) {
+                WAcc a[32]; memset(a, 0, sizeof a);
+                wemu::run(W, [&]() { write_unit(S, S.set[cur], A, TBL, R[wemu::lane()], nunits, my_base, a[wemu::lane()]); });
+                add_acc(a);
+            } else { memcpy(pend, R, sizeof R); pend_base = my_base; have_pend = true; cur ^= 1u; }
         }
     }
-    (void)acc_sum;
+    if (have_pend) {
+        WAcc a[32]; memset(a, 0, sizeof a);
+        wemu::run(W, [&]() { write_unit(S, S.set[cur ^ 1u], A, TBL, pend[wemu::lane()], nunits, pend_base, a[wemu::lane()]); });
+        add_acc(a);
+    }
+    for (uint32_t dl : large_docs) {
+        const uint64_t at = tuple_off[dl];
+        obm::WriteSink sink(out + at, at < cap ? cap - at : 0);
+        obm::Lexer<obm::WriteSink> lx(TBL, bytes + doc_off[dl], (uint32_t)(doc_off[dl + 1] - doc_off[dl]), sink);
+        lx.run<false>();
+    }
     if (ndocs == 0) tuple_off[0] = 0;
     if (stats) { stats[0] = st_m; stats[1] = st_l; stats[2] = st_e; stats[3] = st_f; }
-    return H.base;
+    return chain;
 }

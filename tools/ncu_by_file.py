@@ -10,7 +10,7 @@ kfilter = sys.argv[5] if len(sys.argv) > 5 else None  # substring of the kernel 
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 files = {}
-for f in ["obm_core.h", "obm_tile.h", "obm_fast.cuh", "obm_lib.cu", "obm_pipe.h", "obm_pipe.cuh"]:
+for f in ["obm_warp.h", "obm_warp_core.h", "obm_warp.cuh", "obm_core.h", "obm_tile.h", "obm_fast.cuh", "obm_lib.cu", "obm_pipe.h", "obm_pipe.cuh"]:
     for i, l in enumerate(open("operator-builder_b200/csrc/" + f).read().split("\n"), 1):
         files.setdefault((i, l.strip()[:60]), f)
 ie = None; cur = None

@@ -115,10 +115,10 @@ __device__ __forceinline__ uint64_t chain_resolve(const WArgs &A, uint32_t u, ui
     return P + partial;
 }
 
-/* Software pipeline over the warp's units: scan unit i (compute_unit), publish its tuple count to the look-back
- * chain, THEN write unit i-1 (whose exclusive prefix has had a whole unit's time to arrive: no waiting on the
- * chain), then scan unit i+1 ...  A unit whose write needs the staged text (documents for the exact lexer,
- * marker lines that are not staged) is written at once instead. */
+/* Software pipeline over the warp's units: scan unit i (compute_unit), publish its tuple count to the chain, THEN
+ * write unit i-1 from W.fin (its exclusive prefix has had a whole unit's time to arrive: no waiting on the chain),
+ * assemble unit i into W.fin, scan unit i+1 ...  A unit whose write needs the staged text (documents for the exact
+ * lexer, marker lines that are not staged) or that does not fit W.fin is written at once instead. */
 __global__ void __launch_bounds__(WPC * 32)
 k_warp_scan(WArgs A) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -131,7 +131,7 @@ k_warp_scan(WArgs A) {
     const uint32_t nblocks = (uint32_t)(A.units_max / 32 + 2); /* layout of st_blocks: blk[nblocks] | bex[nblocks] */
     DevHooks H{0};
     WAcc acc{0, 0, 0, 0};
-    UnitRegs pend; bool have_pend = false; uint32_t cur = 0;
+    UnitRegs pend; bool have_pend = false;
     /* the next tile's ticket is taken while this one is processed (the atomic's round trip is off the critical path) */
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(&A.ctl[WC_TICKET], 1u);
@@ -145,24 +145,15 @@ k_warp_scan(WArgs A) {
             uint32_t da, db, extra;
             wrec_unit(rec, k, da, db, extra);
             UnitRegs R;
-            compute_unit(S, S.set[cur], A, T, H, u0 + k, da, db, extra, R);
+            compute_unit(S, S.set, A, T, H, u0 + k, da, db, extra, R);
             chain_publish(A, R.u, R.total);
-            if (have_pend) {
-                const uint64_t base = chain_resolve(A, pend.u, nblocks);
-                write_unit(S, S.set[cur ^ 1u], A, T, pend, nunits, base, acc);
-                have_pend = false;
-            }
-            if (R.needs_text) {
-                const uint64_t base = chain_resolve(A, R.u, nblocks);
-                write_unit(S, S.set[cur], A, T, R, nunits, base, acc);
-            } else { pend = R; have_pend = true; cur ^= 1u; }
+            if (have_pend) { write_fin(S, A, pend, nunits, chain_resolve(A, pend.u, nblocks)); have_pend = false; }
+            if (!R.needs_text && assemble_fin(S, S.set, R, acc)) { pend = R; have_pend = true; }
+            else write_unit(S, S.set, A, T, R, nunits, chain_resolve(A, R.u, nblocks), acc);
         }
         t = __shfl_sync(0xffffffffu, tn, 0);
     }
-    if (have_pend) {
-        const uint64_t base = chain_resolve(A, pend.u, nblocks);
-        write_unit(S, S.set[cur ^ 1u], A, T, pend, nunits, base, acc);
-    }
+    if (have_pend) write_fin(S, A, pend, nunits, chain_resolve(A, pend.u, nblocks));
     uint32_t markers = acc.markers, lexemes = acc.lexemes, exact = acc.exact, fatal = acc.fatal;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

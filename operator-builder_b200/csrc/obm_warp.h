@@ -48,6 +48,7 @@ constexpr uint32_t DMAX = 31;             /* documents per unit: one lane each, 
 constexpr uint32_t OWN_CAP = 256;         /* owning lines per unit (more: the unit's documents take the exact lexer) */
 constexpr uint32_t MLCAP = 32;            /* marker lines whose tuples are staged: one per lane */
 constexpr uint32_t LTS = 24;              /* staged tuples per marker line */
+constexpr uint32_t FIN_CAP = TILE / 16;   /* tuples of a unit whose write is deferred (0.5 B of tuples per input byte: manifests need 0.35) */
 static_assert(BUFB % ROW == 0 && BUFB >= TILE + 16 && BUFB <= 16384 + ROW, "buffer geometry");
 
 enum : uint32_t { DF_NONASCII = 1, DF_INTERACT = 2, DF_QOVERFLOW = 4 };

@@ -30,8 +30,7 @@
 
 namespace obmw {
 
-/* what the (deferred) write of a unit needs; double-buffered so that a warp can scan its next unit while the tuple
- * counts of the previous one travel through the look-back chain */
+/* scratch of the unit being scanned */
 struct UnitSet {
     union {
         struct { uint32_t nlw[NWORDS]; uint32_t spw[NWORDS]; } bm; /* phases A, B */
@@ -44,7 +43,9 @@ struct UnitSet {
 };
 struct WarpSmem {
     alignas(16) uint8_t text[BUFB + 64];
-    UnitSet set[2];
+    UnitSet set;
+    uint32_t fin[FIN_CAP];      /* the unit's tuples, packed (st_pack), in final order: what the DEFERRED write needs -- a warp scans
+                                 * its next unit while this unit's tuple count travels through the chain (obm_warp.cuh) */
     uint16_t nlpre[NWORDS];     /* newline bits in words [0, w) */
     uint32_t dstart[DMAX + 2];  /* document starts, buffer-relative; [nd] = end */
     uint32_t dflag[DMAX + 1];
@@ -57,7 +58,7 @@ static_assert(OWN_CAP <= 256, "mlist holds owner indices in a byte");
 
 /* a scanned unit between its two halves: warp-uniform values, and one document per lane */
 struct UnitRegs {
-    uint32_t u, da, nd, extra, n_owners, n_ml; uint64_t total; bool needs_text;
+    uint32_t u, da, nd, extra, n_owners, n_ml, n_small /* tuples of the unit's small documents */; uint64_t total; bool needs_text;
     uint32_t dflag, dtot, dexcl, dlen; /* lane d < nd: document da + d */
 };
 
@@ -343,14 +344,66 @@ OBMW_DEV void compute_unit(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::T
         if (o < n_owners) S.opos[o] = (uint16_t)(W.dcnt[or_doc(S.orec[o])] + S.opos[o]);
     }
     WSYNC();
+    R.n_small = (uint32_t)total;
     if (extra) total += A.counts[da + nd];
     R.u = u; R.da = da; R.nd = nd; R.extra = extra; R.n_owners = n_owners; R.n_ml = n_ml; R.total = total;
     R.dflag = dflag; R.dtot = dtot; R.dexcl = dexcl; R.dlen = dlen;
     R.needs_text = WBALLOT(unstaged || dflag != 0) != 0;
 }
 
+/* ---- deferred path: the unit's tuples packed into W.fin in final order (only units without needs_text) -------
+ * Returns false when the unit does not fit (more than FIN_CAP tuples, a line number beyond the packed form): the
+ * caller then writes it directly (write_unit). */
+OBMW_DEV bool assemble_fin(WarpSmem &W, UnitSet &S, const UnitRegs &R, WAcc &acc) {
+    const uint32_t lane = WLANE();
+    const uint32_t nd = R.nd, n_owners = R.n_owners, n_ml = R.n_ml;
+    bool bad = R.n_small > FIN_CAP;
+    for (uint32_t o0 = 0; o0 < n_owners && !bad; o0 += 32) {
+        const uint32_t o = o0 + lane;
+        if (o < n_owners && or_line(S.orec[o]) > ST_MAXLEN) bad = true;
+    }
+    if (WBALLOT(bad)) return false;
+    if (lane < nd) { W.fin[R.dexcl + R.dtot - 1u] = st_pack(OBM_K_EOF, R.dlen, 0); acc.lexemes++; }
+    for (uint32_t o0 = 0; o0 < n_owners; o0 += 32) {
+        const uint32_t o = o0 + lane;
+        if (o >= n_owners) continue;
+        const orec_t r = S.orec[o];
+        if (or_dead(r) || or_marker(r)) continue;
+        uint32_t at = S.opos[o];
+        if (or_line(r) != 1) W.fin[at++] = st_pack(OBM_K_LINE, or_ls(r), or_line(r));
+        W.fin[at] = st_pack(OBM_K_COMMENT, or_first(r), or_slash2(r) ? 2 : 1);
+        acc.lexemes++;
+    }
+    {
+        const uint32_t ns = n_ml < MLCAP ? n_ml : MLCAP;
+        uint32_t c = 0, rel = 0;
+        if (lane < ns) {
+            const uint32_t ms = S.mstat[lane]; /* never MS_NONE here: every marker line with tuples is staged */
+            if (ms != MS_NONE) { c = ms >> 16; rel = S.opos[S.mlist[lane]]; acc.markers += ms & 0xFFu; acc.lexemes += (ms >> 8) & 0xFFu; }
+        }
+        for (uint32_t k = 0; k < ns; k++) {
+            const uint32_t ck = WSHFL(c, k), rk = WSHFL(rel, k);
+            if (lane < ck) W.fin[rk + lane] = S.u.stage[k * LTS + lane];
+        }
+    }
+    WSYNC();
+    return true;
+}
+OBMW_DEV void write_fin(const WarpSmem &W, const WArgs &A, const UnitRegs &R, uint32_t nunits, uint64_t base) {
+    const uint32_t lane = WLANE();
+    if (lane == 0) {
+        if (R.u == 0) A.tuple_off[0] = 0;
+        if (R.u == nunits - 1 && A.out && base + R.total > A.out_cap) A.status[0] = 1;
+        if (R.extra) A.tuple_off[R.da + R.nd + 1] = base + R.total;
+    }
+    if (lane < R.nd) A.tuple_off[R.da + lane + 1] = base + R.dexcl + R.dtot;
+    if (A.out != nullptr && A.out_cap != 0)
+        for (uint32_t f = lane; f < R.n_small; f += 32) { const uint64_t at = base + f; if (at < A.out_cap) A.out[at] = st_unpack(W.fin[f]); }
+    WSYNC(); /* fin is free again */
+}
+
 /* ---- second half: the unit's tuples at their final positions (base = tuples of all earlier units) ----------
- * Units with needs_text are written before the warp stages its next unit; all others only use the UnitSet. */
+ * The direct path: units with needs_text, or too large for W.fin; written before the warp stages its next unit. */
 OBMW_DEV void write_unit(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tables &T, const UnitRegs &R, uint32_t nunits, uint64_t base, WAcc &acc) {
     const uint32_t lane = WLANE();
     const uint32_t nd = R.nd, n_owners = R.n_owners, n_ml = R.n_ml;

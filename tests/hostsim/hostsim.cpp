@@ -538,7 +538,7 @@ extern "C" uint64_t hs_warp_batch(const uint8_t *bytes, const uint64_t *doc_off,
     const uint32_t nunits = (uint32_t)ubase[ntiles];
     HostHooks H;
     uint64_t st_m = 0, st_l = 0, st_e = 0, st_f = 0, chain = 0;
-    UnitRegs pend[32]; uint64_t pend_base = 0; bool have_pend = false; uint32_t cur = 0;
+    UnitRegs pend[32]; uint64_t pend_base = 0; bool have_pend = false;
     std::vector<uint32_t> large_docs;
     auto add_acc = [&](WAcc *a) { for (int l = 0; l < 32; l++) { st_m += a[l].markers; st_l += a[l].lexemes; st_e += a[l].exact; st_f += a[l].fatal; } };
     for (uint64_t t = 0; t < ntiles; t++) {
@@ -553,25 +553,18 @@ extern "C" uint64_t hs_warp_batch(const uint8_t *bytes, const uint64_t *doc_off,
             }
             const uint32_t u = (uint32_t)ubase[t] + k;
             UnitRegs R[32];
-            wemu::run(W, [&]() { compute_unit(S, S.set[cur], A, TBL, H, u, da, db, extra, R[wemu::lane()]); });
+            wemu::run(W, [&]() { compute_unit(S, S.set, A, TBL, H, u, da, db, extra, R[wemu::lane()]); });
             const uint64_t my_base = chain; chain += R[0].total; /* publish */
-            if (have_pend) {
-                WAcc a[32]; memset(a, 0, sizeof a);
-                wemu::run(W, [&]() { write_unit(S, S.set[cur ^ 1u], A, TBL, pend[wemu::lane()], nunits, pend_base, a[wemu::lane()]); });
-                add_acc(a); have_pend = false;
-            }
-            if (R[0].needs_text) {
-                WAcc a[32]; memset(a, 0, sizeof a);
-                wemu::run(W, [&]() { write_unit(S, S.set[cur], A, TBL, R[wemu::lane()], nunits, my_base, a[wemu::lane()]); });
-                add_acc(a);
-            } else { memcpy(pend, R, sizeof R); pend_base = my_base; have_pend = true; cur ^= 1u; }
+            if (have_pend) { wemu::run(W, [&]() { write_fin(S, A, pend[wemu::lane()], nunits, pend_base); }); have_pend = false; }
+            WAcc a[32]; memset(a, 0, sizeof a);
+            bool deferred[32]; memset(deferred, 0, sizeof deferred);
+            if (!R[0].needs_text) wemu::run(W, [&]() { deferred[wemu::lane()] = assemble_fin(S, S.set, R[wemu::lane()], a[wemu::lane()]); });
+            if (deferred[0]) { memcpy(pend, R, sizeof R); pend_base = my_base; have_pend = true; }
+            else wemu::run(W, [&]() { write_unit(S, S.set, A, TBL, R[wemu::lane()], nunits, my_base, a[wemu::lane()]); });
+            add_acc(a);
         }
     }
-    if (have_pend) {
-        WAcc a[32]; memset(a, 0, sizeof a);
-        wemu::run(W, [&]() { write_unit(S, S.set[cur ^ 1u], A, TBL, pend[wemu::lane()], nunits, pend_base, a[wemu::lane()]); });
-        add_acc(a);
-    }
+    if (have_pend) wemu::run(W, [&]() { write_fin(S, A, pend[wemu::lane()], nunits, pend_base); });
     for (uint32_t dl : large_docs) {
         const uint64_t at = tuple_off[dl];
         obm::WriteSink sink(out + at, at < cap ? cap - at : 0);

@@ -298,6 +298,11 @@ OBM_HD uint32_t src_mis(const uint8_t *d, uint32_t q) { return (uint32_t)((uintp
 OBM_HD uint32_t src_ldw(const uint8_t *d, int32_t off) { return *reinterpret_cast<const uint32_t *>(d + off); }
 OBM_HD const uint8_t *src_raw(const uint8_t *d) { return d; }
 OBM_HD const uint8_t *src_add(const uint8_t *d, uint32_t off) { return d + off; }
+struct Quad { uint32_t w[4]; };
+OBM_HD Quad src_ldq(const uint8_t *d, uint32_t off16) { /* 16 bytes at a 16-byte aligned offset of a 16-byte aligned base */
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(d + off16);
+    return Quad{{q[0], q[1], q[2], q[3]}};
+}
 #if defined(__CUDACC__)
 struct ShBytes {
     uint32_t sh; const uint8_t *g;
@@ -307,6 +312,11 @@ __device__ __forceinline__ uint32_t src_mis(const ShBytes &d, uint32_t q) { retu
 __device__ __forceinline__ uint32_t src_ldw(const ShBytes &d, int32_t off) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(d.sh + (uint32_t)off)); return v; }
 __device__ __forceinline__ const uint8_t *src_raw(const ShBytes &d) { return d.g; }
 __device__ __forceinline__ ShBytes src_add(const ShBytes &d, uint32_t off) { return ShBytes{d.sh + off, d.g + off}; }
+__device__ __forceinline__ Quad src_ldq(const ShBytes &d, uint32_t off16) {
+    Quad q;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.w[0]), "=r"(q.w[1]), "=r"(q.w[2]), "=r"(q.w[3]) : "r"(d.sh + off16));
+    return q;
+}
 #endif
 
 template <class Sink, class Accel = NoAccel, bool ASCII = false, class Src = const uint8_t *>

@@ -132,26 +132,39 @@ k_warp_scan(WArgs A) {
     DevHooks H{0};
     WAcc acc{0, 0, 0, 0};
     UnitRegs pend; bool have_pend = false;
-    /* the next tile's ticket is taken while this one is processed (the atomic's round trip is off the critical path) */
-    uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(&A.ctl[WC_TICKET], 1u);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    while (t < A.ntiles) {
-        uint32_t tn = 0;
-        if (lane == 0) tn = atomicAdd(&A.ctl[WC_TICKET], 1u);
-        const WRec rec = A.wrec[t];
-        const uint32_t u0 = (uint32_t)A.ubase[t];
-        for (uint32_t k = 0; k < rec.n_units; k++) {
-            uint32_t da, db, extra;
-            wrec_unit(rec, k, da, db, extra);
-            UnitRegs R;
-            compute_unit(S, S.set, A, T, H, u0 + k, da, db, extra, R);
-            chain_publish(A, R.u, R.total);
-            if (have_pend) { write_fin(S, A, pend, nunits, chain_resolve(A, pend.u, nblocks)); have_pend = false; }
-            if (!R.needs_text && assemble_fin(S, S.set, R, acc)) { pend = R; have_pend = true; }
-            else write_unit(S, S.set, A, T, R, nunits, chain_resolve(A, R.u, nblocks), acc);
+    /* unit iterator: tiles by ticket; the next tile's ticket is taken while this one is processed, and the NEXT unit's
+     * descriptor (document offsets -> source address of its text) is ready one unit ahead */
+    uint32_t t = 0, k = 0, tn = 0; WRec rec{0, 0, 0, 0}; uint32_t u0 = 0;
+    auto next_unit = [&]() -> UnitDesc {
+        for (;;) {
+            if (k < rec.n_units) {
+                uint32_t da, db, extra;
+                wrec_unit(rec, k, da, db, extra);
+                const UnitDesc d = make_desc(A, u0 + k, da, db, extra);
+                k++;
+                return d;
+            }
+            t = __shfl_sync(0xffffffffu, tn, 0);
+            if (t >= A.ntiles) { UnitDesc d{0, 0, 0, 0, 0, 0, 0, false}; return d; }
+            if (lane == 0) tn = atomicAdd(&A.ctl[WC_TICKET], 1u);
+            rec = A.wrec[t]; u0 = (uint32_t)A.ubase[t]; k = 0;
         }
-        t = __shfl_sync(0xffffffffu, tn, 0);
+    };
+    if (lane == 0) tn = atomicAdd(&A.ctl[WC_TICKET], 1u);
+    UnitDesc cur = next_unit();
+    bool prestaged = false;
+    while (cur.valid) {
+        const UnitDesc nxt = next_unit();
+        UnitRegs R;
+        compute_unit(S, S.set, A, T, H, cur, prestaged, R);
+        chain_publish(A, R.u, R.total);
+        prestaged = false;
+        /* the staged text is dead unless this unit's write needs it: bring in the next unit's text under the assembly and the writes */
+        if (!R.needs_text && nxt.valid && nxt.db > nxt.da) { H.stage(S, (const void *)(uintptr_t)nxt.base_abs, desc_load(nxt)); prestaged = true; }
+        if (have_pend) { write_fin(S, A, pend, nunits, chain_resolve(A, pend.u, nblocks)); have_pend = false; }
+        if (!R.needs_text && assemble_fin(S, S.set, R, acc)) { pend = R; have_pend = true; }
+        else write_unit(S, S.set, A, T, R, nunits, chain_resolve(A, R.u, nblocks), acc);
+        cur = nxt;
     }
     if (have_pend) write_fin(S, A, pend, nunits, chain_resolve(A, pend.u, nblocks));
     uint32_t markers = acc.markers, lexemes = acc.lexemes, exact = acc.exact, fatal = acc.fatal;

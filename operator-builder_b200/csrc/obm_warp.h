@@ -73,7 +73,9 @@ OBM_HD uint32_t or_plusd(orec_t r) { return (uint32_t)((r >> 50) & 0xFF); }
 /* ---- staged tuple (4 bytes): kind 5 | len 13 | off 14 (document-relative) -------------------------------- */
 constexpr uint32_t ST_MAXOFF = (1u << 14) - 1u, ST_MAXLEN = (1u << 13) - 1u;
 OBM_HD uint32_t st_pack(uint32_t kind, uint32_t off, uint32_t len) { return (kind << 27) | (len << 14) | off; }
-OBM_HD obm_tuple st_unpack(uint32_t v) { return OBM_TUPLE(v >> 27, v & ST_MAXOFF, (v >> 14) & ST_MAXLEN); }
+OBM_HD obm_tuple st_unpack(uint32_t v) { /* kind stays in the top 5 bits of the high word */
+    return ((uint64_t)((v & 0xF8000000u) | ((v >> 14) & ST_MAXLEN)) << 32) | (uint64_t)(v & ST_MAXOFF);
+}
 
 /* sink of the stepper: packed into the warp's staging slot (cap LTS), counts always */
 struct PackSink {
@@ -155,38 +157,49 @@ OBM_HD uint32_t nonname4(uint32_t w) {
     const uint32_t digit = (y + 0x73737373u) & ~(y + 0x66666666u);    /* 0x0D <= y <= 0x19 */
     return ~(letter | digit) & 0x80808080u;
 }
-/* first position q in [p, lim) whose byte is a name delimiter (naked: ';' does not count), else lim */
+/* 16 flag bytes (bit 7 of each byte of z[0..3]) -> 16-bit mask, bit i = byte i */
+OBM_HD uint32_t flags16(const uint32_t (&z)[4]) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 3; k >= 0; k--) m = nib_append(m, z[k]);
+    return m;
+}
+/* first position q in [p, lim) whose byte is a name delimiter (naked: ';' does not count), else lim.  16 bytes per step
+ * (one 128-bit shared-memory load, four independent class computations): the lexer is latency-bound, not issue-bound */
 template <class Src>
 OBM_HD uint32_t scan_delim(const Src &t, uint32_t p, uint32_t lim, bool naked) {
-    uint32_t a = p & ~3u;
-    uint32_t z = nonname4(tw_ldw(t, a)) & (0xFFFFFFFFu << ((p & 3u) * 8u));
+    uint32_t a = p & ~15u;
+    uint32_t from = 0xFFFFu << (p & 15u);
     for (;;) {
-        while (z) {
-            const uint32_t q = a + ((OBMW_FFS(z) - 1u) >> 3);
+        const obm::Quad q4 = obm::src_ldq(t, a);
+        const uint32_t z[4] = {nonname4(q4.w[0]), nonname4(q4.w[1]), nonname4(q4.w[2]), nonname4(q4.w[3])};
+        uint32_t m = flags16(z) & from;
+        while (m) {
+            const uint32_t q = a + OBMW_FFS(m) - 1u;
             if (q >= lim) return lim;
             const uint32_t c = t[q];
             if (obm::is_name_delim(c) && !(naked && c == ';')) return q;
-            z &= z - 1u;
+            m &= m - 1u;
         }
-        a += 4u;
+        a += 16u; from = 0xFFFFu;
         if (a >= lim) return lim;
-        z = nonname4(tw_ldw(t, a));
     }
 }
 /* first position q in [p, lim) whose byte equals c (7-bit) or '\n', else lim */
 template <class Src>
 OBM_HD uint32_t scan_byte_or_nl(const Src &t, uint32_t p, uint32_t lim, uint32_t c) {
     const uint32_t rep = c * 0x01010101u;
-    uint32_t a = p & ~3u;
-    const uint32_t from = 0xFFFFFFFFu << ((p & 3u) * 8u);
-    uint32_t w = tw_ldw(t, a) & from; /* bytes below p may belong to a neighbouring document (>= 0x80: their carries would hide a match) */
-    uint32_t z = (zflag7(w ^ rep) | zflag7(w ^ 0x0A0A0A0Au)) & from;
+    uint32_t a = p & ~15u;
+    uint32_t from = 0xFFFFu << (p & 15u);
     for (;;) {
-        if (z) { const uint32_t q = a + ((OBMW_FFS(z) - 1u) >> 3); return q < lim ? q : lim; }
-        a += 4u;
+        const obm::Quad q4 = obm::src_ldq(t, a);
+        uint32_t z[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) z[k] = zflag8(q4.w[k] ^ rep) | zflag8(q4.w[k] ^ 0x0A0A0A0Au); /* exact form: the 16 bytes may hold a neighbour's bytes >= 0x80 */
+        const uint32_t m = flags16(z) & from;
+        if (m) { const uint32_t q = a + OBMW_FFS(m) - 1u; return q < lim ? q : lim; }
+        a += 16u; from = 0xFFFFu;
         if (a >= lim) return lim;
-        w = tw_ldw(t, a);
-        z = zflag7(w ^ rep) | zflag7(w ^ 0x0A0A0A0Au);
     }
 }
 

@@ -72,6 +72,19 @@ struct WArgs {
     obm_tuple *out; uint64_t out_cap; uint64_t *tuple_off;
     uint32_t *status; unsigned long long *totals; uint32_t *ctl;
 };
+/* where a unit's text lies: computed ahead of the unit so that its bulk copy can be issued early */
+struct UnitDesc { uint32_t u, da, db, extra, skew, span; uint64_t base_abs; bool valid; };
+OBM_HD UnitDesc make_desc(const WArgs &A, uint32_t u, uint32_t da, uint32_t db, uint32_t extra) {
+    UnitDesc d{u, da, db, extra, 0, 0, 0, true};
+    if (db > da) {
+        const uint64_t b0 = A.doc_off[da], b1 = A.doc_off[db];
+        const uint64_t abs0 = (uint64_t)(uintptr_t)A.bytes + b0;
+        d.base_abs = abs0 & ~15ull; d.skew = (uint32_t)(abs0 - d.base_abs); d.span = (uint32_t)(b1 - b0) + d.skew;
+    }
+    return d;
+}
+OBM_HD uint32_t desc_load(const UnitDesc &d) { return (d.span + 15u) & ~15u; }
+
 struct WAcc { uint32_t markers, lexemes, exact, fatal; };
 constexpr uint32_t MS_NONE = 0xFFFFFFFFu;
 
@@ -133,19 +146,18 @@ OBM_HD uint32_t generic_line(const obm::Tables &T, const Src &text, orec_t r, ui
 
 /* ---- first half: phases A, B, C and the assembly of the unit's tuple positions --------------------------- */
 template <class Hooks>
-OBMW_DEV void compute_unit(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tables &T, Hooks &H, uint32_t u, uint32_t da, uint32_t db,
-                           uint32_t extra, UnitRegs &R) {
+OBMW_DEV void compute_unit(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tables &T, Hooks &H, const UnitDesc &D, bool prestaged, UnitRegs &R) {
     const uint32_t lane = WLANE();
+    const uint32_t u = D.u, da = D.da, db = D.db, extra = D.extra;
     const uint32_t nd = db - da;
     uint32_t n_owners = 0, n_ml = 0;
     uint32_t lo_pos = 0, hi_pos = 0;
     bool unstaged = false;
     if (nd) {
-        const uint64_t b0 = A.doc_off[da], b1 = A.doc_off[db];
-        const uint64_t abs0 = (uint64_t)(uintptr_t)A.bytes + b0, base_abs = abs0 & ~15ull;
-        const uint32_t skew = (uint32_t)(abs0 - base_abs), span = (uint32_t)(b1 - b0) + skew, load = (span + 15u) & ~15u;
+        const uint32_t skew = D.skew, span = D.span, load = desc_load(D);
+        const uint64_t b0 = (D.base_abs + skew) - (uint64_t)(uintptr_t)A.bytes;
         lo_pos = skew; hi_pos = span;
-        H.stage(W, (const void *)(uintptr_t)base_abs, load);
+        if (!prestaged) H.stage(W, (const void *)(uintptr_t)D.base_abs, load);
         if (lane <= nd) W.dstart[lane] = (uint32_t)(A.doc_off[da + lane] - b0) + skew;
         if (lane < nd) W.dflag[lane] = 0;
         WSYNC();
@@ -397,8 +409,11 @@ OBMW_DEV void write_fin(const WarpSmem &W, const WArgs &A, const UnitRegs &R, ui
         if (R.extra) A.tuple_off[R.da + R.nd + 1] = base + R.total;
     }
     if (lane < R.nd) A.tuple_off[R.da + lane + 1] = base + R.dexcl + R.dtot;
-    if (A.out != nullptr && A.out_cap != 0)
-        for (uint32_t f = lane; f < R.n_small; f += 32) { const uint64_t at = base + f; if (at < A.out_cap) A.out[at] = st_unpack(W.fin[f]); }
+    if (A.out != nullptr && A.out_cap != 0) {
+        obm_tuple *dst = A.out + base;
+        if (base + R.n_small <= A.out_cap) for (uint32_t f = lane; f < R.n_small; f += 32) dst[f] = st_unpack(W.fin[f]);
+        else for (uint32_t f = lane; f < R.n_small; f += 32) if (base + f < A.out_cap) dst[f] = st_unpack(W.fin[f]);
+    }
     WSYNC(); /* fin is free again */
 }
 

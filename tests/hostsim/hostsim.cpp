@@ -553,7 +553,8 @@ extern "C" uint64_t hs_warp_batch(const uint8_t *bytes, const uint64_t *doc_off,
             }
             const uint32_t u = (uint32_t)ubase[t] + k;
             UnitRegs R[32];
-            wemu::run(W, [&]() { compute_unit(S, S.set, A, TBL, H, u, da, db, extra, R[wemu::lane()]); });
+            const UnitDesc D = make_desc(A, u, da, db, extra);
+            wemu::run(W, [&]() { compute_unit(S, S.set, A, TBL, H, D, false, R[wemu::lane()]); });
             const uint64_t my_base = chain; chain += R[0].total; /* publish */
             if (have_pend) { wemu::run(W, [&]() { write_fin(S, A, pend[wemu::lane()], nunits, pend_base); }); have_pend = false; }
             WAcc a[32]; memset(a, 0, sizeof a);

@@ -243,6 +243,46 @@ void obm_registry_free(obm_registry *r);
 int obm_marker_index_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
                             const void *d_tuples, const void *d_doc_tuple_off, void *d_records, uint64_t cap,
                             void *d_doc_rec_off, void *stream);
+/*
+ * The same consumer ON THE DEVICE (csrc/obm_parse_dev.h): one thread per document walks the resident tuple stream as
+ * parser/state.go:13-175 walks lexemes -- registry lookup (definition.go:13-21), known-argument filter
+ * (state.go:79-93), value typing (ParseBool / Atoi class / ParseFloat(., 32) range, state.go:95-153), MarkerText as a
+ * span of the document, error results (error.go:8-22) -- and writes compact records:
+ *   obm_result (32 B)  one per Result, document order; obm_arg (16 B) one per accepted argument
+ * Documents whose stream holds pseudo-tuples the walk does not model (stale-buffer PART / FLUSH, DRIFT, LINEHI, in-band
+ * warnings, lexer errors) get ONE record with OBM_R_HOST: run obm_parse_doc on that document (exact for everything).
+ * d_doc_res_off[ndocs+1]: per-document result offsets; d_totals: device u64[2] = {results, args}.  With d_results ==
+ * NULL only the offsets / totals are computed.  doc_base is added to every record's doc (global ids of a shard).
+ */
+typedef struct obm_result {
+    uint32_t doc;        /* document index + doc_base */
+    uint32_t tuple;      /* index, inside the document, of the marker's MarkerStart tuple (error results: parser.current) */
+    uint32_t text_off;   /* MarkerText = doc[text_off, text_off + text_len) (+ "\n" when OBM_R_NL) */
+    uint32_t text_len;
+    uint16_t reg_id;     /* registry entry; 0xFFFF on OBM_R_HOST records */
+    uint16_t nargs;      /* error results: 1 = {name_off: line, val_off/val_len: the offending literal} */
+    uint32_t arg_base;   /* index of the first obm_arg of this result in the batch's argument array */
+    uint32_t flags;      /* OBM_R_* */
+    uint32_t aux;        /* error results: column of parser.current; OBM_R_HOST: the first unmodelled tuple kind */
+} obm_result;
+typedef struct obm_arg {
+    uint32_t name_off;   /* argument name = doc[name_off, name_off + name_len) */
+    uint32_t val_off;    /* value = doc[val_off, val_off + val_len); OBM_A_SYNTHETIC_TRUE: the value is "true" */
+    uint32_t val_len;
+    uint16_t name_len;
+    uint8_t kind;        /* 0 bool, 1 int, 2 float, 3 string */
+    uint8_t flags;
+} obm_arg;
+enum { OBM_R_OK = 1, OBM_R_NL = 2, OBM_R_ERR_PARSEBOOL = 4, OBM_R_ERR_FLOAT32 = 8, OBM_R_HOST = 16 };
+enum { OBM_A_SYNTHETIC_TRUE = 1 };
+int obm_parse_batch_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs, uint32_t doc_base,
+                           const void *d_tuples, const void *d_doc_tuple_off, void *d_results, uint64_t res_cap, void *d_args, uint64_t arg_cap,
+                           void *d_doc_res_off, void *d_totals, void *stream);
+/* Records of ONE document -> the byte format of obm_parse_doc (so both can be compared / consumed alike); documents
+ * flagged OBM_R_HOST are parsed from `tuples` by obm_parse_doc itself.  Returns the number of Results. */
+int64_t obm_results_format_doc(const obm_registry *reg, const uint8_t *doc, uint64_t doc_len, const obm_tuple *tuples, uint64_t ntuples,
+                               const obm_result *results, uint64_t nresults, const obm_arg *args_base /* the batch's array */,
+                               uint8_t **out, uint64_t *out_len);
 int64_t obm_parse_doc(const obm_registry *reg, const uint8_t *doc, uint64_t doc_len, const obm_tuple *tuples, uint64_t ntuples,
                       uint8_t **out, uint64_t *out_len);
 

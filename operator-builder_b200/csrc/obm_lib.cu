@@ -1315,6 +1315,66 @@ static int two_pass_scratch(obm_handle *h, uint32_t ndocs, cudaStream_t st, uint
     return OBM_OK;
 }
 
+/* ------------------------------------------------------------------------------------------- */
+/* SURVEY.md 8(f) rank 1 proper: the parser on the device (csrc/obm_parse_dev.h), a thread per document */
+/* ------------------------------------------------------------------------------------------- */
+#include "obm_parse_dev.h"
+extern "C" bool obm_registry_flatten(const obm_registry *r, obmr::DevRegistry *D);
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+k_parse_docs(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs, uint32_t doc_base,
+             const obm_tuple *__restrict__ tuples, const uint64_t *__restrict__ tuple_off, const __grid_constant__ obmr::DevRegistry R,
+             uint32_t *__restrict__ cnt_res, uint32_t *__restrict__ cnt_args, const uint64_t *__restrict__ res_off, const uint64_t *__restrict__ arg_off,
+             obm_result *__restrict__ res, uint64_t res_cap, obm_arg *__restrict__ args, uint64_t arg_cap) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndocs) return;
+    const uint64_t t0 = tuple_off[d];
+    obmr::Sink S{WRITE ? res : nullptr, res_cap, WRITE ? args : nullptr, arg_cap, WRITE ? res_off[d] : 0, WRITE ? arg_off[d] : 0, 0, 0};
+    obmr::parse_doc(R, bytes + doc_off[d], tuples + t0, (uint32_t)(tuple_off[d + 1] - t0), d + doc_base, S);
+    if (!WRITE) { cnt_res[d] = S.nres; cnt_args[d] = S.nargs; }
+}
+
+extern "C" int obm_parse_batch_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs, uint32_t doc_base,
+                                      const void *d_tuples, const void *d_doc_tuple_off, void *d_results, uint64_t res_cap, void *d_args, uint64_t arg_cap,
+                                      void *d_doc_res_off, void *d_totals, void *stream) {
+    if (!h || !reg || !d_doc_off || !d_doc_tuple_off || !d_doc_res_off) return OBM_E_ARG;
+    obmr::DevRegistry R;
+    if (!obm_registry_flatten(reg, &R)) { set_err(h, "registry too large for the device parser (8 markers, 64 arguments, 1024 bytes of names)"); return OBM_E_ARG; }
+    OBM_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t *roff = (uint64_t *)d_doc_res_off;
+    if (ndocs == 0) { OBM_CUDA(h, cudaMemsetAsync(roff, 0, 8, st)); if (d_totals) OBM_CUDA(h, cudaMemsetAsync(d_totals, 0, 16, st)); return OBM_OK; }
+    const uint64_t need = 2 * align_up((uint64_t)ndocs * 4 + 4, 256) + align_up(((uint64_t)ndocs + 1) * 8, 256) + align_up((uint64_t)scan_tiles(ndocs) * 8 + 8, 256);
+    if (h->scratch_bytes < need) {
+        if (h->scratch) { OBM_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->scratch); h->scratch = nullptr; h->scratch_bytes = 0; }
+        OBM_CUDA(h, cudaMalloc(&h->scratch, need)); h->scratch_bytes = need;
+    }
+    uint8_t *q = (uint8_t *)h->scratch;
+    uint32_t *cres = (uint32_t *)q; q += align_up((uint64_t)ndocs * 4 + 4, 256);
+    uint32_t *carg = (uint32_t *)q; q += align_up((uint64_t)ndocs * 4 + 4, 256);
+    uint64_t *aoff = (uint64_t *)q; q += align_up(((uint64_t)ndocs + 1) * 8, 256);
+    uint64_t *tile_sums = (uint64_t *)q;
+    const uint32_t nb = (ndocs + 127) / 128, nt = scan_tiles(ndocs);
+    k_parse_docs<false><<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, doc_base, (const obm_tuple *)d_tuples,
+                                            (const uint64_t *)d_doc_tuple_off, R, cres, carg, nullptr, nullptr, nullptr, 0, nullptr, 0);
+    k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(cres, ndocs, roff, tile_sums);
+    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, roff + ndocs);
+    k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(roff, ndocs, tile_sums, ~0ull, nullptr);
+    k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(carg, ndocs, aoff, tile_sums);
+    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, aoff + ndocs);
+    k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(aoff, ndocs, tile_sums, ~0ull, nullptr);
+    if (d_totals) {
+        OBM_CUDA(h, cudaMemcpyAsync(d_totals, roff + ndocs, 8, cudaMemcpyDeviceToDevice, st));
+        OBM_CUDA(h, cudaMemcpyAsync((uint64_t *)d_totals + 1, aoff + ndocs, 8, cudaMemcpyDeviceToDevice, st));
+    }
+    if (d_results && d_args)
+        k_parse_docs<true><<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, doc_base, (const obm_tuple *)d_tuples,
+                                               (const uint64_t *)d_doc_tuple_off, R, nullptr, nullptr, roff, aoff, (obm_result *)d_results, res_cap,
+                                               (obm_arg *)d_args, arg_cap);
+    OBM_CUDA(h, cudaGetLastError());
+    return OBM_OK;
+}
+
 extern "C" int obm_rewrite_collection_markers_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
                                                      void *d_out_bytes, uint64_t out_cap, void *d_out_doc_off, void *stream) {
     if (!h || !d_doc_off || !d_out_doc_off) return OBM_E_ARG;

@@ -231,6 +231,77 @@ struct Parser {
 
 } // namespace
 
+/* registry -> the flat form the device walk uses (csrc/obm_parse_dev.h); false when it does not fit */
+#include "obm_parse_dev.h"
+extern "C" bool obm_registry_flatten(const obm_registry *r, obmr::DevRegistry *D) {
+    memset(D, 0, sizeof *D);
+    if (r->defs.size() > 8) return false;
+    uint32_t o = 0, a = 0;
+    for (size_t i = 0; i < r->defs.size(); i++) {
+        const auto &d = r->defs[i];
+        if (o + d.name.size() > sizeof D->text) return false;
+        D->name_off[i] = o; memcpy(D->text + o, d.name.data(), d.name.size()); o += (uint32_t)d.name.size();
+    }
+    D->name_off[r->defs.size()] = o; D->n = (uint32_t)r->defs.size();
+    for (size_t i = 0; i < r->defs.size(); i++) {
+        D->arg_first[i] = a;
+        for (const auto &n : r->defs[i].args) {
+            if (a >= 64 || o + n.size() > sizeof D->text) return false;
+            D->arg_off[a++] = o; memcpy(D->text + o, n.data(), n.size()); o += (uint32_t)n.size();
+        }
+    }
+    D->arg_first[r->defs.size()] = a; D->arg_off[a] = o;
+    return true;
+}
+
+/* host run of the device walk over one document (test / mirror use: the records the GPU would write) */
+extern "C" int64_t obm_parse_doc_records(const obm_registry *reg, const uint8_t *doc, const obm_tuple *tuples, uint64_t ntuples, uint32_t doc_id,
+                                         obm_result *res, uint64_t res_cap, obm_arg *args, uint64_t arg_cap, uint64_t *nargs_out) {
+    obmr::DevRegistry D;
+    if (!reg || !obm_registry_flatten(reg, &D)) return OBM_E_ARG;
+    obmr::Sink S{res, res_cap, args, arg_cap, 0, 0, 0, 0};
+    obmr::parse_doc(D, doc, tuples, (uint32_t)ntuples, doc_id, S);
+    if (nargs_out) *nargs_out = S.nargs;
+    return S.nres;
+}
+
+extern "C" int64_t obm_results_format_doc(const obm_registry *reg, const uint8_t *doc, uint64_t doc_len, const obm_tuple *tuples, uint64_t ntuples,
+                                          const obm_result *results, uint64_t nresults, const obm_arg *args_base, uint8_t **out, uint64_t *out_len) {
+    if (!reg || !out || !out_len) return OBM_E_ARG;
+    if (nresults == 1 && (results[0].flags & OBM_R_HOST)) return obm_parse_doc(reg, doc, doc_len, tuples, ntuples, out, out_len);
+    std::string o;
+    for (uint64_t i = 0; i < nresults; i++) {
+        const obm_result &r = results[i];
+        if (r.reg_id >= reg->defs.size()) return OBM_E_ARG;
+        const obm_registry::Def &d = reg->defs[r.reg_id];
+        std::string text((const char *)doc + r.text_off, r.text_len);
+        if (r.flags & OBM_R_NL) text.push_back('\n');
+        if (r.flags & OBM_R_OK) {
+            o.push_back(0); put_u32(o, (uint32_t)d.name.size()); o += d.name; put_u32(o, (uint32_t)text.size()); o += text;
+            put_u32(o, r.nargs);
+            for (uint32_t a = 0; a < r.nargs; a++) {
+                const obm_arg &g = args_base[r.arg_base + a];
+                put_u32(o, g.name_len); o.append((const char *)doc + g.name_off, g.name_len); o.push_back((char)g.kind);
+                if (g.flags & OBM_A_SYNTHETIC_TRUE) { put_u32(o, 4); o += "true"; }
+                else { put_u32(o, g.val_len); o.append((const char *)doc + g.val_off, g.val_len); }
+            }
+        } else { /* error.go:8-22: "<msg>, on marker <name> at {line:L column:C}" */
+            const obm_arg &g = args_base[r.arg_base];
+            const std::string v((const char *)doc + g.val_off, g.val_len);
+            std::string m = (r.flags & OBM_R_ERR_PARSEBOOL) ? "strconv.ParseBool: parsing " + go_quote_simple(v) + ": invalid syntax"
+                                                             : "strconv.ParseFloat: parsing " + go_quote_simple(v) + ": value out of range";
+            char pos[96]; snprintf(pos, sizeof pos, "{line:%u column:%u}", g.name_off, r.aux);
+            m += ", on marker " + d.name + " at " + pos;
+            o.push_back(1); put_u32(o, (uint32_t)m.size()); o += m; put_u32(o, (uint32_t)text.size()); o += text;
+        }
+    }
+    uint8_t *buf = (uint8_t *)malloc(o.size() ? o.size() : 1);
+    if (!buf) return OBM_E_NOMEM;
+    memcpy(buf, o.data(), o.size());
+    *out = buf; *out_len = o.size();
+    return (int64_t)nresults;
+}
+
 extern "C" int64_t obm_parse_doc(const obm_registry *reg, const uint8_t *doc, uint64_t doc_len, const obm_tuple *tuples, uint64_t ntuples,
                                  uint8_t **out, uint64_t *out_len) {
     if (!reg || !out || !out_len) return OBM_E_ARG;

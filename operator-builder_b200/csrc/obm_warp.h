@@ -31,10 +31,10 @@
 #include "obm_pipe.h"
 
 #ifndef OBMW_TILE
-#define OBMW_TILE 8192
+#define OBMW_TILE 12288
 #endif
 #ifndef OBMW_BUFB
-#define OBMW_BUFB 12288
+#define OBMW_BUFB 13312
 #endif
 
 namespace obmw {

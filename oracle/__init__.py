@@ -63,6 +63,23 @@ def lib():
     return _LIB
 
 
+def generate_corpus(ndocs: int, doc_bytes: int = 4096, first_doc: int = 0, flavour: int = 0):
+    """The bench corpus (csrc/obm_corpus.h) from a host library of its own (oracle/corpus_gen.cpp): the reference arm of
+    bench.py must not map product code.  -> (uint8 bytes, uint64 doc_off[ndocs+1])"""
+    import numpy as np
+    so = os.path.join(_HERE, "libcorpus_gen.so")
+    if not os.path.exists(so):
+        build(force=True)
+    G = ctypes.CDLL(so)
+    G.obc_generate_corpus_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int]
+    data = np.empty(ndocs * doc_bytes, dtype=np.uint8)
+    off = np.empty(ndocs + 1, dtype=np.uint64)
+    rc = G.obc_generate_corpus_host(data.ctypes.data, off.ctypes.data, ndocs, doc_bytes, first_doc, flavour)
+    if rc != 0:
+        raise RuntimeError(f"obc_generate_corpus_host -> {rc}")
+    return data, off
+
+
 def parse_stream(buf):
     """Serialised stream -> list of (type, value bytes, line, col)."""
     out, i, n = [], 0, len(buf)

@@ -22,6 +22,7 @@ def build(force=False):
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_warp.h"),
             os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_warp_core.h"),
             os.path.join(_HERE, "warp_emu.h"),
+            os.path.join(_ROOT, "operator-builder_b200", "csrc", "obm_parse_dev.h"),
             os.path.join(_ROOT, "include", "obmarkers.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-Wno-unknown-pragmas", *(["-DOBMW_DEBUG"] if os.environ.get("OBMW_DEBUG") else []), "-shared", "-o", so,

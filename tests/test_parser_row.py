@@ -4,8 +4,10 @@ obm_parse_doc (csrc/obm_parse.cpp, mirror of internal/markers/parser/state.go:13
 Python restatement oracle/parser_oracle.py over the oracle lexer's lexemes.  No reference test pins the parser
 (SURVEY section 4): both sides follow the source; this checks they agree and that MarkerText -- what
 markers/markers.go:198-222 splices back into YAML comments -- is byte-exact."""
+import ctypes
 import random
 
+import numpy as np
 import pytest
 
 from tests import corpus_util as cu
@@ -28,11 +30,57 @@ def REG():
     return _REG
 
 
+RES_DT = np.dtype([("doc", "<u4"), ("tuple", "<u4"), ("text_off", "<u4"), ("text_len", "<u4"), ("reg_id", "<u2"), ("nargs", "<u2"),
+                   ("arg_base", "<u4"), ("flags", "<u4"), ("aux", "<u4")])
+ARG_DT = np.dtype([("name_off", "<u4"), ("val_off", "<u4"), ("val_len", "<u4"), ("name_len", "<u2"), ("kind", "u1"), ("flags", "u1")])
+R_HOST = 16
+STATS = {"docs": 0, "host": 0}
+
+
+def format_records(doc, tuples, res, args):
+    """compact device records of one document -> the byte format of obm_parse_doc (obm_results_format_doc)"""
+    import operator_builder_b200 as ob
+    L = ob._native.lib()
+    tuples = np.ascontiguousarray(tuples, dtype=np.uint64)
+    res = np.ascontiguousarray(res); args = np.ascontiguousarray(args)
+    out = ctypes.POINTER(ctypes.c_uint8)(); outlen = ctypes.c_uint64()
+    L.obm_results_format_doc.restype = ctypes.c_int64
+    L.obm_results_format_doc.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p,
+                                         ctypes.c_uint64, ctypes.c_void_p, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.POINTER(ctypes.c_uint64)]
+    n = L.obm_results_format_doc(REG().handle, doc, len(doc), tuples.ctypes.data, len(tuples), res.ctypes.data, len(res),
+                                 args.ctypes.data if len(args) else None, ctypes.byref(out), ctypes.byref(outlen))
+    assert n >= 0
+    data = ctypes.string_at(out, outlen.value)
+    L.obm_free(out)
+    return data
+
+
+def results_via_device_walk(doc, tuples):
+    """csrc/obm_parse_dev.h (the code k_parse_docs runs, one thread per document) on the host"""
+    import operator_builder_b200 as ob
+    L = ob._native.lib()
+    tuples = np.ascontiguousarray(tuples, dtype=np.uint64)
+    res = np.zeros(len(tuples) + 2, dtype=RES_DT); args = np.zeros(len(tuples) + 2, dtype=ARG_DT)
+    nargs = ctypes.c_uint64()
+    L.obm_parse_doc_records.restype = ctypes.c_int64
+    L.obm_parse_doc_records.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p,
+                                        ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
+    n = L.obm_parse_doc_records(REG().handle, doc, tuples.ctypes.data, len(tuples), 0, res.ctypes.data, len(res), args.ctypes.data, len(args),
+                                ctypes.byref(nargs))
+    assert n >= 0
+    STATS["docs"] += 1
+    STATS["host"] += int(n == 1 and (int(res[0]["flags"]) & R_HOST) != 0)
+    return format_records(doc, tuples, res[:n], args[:nargs.value])
+
+
 def check(oracle, doc, tuples=None):
     from oracle import parser_oracle as po
     want = po.serialize(po.parse(oracle.lex(doc), po.OPERATOR_BUILDER_REGISTRY))
-    got = results_via_tuples(doc, hostsim.lex_doc(doc) if tuples is None else tuples)
+    tuples = hostsim.lex_doc(doc) if tuples is None else tuples
+    got = results_via_tuples(doc, tuples)
     assert got == want, (doc, got, want)
+    dev = results_via_device_walk(doc, tuples)
+    assert dev == want, (doc, dev, want)
     return want
 
 
@@ -75,6 +123,16 @@ def test_fixtures_targeted_fuzz(oracle):
         check(oracle, b"".join(rng.choice(words) for _ in range(rng.randint(1, 14))))
     for _ in range(300):
         check(oracle, cu.fuzz_doc_valid(rng))
+    # the device walk handles the regular documents itself; only streams with pseudo-tuples go back to obm_parse_doc
+    import operator_builder_b200 as ob
+    before = dict(STATS)
+    data0, _ = ob.generate_corpus_host(100, 4096, flavour=0)
+    for i in range(100):
+        check(oracle, data0.tobytes()[i * 4096:(i + 1) * 4096])
+    assert STATS["host"] == before["host"], STATS          # synthetic manifests: all on the device walk
+    for _p, doc in cu.fixtures():
+        check(oracle, doc)
+    assert STATS["host"] - before["host"] <= 8, STATS      # the reference's 33 fixtures: the ones with in-band warnings go back
 
 
 @pytest.mark.gpu
@@ -95,6 +153,62 @@ def test_parser_on_gpu_tuples(oracle):
         want = check(oracle, doc, res.tuples[int(res.doc_tuple_off[i]):int(res.doc_tuple_off[i + 1])])
         n_ok += want.count(b"+operator-builder:")
     assert n_ok > 1500
+    sc.close()
+
+
+@pytest.mark.gpu
+def test_device_parser_kernel(oracle):
+    """k_parse_docs through obm_parse_batch_device: records of every document == obm_parse_doc == the parser oracle"""
+    import torch
+    import operator_builder_b200 as ob
+    from operator_builder_b200 import _native
+    from oracle import parser_oracle as po
+    rng = random.Random(78)
+    docs = [d for _p, d in cu.fixtures()] + list(cu.TARGETED) + [cu.fuzz_doc_valid(rng) for _ in range(800)]
+    docs += [b"# +operator-builder:field:name=x,default= true\n", b"# +operator-builder:field:name=x,default=1e39\n# +operator-builder:field:name=y\n",
+             b"# +operator-builder:field:name=x,bogus=1\n# +operator-builder:resource:field=a,value=3.4028235e38,include\n"]
+    for fl in (0, 1):
+        data0, _ = ob.generate_corpus_host(300, 4096, flavour=fl)
+        docs += [data0.tobytes()[i * 4096:(i + 1) * 4096] for i in range(300)]
+    data = np.frombuffer(b"".join(docs), dtype=np.uint8)
+    off = np.zeros(len(docs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(d) for d in docs])
+    sc = ob.Scanner(0)
+    res = sc.lex_batch(data, off)
+    dev = torch.device("cuda:0")
+    d_bytes = torch.from_numpy(data.copy()).to(dev)
+    d_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+    d_tup = torch.from_numpy(res.tuples.view(np.int64).copy()).to(dev)
+    d_toff = torch.from_numpy(res.doc_tuple_off.view(np.int64).copy()).to(dev)
+    cap = len(res.tuples)
+    d_res = torch.zeros(cap * 32, dtype=torch.uint8, device=dev)
+    d_args = torch.zeros(cap * 16, dtype=torch.uint8, device=dev)
+    d_roff = torch.zeros(len(docs) + 1, dtype=torch.int64, device=dev)
+    d_tot = torch.zeros(2, dtype=torch.int64, device=dev)
+    L = _native.lib()
+    L.obm_parse_batch_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    reg = REG()
+    st = torch.cuda.current_stream().cuda_stream
+    rc = L.obm_parse_batch_device(sc.handle, reg.handle, d_bytes.data_ptr(), d_off.data_ptr(), len(docs), 1000, d_tup.data_ptr(), d_toff.data_ptr(),
+                                  d_res.data_ptr(), cap, d_args.data_ptr(), cap, d_roff.data_ptr(), d_tot.data_ptr(), st)
+    assert rc == 0
+    torch.cuda.synchronize()
+    roff = d_roff.cpu().numpy()
+    nres, nargs = [int(x) for x in d_tot.cpu().tolist()]
+    assert nres == int(roff[-1])
+    R = d_res.cpu().numpy()[:nres * 32].view(RES_DT)
+    A = d_args.cpu().numpy()[:nargs * 16].view(ARG_DT)
+    host_docs = 0
+    for i, doc in enumerate(docs):
+        r = R[int(roff[i]):int(roff[i + 1])]
+        assert all(int(x) == i + 1000 for x in r["doc"])
+        host_docs += int(len(r) == 1 and (int(r[0]["flags"]) & R_HOST) != 0)
+        t = res.tuples[int(res.doc_tuple_off[i]):int(res.doc_tuple_off[i + 1])]
+        got = format_records(doc, t, r, A)
+        want = po.serialize(po.parse(oracle.lex(doc), po.OPERATOR_BUILDER_REGISTRY))
+        assert got == want, (doc[:200], got, want)
+    assert host_docs < len(docs) * 0.5 and nres > 4800
     sc.close()
 
 

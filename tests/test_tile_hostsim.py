@@ -118,7 +118,7 @@ def test_synthetic_corpus():
         raw = data.tobytes()
         stats = check_batch([raw[i * 4096:(i + 1) * 4096] for i in range(64)])
         assert stats[0] == 8 * 64 and stats[2] == 0
-    for doc_bytes, n in ((37, 300), (1000, 50), (16368, 3), (16369, 3), (70000, 2)):
+    for doc_bytes, n in ((37, 300), (1000, 50), (13296, 3), (13297, 3), (16368, 3), (16369, 3), (70000, 2)):
         data, off = ob.generate_corpus_host(n, doc_bytes)
         raw = data.tobytes()
         check_batch([raw[i * doc_bytes:(i + 1) * doc_bytes] for i in range(n)], skew=3)

@@ -91,20 +91,35 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """threads the CPU legs may use: the affinity / cgroup view, not os.cpu_count()"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_run(sample_docs, threads, steps, warmup, flavour):
-    """Times the oracle (C restatement of internal/markers/lexer) over a bounded sample on the host cores."""
-    import operator_builder_b200 as ob  # host generator only (no lexing)
+    """Times the oracle (C restatement of internal/markers/lexer) over a bounded sample on the host cores.  This leg maps
+    oracle code only: the corpus comes from oracle/libcorpus_gen.so (the generator's host build), not from libobmarkers.so."""
     import oracle
-    data, off = ob.generate_corpus_host(sample_docs, DOC_BYTES, 0, flavour)
-    for _ in range(warmup):
-        oracle.scan_batch(data[:min(len(data), 64 * DOC_BYTES)], off[:65], threads)
-    t0 = time.perf_counter()
-    markers = lexemes = 0
+    data, off = oracle.generate_corpus(sample_docs, DOC_BYTES, 0, flavour)
+    for _ in range(max(warmup, 1)):
+        oracle.scan_batch(data[:min(len(data), 4096 * DOC_BYTES)], off[:min(sample_docs, 4096) + 1], threads)
+    times, markers, lexemes = [], 0, 0
     for _ in range(steps):
+        t0 = time.perf_counter()
         nl, nm, _h = oracle.scan_batch(data, off, threads)
+        times.append(time.perf_counter() - t0)
         markers, lexemes = nm, nl
-    dt = (time.perf_counter() - t0) / max(steps, 1)
+    dt = sum(times) / len(times)
+    # one thread over a slice of the same sample: what a core does
+    one_docs = min(sample_docs, 2048)
+    t0 = time.perf_counter()
+    oracle.scan_batch(data[:one_docs * DOC_BYTES], off[:one_docs + 1], 1)
+    one = one_docs * DOC_BYTES / (time.perf_counter() - t0) / 1e6
     return {"mb_s": len(data) / dt / 1e6, "ms_per_step": dt * 1e3, "markers_per_s": markers / dt, "lexemes": lexemes,
+            "single_thread_mb_s": one, "pass_ms": [round(t * 1e3, 1) for t in times],
             "sample": f"{sample_docs} docs x {DOC_BYTES} B ({sample_docs * DOC_BYTES / 2**20:.0f} MiB) of the same generator, "
                       f"{steps} pass(es), {threads} pthreads"}
 
@@ -128,12 +143,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cores = os.cpu_count() or 1
+    cores = host_threads()
 
     cfg_name = "configs[3]" if args.flavour == 0 else "configs[2] (workload-collection spelling: +operator-builder:collection:field)"
     config = {"workload": f"{cfg_name}: {args.docs} synthetic manifests x {DOC_BYTES} B = {args.docs * DOC_BYTES / 2**30:.2f} GiB, "
                           f"8 markers/file, sharded by file over {world} rank(s), HBM-resident",
-              "docs": args.docs, "doc_bytes": DOC_BYTES, "flavour": args.flavour, "parallelism": f"file-shard x{world}",
+              "docs": args.docs, "doc_bytes": DOC_BYTES, "flavour": args.flavour,
+              "parallelism": f"file-shard x{world}; step = scan + device parser (compact Results)" + (" + one NCCL all-gather of the Result records (obm_lex_batch_sharded_device)" if world > 1 else ""),
               "l2": "inputs (>= 1.25 GiB per rank) exceed the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
@@ -141,13 +157,18 @@ def main():
         # oracle port of internal/markers/lexer on all host cores (kind "port").  Rank 0 only.
         if rank != 0:
             return 0
-        steps = max(1, min(args.steps, 3))
-        r = cpu_reference_run(args.cpu_docs, cores, steps, min(args.warmup, 1), args.flavour)
+        # a step = one pass of the CPU path over a BOUNDED SAMPLE of the workload (1 GiB by default: ~1 s per pass on this
+        # box's cores); `config.workload` names the full workload, `config.sample` what a step really covers
+        steps = max(3, min(args.steps, 5))
+        ref_docs = max(args.cpu_docs, int(os.environ.get("OBM_BENCH_REF_DOCS", 262144)))
+        r = cpu_reference_run(ref_docs, cores, steps, 1, args.flavour)
+        config["sample"] = r["sample"]
         line = {"impl": "reference", "metric": "manifest_scan_throughput", "value": r["mb_s"], "unit": "MB/s", "n_gpus": world,
-                "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "steps": steps, "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "markers_per_s": r["markers_per_s"],
-                "cpu_baseline": {"value": r["mb_s"], "unit": "MB/s", "cores": cores, "kind": "port", "sample": r["sample"]},
+                "cpu_baseline": {"value": r["mb_s"], "unit": "MB/s", "cores": cores, "kind": "port", "sample": r["sample"],
+                                 "single_thread_mb_s": r["single_thread_mb_s"], "pass_ms": r["pass_ms"]},
                 "e2e": {"value": r["mb_s"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -164,7 +185,11 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)  # NCCL_DEBUG=VERSION|WARN|INFO prints a banner on stdout; rank 0 prints exactly one JSON line
+        # NCCL_DEBUG=VERSION|WARN|INFO prints on stdout by default; rank 0 must print exactly one JSON line, so the log goes
+        # to a file per rank instead (the driver's rank check reads it there)
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     from operator_builder_b200 import shard
@@ -179,27 +204,65 @@ def main():
     d_bytes = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     d_off = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
     sc.generate_corpus_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, DOC_BYTES, d0, args.flavour, sp)
-    cap = nbytes // 16  # tuples (8 B each): 0.5 B of tuples per input byte; measured need is ~0.32
+    cap = nbytes // 16  # tuples (8 B each): 0.5 B of tuples per input byte; measured need is ~0.35
     d_out = torch.empty(cap, dtype=torch.int64, device=dev)
     d_toff = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
     d_status = torch.zeros(4, dtype=torch.int32, device=dev)
     d_counts = torch.zeros(2, dtype=torch.int64, device=dev)
-    # N>1: the one exchange step -- every rank learns every document's tuple count (the global
-    # doc_tuple_off index), 4 B/document, one all-gather.  Full-tuple all-gather is timed separately.
-    counts_local = torch.empty(ndocs, dtype=torch.int32, device=dev) if world > 1 else None
-    counts_all = torch.empty(args.docs, dtype=torch.int32, device=dev) if world > 1 else None
+    # the parser on the device: compact Result records, 32 B each + 16 B per argument
+    reg = ob.Registry()
+    max_docs = (args.docs + world - 1) // world
+    res_cap, arg_cap = max_docs * 12, max_docs * 48
+    d_res = torch.empty(res_cap * 32, dtype=torch.uint8, device=dev)
+    d_args = torch.empty(arg_cap * 16, dtype=torch.uint8, device=dev)
+    d_roff = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
+    d_tot = torch.zeros(2, dtype=torch.int64, device=dev)
+    comm = d_res_all = None
+    if world > 1:
+        # the multi-GPU path behind the C ABI: obm_comm_* (NCCL bound inside libobmarkers.so); torch.distributed only carries
+        # the 128-byte unique id from rank 0 to the others and the barriers / max-over-ranks of this harness
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(ob.Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        comm = ob.Comm(sc, bytes(idt.cpu().numpy().tobytes()), rank, world)
+        d_res_all = torch.empty(world * res_cap * 32, dtype=torch.uint8, device=dev)
+    exch = {}
 
-    def step():
+    def scan_only():
         sc.lex_batch_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, nbytes, d_out.data_ptr(), cap, d_toff.data_ptr(),
                             d_status.data_ptr(), d_counts.data_ptr(), sp)
-        if counts_all is not None:
-            shard.counts_from_offsets(d_toff, out=counts_local)
-            shard.exchange_counts(counts_local, args.docs, rank, world, counts_all=counts_all)
+
+    def parse_only():
+        sc.parse_batch_device(reg, d_bytes.data_ptr(), d_off.data_ptr(), ndocs, d0, d_out.data_ptr(), d_toff.data_ptr(), d_res.data_ptr(), res_cap,
+                              d_args.data_ptr(), arg_cap, d_roff.data_ptr(), d_tot.data_ptr(), sp)
+
+    def step():
+        """one pass of the hot path over the rank's shard: scan + emit, the parser's compact Results, and (N > 1) the one
+        exchange step -- an NCCL all-gather of those records over NVLink"""
+        if comm is None:
+            scan_only()
+            parse_only()
+        else:
+            per_rank, stride = comm.lex_batch_sharded_device(reg, d_bytes.data_ptr(), d_off.data_ptr(), ndocs, nbytes, d0, d_out.data_ptr(), cap,
+                                                             d_toff.data_ptr(), d_status.data_ptr(), d_counts.data_ptr(), d_res.data_ptr(), res_cap,
+                                                             d_args.data_ptr(), arg_cap, d_roff.data_ptr(), d_res_all.data_ptr(), world * res_cap, sp)
+            exch["per_rank"], exch["stride"] = per_rank, stride
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(fn, n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record(stream)
+        for _ in range(n):
+            fn()
+        b.record(stream)
+        barrier()
+        return a.elapsed_time(b) / n
 
     for _ in range(args.warmup):
         step()
@@ -207,104 +270,43 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
+    ms = timed(step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1) / args.steps
-    launches = ob._native.lib().obm_launches_last_call(sc.handle) * args.steps
+    launches = (ob._native.lib().obm_launches_last_call(sc.handle) + 8) * args.steps  # scan kernels + the parser's 2 kernels and 6 scan launches
 
-    # scan-only time (no collective) for the roofline, same stream, same events
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    k0.record(stream)
-    for _ in range(args.steps):
-        sc.lex_batch_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, nbytes, d_out.data_ptr(), cap, d_toff.data_ptr(),
-                            d_status.data_ptr(), d_counts.data_ptr(), sp)
-    k1.record(stream)
-    barrier()
-    ms_scan = k0.elapsed_time(k1) / args.steps
+    # the parts, same stream, same events: scan-only time is the roofline's denominator
+    ms_scan = timed(scan_only, args.steps)
+    ms_parse = timed(parse_only, max(3, args.steps // 2))
 
     n_tuples = int(d_toff[-1].item())
     n_markers, n_lexemes = int(d_counts[0].item()), int(d_counts[1].item())
+    n_results, n_args = [int(x) for x in d_tot.cpu().tolist()]
     status = d_status.cpu().tolist()
     if status[0]:
         print(json.dumps({"error": "tuple buffer overflow in bench", "needed": n_tuples, "cap": cap}))
         return 3
 
-    # full-tuple all-gather, timed separately (SURVEY.md section 7 hard part 1: it, not the scan, bounds N=8)
-    gather = compact = None
+    # full-tuple all-gather, timed separately (SURVEY.md section 7 hard part 1: at 0.35 B/B it moves more bytes per GPU than the
+    # scan reads at N=8, so the path exchanges the parser's records instead and the tuples stay resident on their owner)
+    gather = None
     if world > 1:
         mx = torch.tensor([n_tuples], dtype=torch.int64, device=dev)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         pad = int(mx.item())
         g_out = torch.empty(pad * world, dtype=torch.int64, device=dev)
         src = d_out[:pad]
-        dist.all_gather_into_tensor(g_out, src)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        for _ in range(3):
-            dist.all_gather_into_tensor(g_out, src)
-        g1.record(stream)
-        barrier()
-        gms = g0.elapsed_time(g1) / 3
+        gms = timed(lambda: dist.all_gather_into_tensor(g_out, src), 3)
         gather = {"ms": gms, "bytes_received_per_rank": pad * 8 * (world - 1), "gb_s_per_rank": pad * 8 * (world - 1) / gms / 1e6}
         del g_out
-        # the compact alternative: one 16-byte record per REGISTERED marker instead of every tuple;
-        # index kernel over the resident tuples, then an all-gather of the records (padded to the largest rank)
-        from operator_builder_b200 import _native
-        L = _native.lib()
-        reg = ob.Registry()
-        rec_cap = ndocs * 16
-        d_rec = torch.empty(rec_cap * 4, dtype=torch.int32, device=dev)
-        d_roff = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
-
-        def index():
-            rc = L.obm_marker_index_device(sc.handle, reg.handle, d_bytes.data_ptr(), d_off.data_ptr(), ndocs, d_out.data_ptr(), d_toff.data_ptr(),
-                                           d_rec.data_ptr(), rec_cap, d_roff.data_ptr(), sp)
-            assert rc == 0
-        index()
-        barrier()
-        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        i0.record(stream)
-        for _ in range(3):
-            index()
-        i1.record(stream)
-        barrier()
-        ims = i0.elapsed_time(i1) / 3
-        nrec = int(d_roff[-1].item())
-        mxr = torch.tensor([nrec], dtype=torch.int64, device=dev)
-        dist.all_reduce(mxr, op=dist.ReduceOp.MAX)
-        rpad = int(mxr.item()) * 4
-        r_out = torch.empty(rpad * world, dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(r_out, d_rec[:rpad])
-        barrier()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record(stream)
-        for _ in range(3):
-            dist.all_gather_into_tensor(r_out, d_rec[:rpad])
-        r1.record(stream)
-        barrier()
-        rms = r0.elapsed_time(r1) / 3
-        tm = torch.tensor([ims, rms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        compact = {"index_ms": float(tm[0]), "allgather_ms": float(tm[1]), "records_this_rank": nrec,
-                   "bytes_received_per_rank": rpad * 4 * (world - 1)}
-        del r_out
 
     # max over ranks
-    t = torch.tensor([ms, ms_scan], dtype=torch.float64, device=dev)
-    agg = torch.tensor([n_tuples, n_markers, n_lexemes, status[1], status[2]], dtype=torch.int64, device=dev)
+    t = torch.tensor([ms, ms_scan, ms_parse], dtype=torch.float64, device=dev)
+    agg = torch.tensor([n_tuples, n_markers, n_lexemes, status[1], status[2], n_results, n_args], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    ms, ms_scan = float(t[0].item()), float(t[1].item())
-    tot_tuples, tot_markers, tot_lexemes, docs_exact, docs_fatal = [int(x) for x in agg.tolist()]
+    ms, ms_scan, ms_parse = [float(x) for x in t.tolist()]
+    tot_tuples, tot_markers, tot_lexemes, docs_exact, docs_fatal, tot_results, tot_args = [int(x) for x in agg.tolist()]
     total_bytes = args.docs * DOC_BYTES
 
     # ---- e2e: C-ABI host entry point, pinned host buffers, H2D + D2H inside the timed region ----
@@ -339,6 +341,8 @@ def main():
                "sample": f"{e_docs} docs x {DOC_BYTES} B per rank", "markers_per_s": res.stats["n_markers"] * world / dt,
                "ms_kernels_inside": res.stats["ms_kernels"]}
 
+    if comm is not None:
+        comm.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -355,9 +359,9 @@ def main():
         pass
     cpu = None
     if not args.no_cpu and world >= 1:
-        r = cpu_reference_run(args.cpu_docs, cores, 1, 1, args.flavour)
+        r = cpu_reference_run(args.cpu_docs, cores, 2, 1, args.flavour)
         cpu = {"value": r["mb_s"], "unit": "MB/s", "cores": cores, "kind": "port", "sample": r["sample"],
-               "markers_per_s": r["markers_per_s"]}
+               "markers_per_s": r["markers_per_s"], "single_thread_mb_s": r["single_thread_mb_s"]}
 
     line = {"metric": "manifest_scan_throughput", "value": total_bytes / (ms / 1e3) / 1e6, "unit": "MB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
@@ -370,8 +374,12 @@ def main():
                          "algorithmic_bytes_per_launch": total_bytes // world,
                          "note": "1 B read per input byte (SURVEY 8d); time = all kernels of one scan, per GPU"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "exchange": ({"index_allgather": "4 B/doc counts inside the timed step", "full_tuple_allgather": gather,
-                          "marker_index_allgather": compact} if world > 1 else None)}
+            "parts": {"ms_scan": ms_scan, "ms_parse": ms_parse, "results": tot_results, "args": tot_args,
+                      "result_bytes_per_input_byte": tot_results * 32 / total_bytes},
+            "exchange": ({"in_step": "ncclAllGather of 32-byte Result records (+ an 8-byte count gather), through the C ABI",
+                          "records_per_rank": exch.get("per_rank"), "slot_stride": exch.get("stride"),
+                          "bytes_received_per_rank": (exch.get("stride") or 0) * 32 * (world - 1),
+                          "full_tuple_allgather_not_in_step": gather} if world > 1 else None)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

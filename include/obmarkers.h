@@ -90,6 +90,7 @@ enum obm_status {
 };
 
 typedef struct obm_handle obm_handle;
+typedef struct obm_registry obm_registry; /* marker.Registry stand-in, below */
 
 /* Counters filled by a scan (all per call). */
 typedef struct obm_stats {
@@ -195,6 +196,30 @@ int obm_rewrite_collection_markers_device(obm_handle *h, const void *d_bytes, co
 int obm_split_docs_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs, void *d_records, uint64_t cap,
                           void *d_doc_rec_off, void *stream);
 
+/* --- multi-GPU: manifests shard by file (lexer.go:27-40: one lexer per input), one rank per GPU ------------------
+ * The one exchange step of the path is an NCCL all-gather over NVLink of the shard's compact Result records (what the
+ * parser would hand to internal/workload, ~6 % of the input) -- the full tuple stream (~35 %) stays resident on its
+ * owner.  NCCL is loaded at run time (libnccl.so.2); the caller moves the 128-byte unique id from rank 0 to the other
+ * ranks by whatever channel it has (the Go host: its own RPC; bench.py: torch.distributed).                         */
+typedef struct obm_comm obm_comm;
+#define OBM_COMM_ID_BYTES 128
+int obm_comm_unique_id(uint8_t *id /* OBM_COMM_ID_BYTES */);
+int obm_comm_create(obm_handle *h, const uint8_t *id, int rank, int nranks, obm_comm **out);
+void obm_comm_destroy(obm_comm *c);
+/*
+ * One sharded step on this rank's device-resident shard (documents first_doc .. first_doc + ndocs of the global batch):
+ * scan (obm_lex_batch_device), parse (obm_parse_batch_device; records carry global document ids), then one
+ * ncclAllGather of the obm_result records.  d_results_all receives nranks slots of *stride records each (stride = the
+ * largest per-rank count, chosen inside: one 8-byte count all-gather + host read); rank_results[r] = valid records
+ * of slot r.  Returns OBM_E_CAPACITY (with *stride set) when results_all_cap < nranks * stride.  Tuples, arguments
+ * and offsets of the shard stay in the caller's buffers (d_out, d_args, ...).  The collective is enqueued on `stream`.
+ */
+int obm_lex_batch_sharded_device(obm_comm *c, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
+                                 uint64_t total_bytes, uint32_t first_doc, void *d_out, uint64_t out_cap, void *d_doc_tuple_off, void *d_status,
+                                 void *d_counts, void *d_results, uint64_t res_cap, void *d_args, uint64_t arg_cap, void *d_doc_res_off,
+                                 void *d_results_all, uint64_t results_all_cap, uint64_t *rank_results /* host u64[nranks] */, uint64_t *stride,
+                                 void *stream);
+
 /* --- host-side consumers of the tuple stream (no GPU needed; no lexing happens here) ------- */
 /*
  * Replays one document's tuples as the reference's Lexeme sequence.  Mirrors
@@ -227,7 +252,6 @@ void obm_free(void *p);
  * (marker/marker.go LookupArgument).  obm_parse_doc returns the number of Results and a malloc'd record
  * buffer (format: csrc/obm_parse.cpp); Argument.SetValue / InflateObject type checks are not modelled.
  */
-typedef struct obm_registry obm_registry;
 obm_registry *obm_registry_new(void);
 obm_registry *obm_registry_operator_builder(void); /* field / collection:field / resource markers */
 int obm_registry_add(obm_registry *r, const char *marker_name, const char *const *arg_names, uint32_t nargs);

@@ -7,4 +7,4 @@ directory name is what the project brief prescribes; operator_builder_b200.py al
 """
 from ._native import NativeError, SO_PATH  # noqa: F401
 from .lexer import (BatchResult, Lexeme, LexemeType, Lexer, Position, Scanner, ZERO_LEXEME,  # noqa: F401
-                    decode_doc_raw, generate_corpus_host, Registry, parse_doc_raw)
+                    decode_doc_raw, generate_corpus_host, Registry, parse_doc_raw, Comm)

@@ -18,6 +18,7 @@
  * There is no CPU fallback: without a CUDA device every lexing entry point returns OBM_E_NO_DEVICE.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cstdarg>
 #include <cstdint>
@@ -381,7 +382,7 @@ struct obm_handle {
     /* obm_lex_batch pipelines large host batches in chunks over three slots: H2D of chunk k+1, scan of
      * chunk k and D2H of chunk k-1 overlap (each slot has its own stream, staging and scratch) */
     struct Slot {
-        cudaStream_t st; cudaEvent_t ev_scan;
+        cudaStream_t st; cudaEvent_t ev_scan; cudaEvent_t ev_k0, ev_k1; /* around the chunk's scan kernels (timing) */
         uint8_t *d_bytes; uint64_t d_bytes_cap;
         uint64_t *d_doc_off; uint64_t d_doc_off_cap;
         uint64_t *d_tuple_off; uint64_t d_tuple_off_cap;
@@ -457,7 +458,7 @@ extern "C" void obm_destroy(obm_handle *h) {
         cudaStreamSynchronize(sl.st);
         cudaFree(sl.d_bytes); cudaFree(sl.d_doc_off); cudaFree(sl.d_tuple_off); cudaFree(sl.d_out); cudaFree(sl.scratch);
         cudaFree(sl.d_status); cudaFree(sl.d_counts); cudaFreeHost(sl.h_doc_off); cudaFreeHost(sl.h_info);
-        cudaEventDestroy(sl.ev_scan); cudaStreamDestroy(sl.st);
+        cudaEventDestroy(sl.ev_scan); cudaEventDestroy(sl.ev_k0); cudaEventDestroy(sl.ev_k1); cudaStreamDestroy(sl.st);
     }
     for (int i = 0; i < 4; i++) cudaEventDestroy(h->ev[i]);
     cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaStreamDestroy(h->side);
@@ -771,6 +772,7 @@ static int slots_init(obm_handle *h) {
         memset(&sl, 0, sizeof sl);
         OBM_CUDA(h, cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));
         OBM_CUDA(h, cudaEventCreateWithFlags(&sl.ev_scan, cudaEventDisableTiming));
+        OBM_CUDA(h, cudaEventCreate(&sl.ev_k0)); OBM_CUDA(h, cudaEventCreate(&sl.ev_k1));
         OBM_CUDA(h, cudaMalloc(&sl.d_status, 4 * sizeof(uint32_t)));
         OBM_CUDA(h, cudaMalloc(&sl.d_counts, 2 * sizeof(unsigned long long)));
         OBM_CUDA(h, cudaHostAlloc((void **)&sl.h_info, 8 * sizeof(uint64_t), cudaHostAllocDefault));
@@ -800,9 +802,11 @@ static int chunk_issue(obm_handle *h, obm_handle::Slot &sl, const uint8_t *bytes
     for (uint32_t d = 0; d <= nd; d++) sl.h_doc_off[d] = doc_off[d0 + d] - b0;
     OBM_CUDA(h, cudaMemcpyAsync(sl.d_doc_off, sl.h_doc_off, ((uint64_t)nd + 1) * 8, cudaMemcpyHostToDevice, sl.st));
     if (nb) OBM_CUDA(h, cudaMemcpyAsync(sl.d_bytes, bytes + b0, nb, cudaMemcpyHostToDevice, sl.st));
+    OBM_CUDA(h, cudaEventRecord(sl.ev_k0, sl.st));
     rc = lex_device_impl(h, sl.d_bytes, sl.d_doc_off, nd, nb, want_out ? sl.d_out : nullptr, want_out ? sl.d_out_cap : 0, sl.d_tuple_off,
                          sl.d_status, sl.d_counts, sl.st, &sl.scratch, &sl.scratch_bytes);
     if (rc != OBM_OK) return rc;
+    OBM_CUDA(h, cudaEventRecord(sl.ev_k1, sl.st));
     OBM_CUDA(h, cudaMemcpyAsync(&sl.h_info[0], sl.d_tuple_off + nd, 8, cudaMemcpyDeviceToHost, sl.st));
     OBM_CUDA(h, cudaMemcpyAsync(&sl.h_info[1], sl.d_status, 16, cudaMemcpyDeviceToHost, sl.st));
     OBM_CUDA(h, cudaMemcpyAsync(&sl.h_info[3], sl.d_counts, 16, cudaMemcpyDeviceToHost, sl.st));
@@ -811,12 +815,13 @@ static int chunk_issue(obm_handle *h, obm_handle::Slot &sl, const uint8_t *bytes
     return OBM_OK;
 }
 
-struct ChunkTotals { uint64_t tuples, markers, lexemes, exact, fatal; bool overflow, need_exact; };
+struct ChunkTotals { uint64_t tuples, markers, lexemes, exact, fatal; bool overflow, need_exact; float ms_kernels; };
 
 /* wait for the slot's scan, then enqueue the D2H of its tuples / offsets at their final host positions */
 static int chunk_retire(obm_handle *h, obm_handle::Slot &sl, obm_tuple *out, uint64_t out_cap, uint64_t *doc_tuple_off,
                         uint64_t *chunk_base /* per document's chunk base, filled for the fix-up */, ChunkTotals &T) {
     OBM_CUDA(h, cudaEventSynchronize(sl.ev_scan));
+    { float ms = 0.f; if (cudaEventElapsedTime(&ms, sl.ev_k0, sl.ev_k1) == cudaSuccess) T.ms_kernels += ms; }
     const uint32_t nd = sl.d1 - sl.d0;
     const uint64_t total = sl.h_info[0];
     const uint32_t *st = (const uint32_t *)&sl.h_info[1];
@@ -841,7 +846,7 @@ static int lex_batch_chunked(obm_handle *h, const uint8_t *bytes, const uint64_t
     int rc;
     if ((rc = slots_init(h)) != OBM_OK) return rc;
     OBM_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
-    ChunkTotals T = {0, 0, 0, 0, 0, false, false};
+    ChunkTotals T = {0, 0, 0, 0, 0, false, false, 0.f};
     /* chunk boundaries (document aligned) and the per-chunk tuple base for the final offset fix-up */
     struct Ck { uint32_t d0, d1; uint64_t base; };
     Ck *cks = nullptr; uint32_t nck = 0, capck = 0;
@@ -883,7 +888,7 @@ static int lex_batch_chunked(obm_handle *h, const uint8_t *bytes, const uint64_t
         stats->n_tuples = T.tuples; stats->n_markers = T.markers; stats->n_lexemes = T.lexemes;
         stats->n_docs_exact = T.exact; stats->n_docs_fatal = T.fatal; stats->bytes = total;
         cudaEventElapsedTime(&stats->ms_total, h->ev[0], h->ev[3]);
-        stats->ms_kernels = 0.f; /* scans overlap the copies in this path; see the device entry point for kernel time */
+        stats->ms_kernels = T.ms_kernels; /* sum over the chunks (their scans overlap the copies of other chunks) */
     }
     return 1;
 }
@@ -1421,6 +1426,111 @@ extern "C" int obm_split_docs_device(obm_handle *h, const void *d_bytes, const v
     if (d_records && cap)
         k_split_docs<true><<<nb, 256, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, nullptr, roff, (uint4 *)d_records, cap);
     OBM_CUDA(h, cudaGetLastError());
+    return OBM_OK;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* multi-GPU: one rank per GPU, one NCCL all-gather of the Result records  */
+/* ------------------------------------------------------------------------------------------- */
+/* NCCL is bound at run time so that libobmarkers.so loads (and the single-GPU path works) on a box without it */
+namespace {
+typedef struct ncclComm *ncclComm_t;
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi {
+    void *lib;
+    int (*GetUniqueId)(NcclUniqueId *);
+    int (*CommInitRank)(ncclComm_t *, int, NcclUniqueId, int);
+    int (*CommDestroy)(ncclComm_t);
+    int (*AllGather)(const void *, void *, size_t, int /* ncclDataType_t */, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(int);
+};
+NcclApi *nccl_api() {
+    static NcclApi api; static int state = 0; /* 0 untried, 1 ok, -1 failed */
+    if (state == 0) {
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+        state = -1;
+        if (api.lib) {
+            api.GetUniqueId = (int (*)(NcclUniqueId *))dlsym(api.lib, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(ncclComm_t *, int, NcclUniqueId, int))dlsym(api.lib, "ncclCommInitRank");
+            api.CommDestroy = (int (*)(ncclComm_t))dlsym(api.lib, "ncclCommDestroy");
+            api.AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))dlsym(api.lib, "ncclAllGather");
+            api.GetErrorString = (const char *(*)(int))dlsym(api.lib, "ncclGetErrorString");
+            if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString) state = 1;
+        }
+    }
+    return state == 1 ? &api : nullptr;
+}
+constexpr int NCCL_UINT8 = 1, NCCL_UINT64 = 5; /* ncclDataType_t: ncclUint8 = 1, ncclUint64 = 5 (nccl.h) */
+}
+struct obm_comm {
+    obm_handle *h; ncclComm_t comm; int rank, nranks;
+    uint64_t *d_counts_all; uint64_t *h_counts; /* [nranks]: device / pinned host */
+    uint64_t *d_totals;                        /* {results, args} of the last step */
+};
+#define OBM_NCCL(h, call)                                                                                 \
+    do { int e_ = (call); if (e_ != 0) { set_err((h), "%s failed: %s", #call, nccl_api()->GetErrorString(e_)); return OBM_E_CUDA; } } while (0)
+
+extern "C" int obm_comm_unique_id(uint8_t *id) {
+    NcclApi *N = nccl_api();
+    if (!id) return OBM_E_ARG;
+    if (!N) { set_err(nullptr, "libnccl.so.2 not found: the multi-GPU entry points need NCCL"); return OBM_E_NO_DEVICE; }
+    NcclUniqueId u;
+    if (N->GetUniqueId(&u) != 0) { set_err(nullptr, "ncclGetUniqueId failed"); return OBM_E_CUDA; }
+    memcpy(id, u.internal, OBM_COMM_ID_BYTES);
+    return OBM_OK;
+}
+extern "C" int obm_comm_create(obm_handle *h, const uint8_t *id, int rank, int nranks, obm_comm **out) {
+    if (!h || !id || !out || nranks < 1 || rank < 0 || rank >= nranks) return OBM_E_ARG;
+    *out = nullptr;
+    NcclApi *N = nccl_api();
+    if (!N) { set_err(h, "libnccl.so.2 not found: the multi-GPU entry points need NCCL"); return OBM_E_NO_DEVICE; }
+    OBM_CUDA(h, cudaSetDevice(h->device));
+    obm_comm *c = new (std::nothrow) obm_comm();
+    if (!c) return OBM_E_NOMEM;
+    memset(c, 0, sizeof *c);
+    c->h = h; c->rank = rank; c->nranks = nranks;
+    NcclUniqueId u; memcpy(u.internal, id, OBM_COMM_ID_BYTES);
+    int e = N->CommInitRank(&c->comm, nranks, u, rank);
+    if (e != 0) { set_err(h, "ncclCommInitRank failed: %s", N->GetErrorString(e)); delete c; return OBM_E_CUDA; }
+    if (cudaMalloc(&c->d_counts_all, (size_t)nranks * 8) != cudaSuccess || cudaMalloc(&c->d_totals, 16) != cudaSuccess ||
+        cudaHostAlloc((void **)&c->h_counts, (size_t)nranks * 8, cudaHostAllocDefault) != cudaSuccess) {
+        set_err(h, "obm_comm_create: allocation failed"); N->CommDestroy(c->comm); delete c; return OBM_E_CUDA;
+    }
+    *out = c;
+    return OBM_OK;
+}
+extern "C" void obm_comm_destroy(obm_comm *c) {
+    if (!c) return;
+    cudaSetDevice(c->h->device);
+    if (nccl_api()) nccl_api()->CommDestroy(c->comm);
+    cudaFree(c->d_counts_all); cudaFree(c->d_totals); cudaFreeHost(c->h_counts);
+    delete c;
+}
+extern "C" int obm_lex_batch_sharded_device(obm_comm *c, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
+                                            uint64_t total_bytes, uint32_t first_doc, void *d_out, uint64_t out_cap, void *d_doc_tuple_off, void *d_status,
+                                            void *d_counts, void *d_results, uint64_t res_cap, void *d_args, uint64_t arg_cap, void *d_doc_res_off,
+                                            void *d_results_all, uint64_t results_all_cap, uint64_t *rank_results, uint64_t *stride, void *stream) {
+    if (!c || !reg || !d_results || !d_args || !d_doc_res_off || !d_results_all || !rank_results || !stride) return OBM_E_ARG;
+    obm_handle *h = c->h; NcclApi *N = nccl_api(); cudaStream_t st = (cudaStream_t)stream;
+    int rc = obm_lex_batch_device(h, d_bytes, d_doc_off, ndocs, total_bytes, d_out, out_cap, d_doc_tuple_off, d_status, d_counts, stream);
+    if (rc != OBM_OK) return rc;
+    rc = obm_parse_batch_device(h, reg, d_bytes, d_doc_off, ndocs, first_doc, d_out, d_doc_tuple_off, d_results, res_cap, d_args, arg_cap, d_doc_res_off,
+                                c->d_totals, stream);
+    if (rc != OBM_OK) return rc;
+    /* how many records does every rank hold?  (8 bytes per rank; the host needs the largest to size the slots) */
+    OBM_NCCL(h, N->AllGather(c->d_totals, c->d_counts_all, 1, NCCL_UINT64, c->comm, st));
+    OBM_CUDA(h, cudaMemcpyAsync(c->h_counts, c->d_counts_all, (size_t)c->nranks * 8, cudaMemcpyDeviceToHost, st));
+    OBM_CUDA(h, cudaStreamSynchronize(st));
+    uint64_t mx = 0;
+    for (int r = 0; r < c->nranks; r++) { rank_results[r] = c->h_counts[r]; if (c->h_counts[r] > mx) mx = c->h_counts[r]; }
+    *stride = mx;
+    if (c->h_counts[c->rank] > res_cap) { set_err(h, "result capacity %llu < %llu records of this shard", (unsigned long long)res_cap, (unsigned long long)c->h_counts[c->rank]); return OBM_E_CAPACITY; }
+    if (mx > res_cap || mx * (uint64_t)c->nranks > results_all_cap) {
+        set_err(h, "gather capacity: need %llu records per slot (send buffer) and %llu in all", (unsigned long long)mx, (unsigned long long)(mx * c->nranks));
+        return OBM_E_CAPACITY;
+    }
+    if (mx) OBM_NCCL(h, N->AllGather(d_results, d_results_all, (size_t)mx * sizeof(obm_result), NCCL_UINT8, c->comm, st));
     return OBM_OK;
 }
 

@@ -171,6 +171,12 @@ class Scanner:
         self._check(self._L.obm_lex_batch_device(self._h, d_bytes, d_doc_off, ndocs, total_bytes, d_out, out_cap,
                                                  d_tuple_off, d_status, d_counts, stream))
 
+    def parse_batch_device(self, registry, d_bytes, d_doc_off, ndocs, doc_base, d_tuples, d_tuple_off, d_results, res_cap, d_args, arg_cap,
+                           d_doc_res_off, d_totals=None, stream=None):
+        """The parser on the device (include/obmarkers.h: obm_parse_batch_device). Asynchronous."""
+        self._check(self._L.obm_parse_batch_device(self._h, registry.handle, d_bytes, d_doc_off, ndocs, doc_base, d_tuples, d_tuple_off, d_results,
+                                                   res_cap, d_args, arg_cap, d_doc_res_off, d_totals, stream))
+
     def generate_corpus_device(self, d_bytes, d_doc_off, ndocs, doc_bytes, first_doc=0, flavour=0, stream=None):
         self._check(self._L.obm_generate_corpus_device(self._h, d_bytes, d_doc_off, ndocs, doc_bytes, first_doc, flavour, stream))
 
@@ -185,6 +191,52 @@ class Scanner:
         if self._h:
             self._L.obm_destroy(self._h)
             self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Comm:
+    """One rank of the multi-GPU path (obm_comm_*): file shards, one NCCL all-gather of the compact Result records."""
+
+    def __init__(self, scanner: Scanner, unique_id: bytes, rank: int, nranks: int):
+        self._L = _native.lib()
+        self.scanner, self.rank, self.nranks = scanner, rank, nranks
+        c = ctypes.c_void_p()
+        idbuf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        rc = self._L.obm_comm_create(scanner.handle, idbuf, rank, nranks, ctypes.byref(c))
+        if rc != 0:
+            raise NativeError(rc, self._L.obm_last_error(scanner.handle).decode())
+        self._c = c
+
+    @staticmethod
+    def unique_id() -> bytes:
+        L = _native.lib()
+        buf = (ctypes.c_uint8 * 128)()
+        rc = L.obm_comm_unique_id(buf)
+        if rc != 0:
+            raise NativeError(rc, L.obm_last_error(None).decode())
+        return bytes(buf)
+
+    def lex_batch_sharded_device(self, registry, d_bytes, d_doc_off, ndocs, total_bytes, first_doc, d_out, out_cap, d_tuple_off, d_status, d_counts,
+                                 d_results, res_cap, d_args, arg_cap, d_doc_res_off, d_results_all, results_all_cap, stream=None):
+        """-> (records per rank, slot stride) ; the all-gather is enqueued on `stream`"""
+        per_rank = (ctypes.c_uint64 * self.nranks)()
+        stride = ctypes.c_uint64()
+        rc = self._L.obm_lex_batch_sharded_device(self._c, registry.handle, d_bytes, d_doc_off, ndocs, total_bytes, first_doc, d_out, out_cap,
+                                                  d_tuple_off, d_status, d_counts, d_results, res_cap, d_args, arg_cap, d_doc_res_off,
+                                                  d_results_all, results_all_cap, per_rank, ctypes.byref(stride), stream)
+        if rc != 0:
+            raise NativeError(rc, self._L.obm_last_error(self.scanner.handle).decode())
+        return list(per_rank), int(stride.value)
+
+    def close(self):
+        if self._c:
+            self._L.obm_comm_destroy(self._c)
+            self._c = None
 
     def __del__(self):
         try:

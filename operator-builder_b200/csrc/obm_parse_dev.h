@@ -29,7 +29,7 @@ struct DevRegistry { /* names and argument names back to back in text[] */
 OBM_HD bool slice_eq(const uint8_t *doc, uint32_t off, uint32_t len, const uint8_t *t, uint32_t tlen) {
     if (len != tlen) return false;
     uint32_t diff = 0;
-    for (uint32_t k = 0; k < len; k++) diff |= (uint32_t)doc[off + k] ^ (uint32_t)t[k];
+    for (uint32_t k = 0; k < len; k++) diff |= (uint32_t)doc[off + k] ^ (uint32_t)t[k]; /* independent loads: they pipeline */
     return diff == 0;
 }
 OBM_HD int lookup_marker(const DevRegistry &R, const uint8_t *doc, uint32_t off, uint32_t len) {

@@ -53,13 +53,14 @@ type Lexer struct {
 	stream *C.obm_stream
 	keep   *Batch // keeps the C buffers alive
 	closed bool
+	failure string // infrastructure failure, reported in band by the first NextLexeme
 }
 
 // Batch owns the C copies of the documents and the tuple stream of one obm_lex_batch call.
 type Batch struct {
-	bytes    unsafe.Pointer // C memory: packed documents
+	bytes    unsafe.Pointer // page-locked C memory: packed documents
 	docOff   []C.uint64_t
-	tuples   unsafe.Pointer // C memory: obm_tuple[]
+	tuples   unsafe.Pointer // page-locked C memory: obm_tuple[]
 	tupleOff []C.uint64_t
 	Stats    C.obm_stats
 }
@@ -83,7 +84,10 @@ func getHandle() (*C.obm_handle, error) {
 	return handle, handleErr
 }
 
-// LexBatch lexes every document in one GPU call.
+// LexBatch lexes every document in ONE obm_lex_batch call.  The packed documents and the tuple buffer live in
+// page-locked C memory (obm_pinned_alloc) so that the library's H2D / D2H copies run at DMA speed; the tuple buffer is
+// sized from the input (manifests need ~0.35 B of tuples per byte, 1 B/byte + 4 tuples per document is a safe first
+// guess) and grown once if the library answers OBM_E_CAPACITY with the exact count.
 func LexBatch(docs [][]byte) (*Batch, error) {
 	h, err := getHandle()
 	if err != nil {
@@ -94,7 +98,11 @@ func LexBatch(docs [][]byte) (*Batch, error) {
 		total += len(d)
 	}
 	b := &Batch{docOff: make([]C.uint64_t, len(docs)+1), tupleOff: make([]C.uint64_t, len(docs)+1)}
-	b.bytes = C.malloc(C.size_t(total + 1))
+	b.bytes = C.obm_pinned_alloc(C.uint64_t(total + 64))
+	if b.bytes == nil {
+		return nil, errors.New("obm_pinned_alloc failed")
+	}
+	runtime.SetFinalizer(b, func(b *Batch) { C.obm_pinned_free(b.bytes); C.obm_pinned_free(b.tuples) })
 	off := 0
 	for i, d := range docs {
 		b.docOff[i] = C.uint64_t(off)
@@ -104,22 +112,30 @@ func LexBatch(docs [][]byte) (*Batch, error) {
 		off += len(d)
 	}
 	b.docOff[len(docs)] = C.uint64_t(off)
-	runtime.SetFinalizer(b, func(b *Batch) { C.free(b.bytes); C.free(b.tuples) })
 
 	handleMu.Lock()
 	defer handleMu.Unlock()
-	var need C.uint64_t
-	// sizing call, then the real one (the callee keeps no pointer after return)
-	rc := C.obm_lex_batch(h, (*C.uint8_t)(b.bytes), &b.docOff[0], C.uint32_t(len(docs)), nil, 0, &need, &b.tupleOff[0], nil)
-	if rc != C.OBM_OK && rc != C.OBM_E_CAPACITY {
-		return nil, errors.New(C.GoString(C.obm_last_error(h)))
+	capTuples := C.uint64_t(total/8 + 4*len(docs) + 64)
+	for attempt := 0; attempt < 2; attempt++ {
+		if b.tuples != nil {
+			C.obm_pinned_free(b.tuples)
+		}
+		b.tuples = C.obm_pinned_alloc(capTuples * 8)
+		if b.tuples == nil {
+			return nil, errors.New("obm_pinned_alloc failed")
+		}
+		var need C.uint64_t
+		rc := C.obm_lex_batch(h, (*C.uint8_t)(b.bytes), &b.docOff[0], C.uint32_t(len(docs)), (*C.obm_tuple)(b.tuples), capTuples, &need,
+			&b.tupleOff[0], &b.Stats)
+		if rc == C.OBM_OK {
+			return b, nil
+		}
+		if rc != C.OBM_E_CAPACITY {
+			return nil, errors.New(C.GoString(C.obm_last_error(h)))
+		}
+		capTuples = need // exact, reported by the library: the second attempt cannot fail for capacity
 	}
-	b.tuples = C.malloc(C.size_t(need+1) * 8)
-	rc = C.obm_lex_batch(h, (*C.uint8_t)(b.bytes), &b.docOff[0], C.uint32_t(len(docs)), (*C.obm_tuple)(b.tuples), need, &need, &b.tupleOff[0], &b.Stats)
-	if rc != C.OBM_OK {
-		return nil, errors.New(C.GoString(C.obm_last_error(h)))
-	}
-	return b, nil
+	return nil, errors.New("obm_lex_batch: capacity retry failed")
 }
 
 // Lexer returns the pre-lexed stream of document i.
@@ -133,13 +149,18 @@ func (b *Batch) Lexer(i int) *Lexer {
 	return l
 }
 
-// NewLexer creates a lexer for the input reader (lexer.go:27): a batch of one document.
+// NewLexer creates a lexer for the input reader (lexer.go:27): a batch of one document.  An infrastructure failure
+// (no device, CUDA error) cannot be returned from this signature; it is surfaced the way the reference surfaces lexical
+// errors -- in band: the first NextLexeme yields a LexemeError whose Value carries the library's message, then the
+// stream is closed.  (The parser turns a LexemeError into an error Result, parser/state.go:33-37.)
 func NewLexer(r io.Reader) *Lexer {
-	data, _ := io.ReadAll(r)
+	data, rerr := io.ReadAll(r)
+	if rerr != nil {
+		return &Lexer{failure: "reading the lexer input: " + rerr.Error()}
+	}
 	b, err := LexBatch([][]byte{data})
 	if err != nil {
-		// infrastructure failure: surface it the way the reference surfaces lexical errors, in-band
-		return &Lexer{closed: true}
+		return &Lexer{failure: "operator-builder GPU lexer: " + err.Error()}
 	}
 	return b.Lexer(0)
 }
@@ -150,6 +171,10 @@ func (l *Lexer) Run() {}
 // NextLexeme returns the next lexeme; after the last one it returns the zero Lexeme, like a receive
 // from the closed channel in the reference (lexer.go:47,51-53).
 func (l *Lexer) NextLexeme() Lexeme {
+	if l.failure != "" && !l.closed {
+		l.closed = true
+		return Lexeme{Type: LexemeError, Value: l.failure}
+	}
 	if l.closed || l.stream == nil {
 		return Lexeme{}
 	}

@@ -299,6 +299,15 @@ typedef struct obm_arg {
 } obm_arg;
 enum { OBM_R_OK = 1, OBM_R_NL = 2, OBM_R_ERR_PARSEBOOL = 4, OBM_R_ERR_FLOAT32 = 8, OBM_R_HOST = 16 };
 enum { OBM_A_SYNTHETIC_TRUE = 1 };
+/*
+ * Per-document 64-bit hash of the DECODED lexeme stream, computed on the device from the resident tuples: FNV-1a over
+ * the records [u8 type][u32 line][u32 col][u32 vlen][value] that obm_decode_doc serialises (and that the reference
+ * lexer would send: Type, Pos, Value).  Lets a full-size batch (4 GiB, 10 GiB) be checked document by document against a
+ * CPU run without moving the tuples.  Documents the device walk does not model (pseudo-tuples other than LINE, bytes
+ * >= 0x80 inside a value) get hash 0 and are counted in *d_n_host (device u32): hash those from obm_decode_doc.
+ */
+int obm_hash_batch_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs, const void *d_tuples,
+                          const void *d_doc_tuple_off, void *d_hashes /* u64[ndocs] */, void *d_n_host, void *stream);
 int obm_parse_batch_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs, uint32_t doc_base,
                            const void *d_tuples, const void *d_doc_tuple_off, void *d_results, uint64_t res_cap, void *d_args, uint64_t arg_cap,
                            void *d_doc_res_off, void *d_totals, void *stream);

@@ -1358,6 +1358,76 @@ k_parse_docs(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc
     }
 }
 
+/* ------------------------------------------------------------------------------------------- */
+/* per-document hash of the DECODED lexeme stream, on the device: the check BASELINE.md section 2 asks for at full size */
+/* ------------------------------------------------------------------------------------------- */
+/* FNV-1a (offset basis 0xcbf29ce484222325) over exactly the bytes obm_decode_doc / the oracle serialise per lexeme:
+ * [u8 type][u32 line][u32 col][u32 vlen][value].  Walks plain lexemes and LINE tuples (Pos = {line, off - base + 1};
+ * synthetic lexemes {0, 0} with values "true" / "\n" / ""); a document with pseudo-tuples the walk does not model or with
+ * bytes >= 0x80 in a value (the decoder substitutes U+FFFD for invalid ones) gets hash 0 and counts in *n_host: hash those
+ * on the host from obm_decode_doc.  Same staging as k_parse_docs: 32 documents' tuples per warp in shared memory. */
+__device__ __forceinline__ uint64_t fnv1a_u8(uint64_t h, uint32_t b) { return (h ^ (uint64_t)b) * 0x100000001b3ull; }
+__device__ __forceinline__ uint64_t fnv1a_u32(uint64_t h, uint32_t v) { h = fnv1a_u8(h, v & 0xFF); h = fnv1a_u8(h, (v >> 8) & 0xFF); h = fnv1a_u8(h, (v >> 16) & 0xFF); return fnv1a_u8(h, v >> 24); }
+__global__ void __launch_bounds__(PD_WARPS * 32)
+k_hash_docs(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs, const obm_tuple *__restrict__ tuples,
+            const uint64_t *__restrict__ tuple_off, uint64_t *__restrict__ hashes, uint32_t *__restrict__ n_host) {
+    extern __shared__ __align__(16) uint8_t pd_smem[];
+    obm_tuple *sm = reinterpret_cast<obm_tuple *>(pd_smem) + (size_t)(threadIdx.x >> 5) * PD_CAP;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ngroups = (ndocs + 31) / 32;
+    for (uint32_t g = blockIdx.x * PD_WARPS + (threadIdx.x >> 5); g < ngroups; g += gridDim.x * PD_WARPS) {
+        const uint32_t dlo = g * 32, dhi = min(dlo + 32, ndocs);
+        const uint64_t t_lo = tuple_off[dlo], t_hi = tuple_off[dhi];
+        const bool staged = t_hi - t_lo <= PD_CAP;
+        __syncwarp();
+        if (staged) for (uint32_t k = lane; k < (uint32_t)(t_hi - t_lo); k += 32) sm[k] = tuples[t_lo + k];
+        __syncwarp();
+        const uint32_t d = dlo + lane;
+        if (d >= dhi) continue;
+        const uint64_t t0 = tuple_off[d];
+        const obm_tuple *t = staged ? sm + (t0 - t_lo) : tuples + t0;
+        const uint32_t nt = (uint32_t)(tuple_off[d + 1] - t0);
+        const uint8_t *doc = bytes + doc_off[d];
+        uint64_t h = 0xcbf29ce484222325ull;
+        uint32_t line = 1, base = 0; bool host = false;
+        for (uint32_t i = 0; i < nt && !host; i++) {
+            const obm_tuple tu = t[i];
+            const uint32_t k = OBM_TUPLE_KIND(tu), off = OBM_TUPLE_OFF(tu), len = OBM_TUPLE_LEN(tu);
+            if (k == OBM_K_LINE) { base = off; line = len; continue; }
+            if (k > OBM_K_EOF) { host = true; break; }
+            const bool synthetic = k == OBM_K_SYNTHETIC_BOOL || k == OBM_K_MARKER_END || k == OBM_K_EOF;
+            const uint32_t vlen = k == OBM_K_SYNTHETIC_BOOL ? 4u : k == OBM_K_MARKER_END ? 1u : k == OBM_K_EOF ? 0u : len;
+            h = fnv1a_u8(h, k);
+            h = fnv1a_u32(h, synthetic ? 0u : line);
+            h = fnv1a_u32(h, synthetic ? 0u : off - base + 1u);
+            h = fnv1a_u32(h, vlen);
+            if (k == OBM_K_SYNTHETIC_BOOL) { h = fnv1a_u8(h, 't'); h = fnv1a_u8(h, 'r'); h = fnv1a_u8(h, 'u'); h = fnv1a_u8(h, 'e'); }
+            else if (k == OBM_K_MARKER_END) h = fnv1a_u8(h, '\n');
+            else if (k != OBM_K_EOF) for (uint32_t b = 0; b < len; b++) { const uint32_t c = doc[off + b]; if (c >= 0x80) host = true; h = fnv1a_u8(h, c); }
+        }
+        if (host) { atomicAdd(n_host, 1u); h = 0; }
+        hashes[d] = h;
+    }
+}
+extern "C" int obm_hash_batch_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs, const void *d_tuples,
+                                     const void *d_doc_tuple_off, void *d_hashes, void *d_n_host, void *stream) {
+    if (!h || !d_doc_off || !d_doc_tuple_off || !d_hashes || !d_n_host) return OBM_E_ARG;
+    OBM_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    OBM_CUDA(h, cudaMemsetAsync(d_n_host, 0, 4, st));
+    if (ndocs == 0) return OBM_OK;
+    const size_t pd_smem = (size_t)PD_WARPS * PD_CAP * sizeof(obm_tuple);
+    OBM_CUDA(h, cudaFuncSetAttribute(k_hash_docs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd_smem));
+    int sms_p = 0;
+    OBM_CUDA(h, cudaDeviceGetAttribute(&sms_p, cudaDevAttrMultiProcessorCount, h->device));
+    uint32_t nb = (uint32_t)sms_p * 2u;
+    { const uint32_t gmax = ((ndocs + 31) / 32 + PD_WARPS - 1) / PD_WARPS; if (nb > gmax) nb = gmax; }
+    k_hash_docs<<<nb, PD_WARPS * 32, pd_smem, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, (const obm_tuple *)d_tuples,
+                                                   (const uint64_t *)d_doc_tuple_off, (uint64_t *)d_hashes, (uint32_t *)d_n_host);
+    OBM_CUDA(h, cudaGetLastError());
+    return OBM_OK;
+}
+
 extern "C" int obm_parse_batch_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs, uint32_t doc_base,
                                       const void *d_tuples, const void *d_doc_tuple_off, void *d_results, uint64_t res_cap, void *d_args, uint64_t arg_cap,
                                       void *d_doc_res_off, void *d_totals, void *stream) {

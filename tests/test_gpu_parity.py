@@ -339,3 +339,50 @@ def test_full_size_properties_on_device(scanner):
     a, b = int(full_toff[100000].item()), int(full_toff[100000 + sub].item())
     assert b - a == int(s_toff[-1].item())
     assert torch.equal(full_out[a:b], s_out[:b - a])
+
+
+@pytest.mark.parametrize("ndocs,flavour,name", [(1048576, 1, "C3: workload-collection spelling, 4 GiB"), (2621440, 0, "C4: 10 GiB")])
+def test_full_size_corpus_per_document_hash(scanner, oracle, ndocs, flavour, name):
+    """BASELINE.md section 2 at the benched sizes: EVERY document of the resident batch, through a 64-bit hash of its decoded
+    lexeme stream (Type, Pos, Value).  GPU side: obm_hash_batch_device over the tuples of the fused warp kernel's scan;
+    CPU side: the oracle's own per-document hash (oracle.scan_batch(want_doc_hash=True)) over the same bytes copied back."""
+    import ctypes
+    import torch
+    from operator_builder_b200 import _native
+    dev = torch.device("cuda:0")
+    doc_bytes = 4096
+    free, _total = torch.cuda.mem_get_info()
+    if free < ndocs * doc_bytes * 1.8 + (2 << 30):
+        pytest.skip("not enough free HBM for " + name)
+    st = torch.cuda.current_stream().cuda_stream
+    d_bytes = torch.empty(ndocs * doc_bytes, dtype=torch.uint8, device=dev)
+    d_off = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
+    scanner.generate_corpus_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, doc_bytes, 0, flavour, st)
+    cap = ndocs * doc_bytes // 16
+    d_out = torch.empty(cap, dtype=torch.int64, device=dev)
+    d_toff = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
+    d_status = torch.zeros(4, dtype=torch.int32, device=dev)
+    d_counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    scanner.set_mode(0)
+    scanner.lex_batch_device(d_bytes.data_ptr(), d_off.data_ptr(), ndocs, ndocs * doc_bytes, d_out.data_ptr(), cap, d_toff.data_ptr(),
+                             d_status.data_ptr(), d_counts.data_ptr(), st)
+    d_hash = torch.zeros(ndocs, dtype=torch.int64, device=dev)
+    d_nhost = torch.zeros(1, dtype=torch.int32, device=dev)
+    L = _native.lib()
+    rc = L.obm_hash_batch_device(scanner.handle, d_bytes.data_ptr(), d_off.data_ptr(), ndocs, d_out.data_ptr(), d_toff.data_ptr(), d_hash.data_ptr(),
+                                 d_nhost.data_ptr(), st)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert int(d_status[0].item()) == 0 and int(d_counts[0].item()) == 8 * ndocs
+    assert int(d_nhost.item()) == 0  # synthetic manifests: every document is hashed on the device
+    got = d_hash.cpu().numpy().view(np.uint64)
+    host = d_bytes.cpu().numpy()
+    off = d_off.cpu().numpy().astype(np.uint64)
+    del d_bytes, d_out
+    torch.cuda.empty_cache()
+    import os
+    threads = max(1, len(os.sched_getaffinity(0)))
+    n_lex, n_mark, _h, want = oracle.scan_batch(host, off, threads, want_doc_hash=True)
+    assert n_mark == 8 * ndocs and n_lex == int(d_counts[1].item())
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, (name, len(bad), bad[:10])

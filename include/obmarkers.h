@@ -76,8 +76,9 @@ enum obm_kind {
 #define OBM_TUPLE_LEN(t) ((uint32_t)(((t) >> 32) & OBM_MAX_LEN))
 #define OBM_TUPLE_OFF(t) ((uint32_t)((t) & 0xFFFFFFFFu))
 
-/* A document may be at most 2^32 - 2 bytes (offsets are 32-bit inside a document). */
-#define OBM_MAX_DOC_BYTES 0xFFFFFFFEull
+/* A document may be at most 2^31 - 2 bytes: offsets are 32-bit inside a document and the per-document tuple counts are
+ * 32-bit too (the grammar emits up to 1.5 tuples per byte: ",c" is Arg + SyntheticBool + ArgDelimiter). */
+#define OBM_MAX_DOC_BYTES 0x7FFFFFFEull
 
 /* return codes */
 enum obm_status {
@@ -120,7 +121,8 @@ const char *obm_last_error(const obm_handle *h);
  *   doc_off      ndocs+1 ascending byte offsets into `bytes`
  *   out          receives tuples; document d's tuples are out[doc_tuple_off[d] .. doc_tuple_off[d+1])
  *   out_cap      capacity of `out` in tuples.  If too small: returns OBM_E_CAPACITY with the needed
- *                count in *out_count and doc_tuple_off filled; nothing is written to `out`.
+ *                count in *out_count and doc_tuple_off filled; the contents of `out` are then unspecified (the
+ *                chunked path may already have copied the tuples of earlier chunks).
  *                Pass out = NULL, out_cap = 0 to size a buffer.
  *   stats        optional
  */
@@ -150,7 +152,7 @@ int obm_lex_batch_device(obm_handle *h, const void *d_bytes, const void *d_doc_o
 uint64_t obm_scratch_bytes(uint32_t ndocs, uint64_t total_bytes);
 
 /* Deterministic synthetic corpus generated ON DEVICE (BASELINE.md config C2/C3/C4 generator; the
- * same generator exists on the host in operator-builder_b200/corpus.py for parity tests).
+ * same generator exists on the host: obm_generate_corpus_host below, oracle/corpus_gen.cpp for the reference arm).
  * Writes ndocs documents of exactly doc_bytes bytes starting at global document index first_doc.
  * flavour: 0 = standalone markers, 1 = collection markers. */
 int obm_generate_corpus_device(obm_handle *h, void *d_bytes, void *d_doc_off, uint32_t ndocs,
@@ -260,8 +262,10 @@ void obm_registry_free(obm_registry *r);
  * Device side of the same row: a compact index of the REGISTERED markers in a tuple stream that is still in
  * HBM -- one 16-byte record {u32 doc, u32 tuple index in the document, u32 offset of '+', u16 registry id,
  * u16 scope count} per marker whose name parser/definition.go:13-21 would find in the registry (at most 8
- * names, 512 bytes).  d_doc_rec_off[ndocs+1] receives the per-document record offsets (last = total).  With
- * d_records == NULL only the offsets are computed.  This index (~3 % of the input), not the tuple stream
+ * names, 512 bytes: more is OBM_E_ARG).  d_doc_rec_off[ndocs+1] receives the per-document record offsets (last =
+ * total); records beyond `cap` are not written -- compare the total with cap (the same holds for obm_split_docs_device).
+ * With d_records == NULL only the offsets are computed.  These next-row entry points use the handle's scratch: enqueue
+ * them on the stream the handle's scans run on (one stream per handle).  This index (~3 % of the input), not the tuple stream
  * (~35 %), is what ranks exchange over NVLink.
  */
 int obm_marker_index_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,

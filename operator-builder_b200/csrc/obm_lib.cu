@@ -1101,6 +1101,7 @@ extern "C" int obm_marker_index_device(obm_handle *h, const obm_registry *reg, c
     DevRegistry R; memset(&R, 0, sizeof R);
     uint32_t nm = 0; const char *nmv[8]; uint32_t nml[8];
     nm = obm_registry_names(reg, nmv, nml, 8);
+    if (obm_registry_names(reg, nullptr, nullptr, 0xFFFFFFFFu) > 8) { set_err(h, "the device index holds at most 8 marker names"); return OBM_E_ARG; }
     uint32_t o = 0;
     for (uint32_t r = 0; r < nm; r++) {
         if (o + nml[r] > sizeof R.text) { set_err(h, "registry too large for the device index"); return OBM_E_ARG; }
@@ -1494,7 +1495,12 @@ extern "C" int obm_rewrite_collection_markers_device(obm_handle *h, const void *
     k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(counts, ndocs, noff, tile_sums);
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, noff + ndocs);
     k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(noff, ndocs, tile_sums, ~0ull, nullptr);
-    (void)out_cap; /* the rewrite only shrinks: a buffer of the input size always suffices */
+    if (d_out_bytes) { /* the rewritten size is known now: never write past the caller's buffer */
+        uint64_t total = 0;
+        OBM_CUDA(h, cudaMemcpyAsync(&total, noff + ndocs, 8, cudaMemcpyDeviceToHost, st));
+        OBM_CUDA(h, cudaStreamSynchronize(st));
+        if (total > out_cap) { set_err(h, "rewrite needs %llu bytes, out_cap is %llu", (unsigned long long)total, (unsigned long long)out_cap); return OBM_E_CAPACITY; }
+    }
     if (d_out_bytes)
         k_rewrite_collection<true><<<nb, 256, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, nullptr, noff, (uint8_t *)d_out_bytes);
     OBM_CUDA(h, cudaGetLastError());

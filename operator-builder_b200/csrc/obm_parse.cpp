@@ -57,6 +57,7 @@ extern "C" obm_registry *obm_registry_operator_builder(void) {
 
 /* names of the registry (internal use by the device index, obm_lib.cu) */
 extern "C" uint32_t obm_registry_names(const obm_registry *r, const char **names, uint32_t *lens, uint32_t cap) {
+    if (cap == 0xFFFFFFFFu) return (uint32_t)r->defs.size(); /* count only */
     uint32_t n = 0;
     for (const auto &d : r->defs) { if (n >= cap) break; names[n] = d.name.data(); lens[n] = (uint32_t)d.name.size(); n++; }
     return n;

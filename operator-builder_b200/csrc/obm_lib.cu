@@ -1326,37 +1326,22 @@ static int two_pass_scratch(obm_handle *h, uint32_t ndocs, cudaStream_t st, uint
 /* ------------------------------------------------------------------------------------------- */
 #include "obm_parse_dev.h"
 extern "C" bool obm_registry_flatten(const obm_registry *r, obmr::DevRegistry *D);
-/* A warp takes 32 consecutive documents: their tuples are one contiguous range of the stream, staged into the warp's slice of
- * shared memory with coalesced loads; then every lane walks ITS document from shared memory (the walk is a dependent chain of
- * ~180 tuple reads: from global memory it is latency-bound -- 25 ms per 10 GiB of corpus -- from shared memory it is not).
- * Groups whose tuples do not fit the slice are walked from global memory. */
-constexpr uint32_t PD_WARPS = 2, PD_CAP = 6144; /* warps per block; tuples staged per warp (48 KiB) */
+/* A thread per document, as many threads as the SM holds: the walk is a dependent chain of ~180 tuple reads per document,
+ * i.e. latency-bound -- what hides the latency is the number of documents in flight, not staging (a version that staged 32
+ * documents' tuples per warp in 48 KiB of shared memory ran at 4 warps per SM and was 11x slower). */
+constexpr uint32_t PD_WARPS = 2, PD_CAP = 6144; /* k_hash_docs: warps per block; tuples staged per warp (48 KiB) */
 template <bool WRITE>
-__global__ void __launch_bounds__(PD_WARPS * 32)
+__global__ void __launch_bounds__(128)
 k_parse_docs(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs, uint32_t doc_base,
              const obm_tuple *__restrict__ tuples, const uint64_t *__restrict__ tuple_off, const __grid_constant__ obmr::DevRegistry R,
              uint32_t *__restrict__ cnt_res, uint32_t *__restrict__ cnt_args, const uint64_t *__restrict__ res_off, const uint64_t *__restrict__ arg_off,
              obm_result *__restrict__ res, uint64_t res_cap, obm_arg *__restrict__ args, uint64_t arg_cap) {
-    extern __shared__ __align__(16) uint8_t pd_smem[];
-    obm_tuple *sm = reinterpret_cast<obm_tuple *>(pd_smem) + (size_t)(threadIdx.x >> 5) * PD_CAP;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t ngroups = (ndocs + 31) / 32;
-    for (uint32_t g = blockIdx.x * PD_WARPS + (threadIdx.x >> 5); g < ngroups; g += gridDim.x * PD_WARPS) {
-        const uint32_t dlo = g * 32, dhi = min(dlo + 32, ndocs);
-        const uint64_t t_lo = tuple_off[dlo], t_hi = tuple_off[dhi];
-        const bool staged = t_hi - t_lo <= PD_CAP;
-        __syncwarp();
-        if (staged) for (uint32_t k = lane; k < (uint32_t)(t_hi - t_lo); k += 32) sm[k] = tuples[t_lo + k];
-        __syncwarp();
-        const uint32_t d = dlo + lane;
-        if (d < dhi) {
-            const uint64_t t0 = tuple_off[d];
-            const obm_tuple *t = staged ? sm + (t0 - t_lo) : tuples + t0;
-            obmr::Sink S{WRITE ? res : nullptr, res_cap, WRITE ? args : nullptr, arg_cap, WRITE ? res_off[d] : 0, WRITE ? arg_off[d] : 0, 0, 0};
-            obmr::parse_doc(R, bytes + doc_off[d], t, (uint32_t)(tuple_off[d + 1] - t0), d + doc_base, S);
-            if (!WRITE) { cnt_res[d] = S.nres; cnt_args[d] = S.nargs; }
-        }
-    }
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndocs) return;
+    const uint64_t t0 = tuple_off[d];
+    obmr::Sink S{WRITE ? res : nullptr, res_cap, WRITE ? args : nullptr, arg_cap, WRITE ? res_off[d] : 0, WRITE ? arg_off[d] : 0, 0, 0};
+    obmr::parse_doc(R, bytes + doc_off[d], tuples + t0, (uint32_t)(tuple_off[d + 1] - t0), d + doc_base, S);
+    if (!WRITE) { cnt_res[d] = S.nres; cnt_args[d] = S.nargs; }
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -1449,15 +1434,8 @@ extern "C" int obm_parse_batch_device(obm_handle *h, const obm_registry *reg, co
     uint32_t *carg = (uint32_t *)q; q += align_up((uint64_t)ndocs * 4 + 4, 256);
     uint64_t *aoff = (uint64_t *)q; q += align_up(((uint64_t)ndocs + 1) * 8, 256);
     uint64_t *tile_sums = (uint64_t *)q;
-    const size_t pd_smem = (size_t)PD_WARPS * PD_CAP * sizeof(obm_tuple);
-    OBM_CUDA(h, cudaFuncSetAttribute(k_parse_docs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd_smem));
-    OBM_CUDA(h, cudaFuncSetAttribute(k_parse_docs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pd_smem));
-    int sms_p = 0;
-    OBM_CUDA(h, cudaDeviceGetAttribute(&sms_p, cudaDevAttrMultiProcessorCount, h->device));
-    uint32_t nb = (uint32_t)sms_p * 2u; /* persistent: 2 blocks of 96 KiB per SM */
-    { const uint32_t gmax = ((ndocs + 31) / 32 + PD_WARPS - 1) / PD_WARPS; if (nb > gmax) nb = gmax; }
-    const uint32_t nt = scan_tiles(ndocs);
-    k_parse_docs<false><<<nb, PD_WARPS * 32, pd_smem, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, doc_base, (const obm_tuple *)d_tuples,
+    const uint32_t nb = (ndocs + 127) / 128, nt = scan_tiles(ndocs);
+    k_parse_docs<false><<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, doc_base, (const obm_tuple *)d_tuples,
                                             (const uint64_t *)d_doc_tuple_off, R, cres, carg, nullptr, nullptr, nullptr, 0, nullptr, 0);
     k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(cres, ndocs, roff, tile_sums);
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, roff + ndocs);
@@ -1470,7 +1448,7 @@ extern "C" int obm_parse_batch_device(obm_handle *h, const obm_registry *reg, co
         OBM_CUDA(h, cudaMemcpyAsync((uint64_t *)d_totals + 1, aoff + ndocs, 8, cudaMemcpyDeviceToDevice, st));
     }
     if (d_results && d_args)
-        k_parse_docs<true><<<nb, PD_WARPS * 32, pd_smem, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, doc_base, (const obm_tuple *)d_tuples,
+        k_parse_docs<true><<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, doc_base, (const obm_tuple *)d_tuples,
                                                (const uint64_t *)d_doc_tuple_off, R, nullptr, nullptr, roff, aoff, (obm_result *)d_results, res_cap,
                                                (obm_arg *)d_args, arg_cap);
     OBM_CUDA(h, cudaGetLastError());

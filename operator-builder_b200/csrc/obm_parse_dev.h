@@ -111,119 +111,128 @@ struct Sink {
     }
 };
 
-/* One document.  tuples: the document's slice of the stream.  doc_id: what goes into the records. */
+/* 8 bytes of the document at an arbitrary offset (two aligned loads + funnel shift; the batch buffer is readable up to the
+ * next 16-byte boundary behind its end, obmarkers.h) */
+OBM_HD uint64_t load8(const uint8_t *p) {
+    const uintptr_t a = (uintptr_t)p & ~(uintptr_t)7; const uint32_t s = (uint32_t)((uintptr_t)p & 7u) * 8u;
+    const uint64_t lo = *reinterpret_cast<const uint64_t *>(a);
+    if (s == 0) return lo;
+    const uint64_t hi = *reinterpret_cast<const uint64_t *>(a + 8);
+    return (lo >> s) | (hi << (64u - s));
+}
+OBM_HD bool slice_eq8(const uint8_t *doc, uint32_t off, uint32_t len, const uint8_t *t, uint32_t tlen) {
+    if (len != tlen) return false;
+    uint64_t diff = 0;
+    uint32_t k = 0;
+    for (; k + 8 <= len; k += 8) { uint64_t w = 0; for (int b = 7; b >= 0; b--) w = (w << 8) | t[k + b]; diff |= load8(doc + off + k) ^ w; }
+    for (; k < len; k++) diff |= (uint64_t)((uint32_t)doc[off + k] ^ (uint32_t)t[k]);
+    return diff == 0;
+}
+
+/* One document.  t: the document's slice of the tuple stream.  doc_id: what goes into the records.
+ * Written as a DFA that consumes exactly ONE tuple per iteration of the outer loop (a state may hand the same tuple to
+ * another state first: the parser's "peeked, not consumed" moves): a warp runs 32 documents, one per lane, and with one
+ * tuple per iteration the lanes stay converged on the loop -- the walk is latency-bound on the tuple loads, which now issue
+ * for all lanes at once. */
 OBM_HD void parse_doc(const DevRegistry &R, const uint8_t *doc, const obm_tuple *t, uint32_t nt, uint32_t doc_id, Sink &S) {
-    /* pass 0: anything the device walk does not model? */
-    for (uint32_t i = 0; i < nt; i++) {
-        const uint32_t k = OBM_TUPLE_KIND(t[i]);
-        if (k > OBM_K_EOF && k != OBM_K_LINE) { S.result(doc_id, i, 0, 0, 0xFFFFu, 0, 0, OBM_R_HOST, k); return; }
-    }
-    enum St { S_START, S_PARSE, S_MARKER_START, S_SCOPE, S_SEPARATOR, S_ARG, S_MORE, S_STOP };
-    uint32_t i = 0;                                  /* next lexeme (LINE tuples are skipped on the way) */
-    uint32_t line = 1, base = 0;                     /* position basis of the lexeme at i */
+    enum St { P_PARSE, P_MSTART, P_SCOPE, P_SEP, P_ARG, P_AV1, P_AV2, P_VAL, P_VQ, P_MORE };
+    uint32_t line = 1, base = 0;                                                  /* position basis (LINE tuples) */
     uint32_t sc_off = 0, sc_len = 0; bool sc_any = false, sc_nl = false, sc_broken = false; /* scopeBuffer as a span (+ "\n") */
-    uint32_t cur_tuple = 0, cur_line = 0, cur_col = 0; /* parser.current */
+    uint32_t cur_tuple = 0, cur_line = 0, cur_col = 0;                            /* parser.current */
     int def = -1; uint32_t marker_tuple = 0, n_args = 0; uint64_t arg_base = 0;
-    auto skip_line = [&]() { while (i < nt && OBM_TUPLE_KIND(t[i]) == OBM_K_LINE) { base = OBM_TUPLE_OFF(t[i]); line = OBM_TUPLE_LEN(t[i]); i++; } };
-    auto kind_at = [&]() -> uint32_t { skip_line(); return i < nt ? OBM_TUPLE_KIND(t[i]) : 0u /* closed channel: zero Lexeme */; };
-    auto scope_clear = [&]() { sc_any = false; sc_nl = false; sc_len = 0; sc_broken = false; };
-    auto next = [&]() { /* position.go:7-20: consume the lexeme, append its Value to scopeBuffer */
-        skip_line();
-        if (i >= nt) { cur_tuple = nt; cur_line = cur_col = 0; return; }
+    uint32_t a_off = 0, a_len = 0;                                                /* the argument being valued */
+    uint32_t st = P_PARSE;
+    for (uint32_t i = 0; i < nt; i++) {
         const obm_tuple tu = t[i];
         const uint32_t k = OBM_TUPLE_KIND(tu), off = OBM_TUPLE_OFF(tu), len = OBM_TUPLE_LEN(tu);
-        cur_tuple = i;
-        const bool synthetic = (k == OBM_K_SYNTHETIC_BOOL || k == OBM_K_MARKER_END || k == OBM_K_EOF);
-        if (synthetic) { cur_line = cur_col = 0; } else { cur_line = line; cur_col = off - base + 1; }
-        if (k == OBM_K_MARKER_END) { if (sc_nl) sc_broken = true; sc_nl = true; if (!sc_any) { sc_any = true; sc_off = off; sc_len = 0; } }
-        else if (k == OBM_K_SYNTHETIC_BOOL) sc_broken = true;   /* "true" is not input text (only reachable through the catch-all of parse) */
-        else if (len) {
-            if (!sc_any) { sc_any = true; sc_off = off; sc_len = len; }
-            else if (sc_nl || off != sc_off + sc_len) sc_broken = true;
-            else sc_len += len;
-        }
-        i++;
-    };
-    auto discard = [&]() { skip_line(); if (i < nt) i++; };
-    uint32_t st = S_START;
-    while (st != S_STOP) {
-        const uint32_t k = kind_at();
-        switch (st) {
-        case S_START: case S_PARSE: /* state.go:13-46 */
-            if (k == OBM_K_COMMENT && i < nt) { discard(); st = S_PARSE; }
-            else if (k == OBM_K_MARKER_START && i < nt) { marker_tuple = i; next(); st = S_MARKER_START; }
-            else if (k == OBM_K_EOF && i < nt) { next(); st = S_STOP; }
-            else if (i >= nt) { st = S_STOP; /* closed channel: the zero lexeme is an Error lexeme with an empty value -- cannot happen: EOF or a fatal error ends every stream */ }
-            else if (st == S_START) st = S_PARSE;
-            else { next(); scope_clear(); st = S_PARSE; }
-            break;
-        case S_MARKER_START: if (k == OBM_K_SCOPE && i < nt) { next(); st = S_SCOPE; } else st = S_PARSE; break;
-        case S_SCOPE: if (k == OBM_K_SEPARATOR && i < nt) { next(); st = S_SEPARATOR; } else st = S_PARSE; break;
-        case S_SEPARATOR: /* state.go:64-77 */
-            if (k == OBM_K_SCOPE && i < nt) { next(); st = S_SCOPE; break; }
-            if (k == OBM_K_ARG && i < nt && sc_any && (sc_len || sc_nl)) {
-                if (sc_broken || sc_nl) { S.nres = 0; S.nargs = 0; S.result(doc_id, i, 0, 0, 0xFFFFu, 0, 0, OBM_R_HOST, 0); return; }
-                def = lookup_marker(R, doc, sc_off, sc_len - 1);
-                if (def >= 0) { n_args = 0; arg_base = S.arg_at + S.nargs; st = S_ARG; break; }
+        if (k == OBM_K_LINE) { base = off; line = len; continue; }
+        if (k > OBM_K_EOF) { S.nres = 0; S.nargs = 0; S.result(doc_id, i, 0, 0, 0xFFFFu, 0, 0, OBM_R_HOST, k); return; } /* not modelled: obm_parse_doc decides */
+        bool consumed = false, append = true, stop = false;
+        for (int hop = 0; hop < 6 && !consumed; hop++) { /* at most: MSTART/SCOPE/SEP/ARG/AV1/AV2/VAL/VQ/MORE -> PARSE */
+            const uint32_t was = st;
+            switch (st) {
+            case P_PARSE: /* state.go:13-46 */
+                consumed = true;
+                if (k == OBM_K_COMMENT) append = false;                              /* discard() */
+                else if (k == OBM_K_MARKER_START) { marker_tuple = i; st = P_MSTART; }
+                else if (k == OBM_K_EOF) stop = true;
+                else { /* next(); scopeBuffer = "" */ }
+                break;
+            case P_MSTART: if (k == OBM_K_SCOPE) { consumed = true; st = P_SCOPE; } else st = P_PARSE; break;
+            case P_SCOPE: if (k == OBM_K_SEPARATOR) { consumed = true; st = P_SEP; } else st = P_PARSE; break;
+            case P_SEP: /* state.go:64-77 */
+                if (k == OBM_K_SCOPE) { consumed = true; st = P_SCOPE; break; }
+                st = P_PARSE;
+                if (k == OBM_K_ARG && sc_any && (sc_len || sc_nl)) {
+                    if (sc_broken || sc_nl) { S.nres = 0; S.nargs = 0; S.result(doc_id, i, 0, 0, 0xFFFFu, 0, 0, OBM_R_HOST, 0); return; }
+                    def = -1;
+                    for (uint32_t r = 0; r < R.n; r++)
+                        if (slice_eq8(doc, sc_off, sc_len - 1, R.text + R.name_off[r], R.name_off[r + 1] - R.name_off[r])) { def = (int)r; break; }
+                    if (def >= 0) { n_args = 0; arg_base = S.arg_at + S.nargs; st = P_ARG; }
+                }
+                if (st == P_PARSE) { sc_any = false; sc_nl = false; sc_len = 0; sc_broken = false; def = -1; } /* flush() */
+                break;
+            case P_ARG: /* state.go:79-93 */
+                if (k != OBM_K_ARG) { st = P_PARSE; break; }
+                consumed = true; a_off = off; a_len = len;
+                st = P_PARSE;
+                for (uint32_t a = R.arg_first[def]; a < R.arg_first[def + 1]; a++)
+                    if (slice_eq8(doc, off, len, R.text + R.arg_off[a], R.arg_off[a + 1] - R.arg_off[a])) { st = P_AV1; break; }
+                break;
+            case P_AV1: if (k == OBM_K_ARG_ASSIGNMENT) consumed = true; st = P_AV2; break;
+            case P_AV2: if (k == OBM_K_QUOTE) consumed = true; st = P_VAL; break;
+            case P_VAL: /* parseArgValue, state.go:95-153 */
+                if (k == OBM_K_SYNTHETIC_BOOL) { consumed = true; append = false; S.arg(a_off, a_len, 0, off, 0, OBM_A_SYNTHETIC_TRUE); n_args++; st = P_MORE; }
+                else if (k == OBM_K_BOOL_LITERAL || k == OBM_K_FLOAT_LITERAL) {
+                    consumed = true;
+                    const bool bad = k == OBM_K_BOOL_LITERAL ? !parse_bool_ok(doc + off, len) : float32_overflows(doc + off, len);
+                    if (bad) { /* error.go:8-22: the error Result carries scopeBuffer INCLUDING this lexeme and parser.current = it */
+                        if (sc_any && !sc_nl && off == sc_off + sc_len) sc_len += len; else sc_broken = true;
+                        if (sc_broken) { S.nres = 0; S.nargs = 0; S.result(doc_id, i, 0, 0, 0xFFFFu, 0, 0, OBM_R_HOST, 0); return; }
+                        S.nargs -= n_args;
+                        const uint64_t ab = S.arg_at + S.nargs;
+                        S.arg(line, 0, k == OBM_K_BOOL_LITERAL ? 0u : 2u, off, len, 0);
+                        S.result(doc_id, i, sc_off, sc_len, (uint32_t)def, 1, ab, k == OBM_K_BOOL_LITERAL ? OBM_R_ERR_PARSEBOOL : OBM_R_ERR_FLOAT32, off - base + 1);
+                        return;
+                    }
+                    S.arg(a_off, a_len, k == OBM_K_BOOL_LITERAL ? 0u : 2u, off, len, 0); n_args++; st = P_MORE;
+                } else if (k == OBM_K_INTEGER_LITERAL) { consumed = true; S.arg(a_off, a_len, 1, off, len, 0); n_args++; st = P_MORE; }
+                else if (k == OBM_K_STRING_LITERAL) { consumed = true; S.arg(a_off, a_len, 3, off, len, 0); n_args++; st = P_VQ; }
+                else st = P_PARSE;
+                break;
+            case P_VQ: if (k == OBM_K_QUOTE) consumed = true; st = P_MORE; break;
+            default: /* P_MORE, state.go:155-169 */
+                if (k == OBM_K_ARG_DELIMITER) { consumed = true; st = P_ARG; }
+                else if (k == OBM_K_MARKER_END) { consumed = true; st = P_PARSE; }
+                else st = P_PARSE;
+                break;
             }
-            scope_clear(); def = -1; st = S_PARSE;
-            break;
-        case S_ARG: { /* state.go:79-93 + parseArgValue :95-153 */
-            if (!(k == OBM_K_ARG && i < nt)) { st = S_PARSE; break; }
-            const uint32_t a_off = OBM_TUPLE_OFF(t[i]), a_len = OBM_TUPLE_LEN(t[i]);
-            next();
-            if (!lookup_arg(R, (uint32_t)def, doc, a_off, a_len)) { st = S_PARSE; break; }
-            if (kind_at() == OBM_K_ARG_ASSIGNMENT && i < nt) next();
-            if (kind_at() == OBM_K_QUOTE && i < nt) next();
-            const uint32_t vk = kind_at();
-            const uint32_t v_off = i < nt ? OBM_TUPLE_OFF(t[i]) : 0u, v_len = i < nt ? OBM_TUPLE_LEN(t[i]) : 0u;
-            if (i >= nt) { st = S_PARSE; break; }
-            if (vk == OBM_K_SYNTHETIC_BOOL) { S.arg(a_off, a_len, 0, v_off, 0, OBM_A_SYNTHETIC_TRUE); n_args++; discard(); }
-            else if (vk == OBM_K_BOOL_LITERAL) {
-                next();
-                if (!parse_bool_ok(doc + v_off, v_len)) {
-                    S.nargs -= n_args; /* an error result replaces the marker's arguments */
-                    const uint64_t ab = S.arg_at + S.nargs;
-                    S.arg(cur_line, 0, 0, v_off, v_len, 0);
-                    S.result(doc_id, cur_tuple, sc_off, sc_len, (uint32_t)def, 1, ab, OBM_R_ERR_PARSEBOOL | (sc_broken ? OBM_R_HOST : 0u), cur_col);
-                    if (sc_broken) { S.nres = 0; S.nargs = 0; S.result(doc_id, i, 0, 0, 0xFFFFu, 0, 0, OBM_R_HOST, 0); }
-                    return;
+            /* arguments collected for a marker that is abandoned (unknown argument, unexpected lexeme) are dropped */
+            if (st == P_PARSE && was != P_PARSE && def >= 0 && !(was == P_MORE && k == OBM_K_MARKER_END && consumed)) { S.nargs -= n_args; n_args = 0; def = -1; }
+            if (consumed) {
+                /* next(): the lexeme becomes parser.current and its Value is appended to scopeBuffer (position.go:7-20) */
+                const bool synthetic = (k == OBM_K_SYNTHETIC_BOOL || k == OBM_K_MARKER_END || k == OBM_K_EOF);
+                if (append) {
+                    cur_tuple = i; cur_line = synthetic ? 0u : line; cur_col = synthetic ? 0u : off - base + 1u;
+                    if (k == OBM_K_MARKER_END) { if (sc_nl) sc_broken = true; sc_nl = true; if (!sc_any) { sc_any = true; sc_off = off; sc_len = 0; } }
+                    else if (k == OBM_K_SYNTHETIC_BOOL) sc_broken = true;
+                    else if (len) {
+                        if (!sc_any) { sc_any = true; sc_off = off; sc_len = len; }
+                        else if (sc_nl || off != sc_off + sc_len) sc_broken = true;
+                        else sc_len += len;
+                    }
                 }
-                S.arg(a_off, a_len, 0, v_off, v_len, 0); n_args++;
-            } else if (vk == OBM_K_INTEGER_LITERAL) { next(); S.arg(a_off, a_len, 1, v_off, v_len, 0); n_args++; }
-            else if (vk == OBM_K_FLOAT_LITERAL) {
-                next();
-                if (float32_overflows(doc + v_off, v_len)) {
-                    S.nargs -= n_args;
-                    const uint64_t ab = S.arg_at + S.nargs;
-                    S.arg(cur_line, 0, 2, v_off, v_len, 0);
-                    S.result(doc_id, cur_tuple, sc_off, sc_len, (uint32_t)def, 1, ab, OBM_R_ERR_FLOAT32 | (sc_broken ? OBM_R_HOST : 0u), cur_col);
-                    if (sc_broken) { S.nres = 0; S.nargs = 0; S.result(doc_id, i, 0, 0, 0xFFFFu, 0, 0, OBM_R_HOST, 0); }
-                    return;
+                if (was == P_PARSE && st == P_PARSE && k != OBM_K_COMMENT) { sc_any = false; sc_nl = false; sc_len = 0; sc_broken = false; } /* the catch-all of parse */
+                if (was == P_MORE && k == OBM_K_MARKER_END) { /* emit.go:8-24 */
+                    if (sc_broken) { S.nres = 0; S.nargs = 0; S.result(doc_id, i, 0, 0, 0xFFFFu, 0, 0, OBM_R_HOST, 0); return; }
+                    S.result(doc_id, marker_tuple, sc_off, sc_len, (uint32_t)def, n_args, arg_base, OBM_R_OK | OBM_R_NL, 0);
+                    sc_any = false; sc_nl = false; sc_len = 0; sc_broken = false; def = -1; n_args = 0;
                 }
-                S.arg(a_off, a_len, 2, v_off, v_len, 0); n_args++;
-            } else if (vk == OBM_K_STRING_LITERAL) {
-                next(); S.arg(a_off, a_len, 3, v_off, v_len, 0); n_args++;
-                if (kind_at() == OBM_K_QUOTE && i < nt) next();
-            } else { st = S_PARSE; break; }
-            st = S_MORE;
-            break;
+            }
         }
-        case S_MORE: /* state.go:155-169 */
-            if (k == OBM_K_ARG_DELIMITER && i < nt) { next(); st = S_ARG; }
-            else if (k == OBM_K_MARKER_END && i < nt) {
-                next();
-                if (sc_broken) { S.nres = 0; S.nargs = 0; S.result(doc_id, i, 0, 0, 0xFFFFu, 0, 0, OBM_R_HOST, 0); return; }
-                S.result(doc_id, marker_tuple, sc_off, sc_len, (uint32_t)def, n_args, arg_base, OBM_R_OK | OBM_R_NL, 0); /* emit.go:8-24 */
-                scope_clear(); def = -1; n_args = 0;
-                st = S_PARSE;
-            } else st = S_PARSE;
-            break;
-        default: st = S_STOP;
-        }
-        /* arguments collected for a marker that is abandoned (unknown argument, unexpected lexeme) are dropped */
-        if (st == S_PARSE && def >= 0) { S.nargs -= n_args; n_args = 0; def = -1; }
+        if (stop) break;
     }
+    (void)cur_tuple; (void)cur_line; (void)cur_col;
 }
 
 } /* namespace obmr */

@@ -1339,9 +1339,14 @@ k_parse_docs(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= ndocs) return;
     const uint64_t t0 = tuple_off[d];
-    obmr::Sink S{WRITE ? res : nullptr, res_cap, WRITE ? args : nullptr, arg_cap, WRITE ? res_off[d] : 0, WRITE ? arg_off[d] : 0, 0, 0};
+    obmr::Sink S{nullptr, 0, nullptr, 0, 0, 0, 0, 0};
+    if (WRITE) { /* this document's slots: [res_off[d], res_off[d+1]) and [arg_off[d], arg_off[d+1]), clipped to the caller's capacity */
+        S.res = res; S.args = args; S.res_at = res_off[d]; S.arg_at = arg_off[d];
+        S.res_end = res_off[d + 1] < res_cap ? res_off[d + 1] : res_cap; S.arg_end = arg_off[d + 1] < arg_cap ? arg_off[d + 1] : arg_cap;
+    }
     obmr::parse_doc(R, bytes + doc_off[d], tuples + t0, (uint32_t)(tuple_off[d + 1] - t0), d + doc_base, S);
     if (!WRITE) { cnt_res[d] = S.nres; cnt_args[d] = S.nargs; }
+    else if (cnt_res && (cnt_res[d] != S.nres || cnt_args[d] != S.nargs)) printf("k_parse_docs: doc %u count pass (%u, %u) != write pass (%u, %u)\n", d, cnt_res[d], cnt_args[d], S.nres, S.nargs);
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -1449,7 +1454,7 @@ extern "C" int obm_parse_batch_device(obm_handle *h, const obm_registry *reg, co
     }
     if (d_results && d_args)
         k_parse_docs<true><<<nb, 128, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, doc_base, (const obm_tuple *)d_tuples,
-                                               (const uint64_t *)d_doc_tuple_off, R, nullptr, nullptr, roff, aoff, (obm_result *)d_results, res_cap,
+                                               (const uint64_t *)d_doc_tuple_off, R, cres, carg, roff, aoff, (obm_result *)d_results, res_cap,
                                                (obm_arg *)d_args, arg_cap);
     OBM_CUDA(h, cudaGetLastError());
     return OBM_OK;

@@ -89,20 +89,22 @@ OBM_HD bool float32_overflows(const uint8_t *v, uint32_t n) {
     return true;
 }
 
-/* sink: counts always, writes when the arrays are given */
+/* sink: counts always, writes when the arrays are given.  res_end / arg_end: end of THIS document's slots (known from the count
+ * pass): arguments of a marker that is abandoned later are written first and given back afterwards -- such transient records
+ * must never land in a neighbouring document's slots (another thread writes those, in any order) */
 struct Sink {
-    obm_result *res; uint64_t res_cap; obm_arg *args; uint64_t arg_cap;
-    uint64_t res_at, arg_at; /* next free index (batch-global) */
+    obm_result *res; uint64_t res_end; obm_arg *args; uint64_t arg_end;
+    uint64_t res_at, arg_at; /* first slot of the document (batch-global) */
     uint32_t nres, nargs;
     OBM_HD void arg(uint32_t name_off, uint32_t name_len, uint32_t kind, uint32_t val_off, uint32_t val_len, uint32_t flags) {
-        if (args && arg_at + nargs < arg_cap) {
+        if (args && arg_at + nargs < arg_end) {
             obm_arg a; a.name_off = name_off; a.val_off = val_off; a.val_len = val_len; a.name_len = (uint16_t)name_len; a.kind = (uint8_t)kind; a.flags = (uint8_t)flags;
             args[arg_at + nargs] = a;
         }
         nargs++;
     }
     OBM_HD void result(uint32_t doc, uint32_t tuple, uint32_t text_off, uint32_t text_len, uint32_t reg_id, uint32_t n_args, uint64_t arg_base, uint32_t flags, uint32_t aux) {
-        if (res && res_at + nres < res_cap) {
+        if (res && res_at + nres < res_end) {
             obm_result r; r.doc = doc; r.tuple = tuple; r.text_off = text_off; r.text_len = text_len; r.reg_id = (uint16_t)reg_id; r.nargs = (uint16_t)n_args;
             r.arg_base = (uint32_t)arg_base; r.flags = flags; r.aux = aux;
             res[res_at + nres] = r;

@@ -80,10 +80,12 @@ __device__ __forceinline__ uint64_t chain_resolve(const WArgs &A, uint32_t u, ui
     const uint32_t b = u >> 5, r = u & 31;
     volatile uint64_t *st0 = A.st_tuples, *blk = A.st_blocks, *bex = A.st_blocks + nblocks;
     uint64_t s;
+    uint32_t backoff = 32; /* ns; doubles up to ~2 us: a thousand warps polling at a fixed short interval saturate L2 and slow the
+                            * very warps they wait for (marker-dense units resolve right after publishing) */
     for (;;) {
         s = lane < r ? st0[(b << 5) + lane] : LB_AGG;
         if (__ballot_sync(0xffffffffu, (s >> 62) == 0) == 0) break;
-        __nanosleep(64);
+        __nanosleep(backoff); if (backoff < 2048) backoff <<= 1;
     }
     uint64_t partial = s & LB_MASK;
 #pragma unroll
@@ -101,7 +103,7 @@ __device__ __forceinline__ uint64_t chain_resolve(const WArgs &A, uint32_t u, ui
             const uint32_t part = __ballot_sync(0xffffffffu, (a >> 56) != 32u); /* every block before b is a full one */
             const uint32_t upto = have ? (uint32_t)__ffs((int)have) - 1u : 31u;
             const uint32_t need = upto == 31u ? 0xffffffffu : ((2u << upto) - 1u);
-            if (part & need) { __nanosleep(64); continue; }
+            if (part & need) { __nanosleep(backoff); if (backoff < 2048) backoff <<= 1; continue; }
             uint64_t v = lane <= upto ? (a & ((1ull << 56) - 1)) : 0;
             if (have && lane == upto) v += e & ~BEX_FLAG;
 #pragma unroll

@@ -207,7 +207,16 @@ def test_device_parser_kernel(oracle):
         t = res.tuples[int(res.doc_tuple_off[i]):int(res.doc_tuple_off[i + 1])]
         got = format_records(doc, t, r, A)
         want = po.serialize(po.parse(oracle.lex(doc), po.OPERATOR_BUILDER_REGISTRY))
-        assert got == want, (doc[:200], got, want)
+        if got != want:  # which record differs from the host run of the same walk?
+            L.obm_parse_doc_records.restype = ctypes.c_int64
+            L.obm_parse_doc_records.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p,
+                                                ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
+            hr = np.zeros(len(t) + 2, dtype=RES_DT); ha = np.zeros(len(t) + 2, dtype=ARG_DT); na = ctypes.c_uint64()
+            tt = np.ascontiguousarray(t, dtype=np.uint64)
+            n = L.obm_parse_doc_records(reg.handle, doc, tt.ctypes.data, len(tt), i + 1000, hr.ctypes.data, len(hr), ha.ctypes.data, len(ha), ctypes.byref(na))
+            dev_args = [A[int(x["arg_base"]):int(x["arg_base"]) + int(x["nargs"])].tolist() for x in r]
+            host_args = [ha[int(x["arg_base"]):int(x["arg_base"]) + int(x["nargs"])].tolist() for x in hr[:n]]
+            raise AssertionError(f"doc {i}: device records {r.tolist()} args {dev_args}\n host records {hr[:n].tolist()} args {host_args}\n roff {roff[i]}..{roff[i+1]}")
     assert host_docs < len(docs) * 0.75 and nres >= 4800, (host_docs, len(docs), nres)
     sc.close()
 

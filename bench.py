@@ -185,11 +185,12 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL_DEBUG=VERSION|WARN|INFO prints on stdout by default; rank 0 must print exactly one JSON line, so the log goes
-        # to a file per rank instead (the driver's rank check reads it there)
-        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_debug.%h.%p.log")
+        # NCCL prints its banner / NCCL_DEBUG lines on stdout when the first communicator comes up; rank 0 must print exactly one
+        # JSON line there, so stdout points at stderr until both communicators (torch's, and obm_comm_create's below) exist.
+        # NCCL_DEBUG itself is left alone: the driver's rank check reads the lines from stderr.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     from operator_builder_b200 import shard
@@ -227,6 +228,8 @@ def main():
         dist.broadcast(idt, 0)
         comm = ob.Comm(sc, bytes(idt.cpu().numpy().tobytes()), rank, world)
         d_res_all = torch.empty(world * res_cap * 32, dtype=torch.uint8, device=dev)
+        warm = torch.zeros(1, device=dev); dist.all_reduce(warm); torch.cuda.synchronize()
+        sys.stdout.flush(); os.dup2(saved_stdout, 1); os.close(saved_stdout)  # both communicators are up: stdout is ours again
     exch = {}
 
     def scan_only():

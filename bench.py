@@ -149,7 +149,7 @@ def main():
     config = {"workload": f"{cfg_name}: {args.docs} synthetic manifests x {DOC_BYTES} B = {args.docs * DOC_BYTES / 2**30:.2f} GiB, "
                           f"8 markers/file, sharded by file over {world} rank(s), HBM-resident",
               "docs": args.docs, "doc_bytes": DOC_BYTES, "flavour": args.flavour,
-              "parallelism": f"file-shard x{world}; step = scan + emit" + (" + device parser (compact Results) + one NCCL all-gather of the Result records (obm_lex_batch_sharded_device, C ABI)" if world > 1 else ""),
+              "parallelism": f"file-shard x{world}; step = scan + emit" + (" + marker index (16 B per registered marker) + one NCCL all-gather of the index records (obm_lex_batch_sharded_device, C ABI)" if world > 1 else ""),
               "l2": "inputs (>= 1.25 GiB per rank) exceed the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
@@ -218,7 +218,7 @@ def main():
     d_args = torch.empty(arg_cap * 16, dtype=torch.uint8, device=dev)
     d_roff = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
     d_tot = torch.zeros(2, dtype=torch.int64, device=dev)
-    comm = d_res_all = None
+    comm = d_idx = d_idx_all = None
     if world > 1:
         # the multi-GPU path behind the C ABI: obm_comm_* (NCCL bound inside libobmarkers.so); torch.distributed only carries
         # the 128-byte unique id from rank 0 to the others and the barriers / max-over-ranks of this harness
@@ -227,7 +227,9 @@ def main():
             idt.copy_(torch.frombuffer(bytearray(ob.Comm.unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         comm = ob.Comm(sc, bytes(idt.cpu().numpy().tobytes()), rank, world)
-        d_res_all = torch.empty(world * res_cap * 32, dtype=torch.uint8, device=dev)
+        idx_cap = max_docs * 12
+        d_idx = torch.empty(idx_cap * 16, dtype=torch.uint8, device=dev)
+        d_idx_all = torch.empty(world * idx_cap * 16, dtype=torch.uint8, device=dev)
         warm = torch.zeros(1, device=dev); dist.all_reduce(warm); torch.cuda.synchronize()
         sys.stdout.flush(); os.dup2(saved_stdout, 1); os.close(saved_stdout)  # both communicators are up: stdout is ours again
     exch = {}
@@ -241,14 +243,14 @@ def main():
                               d_args.data_ptr(), arg_cap, d_roff.data_ptr(), d_tot.data_ptr(), sp)
 
     def step():
-        """one pass of the hot path over the rank's shard: scan + emit, the parser's compact Results, and (N > 1) the one
-        exchange step -- an NCCL all-gather of those records over NVLink"""
+        """one pass of the hot path over the rank's shard: scan + emit and (N > 1) the one exchange step -- the compact index of
+        the registered markers, all-gathered over NVLink by NCCL, all behind the C ABI"""
         if comm is None:
             scan_only()  # N = 1: the lexer's work, what the reference arm times on the CPU; the parser is timed beside it (parts)
         else:
             per_rank, stride = comm.lex_batch_sharded_device(reg, d_bytes.data_ptr(), d_off.data_ptr(), ndocs, nbytes, d0, d_out.data_ptr(), cap,
-                                                             d_toff.data_ptr(), d_status.data_ptr(), d_counts.data_ptr(), d_res.data_ptr(), res_cap,
-                                                             d_args.data_ptr(), arg_cap, d_roff.data_ptr(), d_res_all.data_ptr(), world * res_cap, sp)
+                                                             d_toff.data_ptr(), d_status.data_ptr(), d_counts.data_ptr(), d_idx.data_ptr(), idx_cap,
+                                                             d_idx_all.data_ptr(), world * idx_cap, sp)
             exch["per_rank"], exch["stride"] = per_rank, stride
 
     def barrier():
@@ -274,7 +276,7 @@ def main():
         sampler.start()
     ms = timed(step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    launches = (ob._native.lib().obm_launches_last_call(sc.handle) + (8 if world > 1 else 0)) * args.steps  # scan kernels (+ N > 1: the parser's 2 kernels and 6 scan launches)
+    launches = (ob._native.lib().obm_launches_last_call(sc.handle) + (5 if world > 1 else 0)) * args.steps  # scan kernels (+ N > 1: the index's 2 kernels and 3 scan launches)
 
     # the parts, same stream, same events: scan-only time is the roofline's denominator
     ms_scan = timed(scan_only, args.steps)
@@ -378,9 +380,9 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "parts": {"ms_scan": ms_scan, "ms_parse": ms_parse, "results": tot_results, "args": tot_args,
                       "result_bytes_per_input_byte": tot_results * 32 / total_bytes},
-            "exchange": ({"in_step": "ncclAllGather of 32-byte Result records (+ an 8-byte count gather), through the C ABI",
+            "exchange": ({"in_step": "ncclAllGather of 16-byte marker-index records (+ an 8-byte count gather), through the C ABI",
                           "records_per_rank": exch.get("per_rank"), "slot_stride": exch.get("stride"),
-                          "bytes_received_per_rank": (exch.get("stride") or 0) * 32 * (world - 1),
+                          "bytes_received_per_rank": (exch.get("stride") or 0) * 16 * (world - 1),
                           "full_tuple_allgather_not_in_step": gather} if world > 1 else None)}
     print(json.dumps(line))
     if world > 1:

@@ -199,9 +199,8 @@ int obm_split_docs_device(obm_handle *h, const void *d_bytes, const void *d_doc_
                           void *d_doc_rec_off, void *stream);
 
 /* --- multi-GPU: manifests shard by file (lexer.go:27-40: one lexer per input), one rank per GPU ------------------
- * The one exchange step of the path is an NCCL all-gather over NVLink of the shard's compact Result records (what the
- * parser would hand to internal/workload, ~6 % of the input) -- the full tuple stream (~35 %) stays resident on its
- * owner.  NCCL is loaded at run time (libnccl.so.2); the caller moves the 128-byte unique id from rank 0 to the other
+ * The one exchange step of the path is an NCCL all-gather over NVLink of the shard's compact index of registered
+ * markers (16 bytes per marker, ~3 % of the input) -- the full tuple stream (~35 %) stays resident on its owner.  NCCL is loaded at run time (libnccl.so.2); the caller moves the 128-byte unique id from rank 0 to the other
  * ranks by whatever channel it has (the Go host: its own RPC; bench.py: torch.distributed).                         */
 typedef struct obm_comm obm_comm;
 #define OBM_COMM_ID_BYTES 128
@@ -210,17 +209,17 @@ int obm_comm_create(obm_handle *h, const uint8_t *id, int rank, int nranks, obm_
 void obm_comm_destroy(obm_comm *c);
 /*
  * One sharded step on this rank's device-resident shard (documents first_doc .. first_doc + ndocs of the global batch):
- * scan (obm_lex_batch_device), parse (obm_parse_batch_device; records carry global document ids), then one
- * ncclAllGather of the obm_result records.  d_results_all receives nranks slots of *stride records each (stride = the
- * largest per-rank count, chosen inside: one 8-byte count all-gather + host read); rank_results[r] = valid records
- * of slot r.  Returns OBM_E_CAPACITY (with *stride set) when results_all_cap < nranks * stride.  Tuples, arguments
- * and offsets of the shard stay in the caller's buffers (d_out, d_args, ...).  The collective is enqueued on `stream`.
+ * scan (obm_lex_batch_device), the compact index of the registered markers (obm_marker_index_flat_device; records carry
+ * global document ids), then ONE ncclAllGather of the 16-byte index records.  d_index_all receives nranks slots of
+ * *stride records each (stride = the largest per-rank count, chosen inside: an 8-byte count all-gather + host read);
+ * rank_records[r] = valid records of slot r.  Returns OBM_E_CAPACITY (with *stride set) when index_cap < this rank's
+ * count or index_all_cap < nranks * stride.  The shard's tuples and offsets stay in the caller's buffers (d_out, ...):
+ * the index says which rank and which tuple to ask for.  The collective is enqueued on `stream`.
  */
 int obm_lex_batch_sharded_device(obm_comm *c, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
                                  uint64_t total_bytes, uint32_t first_doc, void *d_out, uint64_t out_cap, void *d_doc_tuple_off, void *d_status,
-                                 void *d_counts, void *d_results, uint64_t res_cap, void *d_args, uint64_t arg_cap, void *d_doc_res_off,
-                                 void *d_results_all, uint64_t results_all_cap, uint64_t *rank_results /* host u64[nranks] */, uint64_t *stride,
-                                 void *stream);
+                                 void *d_counts, void *d_index, uint64_t index_cap, void *d_index_all, uint64_t index_all_cap,
+                                 uint64_t *rank_records /* host u64[nranks] */, uint64_t *stride, void *stream);
 
 /* --- host-side consumers of the tuple stream (no GPU needed; no lexing happens here) ------- */
 /*
@@ -271,6 +270,12 @@ void obm_registry_free(obm_registry *r);
 int obm_marker_index_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
                             const void *d_tuples, const void *d_doc_tuple_off, void *d_records, uint64_t cap,
                             void *d_doc_rec_off, void *stream);
+/* The same records (document order, doc_base added to the document ids) from a FLAT pass over the tuple stream: a thread per 8
+ * tuples instead of a warp per document, ~10x faster; no per-document offsets.  ntuples_bound: an upper bound of the stream's
+ * length known on the host (the capacity of d_tuples does); *d_total (device u64) = number of records. */
+int obm_marker_index_flat_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs, uint32_t doc_base,
+                                 const void *d_tuples, const void *d_doc_tuple_off, uint64_t ntuples_bound, void *d_records, uint64_t cap,
+                                 void *d_total, void *stream);
 /*
  * The same consumer ON THE DEVICE (csrc/obm_parse_dev.h): one thread per document walks the resident tuple stream as
  * parser/state.go:13-175 walks lexemes -- registry lookup (definition.go:13-21), known-argument filter

@@ -1134,6 +1134,151 @@ extern "C" int obm_marker_index_device(obm_handle *h, const obm_registry *reg, c
     return OBM_OK;
 }
 
+/* ---- the same index, FLAT over the tuple stream (the exchange payload of the multi-GPU step) ----------------------------
+ * k_marker_index above is a warp per document and spends its time on per-document bookkeeping (1.8 ms per GiB of corpus).
+ * Here a thread takes 8 consecutive tuples of the whole stream (four 16-byte loads, coalesced across the warp); the rare
+ * MarkerStart candidates (4 % of the tuples) look around through the cache: back for a stale buffer, forward along the
+ * Scope / Separator chain (a document's tuples end with EOF or a fatal error, so neither walk leaves the document), then the
+ * name is compared with the registry.  Two passes (per-tile counts, scan, write in tuple order); the document of a hit is
+ * found by bisection of doc_tuple_off.  Records: {u32 doc + doc_base, u32 tuple index in the document, u32 offset of '+',
+ * u16 registry id | u16 scopes << 16}. */
+constexpr uint32_t FI_THREADS = 256, FI_PER = 8, FI_TILE = FI_THREADS * FI_PER;
+__device__ __forceinline__ int flat_index_hit(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs,
+                                              const obm_tuple *__restrict__ t, const uint64_t *__restrict__ tuple_off, uint64_t ntup, uint64_t i,
+                                              const DevRegistry &reg, uint32_t *doc_out, uint32_t *scopes_out) {
+    const obm_tuple tu = t[i];
+    /* stale buffer?  walk back over tuples that carry no buffer text; the first PART / FLUSH / slice tuple decides */
+    for (uint64_t j = i; j-- > 0;) {
+        const uint32_t kj = OBM_TUPLE_KIND(t[j]);
+        if (kj == OBM_K_PART) return -1;
+        if (kj == OBM_K_FLUSH || (kj >= OBM_K_COMMENT && kj <= OBM_K_QUOTE) || kj == OBM_K_EOF || kj >= OBM_K_ERR_MALFORMED) break;
+    }
+    uint32_t pos = 1, scopes = 0; uint64_t j = i + 1; bool contiguous = true;
+    const uint32_t off = OBM_TUPLE_OFF(tu);
+    for (;;) {
+        if (j + 1 >= ntup) break;
+        const obm_tuple a = t[j], b = t[j + 1];
+        if (OBM_TUPLE_KIND(a) != OBM_K_SCOPE || OBM_TUPLE_KIND(b) != OBM_K_SEPARATOR) break;
+        contiguous &= OBM_TUPLE_OFF(a) == off + pos + (scopes ? 1u : 0u);
+        pos += OBM_TUPLE_LEN(a) + (scopes ? 1u : 0u); scopes++; j += 2;
+    }
+    if (!scopes || j >= ntup || OBM_TUPLE_KIND(t[j]) != OBM_K_ARG) return -1;
+    bool len_ok = false;
+    for (uint32_t r = 0; r < reg.n; r++) len_ok |= reg.off[r + 1] - reg.off[r] == pos;
+    if (!len_ok) return -1;
+    uint32_t lo = 0, hi = ndocs; /* last d with tuple_off[d] <= i */
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (tuple_off[mid] <= i) lo = mid; else hi = mid; }
+    const uint8_t *doc = bytes + doc_off[lo];
+    int hit = -1;
+    for (uint32_t r = 0; r < reg.n; r++) {
+        if (reg.off[r + 1] - reg.off[r] != pos) continue;
+        uint32_t diff = 0;
+        if (contiguous) for (uint32_t b = 0; b < pos; b++) diff |= (uint32_t)doc[off + b] ^ (uint32_t)(uint8_t)reg.text[reg.off[r] + b];
+        else { /* scope slices apart from each other: piece by piece */
+            uint32_t q = 1; diff = (uint32_t)(uint8_t)reg.text[reg.off[r]] ^ (uint32_t)'+';
+            uint64_t jj = i + 1;
+            for (uint32_t sc = 0; sc < scopes; jj += 2, sc++) {
+                const obm_tuple a = t[jj];
+                if (sc) { diff |= (uint32_t)(uint8_t)reg.text[reg.off[r] + q] ^ (uint32_t)':'; q++; }
+                for (uint32_t b = 0; b < OBM_TUPLE_LEN(a); b++) diff |= (uint32_t)doc[OBM_TUPLE_OFF(a) + b] ^ (uint32_t)(uint8_t)reg.text[reg.off[r] + q + b];
+                q += OBM_TUPLE_LEN(a);
+            }
+        }
+        if (diff == 0) hit = (int)r;
+    }
+    *doc_out = lo; *scopes_out = scopes;
+    return hit;
+}
+template <bool WRITE>
+__global__ void __launch_bounds__(FI_THREADS)
+k_marker_index_flat(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs, uint32_t doc_base,
+                    const obm_tuple *__restrict__ tuples, const uint64_t *__restrict__ tuple_off, const __grid_constant__ DevRegistry reg,
+                    uint32_t *__restrict__ counts, const uint64_t *__restrict__ rec_off, uint4 *__restrict__ records, uint64_t cap) {
+    __shared__ uint32_t wsum[FI_THREADS / 32];
+    const uint64_t ntup = tuple_off[ndocs];
+    const uint64_t i0 = (uint64_t)blockIdx.x * FI_TILE + (uint64_t)threadIdx.x * FI_PER;
+    obm_tuple v[FI_PER];
+    if (i0 + FI_PER <= ntup) { /* the stream is 8-byte aligned and i0 a multiple of 8 tuples: 64-byte chunks */
+        const uint4 *p = reinterpret_cast<const uint4 *>(tuples + i0);
+#pragma unroll
+        for (uint32_t q = 0; q < FI_PER / 2; q++) { const uint4 x = p[q]; v[2 * q] = (uint64_t)x.x | ((uint64_t)x.y << 32); v[2 * q + 1] = (uint64_t)x.z | ((uint64_t)x.w << 32); }
+    } else {
+#pragma unroll
+        for (uint32_t q = 0; q < FI_PER; q++) v[q] = i0 + q < ntup ? tuples[i0 + q] : 0;
+    }
+    uint32_t cand = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < FI_PER; q++) if (i0 + q < ntup && OBM_TUPLE_KIND(v[q]) == OBM_K_MARKER_START && OBM_TUPLE_LEN(v[q]) == 1) cand |= 1u << q;
+    uint32_t hits = 0; uint4 rec[2]; uint32_t nrec = 0; /* at most FI_PER / 4 markers among 8 consecutive tuples ("+a:b" is 6 tuples: <= 2) */
+    for (uint32_t m = cand; m; m &= m - 1) {
+        const uint32_t q = (uint32_t)__ffs((int)m) - 1u;
+        uint32_t d = 0, scopes = 0;
+        const int hit = flat_index_hit(bytes, doc_off, ndocs, tuples, tuple_off, ntup, i0 + q, reg, &d, &scopes);
+        if (hit >= 0) {
+            hits++;
+            if (WRITE && nrec < 2) rec[nrec++] = make_uint4(d + doc_base, (uint32_t)(i0 + q - tuple_off[d]), OBM_TUPLE_OFF(v[q]), (uint32_t)hit | (scopes << 16));
+        }
+    }
+    /* block-wide exclusive scan of the per-thread hit counts (threads are in tuple order) */
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = hits;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += x; }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < FI_THREADS / 32; w++) { const uint32_t c = wsum[w]; if (w < wid) pre += c; tot += c; }
+    if (!WRITE) { if (threadIdx.x == 0) counts[blockIdx.x] = tot; return; }
+    const uint64_t at = rec_off[blockIdx.x] + pre + incl - hits;
+    for (uint32_t k = 0; k < nrec; k++) if (at + k < cap) records[at + k] = rec[k];
+}
+
+/* records of the REGISTERED markers of a resident tuple stream, in document order; *d_total (device u64) = their number.
+ * Records beyond `cap` are not written.  doc_base is added to the document ids (global ids of a shard). */
+extern "C" int obm_marker_index_flat_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs, uint32_t doc_base,
+                                            const void *d_tuples, const void *d_doc_tuple_off, uint64_t ntuples_bound, void *d_records, uint64_t cap,
+                                            void *d_total, void *stream) {
+    if (!h || !reg || !d_doc_off || !d_doc_tuple_off || !d_total) return OBM_E_ARG;
+    OBM_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DevRegistry R; memset(&R, 0, sizeof R);
+    const char *nmv[8]; uint32_t nml[8];
+    if (obm_registry_names(reg, nullptr, nullptr, 0xFFFFFFFFu) > 8) { set_err(h, "the device index holds at most 8 marker names"); return OBM_E_ARG; }
+    const uint32_t nm = obm_registry_names(reg, nmv, nml, 8);
+    uint32_t o = 0;
+    for (uint32_t r = 0; r < nm; r++) {
+        if (o + nml[r] > sizeof R.text) { set_err(h, "registry too large for the device index"); return OBM_E_ARG; }
+        R.off[r] = o; memcpy(R.text + o, nmv[r], nml[r]); o += nml[r];
+    }
+    R.off[nm] = o; R.n = nm;
+    if (ndocs == 0 || ntuples_bound == 0) { OBM_CUDA(h, cudaMemsetAsync(d_total, 0, 8, st)); return OBM_OK; }
+    /* the tuple count lives on the device (doc_tuple_off[ndocs]); the grid is sized for the caller's bound (its out_cap) */
+    const uint64_t ntiles64 = (ntuples_bound + FI_TILE - 1) / FI_TILE;
+    if (ntiles64 > 0x7FFFFFF0ull) { set_err(h, "tuple stream too large for the flat index"); return OBM_E_ARG; }
+    const uint32_t ntiles = (uint32_t)ntiles64, nt = scan_tiles(ntiles);
+    const uint64_t need = align_up((uint64_t)ntiles * 4 + 4, 256) + align_up(((uint64_t)ntiles + 1) * 8, 256) + align_up((uint64_t)nt * 8 + 8, 256);
+    if (h->scratch_bytes < need) {
+        if (h->scratch) { OBM_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->scratch); h->scratch = nullptr; h->scratch_bytes = 0; }
+        OBM_CUDA(h, cudaMalloc(&h->scratch, need)); h->scratch_bytes = need;
+    }
+    uint8_t *q = (uint8_t *)h->scratch;
+    uint32_t *counts = (uint32_t *)q; q += align_up((uint64_t)ntiles * 4 + 4, 256);
+    uint64_t *roff = (uint64_t *)q; q += align_up(((uint64_t)ntiles + 1) * 8, 256);
+    uint64_t *tile_sums = (uint64_t *)q;
+    k_marker_index_flat<false><<<ntiles, FI_THREADS, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, doc_base, (const obm_tuple *)d_tuples,
+                                                             (const uint64_t *)d_doc_tuple_off, R, counts, nullptr, nullptr, 0);
+    k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(counts, ntiles, roff, tile_sums);
+    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, roff + ntiles);
+    k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(roff, ntiles, tile_sums, ~0ull, nullptr);
+    OBM_CUDA(h, cudaMemcpyAsync(d_total, roff + ntiles, 8, cudaMemcpyDeviceToDevice, st));
+    if (d_records && cap)
+        k_marker_index_flat<true><<<ntiles, FI_THREADS, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, doc_base, (const obm_tuple *)d_tuples,
+                                                                (const uint64_t *)d_doc_tuple_off, R, nullptr, roff, (uint4 *)d_records, cap);
+    OBM_CUDA(h, cudaGetLastError());
+    return OBM_OK;
+}
+
 /* ------------------------------------------------------------------------------------------- */
 /* collection prefix rewrite (manifests/manifest.go:89-95) on the device  */
 /* manifest splitting on "---" lines (manifests/manifest.go:57-80)         */
@@ -1592,30 +1737,31 @@ extern "C" void obm_comm_destroy(obm_comm *c) {
     cudaFree(c->d_counts_all); cudaFree(c->d_totals); cudaFreeHost(c->h_counts);
     delete c;
 }
+extern "C" int obm_marker_index_flat_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs, uint32_t doc_base,
+                                            const void *d_tuples, const void *d_doc_tuple_off, uint64_t ntuples_bound, void *d_records, uint64_t cap,
+                                            void *d_total, void *stream);
 extern "C" int obm_lex_batch_sharded_device(obm_comm *c, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
                                             uint64_t total_bytes, uint32_t first_doc, void *d_out, uint64_t out_cap, void *d_doc_tuple_off, void *d_status,
-                                            void *d_counts, void *d_results, uint64_t res_cap, void *d_args, uint64_t arg_cap, void *d_doc_res_off,
-                                            void *d_results_all, uint64_t results_all_cap, uint64_t *rank_results, uint64_t *stride, void *stream) {
-    if (!c || !reg || !d_results || !d_args || !d_doc_res_off || !d_results_all || !rank_results || !stride) return OBM_E_ARG;
+                                            void *d_counts, void *d_index, uint64_t index_cap, void *d_index_all, uint64_t index_all_cap,
+                                            uint64_t *rank_records, uint64_t *stride, void *stream) {
+    if (!c || !reg || !d_out || !d_index || !d_index_all || !rank_records || !stride) return OBM_E_ARG;
     obm_handle *h = c->h; NcclApi *N = nccl_api(); cudaStream_t st = (cudaStream_t)stream;
     int rc = obm_lex_batch_device(h, d_bytes, d_doc_off, ndocs, total_bytes, d_out, out_cap, d_doc_tuple_off, d_status, d_counts, stream);
     if (rc != OBM_OK) return rc;
-    rc = obm_parse_batch_device(h, reg, d_bytes, d_doc_off, ndocs, first_doc, d_out, d_doc_tuple_off, d_results, res_cap, d_args, arg_cap, d_doc_res_off,
-                                c->d_totals, stream);
+    rc = obm_marker_index_flat_device(h, reg, d_bytes, d_doc_off, ndocs, first_doc, d_out, d_doc_tuple_off, out_cap, d_index, index_cap, c->d_totals, stream);
     if (rc != OBM_OK) return rc;
     /* how many records does every rank hold?  (8 bytes per rank; the host needs the largest to size the slots) */
     OBM_NCCL(h, N->AllGather(c->d_totals, c->d_counts_all, 1, NCCL_UINT64, c->comm, st));
     OBM_CUDA(h, cudaMemcpyAsync(c->h_counts, c->d_counts_all, (size_t)c->nranks * 8, cudaMemcpyDeviceToHost, st));
     OBM_CUDA(h, cudaStreamSynchronize(st));
     uint64_t mx = 0;
-    for (int r = 0; r < c->nranks; r++) { rank_results[r] = c->h_counts[r]; if (c->h_counts[r] > mx) mx = c->h_counts[r]; }
+    for (int r = 0; r < c->nranks; r++) { rank_records[r] = c->h_counts[r]; if (c->h_counts[r] > mx) mx = c->h_counts[r]; }
     *stride = mx;
-    if (c->h_counts[c->rank] > res_cap) { set_err(h, "result capacity %llu < %llu records of this shard", (unsigned long long)res_cap, (unsigned long long)c->h_counts[c->rank]); return OBM_E_CAPACITY; }
-    if (mx > res_cap || mx * (uint64_t)c->nranks > results_all_cap) {
-        set_err(h, "gather capacity: need %llu records per slot (send buffer) and %llu in all", (unsigned long long)mx, (unsigned long long)(mx * c->nranks));
+    if (mx > index_cap || mx * (uint64_t)c->nranks > index_all_cap) {
+        set_err(h, "index capacity: need %llu records per rank (send buffer and slot) and %llu in all", (unsigned long long)mx, (unsigned long long)(mx * c->nranks));
         return OBM_E_CAPACITY;
     }
-    if (mx) OBM_NCCL(h, N->AllGather(d_results, d_results_all, (size_t)mx * sizeof(obm_result), NCCL_UINT8, c->comm, st));
+    if (mx) OBM_NCCL(h, N->AllGather(d_index, d_index_all, (size_t)mx * 16, NCCL_UINT8, c->comm, st));
     return OBM_OK;
 }
 

@@ -144,21 +144,8 @@ OBM_HD void parse_doc(const DevRegistry &R, const uint8_t *doc, const obm_tuple 
     int def = -1; uint32_t marker_tuple = 0, n_args = 0; uint64_t arg_base = 0;
     uint32_t a_off = 0, a_len = 0;                                                /* the argument being valued */
     uint32_t st = P_PARSE;
-    /* the tuple loads do not depend on the walk: they are issued a batch ahead (PF tuples in registers, the next PF already in
-     * flight while these are walked), which takes the memory latency out of the dependent chain */
-    constexpr uint32_t PF = 8;
-    obm_tuple cur[PF], nxt[PF];
-#pragma unroll
-    for (uint32_t q = 0; q < PF; q++) nxt[q] = q < nt ? t[q] : 0;
-    for (uint32_t i0 = 0; i0 < nt; i0 += PF) {
-#pragma unroll
-        for (uint32_t q = 0; q < PF; q++) { cur[q] = nxt[q]; nxt[q] = i0 + PF + q < nt ? t[i0 + PF + q] : 0; }
-        bool stop_all = false;
-#pragma unroll
-    for (uint32_t q = 0; q < PF; q++) {
-        const uint32_t i = i0 + q;
-        if (i >= nt || stop_all) continue;
-        const obm_tuple tu = cur[q];
+    for (uint32_t i = 0; i < nt; i++) {
+        const obm_tuple tu = t[i];
         const uint32_t k = OBM_TUPLE_KIND(tu), off = OBM_TUPLE_OFF(tu), len = OBM_TUPLE_LEN(tu);
         if (k == OBM_K_LINE) { base = off; line = len; continue; }
         if (k > OBM_K_EOF) { S.nres = 0; S.nargs = 0; S.result(doc_id, i, 0, 0, 0xFFFFu, 0, 0, OBM_R_HOST, k); return; } /* not modelled: obm_parse_doc decides */
@@ -245,9 +232,7 @@ OBM_HD void parse_doc(const DevRegistry &R, const uint8_t *doc, const obm_tuple 
                 }
             }
         }
-        if (stop) stop_all = true;
-    }
-        if (stop_all) break;
+        if (stop) break;
     }
     (void)cur_tuple; (void)cur_line; (void)cur_col;
 }

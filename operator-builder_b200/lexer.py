@@ -222,13 +222,14 @@ class Comm:
         return bytes(buf)
 
     def lex_batch_sharded_device(self, registry, d_bytes, d_doc_off, ndocs, total_bytes, first_doc, d_out, out_cap, d_tuple_off, d_status, d_counts,
-                                 d_results, res_cap, d_args, arg_cap, d_doc_res_off, d_results_all, results_all_cap, stream=None):
-        """-> (records per rank, slot stride) ; the all-gather is enqueued on `stream`"""
+                                 d_index, index_cap, d_index_all, index_all_cap, stream=None):
+        """scan + marker index + one all-gather of the index records -> (records per rank, slot stride); the all-gather is
+        enqueued on `stream`"""
         per_rank = (ctypes.c_uint64 * self.nranks)()
         stride = ctypes.c_uint64()
         rc = self._L.obm_lex_batch_sharded_device(self._c, registry.handle, d_bytes, d_doc_off, ndocs, total_bytes, first_doc, d_out, out_cap,
-                                                  d_tuple_off, d_status, d_counts, d_results, res_cap, d_args, arg_cap, d_doc_res_off,
-                                                  d_results_all, results_all_cap, per_rank, ctypes.byref(stride), stream)
+                                                  d_tuple_off, d_status, d_counts, d_index, index_cap, d_index_all, index_all_cap,
+                                                  per_rank, ctypes.byref(stride), stream)
         if rc != 0:
             raise NativeError(rc, self._L.obm_last_error(self.scanner.handle).decode())
         return list(per_rank), int(stride.value)

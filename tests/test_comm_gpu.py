@@ -1,5 +1,5 @@
 """The multi-GPU path behind the C ABI (obm_comm_* / obm_lex_batch_sharded_device): file shards, one NCCL all-gather of
-the parser's compact Result records.  nranks = 1 runs on the single-GPU test box; nranks = 2 needs two GPUs (two threads
+the compact index of registered markers.  nranks = 1 runs on the single-GPU test box; nranks = 2 needs two GPUs (two threads
 of this process, one handle + one communicator each -- ncclCommInitRank meets across threads)."""
 import ctypes
 import random
@@ -12,8 +12,7 @@ from tests import corpus_util as cu
 
 pytestmark = pytest.mark.gpu
 
-RES_DT = np.dtype([("doc", "<u4"), ("tuple", "<u4"), ("text_off", "<u4"), ("text_len", "<u4"), ("reg_id", "<u2"), ("nargs", "<u2"),
-                   ("arg_base", "<u4"), ("flags", "<u4"), ("aux", "<u4")])
+REC_DT = np.dtype([("doc", "<u4"), ("tuple", "<u4"), ("off", "<u4"), ("reg_scopes", "<u4")])
 
 
 def make_docs():
@@ -48,19 +47,17 @@ def run_rank(rank, nranks, uid, docs, out, errors):
         d_status = torch.zeros(4, dtype=torch.int32, device=dev)
         d_counts = torch.zeros(2, dtype=torch.int64, device=dev)
         rcap = 16 * len(docs)
-        d_res = torch.zeros(rcap * 32, dtype=torch.uint8, device=dev)
-        d_args = torch.zeros(rcap * 4 * 16, dtype=torch.uint8, device=dev)
-        d_roff = torch.zeros(len(mine) + 1, dtype=torch.int64, device=dev)
-        d_all = torch.zeros(nranks * rcap * 32, dtype=torch.uint8, device=dev)
+        d_idx = torch.zeros(rcap * 16, dtype=torch.uint8, device=dev)
+        d_all = torch.zeros(nranks * rcap * 16, dtype=torch.uint8, device=dev)
         st = torch.cuda.current_stream(dev).cuda_stream
         reg = ob.Registry()
         per_rank, stride = comm.lex_batch_sharded_device(reg, d_bytes.data_ptr(), d_off.data_ptr(), len(mine), nb, d0, d_out.data_ptr(), cap,
-                                                         d_toff.data_ptr(), d_status.data_ptr(), d_counts.data_ptr(), d_res.data_ptr(), rcap,
-                                                         d_args.data_ptr(), rcap * 4, d_roff.data_ptr(), d_all.data_ptr(), nranks * rcap, st)
+                                                         d_toff.data_ptr(), d_status.data_ptr(), d_counts.data_ptr(), d_idx.data_ptr(), rcap,
+                                                         d_all.data_ptr(), nranks * rcap, st)
         torch.cuda.synchronize(dev)
         allr = d_all.cpu().numpy()
-        slots = [allr[r * stride * 32:(r * stride + per_rank[r]) * 32].view(RES_DT).copy() for r in range(nranks)]
-        own = d_res.cpu().numpy()[:per_rank[rank] * 32].view(RES_DT).copy()
+        slots = [allr[r * stride * 16:(r * stride + per_rank[r]) * 16].view(REC_DT).copy() for r in range(nranks)]
+        own = d_idx.cpu().numpy()[:per_rank[rank] * 16].view(REC_DT).copy()
         out[rank] = (per_rank, stride, slots, own, int(d_toff[-1].item()))
         comm.close()
         sc.close()
@@ -92,11 +89,18 @@ def test_sharded_step_gathers_every_ranks_results(nranks):
             assert np.array_equal(slots[q], out[q][3]), (r, q)
     merged = np.concatenate(out[0][2])
     assert list(merged["doc"]) == sorted(merged["doc"]) and int(merged["doc"].max()) < len(docs)
-    # and they are what one rank produces for the whole batch (document ids shift by the shard start, arg_base restarts per shard)
-    if nranks > 1:
-        ref_out, ref_err = {}, []
-        run_rank(0, 1, ob.Comm.unique_id(), docs, ref_out, ref_err)
-        assert not ref_err, ref_err
-        ref = ref_out[0][3]
-        for f in ("doc", "tuple", "text_off", "text_len", "reg_id", "nargs", "flags", "aux"):
-            assert np.array_equal(merged[f], ref[f]), f
+    # ... and they are exactly the markers whose definition the parser would load (definition.go:13-21), per document
+    import oracle
+    from oracle import parser_oracle as po
+    names = [b"+operator-builder:field", b"+operator-builder:collection:field", b"+operator-builder:resource"]
+    k = 0
+    for i, doc in enumerate(docs):
+        prs = po.Parser(oracle.lex(doc), po.OPERATOR_BUILDER_REGISTRY)
+        prs.run()
+        n = len(prs.loaded)
+        got = merged[k:k + n]
+        assert len(got) == n and all(int(x) == i for x in got["doc"]), (i, doc[:100])
+        assert [names[int(x) & 0xFFFF] for x in got["reg_scopes"]] == prs.loaded
+        assert all(doc[int(o)] == ord("+") for o in got["off"])
+        k += n
+    assert k == len(merged)

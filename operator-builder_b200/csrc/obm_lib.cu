@@ -1491,7 +1491,6 @@ k_parse_docs(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc
     }
     obmr::parse_doc(R, bytes + doc_off[d], tuples + t0, (uint32_t)(tuple_off[d + 1] - t0), d + doc_base, S);
     if (!WRITE) { cnt_res[d] = S.nres; cnt_args[d] = S.nargs; }
-    else if (cnt_res && (cnt_res[d] != S.nres || cnt_args[d] != S.nargs)) printf("k_parse_docs: doc %u count pass (%u, %u) != write pass (%u, %u)\n", d, cnt_res[d], cnt_args[d], S.nres, S.nargs);
 }
 
 /* ------------------------------------------------------------------------------------------- */

@@ -3,7 +3,8 @@
  *
  *   k_wtile_index   tile -> first document starting in it; list of large documents (> obmw::MAXDOC)
  *   k_wunits        per tile: unit count + record; an exclusive scan gives every unit a static id in document order
- *   k_warp_scan     persistent warps (no block barrier anywhere): a warp takes a tile by ticket, stages the text of
+ *   k_wunit_tiles   unit -> tile
+ *   k_warp_scan     persistent warps (no block barrier anywhere): a warp takes a unit by ticket, stages the text of
  *                   each of its units with one TMA bulk copy (cp.async.bulk + mbarrier) into its own slice of shared
  *                   memory and runs obmw::process_unit on it
  */
@@ -36,6 +37,15 @@ k_wtile_index(const uint64_t *__restrict__ doc_off, uint32_t ndocs, uint32_t nti
     if (d == ndocs && ndocs > 0 && tprev_plus1 > tcur) return;
     for (uint64_t t = tprev_plus1; t <= tcur && t <= ntiles; t++) tile_first[t] = d;
     if (d < ndocs && doc_off[d + 1] - doc_off[d] > MAXDOC) large_list[atomicAdd(n_large, 1u)] = d;
+}
+
+/* unit -> tile, after the scan of the unit counts */
+__global__ void __launch_bounds__(256)
+k_wunit_tiles(const uint32_t *__restrict__ nunits, const uint64_t *__restrict__ ubase, uint32_t ntiles, uint64_t units_max, uint32_t *__restrict__ unit_tile) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const uint64_t u0 = ubase[t];
+    for (uint32_t k = 0; k < nunits[t] && u0 + k < units_max; k++) unit_tile[u0 + k] = t;
 }
 
 __global__ void __launch_bounds__(256)
@@ -134,23 +144,20 @@ k_warp_scan(WArgs A) {
     DevHooks H{0};
     WAcc acc{0, 0, 0, 0};
     UnitRegs pend; bool have_pend = false;
-    /* unit iterator: tiles by ticket; the next tile's ticket is taken while this one is processed, and the NEXT unit's
-     * descriptor (document offsets -> source address of its text) is ready one unit ahead */
-    uint32_t t = 0, k = 0, tn = 0; WRec rec{0, 0, 0, 0}; uint32_t u0 = 0;
+    /* unit iterator: UNITS by ticket, in document order (not tiles: a warp that held two units of one tile would publish
+     * the second only after writing the first, and with units that resolve right after publishing that serialises the
+     * whole chain).  The ticket after next is taken while this unit is processed, and the NEXT unit's descriptor
+     * (document offsets -> source address of its text) is ready one unit ahead */
+    uint32_t tn = 0;
     auto next_unit = [&]() -> UnitDesc {
-        for (;;) {
-            if (k < rec.n_units) {
-                uint32_t da, db, extra;
-                wrec_unit(rec, k, da, db, extra);
-                const UnitDesc d = make_desc(A, u0 + k, da, db, extra);
-                k++;
-                return d;
-            }
-            t = __shfl_sync(0xffffffffu, tn, 0);
-            if (t >= A.ntiles) { UnitDesc d{0, 0, 0, 0, 0, 0, 0, false}; return d; }
-            if (lane == 0) tn = atomicAdd(&A.ctl[WC_TICKET], 1u);
-            rec = A.wrec[t]; u0 = (uint32_t)A.ubase[t]; k = 0;
-        }
+        const uint32_t u = __shfl_sync(0xffffffffu, tn, 0);
+        if (u >= nunits) { UnitDesc d{0, 0, 0, 0, 0, 0, 0, false}; return d; }
+        if (lane == 0) tn = atomicAdd(&A.ctl[WC_TICKET], 1u);
+        const uint32_t t = A.unit_tile[u];
+        const WRec rec = A.wrec[t];
+        uint32_t da, db, extra;
+        wrec_unit(rec, u - (uint32_t)A.ubase[t], da, db, extra);
+        return make_desc(A, u, da, db, extra);
     };
     if (lane == 0) tn = atomicAdd(&A.ctl[WC_TICKET], 1u);
     UnitDesc cur = next_unit();

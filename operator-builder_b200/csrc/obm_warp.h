@@ -37,6 +37,16 @@
 #define OBMW_BUFB 13312
 #endif
 
+#ifdef OBMW_NI_PUT
+#define OBMW_PUT_FN OBM_HD_NOINLINE
+#else
+#define OBMW_PUT_FN OBM_HD
+#endif
+#ifdef OBMW_NI_SCAN
+#define OBMW_SCAN_FN OBM_HD_NOINLINE
+#else
+#define OBMW_SCAN_FN OBM_HD
+#endif
 namespace obmw {
 
 constexpr uint32_t TILE = OBMW_TILE;      /* a unit = the documents starting in [t*TILE, (t+1)*TILE) (split when > DMAX / > BUFB) */
@@ -81,7 +91,7 @@ OBM_HD obm_tuple st_unpack(uint32_t v) { /* kind stays in the top 5 bits of the 
 struct PackSink {
     uint32_t *st; uint32_t cap, n, mk, lx; bool ovf;
     OBM_HD PackSink(uint32_t *s, uint32_t c) : st(s), cap(c), n(0), mk(0), lx(0), ovf(false) {}
-    OBM_HD void put(uint32_t kind, uint32_t off, uint32_t len) {
+    OBMW_PUT_FN void put(uint32_t kind, uint32_t off, uint32_t len) {
         if (n < cap && len <= ST_MAXLEN) st[n] = st_pack(kind, off, len); else ovf = true;
         n++;
         mk += (kind == OBM_K_MARKER_START);
@@ -167,7 +177,7 @@ OBM_HD uint32_t flags16(const uint32_t (&z)[4]) {
 /* first position q in [p, lim) whose byte is a name delimiter (naked: ';' does not count), else lim.  16 bytes per step
  * (one 128-bit shared-memory load, four independent class computations): the lexer is latency-bound, not issue-bound */
 template <class Src>
-OBM_HD uint32_t scan_delim(const Src &t, uint32_t p, uint32_t lim, bool naked) {
+OBMW_SCAN_FN uint32_t scan_delim(const Src &t, uint32_t p, uint32_t lim, bool naked) {
     uint32_t a = p & ~15u;
     uint32_t from = 0xFFFFu << (p & 15u);
     for (;;) {
@@ -187,7 +197,7 @@ OBM_HD uint32_t scan_delim(const Src &t, uint32_t p, uint32_t lim, bool naked) {
 }
 /* first position q in [p, lim) whose byte equals c (7-bit) or '\n', else lim */
 template <class Src>
-OBM_HD uint32_t scan_byte_or_nl(const Src &t, uint32_t p, uint32_t lim, uint32_t c) {
+OBMW_SCAN_FN uint32_t scan_byte_or_nl(const Src &t, uint32_t p, uint32_t lim, uint32_t c) {
     const uint32_t rep = c * 0x01010101u;
     uint32_t a = p & ~15u;
     uint32_t from = 0xFFFFu << (p & 15u);
@@ -266,10 +276,13 @@ OBM_HD uint32_t fast_line(const Src &t, uint32_t first, uint32_t plus, uint32_t 
                         if (!ok || dots > 1 || digits == 0) return FL_FALLBACK;
                         kind = dots ? OBM_K_FLOAT_LITERAL : OBM_K_INTEGER_LITERAL;
                     } else {
-                        const bool t4 = len >= 4 && t[p] == 't' && t[p + 1] == 'r' && t[p + 2] == 'u' && t[p + 3] == 'e';
-                        const bool f5 = len >= 5 && t[p] == 'f' && t[p + 1] == 'a' && t[p + 2] == 'l' && t[p + 3] == 's' && t[p + 4] == 'e';
-                        if ((t4 && len > 4) || (f5 && len > 5)) return FL_FALLBACK;
-                        kind = (t4 || f5) ? OBM_K_BOOL_LITERAL : OBM_K_STRING_LITERAL;
+                        kind = OBM_K_STRING_LITERAL;
+                        if (c0 == 't' || c0 == 'f') { /* true / false; a longer word that starts with one of them is the generic lexer's (A.7) */
+                            const bool t4 = len >= 4 && c0 == 't' && t[p + 1] == 'r' && t[p + 2] == 'u' && t[p + 3] == 'e';
+                            const bool f5 = len >= 5 && c0 == 'f' && t[p + 1] == 'a' && t[p + 2] == 'l' && t[p + 3] == 's' && t[p + 4] == 'e';
+                            if ((t4 && len > 4) || (f5 && len > 5)) return FL_FALLBACK;
+                            if (t4 || f5) kind = OBM_K_BOOL_LITERAL;
+                        }
                     }
                     o.put(kind, p - dpos, len);
                     p = e2;

@@ -24,8 +24,10 @@
 #endif
 #if defined(__CUDACC__)
 #define OBMW_DEV __device__ __forceinline__
+#define OBMW_DEV_COLD __device__ __noinline__ /* rare paths: their own copy, out of the hot code and of its register allocation */
 #else
 #define OBMW_DEV inline
+#define OBMW_DEV_COLD inline
 #endif
 
 namespace obmw {
@@ -59,6 +61,7 @@ static_assert(OWN_CAP <= 256, "mlist holds owner indices in a byte");
 /* a scanned unit between its two halves: warp-uniform values, and one document per lane */
 struct UnitRegs {
     uint32_t u, da, nd, extra, n_owners, n_ml, n_small /* tuples of the unit's small documents */; uint64_t total; bool needs_text;
+    bool paged; /* more owning lines than OWN_CAP: the unit is scanned (and later written) one document at a time */
     uint32_t dflag, dtot, dexcl, dlen; /* lane d < nd: document da + d */
 };
 
@@ -66,6 +69,7 @@ struct WArgs {
     const uint8_t *bytes; const uint64_t *doc_off; uint32_t ndocs; uint64_t total_bytes;
     const uint32_t *tile_first; uint32_t ntiles;
     const WRec *wrec; const uint64_t *ubase; /* [ntiles + 1] exclusive scan of units per tile */
+    const uint32_t *unit_tile;               /* [units] tile of every unit (device: units are handed out one by one) */
     uint64_t *st_tuples, *st_blocks;         /* chain over the units' tuple counts (obm_warp.cuh: chain_publish / chain_resolve) */
     uint64_t units_max;                      /* capacity the chain arrays were carved for */
     const uint32_t *counts;                  /* tuple counts of large documents (k_large_resolve) */
@@ -134,8 +138,13 @@ OBM_HD uint32_t w_nl_before(const WarpSmem &W, const UnitSet &S, uint32_t q) {
     } while (0)
 
 /* the line of owner record r, lexed by the generic ASCII lexer (hand-over target of the stepper): tuples into out[0..cap) */
+#ifdef OBMW_NI_GEN
+#define OBMW_GEN_FN OBM_HD_NOINLINE
+#else
+#define OBMW_GEN_FN OBM_HD
+#endif
 template <class Src>
-OBM_HD uint32_t generic_line(const obm::Tables &T, const Src &text, orec_t r, uint32_t dpos, uint32_t dend, obm_tuple *out, uint32_t cap,
+OBMW_GEN_FN uint32_t generic_line(const obm::Tables &T, const Src &text, orec_t r, uint32_t dpos, uint32_t dend, obm_tuple *out, uint32_t cap,
                              uint32_t *mk, uint32_t *lx) {
     const uint32_t n = dend - dpos;
     uint32_t e = or_first(r); /* end of the line: the generic lexer's skipping is bounded by it (obmp::LineAccel) */
@@ -144,30 +153,22 @@ OBM_HD uint32_t generic_line(const obm::Tables &T, const Src &text, orec_t r, ui
     return obmp::k2_marker_item(T, obm::src_add(text, dpos), n, it, out, cap, mk, lx);
 }
 
-/* ---- first half: phases A, B, C and the assembly of the unit's tuple positions --------------------------- */
-template <class Hooks>
-OBMW_DEV void compute_unit(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tables &T, Hooks &H, const UnitDesc &D, bool prestaged, UnitRegs &R) {
+/* ---- phases A, B, C and the assembly of the tuple positions of documents [da, da + nd), whose text is staged at
+ * [lo_pos, hi_pos) and whose starts / flags are in W.dstart[0..nd] / W.dflag[0..nd).  Returns false (nothing assembled)
+ * when the range has more owning lines than OWN_CAP and the caller can split it (allow_page). ---- */
+OBMW_DEV bool scan_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tables &T, uint32_t u, uint32_t da, uint32_t nd,
+                         uint32_t lo_pos, uint32_t hi_pos, bool allow_page, UnitRegs &R) {
+    (void)A;
     const uint32_t lane = WLANE();
-    const uint32_t u = D.u, da = D.da, db = D.db, extra = D.extra;
-    const uint32_t nd = db - da;
     uint32_t n_owners = 0, n_ml = 0;
-    uint32_t lo_pos = 0, hi_pos = 0;
     bool unstaged = false;
     if (nd) {
-        const uint32_t skew = D.skew, span = D.span, load = desc_load(D);
-        const uint64_t b0 = (D.base_abs + skew) - (uint64_t)(uintptr_t)A.bytes;
-        lo_pos = skew; hi_pos = span;
-        if (!prestaged) H.stage(W, (const void *)(uintptr_t)D.base_abs, load);
-        if (lane <= nd) W.dstart[lane] = (uint32_t)(A.doc_off[da + lane] - b0) + skew;
-        if (lane < nd) W.dflag[lane] = 0;
-        WSYNC();
-        H.stage_wait(W, load);
         const auto text = WTEXT(W);
 
         /* ---- A: rows ---- */
-        const uint32_t nrows = (span + ROW - 1) / ROW;
+        const uint32_t r0 = lo_pos / ROW, r1 = (hi_pos + ROW - 1) / ROW;
         uint32_t nl_run = 0, own_run = 0, cin_row = 0, prev_top = 0, nextd = 1;
-        for (uint32_t r = 0; r < nrows; r++) {
+        for (uint32_t r = r0; r < r1; r++) {
             const uint32_t row0 = r * ROW, pos0 = row0 + lane * 32u;
             uint32_t x[8];
             {
@@ -212,7 +213,7 @@ OBMW_DEV void compute_unit(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::T
             uint32_t up = WSHFL_UP(top, 1);
             if (lane == 0) up = prev_top;
             uint32_t M = (nl << 1) | up;
-            if (r == 0 && lo_pos < hi_pos && (lo_pos >> 5) == lane) M |= 1u << (lo_pos & 31u);
+            if (r == r0 && lo_pos < hi_pos && ((lo_pos - row0) >> 5) == lane) M |= 1u << (lo_pos & 31u);
             /* first event of every line: (~ev + M) & ev, the carry resolved across lanes by generate / propagate */
             const uint32_t G = (uint32_t)((((uint64_t)(~ev)) + M) >> 32);
             const uint32_t Gb = WBALLOT(G != 0), Pb = WBALLOT(ev == 0 && G == 0);
@@ -239,7 +240,10 @@ OBMW_DEV void compute_unit(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::T
         }
         WSYNC();
         n_owners = own_run;
-        if (n_owners > OWN_CAP) { n_owners = 0; if (lane < nd) W.dflag[lane] |= DF_QOVERFLOW; }
+        if (n_owners > OWN_CAP) {
+            if (allow_page) return false;
+            n_owners = 0; if (lane < nd) W.dflag[lane] |= DF_QOVERFLOW;
+        }
         WSYNC();
 
         /* ---- B: owners ---- */
@@ -357,11 +361,69 @@ OBMW_DEV void compute_unit(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::T
     }
     WSYNC();
     R.n_small = (uint32_t)total;
-    if (extra) total += A.counts[da + nd];
-    R.u = u; R.da = da; R.nd = nd; R.extra = extra; R.n_owners = n_owners; R.n_ml = n_ml; R.total = total;
+    R.u = u; R.da = da; R.nd = nd; R.extra = 0; R.n_owners = n_owners; R.n_ml = n_ml; R.total = total;
     R.dflag = dflag; R.dtot = dtot; R.dexcl = dexcl; R.dlen = dlen;
     R.needs_text = WBALLOT(unstaged || dflag != 0) != 0;
+    R.paged = false;
+    return true;
 }
+
+/* ---- first half of a unit: stage its text, scan it, assemble the tuple positions ---- */
+template <class Hooks>
+OBMW_DEV void compute_unit(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tables &T, Hooks &H, const UnitDesc &D, bool prestaged, UnitRegs &R) {
+    const uint32_t lane = WLANE();
+    const uint32_t u = D.u, da = D.da, nd = D.db - D.da, extra = D.extra;
+    uint32_t lo_pos = 0, hi_pos = 0;
+    if (nd) {
+        const uint32_t skew = D.skew, span = D.span, load = desc_load(D);
+        const uint64_t b0 = (D.base_abs + skew) - (uint64_t)(uintptr_t)A.bytes;
+        lo_pos = skew; hi_pos = span;
+        if (!prestaged) H.stage(W, (const void *)(uintptr_t)D.base_abs, load);
+        if (lane <= nd) W.dstart[lane] = (uint32_t)(A.doc_off[da + lane] - b0) + skew;
+        if (lane < nd) W.dflag[lane] = 0;
+        WSYNC();
+        H.stage_wait(W, load);
+    }
+    /* one scan of the whole range; when it has more owning lines than the owner table holds (lines of a few bytes) the
+     * same call site then counts it document by document (write_unit scans each document again when it writes it) */
+    uint32_t mypos = 0, my_tot = 0, my_flag = 0;
+    for (uint32_t j = 0xFFFFFFFFu;;) {
+        const bool whole = j == 0xFFFFFFFFu;
+        uint32_t pj = lo_pos, ej = hi_pos;
+        if (!whole) {
+            pj = WSHFL(mypos, j); ej = WSHFL(mypos, j + 1);
+            if (lane == 0) { W.dstart[0] = pj; W.dstart[1] = ej; W.dflag[0] = 0; }
+            WSYNC();
+        }
+        const bool ok = scan_range(W, S, A, T, u, whole ? da : da + j, whole ? nd : 1u, pj, ej, whole && nd > 1, R);
+        if (whole) {
+            if (ok) break;
+            mypos = lane <= nd ? W.dstart[lane] : 0u;
+            WSYNC();
+            j = 0;
+            continue;
+        }
+        const uint32_t tj = WSHFL(R.dtot, 0), fj = WSHFL(R.dflag, 0);
+        if (lane == j) { my_tot = tj; my_flag = fj; }
+        WSYNC();
+        if (++j < nd) continue;
+        if (lane <= nd) W.dstart[lane] = mypos;
+        if (lane < nd) W.dflag[lane] = my_flag;
+        WSYNC();
+        uint32_t dincl = lane < nd ? my_tot : 0u;
+        OBMW_SCAN_INCL(dincl);
+        const uint32_t nextpos = WSHFL(mypos, (lane + 1) & 31u);
+        R.u = u; R.da = da; R.nd = nd; R.n_owners = 0; R.n_ml = 0;
+        R.dflag = my_flag; R.dtot = my_tot; R.dexcl = dincl - (lane < nd ? my_tot : 0u);
+        R.dlen = lane < nd ? nextpos - mypos : 0u;
+        R.total = WSHFL(dincl, 31); R.n_small = (uint32_t)R.total;
+        R.needs_text = true; R.paged = true;
+        break;
+    }
+    R.extra = extra;
+    if (extra) R.total += A.counts[da + nd];
+}
+
 
 /* ---- deferred path: the unit's tuples packed into W.fin in final order (only units without needs_text) -------
  * Returns false when the unit does not fit (more than FIN_CAP tuples, a line number beyond the packed form): the
@@ -419,15 +481,36 @@ OBMW_DEV void write_fin(const WarpSmem &W, const WArgs &A, const UnitRegs &R, ui
 
 /* ---- second half: the unit's tuples at their final positions (base = tuples of all earlier units) ----------
  * The direct path: units with needs_text, or too large for W.fin; written before the warp stages its next unit. */
+OBMW_DEV void write_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tables &T, const UnitRegs &R, uint64_t base, WAcc &acc);
 OBMW_DEV void write_unit(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tables &T, const UnitRegs &R, uint32_t nunits, uint64_t base, WAcc &acc) {
     const uint32_t lane = WLANE();
-    const uint32_t nd = R.nd, n_owners = R.n_owners, n_ml = R.n_ml;
-    const bool writing = A.out != nullptr && A.out_cap != 0;
     if (lane == 0) {
         if (R.u == 0) A.tuple_off[0] = 0;
         if (R.u == nunits - 1 && A.out && base + R.total > A.out_cap) A.status[0] = 1;
-        if (R.extra) A.tuple_off[R.da + nd + 1] = base + R.total;
+        if (R.extra) A.tuple_off[R.da + R.nd + 1] = base + R.total;
     }
+    /* a paged unit: every document is scanned again, alone, and written at its place (same call site as the usual case) */
+    const uint32_t mypos = (R.paged && lane <= R.nd) ? W.dstart[lane] : 0u;
+    if (R.paged) WSYNC();
+    const uint32_t npages = R.paged ? R.nd : 1u;
+    for (uint32_t j = 0; j < npages; j++) {
+        UnitRegs Rj = R;
+        uint64_t bj = base;
+        if (R.paged) {
+            const uint32_t pj = WSHFL(mypos, j), ej = WSHFL(mypos, j + 1);
+            bj = base + WSHFL(R.dexcl, j);
+            if (lane == 0) { W.dstart[0] = pj; W.dstart[1] = ej; W.dflag[0] = 0; }
+            WSYNC();
+            scan_range(W, S, A, T, R.u, R.da + j, 1, pj, ej, false, Rj);
+        }
+        write_range(W, S, A, T, Rj, bj, acc);
+    }
+}
+/* the documents of a scanned range: tuples at their final positions (base = tuples before the range's first document) */
+OBMW_DEV void write_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tables &T, const UnitRegs &R, uint64_t base, WAcc &acc) {
+    const uint32_t lane = WLANE();
+    const uint32_t nd = R.nd, n_owners = R.n_owners, n_ml = R.n_ml;
+    const bool writing = A.out != nullptr && A.out_cap != 0;
     if (nd == 0) return;
     if (lane < nd) {
         const uint64_t at = base + R.dexcl;

@@ -49,8 +49,31 @@ def test_dense_marker_lines_long_lines_and_large_documents():
     for skew in (0, 9):
         check_batch(docs, skew)
     check_batch([long_line * 200])  # every line overflows its staging slot
+    # tokens, quoted strings and further markers beyond the 128 bytes the stepper's delimiter mask covers
+    far = b"# +a:b:c=\"" + b"x y,z" * 40 + b"\" +d:e:f=" + b"v" * 150 + b" +g:h +i:j:k='" + b"q;" * 70 + b"',l=1.5\n"
+    for lead in range(0, 33, 5):
+        check_batch([b"x" * lead + b"\n" + far * 3, far[:140] + b"\n" + far, far[:129] + b"\n", far[:127]])
     check_batch([big])  # a batch that is one large document
     check_batch([b""] * 200 + [big] + [b""] * 3)
+
+
+def test_units_with_more_owning_lines_than_the_owner_table():
+    """lines of a few bytes: a unit's documents together have more owning lines than OWN_CAP (256); the fused warp
+    kernel then scans and writes the unit one document at a time instead of handing every document to the exact lexer"""
+    short = [b"".join(b"# c%d\n" % (i % 7) for i in range(n)) for n in (100, 120, 90, 130, 40, 200)]
+    marks = [b"".join(b"# +a:b:c=%d\n" % (i % 10) if i % 3 == 0 else b"# x\n" for i in range(n)) for n in (150, 110, 170)]
+    odd = [b"# +a:b=`x\ny`\n" + b"# k\n" * 120, b"# k\n" * 100 + "é # +a:b\n".encode() + b"# k\n" * 30, b"", b"#\n" * 255, b"#\n" * 257, b"+x:y\n" * 140]
+    for skew in (0, 5):
+        st = check_batch(short * 3, skew, which=2)
+        assert int(st[2]) == 0, st  # no document took the exact lexer
+        st = check_batch(marks * 3 + short, skew, which=2)
+        assert int(st[2]) == 0, st
+        check_batch(short[:2] + odd + marks + short[2:] + odd[::-1], skew)
+    # the adversarial sweep's 16-byte lines: 4 KiB documents of 256 lines each
+    cell = [(b"# " + b"x" * 13 + b"\n") * 256, (b"# +s:a0=0 +s:a\n") * 256, (b"#  +q:v=\"yyyy\"\n") * 256]
+    for doc in cell:
+        st = check_batch([doc] * 7, 0, which=2)
+        assert int(st[2]) == 0, st
 
 
 def test_non_ascii_neighbour_in_the_same_aligned_word():

@@ -37,16 +37,6 @@
 #define OBMW_BUFB 13312
 #endif
 
-#ifdef OBMW_NI_PUT
-#define OBMW_PUT_FN OBM_HD_NOINLINE
-#else
-#define OBMW_PUT_FN OBM_HD
-#endif
-#ifdef OBMW_NI_SCAN
-#define OBMW_SCAN_FN OBM_HD_NOINLINE
-#else
-#define OBMW_SCAN_FN OBM_HD
-#endif
 namespace obmw {
 
 constexpr uint32_t TILE = OBMW_TILE;      /* a unit = the documents starting in [t*TILE, (t+1)*TILE) (split when > DMAX / > BUFB) */
@@ -91,7 +81,7 @@ OBM_HD obm_tuple st_unpack(uint32_t v) { /* kind stays in the top 5 bits of the 
 struct PackSink {
     uint32_t *st; uint32_t cap, n, mk, lx; bool ovf;
     OBM_HD PackSink(uint32_t *s, uint32_t c) : st(s), cap(c), n(0), mk(0), lx(0), ovf(false) {}
-    OBMW_PUT_FN void put(uint32_t kind, uint32_t off, uint32_t len) {
+    OBM_HD void put(uint32_t kind, uint32_t off, uint32_t len) {
         if (n < cap && len <= ST_MAXLEN) st[n] = st_pack(kind, off, len); else ovf = true;
         n++;
         mk += (kind == OBM_K_MARKER_START);
@@ -177,7 +167,7 @@ OBM_HD uint32_t flags16(const uint32_t (&z)[4]) {
 /* first position q in [p, lim) whose byte is a name delimiter (naked: ';' does not count), else lim.  16 bytes per step
  * (one 128-bit shared-memory load, four independent class computations): the lexer is latency-bound, not issue-bound */
 template <class Src>
-OBMW_SCAN_FN uint32_t scan_delim(const Src &t, uint32_t p, uint32_t lim, bool naked) {
+OBM_HD uint32_t scan_delim(const Src &t, uint32_t p, uint32_t lim, bool naked) {
     uint32_t a = p & ~15u;
     uint32_t from = 0xFFFFu << (p & 15u);
     for (;;) {
@@ -197,7 +187,7 @@ OBMW_SCAN_FN uint32_t scan_delim(const Src &t, uint32_t p, uint32_t lim, bool na
 }
 /* first position q in [p, lim) whose byte equals c (7-bit) or '\n', else lim */
 template <class Src>
-OBMW_SCAN_FN uint32_t scan_byte_or_nl(const Src &t, uint32_t p, uint32_t lim, uint32_t c) {
+OBM_HD uint32_t scan_byte_or_nl(const Src &t, uint32_t p, uint32_t lim, uint32_t c) {
     const uint32_t rep = c * 0x01010101u;
     uint32_t a = p & ~15u;
     uint32_t from = 0xFFFFu << (p & 15u);

@@ -24,10 +24,8 @@
 #endif
 #if defined(__CUDACC__)
 #define OBMW_DEV __device__ __forceinline__
-#define OBMW_DEV_COLD __device__ __noinline__ /* rare paths: their own copy, out of the hot code and of its register allocation */
 #else
 #define OBMW_DEV inline
-#define OBMW_DEV_COLD inline
 #endif
 
 namespace obmw {
@@ -138,13 +136,8 @@ OBM_HD uint32_t w_nl_before(const WarpSmem &W, const UnitSet &S, uint32_t q) {
     } while (0)
 
 /* the line of owner record r, lexed by the generic ASCII lexer (hand-over target of the stepper): tuples into out[0..cap) */
-#ifdef OBMW_NI_GEN
-#define OBMW_GEN_FN OBM_HD_NOINLINE
-#else
-#define OBMW_GEN_FN OBM_HD
-#endif
 template <class Src>
-OBMW_GEN_FN uint32_t generic_line(const obm::Tables &T, const Src &text, orec_t r, uint32_t dpos, uint32_t dend, obm_tuple *out, uint32_t cap,
+OBM_HD uint32_t generic_line(const obm::Tables &T, const Src &text, orec_t r, uint32_t dpos, uint32_t dend, obm_tuple *out, uint32_t cap,
                              uint32_t *mk, uint32_t *lx) {
     const uint32_t n = dend - dpos;
     uint32_t e = or_first(r); /* end of the line: the generic lexer's skipping is bounded by it (obmp::LineAccel) */

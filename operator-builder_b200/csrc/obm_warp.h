@@ -51,7 +51,10 @@ constexpr uint32_t LTS = 24;              /* staged tuples per marker line */
 constexpr uint32_t FIN_CAP = TILE / 16;   /* tuples of a unit whose write is deferred (0.5 B of tuples per input byte: manifests need 0.35) */
 static_assert(BUFB % ROW == 0 && BUFB >= TILE + 16 && BUFB <= 16384 + ROW, "buffer geometry");
 
-enum : uint32_t { DF_NONASCII = 1, DF_INTERACT = 2, DF_QOVERFLOW = 4 };
+/* document flags; DF_UNI lives only between phases A and B: a valid-UTF-8 document without Unicode white space stays on the
+ * line-parallel path unless one of its MARKER lines holds bytes >= 0x80 (then: the exact lexer, DF_INTERACT) */
+enum : uint32_t { DF_NONASCII = 1, DF_INTERACT = 2, DF_QOVERFLOW = 4, DF_UNI = 8, DF_EXACT = 7 };
+enum : uint32_t { PD_GENERIC = 255 /* orec plusd: the line is the generic ASCII lexer's */ };
 
 /* ---- owner record (8 bytes), positions document-relative ------------------------------------------------
  *  0..13 ls | 14..27 first special | 28..41 line | 42 marker | 43 slash2 ("//" comment) | 44 dead (no tuple)

@@ -47,6 +47,7 @@ struct WarpSmem {
     uint32_t fin[FIN_CAP];      /* the unit's tuples, packed (st_pack), in final order: what the DEFERRED write needs -- a warp scans
                                  * its next unit while this unit's tuple count travels through the chain (obm_warp.cuh) */
     uint16_t nlpre[NWORDS];     /* newline bits in words [0, w) */
+    uint32_t naw[NWORDS / 32 + 1]; /* per row: the 32-byte words that hold bytes >= 0x80 */
     uint32_t dstart[DMAX + 2];  /* document starts, buffer-relative; [nd] = end */
     uint32_t dflag[DMAX + 1];
     uint32_t dcnt[DMAX + 1];    /* exclusive tuple offsets of the documents inside the unit */
@@ -146,6 +147,39 @@ OBM_HD uint32_t generic_line(const obm::Tables &T, const Src &text, orec_t r, ui
     return obmp::k2_marker_item(T, obm::src_add(text, dpos), n, it, out, cap, mk, lx);
 }
 
+/* Go's utf8.DecodeRune validity over the bytes [q, e) of the staged text and no unicode.IsSpace code point beyond ASCII
+ * (obm_tile.h utf8_plain explains why both): such a document keeps every line independent */
+OBM_FN bool utf8_plain_w(const WarpSmem &W, uint32_t q, uint32_t e) {
+    uint32_t p = q;
+    while (p < e) {
+        const uint32_t w = p >> 5;
+        if (!((W.naw[w >> 5] >> (w & 31)) & 1u)) { p = (w + 1) << 5; continue; } /* all-ASCII word */
+        const uint32_t wend = ((w + 1) << 5) < e ? ((w + 1) << 5) : e;
+        while (p < wend) {
+            const uint32_t b0 = W.text[p];
+            if (b0 < 0x80) { p++; continue; }
+            uint32_t need, lo = 0x80, hi = 0xBF;
+            if (b0 >= 0xC2 && b0 <= 0xDF) need = 1;
+            else if (b0 >= 0xE0 && b0 <= 0xEF) { need = 2; if (b0 == 0xE0) lo = 0xA0; if (b0 == 0xED) hi = 0x9F; }
+            else if (b0 >= 0xF0 && b0 <= 0xF4) { need = 3; if (b0 == 0xF0) lo = 0x90; if (b0 == 0xF4) hi = 0x8F; }
+            else return false;
+            if (p + need >= e) return false; /* truncated at the end of the document */
+            const uint32_t b1 = W.text[p + 1];
+            if (b1 < lo || b1 > hi) return false;
+            uint32_t b2 = 0;
+            if (need >= 2) { b2 = W.text[p + 2]; if (b2 < 0x80 || b2 > 0xBF) return false; }
+            if (need == 3) { const uint32_t b3 = W.text[p + 3]; if (b3 < 0x80 || b3 > 0xBF) return false; }
+            if (b0 == 0xC2 && (b1 == 0x85 || b1 == 0xA0)) return false; /* Unicode white space */
+            if (b0 == 0xE1 && b1 == 0x9A && b2 == 0x80) return false;
+            if (b0 == 0xE2 && b1 == 0x80 && (b2 <= 0x8A || b2 == 0xA8 || b2 == 0xA9 || b2 == 0xAF)) return false;
+            if (b0 == 0xE2 && b1 == 0x81 && b2 == 0x9F) return false;
+            if (b0 == 0xE3 && b1 == 0x80 && b2 == 0x80) return false;
+            p += need + 1;
+        }
+    }
+    return true;
+}
+
 /* ---- phases A, B, C and the assembly of the tuple positions of documents [da, da + nd), whose text is staged at
  * [lo_pos, hi_pos) and whose starts / flags are in W.dstart[0..nd] / W.dflag[0..nd).  Returns false (nothing assembled)
  * when the range has more owning lines than OWN_CAP and the caller can split it (allow_page). ---- */
@@ -179,6 +213,7 @@ OBMW_DEV bool scan_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tab
                 else for (uint32_t k = 0; k < 32; k++) if (((keep >> k) & 1u) && W.text[pos0 + k] >= 0x80) na = true;
             }
             const uint32_t nab = WBALLOT(na);
+            if (lane == 0) W.naw[r] = nab;
             if (nab && lane < nd) { /* rare: exact attribution, byte by byte */
                 const uint32_t q = W.dstart[lane], e = W.dstart[lane + 1];
                 for (uint32_t mm = nab; mm; mm &= mm - 1) {
@@ -237,6 +272,7 @@ OBMW_DEV bool scan_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tab
             if (allow_page) return false;
             n_owners = 0; if (lane < nd) W.dflag[lane] |= DF_QOVERFLOW;
         }
+        if (lane < nd && W.dflag[lane] == DF_NONASCII && utf8_plain_w(W, W.dstart[lane], W.dstart[lane + 1])) W.dflag[lane] = DF_UNI;
         WSYNC();
 
         /* ---- B: owners ---- */
@@ -249,7 +285,18 @@ OBMW_DEV bool scan_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tab
                 uint32_t dlo = 0, dhi = nd; /* last d with dstart[d] <= ls */
                 while (dhi - dlo > 1) { const uint32_t mid = (dlo + dhi) >> 1; if (W.dstart[mid] <= ls) dlo = mid; else dhi = mid; }
                 const uint32_t d = dlo, dpos = W.dstart[d];
-                if (W.dflag[d]) { S.orec[o] = make_orec(ls - dpos, first - dpos, 0, false, false, true, d, 0); S.opos[o] = 0; }
+                const uint32_t df = W.dflag[d];
+                bool uni = false;
+                if (df & DF_UNI) { /* does the line hold bytes >= 0x80?  Only marker lines care:
+                                    * lex / lexComment (state.go:15-57) look for '#', "//", '+' and '\n' and nothing else */
+                    const uint32_t dend = W.dstart[d + 1];
+                    uint32_t e = first;
+                    for (;;) { if (e >= dend) { e = dend; break; } if (w_is_nl(S, e) && text[e] == '\n') break; e = w_next_event(S, e + 1, hi_pos); }
+                    const uint32_t last = e < hi_pos ? e : hi_pos - 1u;
+                    for (uint32_t w = ls >> 5; w <= (last >> 5); w++) uni |= ((W.naw[w >> 5] >> (w & 31)) & 1u) != 0;
+                    if (uni) { uni = false; for (uint32_t q = ls; q <= last; q++) uni |= W.text[q] >= 0x80; } /* the words are shared with the neighbouring lines */
+                }
+                if (df & DF_EXACT) { S.orec[o] = make_orec(ls - dpos, first - dpos, 0, false, false, true, d, 0); S.opos[o] = 0; }
                 else {
                     const uint32_t line = 1 + w_nl_before(W, S, ls) - w_nl_before(W, S, dpos);
                     const uint32_t c = text[first];
@@ -264,7 +311,8 @@ OBMW_DEV bool scan_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tab
                             if (text[e] == '+') { marker = true; plus = e; break; }
                         }
                     }
-                    const uint32_t pd = plus - first < 255u ? plus - first : 255u;
+                    const uint32_t pd = plus - first < PD_GENERIC ? plus - first : PD_GENERIC;
+                    if (marker && uni) WATOMIC_OR(&W.dflag[d], DF_INTERACT); /* names, values and the letter after '+' are judged by Unicode classes: the exact lexer's */
                     S.orec[o] = make_orec(ls - dpos, first - dpos, line, marker, c == '/', false, d, pd);
                     if (!marker) S.opos[o] = (uint16_t)(line == 1 ? 1u : 2u);
                 }
@@ -275,6 +323,8 @@ OBMW_DEV bool scan_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tab
         }
         WSYNC(); /* the bitmaps are dead from here on: their space becomes the staging area */
 
+        if (lane < nd) W.dflag[lane] &= ~DF_UNI; /* from here on a set flag means: the exact lexer */
+        WSYNC();
         /* ---- C: marker lines, a lane per line; the first MLCAP lines stage their tuples ---- */
         for (uint32_t k0 = 0; k0 < n_ml; k0 += 32) {
             const uint32_t k = k0 + lane; const bool on = k < n_ml;
@@ -285,16 +335,17 @@ OBMW_DEV bool scan_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tab
                 const bool staged = k0 == 0;
                 PackSink sink(S.u.stage + lane * LTS, staged ? LTS : 0u);
                 uint32_t res = FL_FALLBACK;
-                if (or_plusd(r) != 255u)
+                if (or_plusd(r) != PD_GENERIC)
                     res = fast_line(text, dpos + or_first(r), dpos + or_first(r) + or_plusd(r), dpos + or_ls(r), or_line(r), dpos, dend, sink);
                 uint32_t cntv; bool stg = staged;
                 if (res == FL_OK) { cntv = sink.n; if (sink.ovf) stg = false; OBMW_STAT(fast); }
                 else { /* outside the well-formed grammar: the generic lexer decides (count only; written in place later) */
                     OBMW_STAT(generic);
                     const uint32_t gr = generic_line(T, text, r, dpos, dend, nullptr, 0, nullptr, nullptr);
-                    cntv = obmp::mres_tuples(gr); stg = false;
-                    S.orec[o] = r | ((orec_t)255u << 50); /* remember: this line is the generic lexer's */
+                    S.orec[o] = r | ((orec_t)PD_GENERIC << 50); /* remember: this line is the generic lexer's */
+                    cntv = obmp::mres_tuples(gr);
                     if (obmp::mres_irregular(gr)) WATOMIC_OR(&W.dflag[d], DF_INTERACT);
+                    stg = false;
                 }
                 if (cntv >= 0xFFFFu) { WATOMIC_OR(&W.dflag[d], DF_INTERACT); cntv = 0; }
                 S.opos[o] = (uint16_t)cntv;
@@ -551,7 +602,7 @@ OBMW_DEV void write_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Ta
             const uint64_t at = base + S.opos[o];
             const uint64_t roomv = at < A.out_cap ? A.out_cap - at : 0;
             const uint32_t rc = roomv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)roomv;
-            if (or_plusd(r) != 255u) {
+            if (or_plusd(r) != PD_GENERIC) {
                 DirectSink sink(A.out + at, rc);
                 fast_line(text, dpos + or_first(r), dpos + or_first(r) + or_plusd(r), dpos + or_ls(r), or_line(r), dpos, dend, sink);
                 acc.markers += sink.mk; acc.lexemes += sink.lx;

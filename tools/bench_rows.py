@@ -49,6 +49,20 @@ def timed(fn):
 ms_idx = timed(lambda: L.obm_marker_index_device(sc.handle, reg.handle, d_bytes.data_ptr(), d_off.data_ptr(), ndocs, d_out.data_ptr(), d_toff.data_ptr(),
                                                   d_rec.data_ptr(), ndocs * 16, d_roff.data_ptr(), st))
 nrec = int(d_roff[-1])
+d_flat = torch.empty(ndocs * 16 * 2, dtype=torch.int64, device=dev)
+d_tot = torch.zeros(4, dtype=torch.int64, device=dev)
+ms_flat = timed(lambda: L.obm_marker_index_flat_device(sc.handle, reg.handle, d_bytes.data_ptr(), d_off.data_ptr(), ndocs, 0, d_out.data_ptr(), d_toff.data_ptr(),
+                                                       ntup, d_flat.data_ptr(), ndocs * 16, d_tot.data_ptr(), st))
+nflat = int(d_tot[0])
+d_res = torch.empty(ndocs * 16 * 4, dtype=torch.int64, device=dev)   # 32 B per result
+d_arg = torch.empty(ndocs * 48 * 2, dtype=torch.int64, device=dev)   # 16 B per argument
+d_dro = torch.empty(ndocs + 1, dtype=torch.int64, device=dev)
+ms_parse = timed(lambda: sc.parse_batch_device(reg, d_bytes.data_ptr(), d_off.data_ptr(), ndocs, 0, d_out.data_ptr(), d_toff.data_ptr(), d_res.data_ptr(), ndocs * 16,
+                                               d_arg.data_ptr(), ndocs * 48, d_dro.data_ptr(), d_tot.data_ptr(), st))
+nres, narg = int(d_tot[0]), int(d_tot[1])
+d_hash = torch.empty(ndocs, dtype=torch.int64, device=dev)
+d_nh = torch.zeros(2, dtype=torch.int32, device=dev)
+ms_hash = timed(lambda: L.obm_hash_batch_device(sc.handle, d_bytes.data_ptr(), d_off.data_ptr(), ndocs, d_out.data_ptr(), d_toff.data_ptr(), d_hash.data_ptr(), d_nh.data_ptr(), st))
 ms_rw = timed(lambda: L.obm_rewrite_collection_markers_device(sc.handle, d_bytes.data_ptr(), d_off.data_ptr(), ndocs, d_rw.data_ptr(), n + 64, d_noff.data_ptr(), st))
 ms_sp = timed(lambda: L.obm_split_docs_device(sc.handle, d_bytes.data_ptr(), d_off.data_ptr(), ndocs, d_rec.data_ptr(), ndocs * 16, d_roff.data_ptr(), st))
 peak = 6583.5
@@ -60,5 +74,8 @@ print(json.dumps({
     "corpus": f"{ndocs} docs x {doc_bytes} B, collection flavour, HBM resident", "peak_gbs": peak,
     "marker_index": {"ms": ms_idx, "tuple_GBps": ntup * 8 / ms_idx / 1e6, "records": nrec, "record_bytes_per_input_byte": nrec * 16 / n,
                      "frac_of_peak_on_tuple_bytes": ntup * 8 / ms_idx / 1e6 / peak},
+    "marker_index_flat": {"ms": ms_flat, "tuple_GBps": ntup * 8 / ms_flat / 1e6, "records": nflat},
+    "device_parser": {"ms": ms_parse, "tuple_GBps": ntup * 8 / ms_parse / 1e6, "results": nres, "args": narg, "record_bytes_per_input_byte": (nres * 32 + narg * 16) / n},
+    "document_hash": {"ms": ms_hash, "tuple_GBps": ntup * 8 / ms_hash / 1e6},
     "collection_rewrite": {"ms": ms_rw, "input_GBps": n / ms_rw / 1e6, "frac_of_peak": n / ms_rw / 1e6 / peak, "out_bytes": int(d_noff[-1])},
     "manifest_split": {"ms": ms_sp, "input_GBps": n / ms_sp / 1e6, "frac_of_peak": n / ms_sp / 1e6 / peak, "manifests": int(d_roff[-1])}}))

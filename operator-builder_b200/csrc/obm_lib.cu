@@ -650,6 +650,7 @@ static uint64_t warp_scratch_bytes(uint32_t ndocs, uint64_t total_bytes) {
 static int obm_warp_launch(obm_handle *h, const uint8_t *d_bytes, const uint64_t *d_doc_off, uint32_t ndocs, uint64_t total_bytes,
                            obm_tuple *d_out, uint64_t out_cap, uint64_t *toff, uint32_t *status, unsigned long long *totals,
                            uint32_t *counts, void *warp_ws, void *large_ws, cudaStream_t st) {
+    static_assert(sizeof(obmw::WarpSmem) * obmw::WPC <= 232448, "the warps of the CTA share the 227 KB of one SM");
     const size_t smem = sizeof(obmw::WarpSmem) * obmw::WPC;
     OBM_CUDA(h, cudaFuncSetAttribute(obmw::k_warp_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); /* per device: set on every call (cheap) */
     const uint64_t nt64 = warp_ntiles(total_bytes), um = warp_units_max(ndocs, total_bytes);

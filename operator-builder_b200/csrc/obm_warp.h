@@ -45,10 +45,10 @@ constexpr uint32_t MAXDOC = (BUFB - 16 < 16368u) ? BUFB - 16 : 16368u; /* larger
 constexpr uint32_t ROW = 1024;            /* bytes per row step: 32 per lane */
 constexpr uint32_t NWORDS = BUFB / 32;    /* 32-byte words of the bitmaps */
 constexpr uint32_t DMAX = 31;             /* documents per unit: one lane each, lane nd holds the end */
-constexpr uint32_t OWN_CAP = 176;         /* owning lines per unit (more: the unit is paged, document by document); manifests have ~30.  176: the tenth warp's shared memory */
+constexpr uint32_t OWN_CAP = 256;         /* owning lines per unit (more: the unit is paged, document by document; a document with more: the exact lexer) */
 constexpr uint32_t MLCAP = 32;            /* marker lines whose tuples are staged: one per lane */
 constexpr uint32_t LTS = 24;              /* staged tuples per marker line */
-constexpr uint32_t FIN_CAP = TILE / 16;   /* tuples of a unit whose write is deferred (0.5 B of tuples per input byte: manifests need 0.35) */
+constexpr uint32_t FIN_CAP = TILE / 16 - 64; /* tuples of a unit whose write is deferred (0.46 B of tuples per input byte: manifests need 0.35) */
 static_assert(BUFB % ROW == 0 && BUFB >= TILE + 16 && BUFB <= 16384 + ROW, "buffer geometry");
 
 /* document flags; DF_UNI lives only between phases A and B: a valid-UTF-8 document without Unicode white space stays on the

@@ -34,23 +34,23 @@ namespace obmw {
 struct UnitSet {
     union {
         struct { uint32_t nlw[NWORDS]; uint32_t spw[NWORDS]; } bm; /* phases A, B */
-        uint32_t stage[MLCAP * LTS];                               /* phase C on (the bitmaps are dead by then) */
+        struct { uint32_t stage[MLCAP * LTS]; uint32_t mstat[MLCAP]; } c; /* phase C on (the bitmaps are dead by then); mstat: staged line =
+                                                                    * markers | lexemes << 8 | tuples << 16; MS_NONE: not staged */
     } u;
     orec_t orec[OWN_CAP];       /* phase A: position of the line's first special; phase B: owner record */
     uint16_t opos[OWN_CAP];     /* tuples of the owner; after the assembly: its tuple position inside the unit */
     uint8_t mlist[OWN_CAP];     /* marker rank -> owner */
-    uint32_t mstat[MLCAP];      /* staged line: markers | lexemes << 8 | tuples << 16; MS_NONE: not staged */
 };
 struct WarpSmem {
     alignas(16) uint8_t text[BUFB + 64];
     UnitSet set;
     uint32_t fin[FIN_CAP];      /* the unit's tuples, packed (st_pack), in final order: what the DEFERRED write needs -- a warp scans
                                  * its next unit while this unit's tuple count travels through the chain (obm_warp.cuh) */
-    uint16_t nlpre[NWORDS];     /* newline bits in words [0, w) */
+    uint16_t nlpre[NWORDS / 2]; /* newline bits in words [0, 2k): every second word, the odd ones add their neighbour's count */
     uint32_t naw[NWORDS / 32 + 1]; /* per row: the 32-byte words that hold bytes >= 0x80 */
     uint32_t dstart[DMAX + 2];  /* document starts, buffer-relative; [nd] = end */
     uint32_t dflag[DMAX + 1];
-    uint32_t dcnt[DMAX + 1];    /* exclusive tuple offsets of the documents inside the unit */
+    uint16_t dcnt[DMAX + 1];    /* exclusive tuple offsets of the documents inside the unit */
     uint16_t dfo[DMAX + 2];     /* first owner of the document */
     alignas(8) uint64_t mbar;
 };
@@ -126,8 +126,9 @@ OBM_FN uint32_t w_line_start(const UnitSet &S, uint32_t pos, uint32_t lo) {
 }
 OBM_HD uint32_t w_nl_before(const WarpSmem &W, const UnitSet &S, uint32_t q) {
     const uint32_t w = q >> 5;
-    if (w >= NWORDS) return (uint32_t)W.nlpre[NWORDS - 1] + OBMT_POPC(S.u.bm.nlw[NWORDS - 1]);
-    return (uint32_t)W.nlpre[w] + OBMT_POPC(S.u.bm.nlw[w] & ((1u << (q & 31)) - 1u));
+    static_assert(NWORDS % 2 == 0, "nlpre pairs the words");
+    if (w >= NWORDS) return (uint32_t)W.nlpre[NWORDS / 2 - 1] + OBMT_POPC(S.u.bm.nlw[NWORDS - 2]) + OBMT_POPC(S.u.bm.nlw[NWORDS - 1]);
+    return (uint32_t)W.nlpre[w >> 1] + ((w & 1u) ? OBMT_POPC(S.u.bm.nlw[w - 1]) : 0u) + OBMT_POPC(S.u.bm.nlw[w] & ((1u << (q & 31)) - 1u));
 }
 
 /* inclusive warp scan of a u32 */
@@ -257,7 +258,7 @@ OBMW_DEV bool scan_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tab
             const uint32_t mine = cnt;
             OBMW_SCAN_INCL(cnt);
             const uint32_t excl = cnt - mine;
-            W.nlpre[r * 32u + lane] = (uint16_t)(nl_run + (excl & 0xFFFFu));
+            if (!(lane & 1u)) W.nlpre[r * 16u + (lane >> 1)] = (uint16_t)(nl_run + (excl & 0xFFFFu));
             uint32_t o = own_run + (excl >> 16);
             while (own) {
                 if (o < OWN_CAP) S.orec[o] = pos0 + (OBMW_FFS(own) - 1u);
@@ -333,7 +334,7 @@ OBMW_DEV bool scan_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tab
                 const orec_t r = S.orec[o];
                 const uint32_t d = or_doc(r), dpos = W.dstart[d], dend = W.dstart[d + 1];
                 const bool staged = k0 == 0;
-                PackSink sink(S.u.stage + lane * LTS, staged ? LTS : 0u);
+                PackSink sink(S.u.c.stage + lane * LTS, staged ? LTS : 0u);
                 uint32_t res = FL_FALLBACK;
                 if (or_plusd(r) != PD_GENERIC)
                     res = fast_line(text, dpos + or_first(r), dpos + or_first(r) + or_plusd(r), dpos + or_ls(r), or_line(r), dpos, dend, sink);
@@ -349,7 +350,7 @@ OBMW_DEV bool scan_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tab
                 }
                 if (cntv >= 0xFFFFu) { WATOMIC_OR(&W.dflag[d], DF_INTERACT); cntv = 0; }
                 S.opos[o] = (uint16_t)cntv;
-                if (staged) S.mstat[lane] = (stg && cntv) ? (sink.mk | (sink.lx << 8) | (cntv << 16)) : MS_NONE; /* cntv <= LTS: the counters fit */
+                if (staged) S.u.c.mstat[lane] = (stg && cntv) ? (sink.mk | (sink.lx << 8) | (cntv << 16)) : MS_NONE; /* cntv <= LTS: the counters fit */
                 if (cntv && !stg) unstaged = true;
             }
         }
@@ -397,7 +398,7 @@ OBMW_DEV bool scan_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Tab
     OBMW_SCAN_INCL(dincl);
     const uint32_t dexcl = dincl - (lane < nd ? dtot : 0u);
     uint64_t total = WSHFL(dincl, 31);
-    if (lane < nd) W.dcnt[lane] = dexcl - p0; /* owner prefix + this = tuple position inside the unit */
+    if (lane < nd) W.dcnt[lane] = (uint16_t)(dexcl - p0); /* owner prefix + this = tuple position inside the unit */
     WSYNC();
     for (uint32_t o0 = 0; o0 < n_owners; o0 += 32) {
         const uint32_t o = o0 + lane;
@@ -496,12 +497,12 @@ OBMW_DEV bool assemble_fin(WarpSmem &W, UnitSet &S, const UnitRegs &R, WAcc &acc
         const uint32_t ns = n_ml < MLCAP ? n_ml : MLCAP;
         uint32_t c = 0, rel = 0;
         if (lane < ns) {
-            const uint32_t ms = S.mstat[lane]; /* never MS_NONE here: every marker line with tuples is staged */
+            const uint32_t ms = S.u.c.mstat[lane]; /* never MS_NONE here: every marker line with tuples is staged */
             if (ms != MS_NONE) { c = ms >> 16; rel = S.opos[S.mlist[lane]]; acc.markers += ms & 0xFFu; acc.lexemes += (ms >> 8) & 0xFFu; }
         }
         for (uint32_t k = 0; k < ns; k++) {
             const uint32_t ck = WSHFL(c, k), rk = WSHFL(rel, k);
-            if (lane < ck) W.fin[rk + lane] = S.u.stage[k * LTS + lane];
+            if (lane < ck) W.fin[rk + lane] = S.u.c.stage[k * LTS + lane];
         }
     }
     WSYNC();
@@ -594,7 +595,7 @@ OBMW_DEV void write_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Ta
         for (uint32_t k0 = 0; k0 < n_ml; k0 += 32) {
             const uint32_t k = k0 + lane;
             if (k >= n_ml) continue;
-            if (k0 == 0 && S.mstat[lane] != MS_NONE) continue; /* staged */
+            if (k0 == 0 && S.u.c.mstat[lane] != MS_NONE) continue; /* staged */
             const uint32_t o = S.mlist[k];
             const orec_t r = S.orec[o];
             const uint32_t d = or_doc(r), dpos = W.dstart[d], dend = W.dstart[d + 1];
@@ -618,7 +619,7 @@ OBMW_DEV void write_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Ta
         const uint32_t ns = n_ml < MLCAP ? n_ml : MLCAP;
         uint32_t c = 0, rel = 0;
         if (lane < ns) {
-            const uint32_t ms = S.mstat[lane];
+            const uint32_t ms = S.u.c.mstat[lane];
             const uint32_t o = S.mlist[lane];
             if (ms != MS_NONE && !(R.needs_text && W.dflag[or_doc(S.orec[o])])) {
                 c = ms >> 16; rel = S.opos[o];
@@ -629,7 +630,7 @@ OBMW_DEV void write_range(WarpSmem &W, UnitSet &S, const WArgs &A, const obm::Ta
             for (uint32_t k = 0; k < ns; k++) {
                 const uint32_t ck = WSHFL(c, k), rk = WSHFL(rel, k);
                 const uint64_t at = base + rk + lane;
-                if (lane < ck && at < A.out_cap) A.out[at] = st_unpack(S.u.stage[k * LTS + lane]);
+                if (lane < ck && at < A.out_cap) A.out[at] = st_unpack(S.u.c.stage[k * LTS + lane]);
             }
         }
     }

@@ -58,7 +58,7 @@ def test_dense_marker_lines_long_lines_and_large_documents():
 
 
 def test_units_with_more_owning_lines_than_the_owner_table():
-    """lines of a few bytes: a unit's documents together have more owning lines than OWN_CAP (176); the fused warp
+    """lines of a few bytes: a unit's documents together have more owning lines than OWN_CAP (256); the fused warp
     kernel then scans and writes the unit one document at a time instead of handing every document to the exact lexer"""
     short = [b"".join(b"# c%d\n" % (i % 7) for i in range(n)) for n in (100, 120, 90, 130, 40, 200)]
     marks = [b"".join(b"# +a:b:c=%d\n" % (i % 10) if i % 3 == 0 else b"# x\n" for i in range(n)) for n in (150, 110, 170)]

@@ -1608,17 +1608,54 @@ extern "C" int obm_parse_batch_device(obm_handle *h, const obm_registry *reg, co
     return OBM_OK;
 }
 
+#include "obm_rewrite.cuh"
+/* one pass (obm_rewrite.cuh) when both buffers are 16-byte aligned, else r01's two passes over the documents */
 extern "C" int obm_rewrite_collection_markers_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
                                                      void *d_out_bytes, uint64_t out_cap, void *d_out_doc_off, void *stream) {
     if (!h || !d_doc_off || !d_out_doc_off) return OBM_E_ARG;
     OBM_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (ndocs == 0) { OBM_CUDA(h, cudaMemsetAsync(d_out_doc_off, 0, 8, st)); return OBM_OK; }
-    uint32_t *counts; uint64_t *tile_sums; int rc;
-    if ((rc = two_pass_scratch(h, ndocs, st, &counts, &tile_sums)) != OBM_OK) return rc;
     uint64_t *noff = (uint64_t *)d_out_doc_off;
     int sms_i = 0;
     OBM_CUDA(h, cudaDeviceGetAttribute(&sms_i, cudaDevAttrMultiProcessorCount, h->device));
+    const bool aligned = (((uintptr_t)d_bytes | (uintptr_t)d_out_bytes) & 15u) == 0;
+    if (aligned && !getenv("OBM_REWRITE_TWO_PASS")) {
+        uint64_t total = 0; /* the batch size: the last offset (8 bytes from the device; the call is synchronous at its end anyway) */
+        OBM_CUDA(h, cudaMemcpyAsync(&total, (const uint64_t *)d_doc_off + ndocs, 8, cudaMemcpyDeviceToHost, st));
+        OBM_CUDA(h, cudaStreamSynchronize(st));
+        const uint64_t nch64 = total / obmrw::RW_CH + 1;
+        if (nch64 > 0xFFFFFFF0ull) { set_err(h, "batch too large for the chunk index"); return OBM_E_ARG; }
+        const uint32_t nchunks = (uint32_t)nch64;
+        const uint64_t need = align_up(((uint64_t)nchunks + 2) * 4, 256) + align_up((uint64_t)nchunks * 8, 256) + 256;
+        if (h->scratch_bytes < need) {
+            if (h->scratch) { OBM_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->scratch); h->scratch = nullptr; h->scratch_bytes = 0; }
+            OBM_CUDA(h, cudaMalloc(&h->scratch, need)); h->scratch_bytes = need;
+        }
+        uint32_t *tile_first = (uint32_t *)h->scratch;
+        uint64_t *state = (uint64_t *)((uint8_t *)h->scratch + align_up(((uint64_t)nchunks + 2) * 4, 256));
+        uint32_t *ticket = (uint32_t *)((uint8_t *)state + align_up((uint64_t)nchunks * 8, 256));
+        OBM_CUDA(h, cudaMemsetAsync(state, 0, align_up((uint64_t)nchunks * 8, 256) + 256, st));
+        obmrw::k_rw_tile_index<<<(ndocs + 1 + 255) / 256, 256, 0, st>>>((const uint64_t *)d_doc_off, ndocs, nchunks, tile_first);
+        uint32_t nb = (uint32_t)sms_i * 8u; /* persistent CTAs, chunks by ticket */
+        if (nb > nchunks) nb = nchunks;
+        if (d_out_bytes)
+            obmrw::k_rw_chunks<true><<<nb, obmrw::RW_THREADS, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total, nchunks, tile_first,
+                                                                        state, ticket, noff, (uint8_t *)d_out_bytes, out_cap);
+        else
+            obmrw::k_rw_chunks<false><<<nb, obmrw::RW_THREADS, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, total, nchunks, tile_first,
+                                                                         state, ticket, noff, nullptr, 0);
+        OBM_CUDA(h, cudaGetLastError());
+        if (d_out_bytes) { /* the kernel never writes past out_cap; tell the caller when that cut the output short */
+            uint64_t nt = 0;
+            OBM_CUDA(h, cudaMemcpyAsync(&nt, noff + ndocs, 8, cudaMemcpyDeviceToHost, st));
+            OBM_CUDA(h, cudaStreamSynchronize(st));
+            if (nt > out_cap) { set_err(h, "rewrite needs %llu bytes, out_cap is %llu", (unsigned long long)nt, (unsigned long long)out_cap); return OBM_E_CAPACITY; }
+        }
+        return OBM_OK;
+    }
+    uint32_t *counts; uint64_t *tile_sums; int rc;
+    if ((rc = two_pass_scratch(h, ndocs, st, &counts, &tile_sums)) != OBM_OK) return rc;
     const uint32_t nt = scan_tiles(ndocs);
     uint32_t nb = (uint32_t)sms_i * 8u; /* persistent warps, a document each per step */
     if (nb > (ndocs + 7) / 8) nb = (ndocs + 7) / 8;

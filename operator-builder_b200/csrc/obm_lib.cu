@@ -1143,13 +1143,20 @@ extern "C" int obm_marker_index_device(obm_handle *h, const obm_registry *reg, c
  * Here a thread takes 8 consecutive tuples of the whole stream (four 16-byte loads, coalesced across the warp); the rare
  * MarkerStart candidates (4 % of the tuples) look around through the cache: back for a stale buffer, forward along the
  * Scope / Separator chain (a document's tuples end with EOF or a fatal error, so neither walk leaves the document), then the
- * name is compared with the registry.  Two passes (per-tile counts, scan, write in tuple order); the document of a hit is
- * found by bisection of doc_tuple_off.  Records: {u32 doc + doc_base, u32 tuple index in the document, u32 offset of '+',
+ * name is compared with the registry.  One pass: tiles by ticket, the tile's hit count goes through a decoupled look-back
+ * (obm_fast.cuh), the records are written in tuple order; the document of a hit is found from the tile's first tuple
+ * (k_flat_tile_docs) in 64 cached offsets.  What bounds the kernel is the number of dependent round trips to memory per tile.  (Until round 2's last session: two passes and a bisection per hit.)  Records: {u32 doc + doc_base, u32 tuple index in the document, u32 offset of '+',
  * u16 registry id | u16 scopes << 16}. */
 constexpr uint32_t FI_THREADS = 256, FI_PER = 8, FI_TILE = FI_THREADS * FI_PER;
+/* the tuple stream as the candidate walks see it: the tile's own tuples from shared memory, the neighbours' from global memory */
+struct TileView {
+    const obm_tuple *g, *s; uint64_t t0;
+    __device__ __forceinline__ obm_tuple operator[](uint64_t j) const { const uint64_t r = j - t0; return r < FI_TILE ? s[r] : g[j]; }
+};
+template <class TV>
 __device__ __forceinline__ int flat_index_hit(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs,
-                                              const obm_tuple *__restrict__ t, const uint64_t *__restrict__ tuple_off, uint64_t ntup, uint64_t i,
-                                              const DevRegistry &reg, uint32_t *doc_out, uint32_t *scopes_out) {
+                                              const TV &t, const uint64_t *__restrict__ tuple_off, uint64_t ntup, uint64_t i,
+                                              const DevRegistry &reg, uint32_t hint, bool exact, uint64_t exact_doc_off, uint32_t *doc_out, uint32_t *scopes_out) {
     const obm_tuple tu = t[i];
     /* stale buffer?  walk back over tuples that carry no buffer text; the first PART / FLUSH / slice tuple decides */
     for (uint64_t j = i; j-- > 0;) {
@@ -1170,14 +1177,33 @@ __device__ __forceinline__ int flat_index_hit(const uint8_t *__restrict__ bytes,
     bool len_ok = false;
     for (uint32_t r = 0; r < reg.n; r++) len_ok |= reg.off[r + 1] - reg.off[r] == pos;
     if (!len_ok) return -1;
-    uint32_t lo = 0, hi = ndocs; /* last d with tuple_off[d] <= i */
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (tuple_off[mid] <= i) lo = mid; else hi = mid; }
-    const uint8_t *doc = bytes + doc_off[lo];
+    uint32_t lo = hint; /* last d with tuple_off[d] <= i; `exact`: the caller found it in its cached offsets, else walk on from the hint */
+    if (!exact) while (lo + 1 < ndocs && tuple_off[lo + 1] <= i) lo++;
+    const uint8_t *doc = bytes + (exact ? exact_doc_off : doc_off[lo]);
     int hit = -1;
+    /* the usual case -- one contiguous name of at most 48 bytes -- with ONE round trip to the text: thirteen aligned words
+     * loaded together, shifted into place, then compared byte by byte in registers (the byte loop below costs a round trip
+     * per few bytes) */
+    constexpr uint32_t NW = 12;
+    uint32_t aw[NW];
+    const bool vec = contiguous && pos <= 4 * NW;
+    if (vec) {
+        const uintptr_t p0 = (uintptr_t)(doc + off);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(p0 & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(p0 & 3u) * 8u, need = ((uint32_t)(p0 & 3u) + pos + 3u) >> 2; /* words that hold the name */
+        uint32_t w[NW + 1];
+#pragma unroll
+        for (uint32_t k = 0; k <= NW; k++) w[k] = k < need ? wp[k] : 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < NW; k++) aw[k] = __funnelshift_r(w[k], w[k + 1], sh);
+    }
     for (uint32_t r = 0; r < reg.n; r++) {
         if (reg.off[r + 1] - reg.off[r] != pos) continue;
         uint32_t diff = 0;
-        if (contiguous) for (uint32_t b = 0; b < pos; b++) diff |= (uint32_t)doc[off + b] ^ (uint32_t)(uint8_t)reg.text[reg.off[r] + b];
+        if (vec) {
+#pragma unroll
+            for (uint32_t b = 0; b < 4 * NW; b++) if (b < pos) diff |= ((aw[b >> 2] >> (8u * (b & 3u))) & 0xFFu) ^ (uint32_t)(uint8_t)reg.text[reg.off[r] + b];
+        } else if (contiguous) for (uint32_t b = 0; b < pos; b++) diff |= (uint32_t)doc[off + b] ^ (uint32_t)(uint8_t)reg.text[reg.off[r] + b];
         else { /* scope slices apart from each other: piece by piece */
             uint32_t q = 1; diff = (uint32_t)(uint8_t)reg.text[reg.off[r]] ^ (uint32_t)'+';
             uint64_t jj = i + 1;
@@ -1193,49 +1219,107 @@ __device__ __forceinline__ int flat_index_hit(const uint8_t *__restrict__ bytes,
     *doc_out = lo; *scopes_out = scopes;
     return hit;
 }
-template <bool WRITE>
-__global__ void __launch_bounds__(FI_THREADS)
+/* tile -> the document of its first tuple: document d owns the tiles whose first tuple lies in [tuple_off[d], tuple_off[d + 1]) */
+__global__ void __launch_bounds__(256)
+k_flat_tile_docs(const uint64_t *__restrict__ tuple_off, uint32_t ndocs, uint32_t ntiles, uint32_t *__restrict__ tile_doc) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndocs) return;
+    const uint64_t a = tuple_off[d], b = tuple_off[d + 1];
+    for (uint64_t t = (a + FI_TILE - 1) / FI_TILE; t * FI_TILE < b && t < ntiles; t++) tile_doc[t] = d;
+}
+/* ONE pass: tiles by ticket.  The rare candidates are compacted (in tuple order) and then looked at a THREAD EACH -- the walks
+ * around a candidate are a few hundred instructions, which single lanes of the loading warps would execute at 1/32 of the
+ * issue rate --; the tile's records are staged in shared memory while its hit count goes through a decoupled look-back. */
+constexpr uint32_t FI_DOCS = 64, FI_RECS = FI_TILE / 4 + 8; /* tuple offsets cached per tile; a hit is at least 4 tuples */
+__global__ void __launch_bounds__(FI_THREADS, 6)
 k_marker_index_flat(const uint8_t *__restrict__ bytes, const uint64_t *__restrict__ doc_off, uint32_t ndocs, uint32_t doc_base,
                     const obm_tuple *__restrict__ tuples, const uint64_t *__restrict__ tuple_off, const __grid_constant__ DevRegistry reg,
-                    uint32_t *__restrict__ counts, const uint64_t *__restrict__ rec_off, uint4 *__restrict__ records, uint64_t cap) {
+                    volatile uint64_t *state, uint32_t *ticket, uint32_t ntiles, const uint32_t *__restrict__ tile_doc, uint64_t *__restrict__ total_out,
+                    uint4 *__restrict__ records, uint64_t cap) {
     __shared__ uint32_t wsum[FI_THREADS / 32];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_doff[FI_DOCS + 1];
+    __shared__ uint64_t s_excl;
+    __shared__ uint16_t cidx[FI_TILE];
+    __shared__ uint64_t s_toff[FI_DOCS + 1];
+    __shared__ uint4 recs[FI_RECS];
+    __shared__ __align__(16) obm_tuple stup[FI_TILE]; /* the tile's tuples: the walks around a candidate stay on chip */
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint64_t ntup = tuple_off[ndocs];
-    const uint64_t i0 = (uint64_t)blockIdx.x * FI_TILE + (uint64_t)threadIdx.x * FI_PER;
-    obm_tuple v[FI_PER];
+    const uint64_t t0 = (uint64_t)tile * FI_TILE, i0 = t0 + (uint64_t)threadIdx.x * FI_PER;
+    uint32_t cand = 0;
     if (i0 + FI_PER <= ntup) { /* the stream is 8-byte aligned and i0 a multiple of 8 tuples: 64-byte chunks */
         const uint4 *p = reinterpret_cast<const uint4 *>(tuples + i0);
 #pragma unroll
-        for (uint32_t q = 0; q < FI_PER / 2; q++) { const uint4 x = p[q]; v[2 * q] = (uint64_t)x.x | ((uint64_t)x.y << 32); v[2 * q + 1] = (uint64_t)x.z | ((uint64_t)x.w << 32); }
+        for (uint32_t q = 0; q < FI_PER / 2; q++) {
+            const uint4 x = p[q]; /* kind and length live in the high word */
+            reinterpret_cast<uint4 *>(stup)[threadIdx.x * (FI_PER / 2) + q] = x;
+            const obm_tuple a = (uint64_t)x.x | ((uint64_t)x.y << 32), b = (uint64_t)x.z | ((uint64_t)x.w << 32);
+            if (OBM_TUPLE_KIND(a) == OBM_K_MARKER_START && OBM_TUPLE_LEN(a) == 1) cand |= 1u << (2 * q);
+            if (OBM_TUPLE_KIND(b) == OBM_K_MARKER_START && OBM_TUPLE_LEN(b) == 1) cand |= 2u << (2 * q);
+        }
     } else {
 #pragma unroll
-        for (uint32_t q = 0; q < FI_PER; q++) v[q] = i0 + q < ntup ? tuples[i0 + q] : 0;
-    }
-    uint32_t cand = 0;
-#pragma unroll
-    for (uint32_t q = 0; q < FI_PER; q++) if (i0 + q < ntup && OBM_TUPLE_KIND(v[q]) == OBM_K_MARKER_START && OBM_TUPLE_LEN(v[q]) == 1) cand |= 1u << q;
-    uint32_t hits = 0; uint4 rec[2]; uint32_t nrec = 0; /* at most FI_PER / 4 markers among 8 consecutive tuples ("+a:b" is 6 tuples: <= 2) */
-    for (uint32_t m = cand; m; m &= m - 1) {
-        const uint32_t q = (uint32_t)__ffs((int)m) - 1u;
-        uint32_t d = 0, scopes = 0;
-        const int hit = flat_index_hit(bytes, doc_off, ndocs, tuples, tuple_off, ntup, i0 + q, reg, &d, &scopes);
-        if (hit >= 0) {
-            hits++;
-            if (WRITE && nrec < 2) rec[nrec++] = make_uint4(d + doc_base, (uint32_t)(i0 + q - tuple_off[d]), OBM_TUPLE_OFF(v[q]), (uint32_t)hit | (scopes << 16));
+        for (uint32_t q = 0; q < FI_PER; q++) {
+            const obm_tuple a = i0 + q < ntup ? tuples[i0 + q] : 0;
+            stup[threadIdx.x * FI_PER + q] = a;
+            if (i0 + q < ntup && OBM_TUPLE_KIND(a) == OBM_K_MARKER_START && OBM_TUPLE_LEN(a) == 1) cand |= 1u << q;
         }
     }
-    /* block-wide exclusive scan of the per-thread hit counts (threads are in tuple order) */
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t incl = hits;
+    /* the candidates of the tile, in tuple order */
+    const uint32_t nc = (uint32_t)__popc(cand);
+    uint32_t incl = nc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += x; }
     if (lane == 31) wsum[wid] = incl;
+    const uint32_t hint = t0 < ntup ? tile_doc[tile] : 0; /* the document of the tile's first tuple (k_flat_tile_docs) */
     __syncthreads();
-    uint32_t pre = 0, tot = 0;
+    uint32_t cbase = incl - nc, ctot = 0;
 #pragma unroll
-    for (uint32_t w = 0; w < FI_THREADS / 32; w++) { const uint32_t c = wsum[w]; if (w < wid) pre += c; tot += c; }
-    if (!WRITE) { if (threadIdx.x == 0) counts[blockIdx.x] = tot; return; }
-    const uint64_t at = rec_off[blockIdx.x] + pre + incl - hits;
-    for (uint32_t k = 0; k < nrec; k++) if (at + k < cap) records[at + k] = rec[k];
+    for (uint32_t w = 0; w < FI_THREADS / 32; w++) { const uint32_t c = wsum[w]; if (w < wid) cbase += c; ctot += c; }
+    for (uint32_t m = cand; m; m &= m - 1) cidx[cbase++] = (uint16_t)(threadIdx.x * FI_PER + (uint32_t)__ffs((int)m) - 1u);
+    if (ctot) for (uint32_t k = threadIdx.x; k <= 2 * FI_DOCS + 1; k += FI_THREADS) { /* ctot > 0 implies t0 < ntup */
+        const uint32_t kk = k <= FI_DOCS ? k : k - FI_DOCS - 1;
+        if (k <= FI_DOCS) s_toff[kk] = hint + kk <= ndocs ? tuple_off[hint + kk] : ~0ull;
+        else s_doff[kk] = hint + kk <= ndocs ? doc_off[hint + kk] : 0;
+    }
+    __syncthreads();
+    /* a thread per candidate, FI_THREADS per round; hits keep the order */
+    uint32_t running = 0;
+    for (uint32_t base = 0; base < ctot; base += FI_THREADS) { /* block-uniform */
+        const uint32_t c = base + threadIdx.x;
+        int hit = -1; uint4 rec = make_uint4(0, 0, 0, 0);
+        if (c < ctot) {
+            const uint64_t i = t0 + cidx[c];
+            uint32_t lo = 0, hi = FI_DOCS + 1; /* last k with s_toff[k] <= i (s_toff[0] <= t0 <= i) */
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_toff[mid] <= i) lo = mid; else hi = mid; }
+            uint32_t d = 0, scopes = 0;
+            const TileView tv{tuples, stup, t0};
+            hit = flat_index_hit(bytes, doc_off, ndocs, tv, tuple_off, ntup, i, reg, hint + lo, lo < FI_DOCS, s_doff[lo], &d, &scopes); /* lo == FI_DOCS: the cache ended, walk on */
+            if (hit >= 0) rec = make_uint4(d + doc_base, (uint32_t)(i - (d - hint <= FI_DOCS ? s_toff[d - hint] : tuple_off[d])), OBM_TUPLE_OFF(tv[i]), (uint32_t)hit | (scopes << 16));
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, hit >= 0);
+        __syncthreads(); /* wsum of the previous use is read */
+        if (lane == 0) wsum[wid] = (uint32_t)__popc(bal);
+        __syncthreads();
+        uint32_t pre = 0, tot = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < FI_THREADS / 32; w++) { const uint32_t x = wsum[w]; if (w < wid) pre += x; tot += x; }
+        const uint32_t at = running + pre + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+        if (hit >= 0 && at < FI_RECS) recs[at] = rec;
+        running += tot;
+    }
+    if (wid == 0) {
+        const uint64_t excl = obmf::lookback_warp(state, tile, running);
+        if (lane == 0) { s_excl = excl; if (tile == ntiles - 1) *total_out = excl + running; }
+    }
+    __syncthreads();
+    if (!records) return;
+    const uint64_t at0 = s_excl;
+    for (uint32_t k = threadIdx.x; k < running && k < FI_RECS; k += FI_THREADS) if (at0 + k < cap) records[at0 + k] = recs[k];
 }
 
 /* records of the REGISTERED markers of a resident tuple stream, in document order; *d_total (device u64) = their number.
@@ -1260,25 +1344,20 @@ extern "C" int obm_marker_index_flat_device(obm_handle *h, const obm_registry *r
     /* the tuple count lives on the device (doc_tuple_off[ndocs]); the grid is sized for the caller's bound (its out_cap) */
     const uint64_t ntiles64 = (ntuples_bound + FI_TILE - 1) / FI_TILE;
     if (ntiles64 > 0x7FFFFFF0ull) { set_err(h, "tuple stream too large for the flat index"); return OBM_E_ARG; }
-    const uint32_t ntiles = (uint32_t)ntiles64, nt = scan_tiles(ntiles);
-    const uint64_t need = align_up((uint64_t)ntiles * 4 + 4, 256) + align_up(((uint64_t)ntiles + 1) * 8, 256) + align_up((uint64_t)nt * 8 + 8, 256);
+    const uint32_t ntiles = (uint32_t)ntiles64;
+    const uint64_t need = align_up((uint64_t)ntiles * 8, 256) + 256 + align_up((uint64_t)ntiles * 4, 256);
     if (h->scratch_bytes < need) {
         if (h->scratch) { OBM_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->scratch); h->scratch = nullptr; h->scratch_bytes = 0; }
         OBM_CUDA(h, cudaMalloc(&h->scratch, need)); h->scratch_bytes = need;
     }
-    uint8_t *q = (uint8_t *)h->scratch;
-    uint32_t *counts = (uint32_t *)q; q += align_up((uint64_t)ntiles * 4 + 4, 256);
-    uint64_t *roff = (uint64_t *)q; q += align_up(((uint64_t)ntiles + 1) * 8, 256);
-    uint64_t *tile_sums = (uint64_t *)q;
-    k_marker_index_flat<false><<<ntiles, FI_THREADS, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, doc_base, (const obm_tuple *)d_tuples,
-                                                             (const uint64_t *)d_doc_tuple_off, R, counts, nullptr, nullptr, 0);
-    k_scan_tiles<<<nt, SCAN_THREADS, 0, st>>>(counts, ntiles, roff, tile_sums);
-    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(tile_sums, nt, roff + ntiles);
-    k_scan_add<<<nt, SCAN_THREADS, 0, st>>>(roff, ntiles, tile_sums, ~0ull, nullptr);
-    OBM_CUDA(h, cudaMemcpyAsync(d_total, roff + ntiles, 8, cudaMemcpyDeviceToDevice, st));
-    if (d_records && cap)
-        k_marker_index_flat<true><<<ntiles, FI_THREADS, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, doc_base, (const obm_tuple *)d_tuples,
-                                                                (const uint64_t *)d_doc_tuple_off, R, nullptr, roff, (uint4 *)d_records, cap);
+    uint64_t *state = (uint64_t *)h->scratch;
+    uint32_t *ticket = (uint32_t *)((uint8_t *)h->scratch + align_up((uint64_t)ntiles * 8, 256));
+    uint32_t *tile_doc = (uint32_t *)((uint8_t *)ticket + 256);
+    OBM_CUDA(h, cudaMemsetAsync(state, 0, need, st));
+    k_flat_tile_docs<<<(ndocs + 255) / 256, 256, 0, st>>>((const uint64_t *)d_doc_tuple_off, ndocs, ntiles, tile_doc);
+    k_marker_index_flat<<<ntiles, FI_THREADS, 0, st>>>((const uint8_t *)d_bytes, (const uint64_t *)d_doc_off, ndocs, doc_base, (const obm_tuple *)d_tuples,
+                                                      (const uint64_t *)d_doc_tuple_off, R, state, ticket, ntiles, tile_doc, (uint64_t *)d_total,
+                                                      (d_records && cap) ? (uint4 *)d_records : nullptr, cap);
     OBM_CUDA(h, cudaGetLastError());
     return OBM_OK;
 }

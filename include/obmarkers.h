@@ -272,8 +272,9 @@ void obm_registry_free(obm_registry *r);
 int obm_marker_index_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
                             const void *d_tuples, const void *d_doc_tuple_off, void *d_records, uint64_t cap,
                             void *d_doc_rec_off, void *stream);
-/* The same records (document order, doc_base added to the document ids) from a FLAT pass over the tuple stream: a thread per 8
- * tuples instead of a warp per document, ~10x faster; no per-document offsets.  ntuples_bound: an upper bound of the stream's
+/* The same records (document order, doc_base added to the document ids) from ONE flat pass over the tuple stream (2,048-tuple
+ * tiles, the rare MarkerStart candidates examined a thread each, tile totals through a look-back) instead of a warp per
+ * document: ~6x faster; no per-document offsets.  ntuples_bound: an upper bound of the stream's
  * length known on the host (the capacity of d_tuples does); *d_total (device u64) = number of records. */
 int obm_marker_index_flat_device(obm_handle *h, const obm_registry *reg, const void *d_bytes, const void *d_doc_off, uint32_t ndocs, uint32_t doc_base,
                                  const void *d_tuples, const void *d_doc_tuple_off, uint64_t ntuples_bound, void *d_records, uint64_t cap,

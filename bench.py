@@ -276,7 +276,7 @@ def main():
         sampler.start()
     ms = timed(step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    launches = (ob._native.lib().obm_launches_last_call(sc.handle) + (5 if world > 1 else 0)) * args.steps  # scan kernels (+ N > 1: the index's 2 kernels and 3 scan launches)
+    launches = (ob._native.lib().obm_launches_last_call(sc.handle) + (2 if world > 1 else 0)) * args.steps  # scan kernels (+ N > 1: the one-pass index = k_flat_tile_docs + k_marker_index_flat)
 
     # the parts, same stream, same events: scan-only time is the roofline's denominator
     ms_scan = timed(scan_only, args.steps)

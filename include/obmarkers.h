@@ -189,6 +189,7 @@ void obm_pinned_free(void *p);
  * input) and its ndocs+1 offsets; with d_out_bytes == NULL only the offsets are produced.  One pass over the batch
  * (csrc/obm_rewrite.cuh) when d_bytes and d_out_bytes are 16-byte aligned, two passes over the documents otherwise.
  * Nothing is written past out_cap; OBM_E_CAPACITY reports an output that did not fit.  Synchronises the stream.
+ * (Test switch: OBM_REWRITE_TWO_PASS=1 in the environment forces the two-pass path.)
  */
 int obm_rewrite_collection_markers_device(obm_handle *h, const void *d_bytes, const void *d_doc_off, uint32_t ndocs,
                                           void *d_out_bytes, uint64_t out_cap, void *d_out_doc_off, void *stream);
